@@ -1,0 +1,218 @@
+/*
+ * spmv_b200.h -- C ABI of the B200-native SpMV engine (libspmv_b200.so).
+ *
+ * Drop-in boundary for the GPU path of andreadiiorio/SpMV_openMP_CUDA (y = A*x, fp64, CSR and
+ * ELLPACK).  Plain C: pointers and sizes only, no torch / C++ types.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions (the reference's): every function returns 0 (EXIT_SUCCESS) on success
+ * and non-zero on failure; a diagnostic goes to stderr (like ERRPRINT, src/include/macros.h:57-58)
+ * and is kept for spmvb200_last_error().  Index arrays coming from the host use the reference's
+ * element type `ulong` == uint64_t (src/include/sparseMatrix.h:26-32); on the device the engine
+ * narrows them to 32 bit (all supported matrices have M, N, NZ < 2^32 / 2^31, checked at upload).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails loudly.
+ *
+ * Threading: call from one host thread per matrix handle (the reference driver is single threaded
+ * around the GPU path, src/main.cu:192-248).  Device-pointer entry points are asynchronous on the
+ * stream given; host-pointer entry points synchronise before returning.
+ */
+#ifndef SPMV_B200_H
+#define SPMV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPMVB200_VERSION 100
+
+/* Kernel selectors.  Values 0..4 are the reference's CUDA compute modes in table order
+ * (SpmvCUDA_CSRFuncs[0..1], SpmvCUDA_ELLFuncs[0..2], src/include/SpMV.h:130-142; mode strings
+ * src/include/SpMV.h:37-41); later values are new modes appended after them. */
+typedef enum {
+    SPMVB200_CSR_ROWS          = 0, /* replaces cudaSpMVRowsCSR                 src/SpMV_CUDA.cu:33-49   */
+    SPMVB200_CSR_ROWS_WARP     = 1, /* replaces cudaSpMVWarpPerRowCSR           src/SpMV_CUDA.cu:52-73   */
+    SPMVB200_ELL_ROWS          = 2, /* replaces cudaSpMVRowsELL (column-major)  src/SpMV_CUDA.cu:79-96   */
+    SPMVB200_ELL_ROWS_NT       = 3, /* replaces cudaSpMVRowsELLNNTransposed     src/SpMV_CUDA.cu:99-115  */
+    SPMVB200_ELL_ROWS_WARP_NT  = 4, /* replaces cudaSpMVWarpsPerRowELLNTrasposed src/SpMV_CUDA.cu:116-135 */
+    SPMVB200_CSR_ADAPTIVE      = 5, /* new: row-length driven split (short rows streamed, long rows shared) */
+    SPMVB200_KIND_COUNT        = 6
+} spmvb200_kind;
+
+/* Storage formats a handle can hold. */
+typedef enum {
+    SPMVB200_FMT_CSR          = 0,
+    SPMVB200_FMT_ELL_COLMAJOR = 1, /* pitched, column-major: slot k of row r at k*pitch + r */
+    SPMVB200_FMT_ELL_ROWMAJOR = 2  /* pitched, row-major:    slot k of row r at r*pitch + k */
+} spmvb200_format;
+
+typedef struct spmvb200_matrix spmvb200_matrix; /* opaque, device resident */
+
+/* ------------------------------------------------------------------ library / device */
+const char* spmvb200_last_error(void);
+int spmvb200_version(void);
+/* number of SpMV kernels this process has launched through the library (all handles) */
+unsigned long long spmvb200_launch_count(void);
+int spmvb200_device_count(int* count);
+int spmvb200_set_device(int device);
+/* name, SM count, L2 bytes, total memory of the current device */
+int spmvb200_device_info(char* name, size_t name_len, int* sm_count, size_t* l2_bytes, size_t* mem_bytes);
+
+/* ------------------------------------------------------------------ upload  (host -> device)
+ * Replaces spMatCpyCSR (src/commons/cudaUtils.cu:20-55).  Copies rows [row_begin,row_end) of a host
+ * CSR matrix (reference layout: IRP[M+1], JA[NZ], AS[NZ], 64-bit indices) to the current device,
+ * narrowing indices to 32 bit on the device, and builds the row-block plan used by the
+ * SPMVB200_CSR_* kernels.  row_begin=0,row_end=M uploads everything; a sub-range is one GPU's
+ * slice of a row-block partition (column ids stay global).  The host arrays are not modified and
+ * may be freed afterwards. */
+int spmvb200_csr_upload(uint64_t M, uint64_t N, const uint64_t* irp, const uint64_t* ja, const double* as,
+                        uint64_t row_begin, uint64_t row_end, spmvb200_matrix** out);
+
+/* Replaces ellTranspose + spMatCpyELL / spMatCpyELLNNPitched (src/commons/sparseUtils.c:145-185,
+ * src/commons/cudaUtils.cu:56-140).  Input is the reference's ROW-MAJOR host ELL (M x K, zero padded:
+ * AS=0, JA=0, src/lib/parser.c:217-296); `rl` is the row-length vector (mat->RL under -DROWLENS) or
+ * NULL, in which case effective lengths are derived on the device (trailing AS==0 slots).
+ * The column-major transposition for SPMVB200_FMT_ELL_COLMAJOR happens on the device. */
+int spmvb200_ell_upload(uint64_t M, uint64_t N, uint64_t K, const uint64_t* ja, const double* as,
+                        const uint64_t* rl, uint64_t row_begin, uint64_t row_end, int format,
+                        spmvb200_matrix** out);
+
+/* Adopt arrays that already live on the current device in the engine's narrow layout (used by the
+ * on-device generators and by callers that build matrices on the GPU).  irp32 has M+1 entries,
+ * ja32/as have NZ entries followed by at least 8 readable padding entries.  With own != 0 the
+ * handle frees the arrays (cudaFree) when destroyed. */
+int spmvb200_csr_adopt_device(uint64_t M, uint64_t N, uint64_t NZ, uint32_t* d_irp32, uint32_t* d_ja32,
+                              double* d_as, int own, spmvb200_matrix** out);
+
+/* Build an ELL handle (either layout) on the device from a CSR handle. */
+int spmvb200_ell_from_csr(const spmvb200_matrix* csr, int format, spmvb200_matrix** out);
+
+/* Replaces cudaFreeSpmat (src/include/cudaUtils.h:70-78). */
+int spmvb200_free(spmvb200_matrix* m);
+
+/* ------------------------------------------------------------------ queries */
+int spmvb200_dims(const spmvb200_matrix* m, uint64_t* M, uint64_t* N, uint64_t* NZ, uint64_t* K, int* format);
+/* algorithmic bytes of one SpMV with this handle:
+ *   CSR: 12*NZ + 4*(M+1) + 8*N + 8*M      ELL: 12*NZ + 4*M + 8*N + 8*M  */
+uint64_t spmvb200_algorithmic_bytes(const spmvb200_matrix* m);
+/* bytes of device memory the handle's arrays occupy (includes ELL padding and the plan) */
+uint64_t spmvb200_device_bytes(const spmvb200_matrix* m);
+/* 1 if `kind` can run on this handle's format */
+int spmvb200_kind_supported(const spmvb200_matrix* m, int kind);
+const char* spmvb200_kind_name(int kind); /* the reference's mode string, e.g. "CUDA_CSR_ROWS" */
+
+/* ------------------------------------------------------------------ compute
+ * Device-resident SpMV: y[0..rows) = A[row_begin..row_end) * x, d_x has N doubles, d_y has
+ * (row_end-row_begin) doubles, both on the handle's device.  Asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = default stream).  This is what replaces the launch
+ *   f<<<Conf.gridSize,Conf.blockSize>>>(dMat,dVect,Conf,dOutV)   src/main.cu:233, test/SpMV_test.cu:112
+ * -- the engine picks its own launch geometry. */
+int spmvb200_spmv_device(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, void* stream);
+
+/* Host-buffer SpMV with the semantics of the reference's SPMV_INTERF
+ *   int f(spmat* mat, double* x, CONFIG* cfg, double* y)        src/include/SpMV.h:63-64
+ * x (N doubles) is copied to the device, the kernel runs, y (rows doubles) is copied back; the call
+ * returns after y is complete.  *kernel_ms (may be NULL) receives the CUDA-event time of the kernel
+ * alone -- the value a driver stores in ElapsedInternal (src/include/config.h:112). */
+int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms);
+
+/* Repeat the kernel `reps` times on device-resident vectors and return per-repetition CUDA-event
+ * times in ms (times_ms[reps]); with flush_l2 != 0 a buffer larger than L2 is overwritten between
+ * repetitions, outside the timed region.  Mirrors the timing loop of testSpMVImplCuda
+ * (test/SpMV_test.cu:103-145) with events instead of a host stopwatch. */
+int spmvb200_time_device(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, int reps, int flush_l2,
+                         float* times_ms);
+
+/* ------------------------------------------------------------------ host adapter cache
+ * One-call form for a driver that only has host arrays (what an SPMV_INTERF adapter needs): the
+ * device copy is created on first use and cached under `key` (e.g. the host spmat*), so the
+ * upload is not repeated on later calls.  is_ell selects ELL (ja/as row-major M x K) or CSR input. */
+int spmvb200_cached_spmv(const void* key, int kind, int is_ell, uint64_t M, uint64_t N, uint64_t K,
+                         const uint64_t* irp, const uint64_t* ja, const double* as, const uint64_t* rl,
+                         const double* x, double* y, double* elapsed_internal_s);
+int spmvb200_cache_drop(const void* key); /* key == NULL drops everything */
+
+/* ------------------------------------------------------------------ device vectors (plumbing) */
+int spmvb200_dmalloc(void** d_ptr, size_t bytes);
+int spmvb200_dfree(void* d_ptr);
+int spmvb200_h2d(void* d_dst, const void* h_src, size_t bytes);
+int spmvb200_d2h(void* h_dst, const void* d_src, size_t bytes);
+int spmvb200_sync(void);
+
+/* ------------------------------------------------------------------ synthetic workloads
+ * Seeded, counter-based generators of the BASELINE.json matrices; every row (R-MAT: every edge) is a
+ * pure function of (seed, index) so the host and the device produce identical matrices and any row
+ * range can be generated on its own.  Not part of the reference (it reads Matrix Market files);
+ * they exist because 1e9 non-zeros cannot go through a text file.   kind:
+ *   1 = 5-point 2-D Laplacian on an n x n grid            (p0 = n)
+ *   2 = 27-point 3-D stencil on an nx x ny x nz grid      (p0 = nx, p1 = ny, p2 = nz)
+ *   4 = random banded: p1 non-zeros per row in [i-p0, i+p0], stratified     (p0 = half width, p1 = nnz/row, p2 = M)
+ *   5 = mixed rows: length p1 with probability p3/2^32, else length 4, uniform columns (p0 = M, p1 = K_max, p3 = prob)
+ * (kind 3, R-MAT, is edge based: see spmvb200_synth_rmat_*). */
+typedef struct {
+    int      kind;
+    uint64_t seed;
+    uint64_t p0, p1, p2, p3;
+} spmvb200_synth;
+
+int spmvb200_synth_dims(const spmvb200_synth* s, uint64_t* M, uint64_t* N);
+/* host, reference layout (64-bit): row lengths, then fill given the local row pointer
+ * (irp_local[0] = 0 for row_begin) */
+int spmvb200_synth_rowlen_host(const spmvb200_synth* s, uint64_t row_begin, uint64_t row_end, uint64_t* rl);
+int spmvb200_synth_fill_host(const spmvb200_synth* s, uint64_t row_begin, uint64_t row_end,
+                             const uint64_t* irp_local, uint64_t* ja, double* as);
+/* device: build rows [row_begin,row_end) directly as a CSR handle on the current device */
+int spmvb200_synth_csr_device(const spmvb200_synth* s, uint64_t row_begin, uint64_t row_end, spmvb200_matrix** out);
+/* R-MAT (a,b,c,d = .57,.19,.19,.05): 64-bit keys row<<32|col of edges [e_begin,e_end) on the host;
+ * on the device the whole matrix (keys sorted, duplicates merged, values hashed from (row,col)). */
+int spmvb200_synth_rmat_keys_host(int scale, uint64_t seed, uint64_t e_begin, uint64_t e_end, uint64_t* keys);
+int spmvb200_synth_rmat_values_host(uint64_t seed, uint64_t n, const uint64_t* keys, double* as);
+int spmvb200_synth_rmat_csr_device(int scale, uint64_t n_edges, uint64_t seed, spmvb200_matrix** out);
+/* x_i = U(-1,1) * scale, hashed from (seed, i) */
+int spmvb200_synth_vector_host(uint64_t seed, uint64_t begin, uint64_t end, double scale, double* x);
+int spmvb200_synth_vector_device(uint64_t seed, uint64_t begin, uint64_t end, double scale, double* d_x);
+
+/* copy a handle's narrow CSR arrays back to the host (tests / CPU baseline on device-built matrices) */
+int spmvb200_csr_download(const spmvb200_matrix* m, uint64_t* irp, uint64_t* ja, double* as);
+
+#ifdef __cplusplus
+}
+#endif
+
+/* ------------------------------------------------------------------ reference-typed adapters
+ * Available when this header is included AFTER the reference's src/include/sparseMatrix.h and
+ * SpMV.h: functions of type SPMV (src/include/SpMV.h:63) that can be appended to SpmvCSRFuncs /
+ * SpmvELLFuncs (src/include/SpMV.h:144-159) and run by the unchanged testSpMVImplOMP
+ * (test/SpMV_test.cu:67-101).  They are compiled in the CALLER's translation unit, so they always
+ * see the caller's own `spmat` layout (-DROWLENS, __CUDACC__: SURVEY.md §2.3-10). */
+#if defined(SPARSEMATRIX) && defined(_SPMV)
+#ifdef ROWLENS
+#define SPMVB200_RL_(m) ((const uint64_t*) (m)->RL)
+#else
+#define SPMVB200_RL_(m) ((const uint64_t*) 0)
+#endif
+#define SPMVB200_DEFINE_CSR_ADAPTER(NAME, KIND)                                                              \
+    static inline int NAME(spmat* mat, double* x, CONFIG* cfg, double* y) {                                  \
+        (void) cfg;                                                                                          \
+        return spmvb200_cached_spmv(mat, KIND, 0, mat->M, mat->N, 0, (const uint64_t*) mat->IRP,             \
+                                    (const uint64_t*) mat->JA, mat->AS, SPMVB200_RL_(mat), x, y,             \
+                                    &ElapsedInternal);                                                       \
+    }
+#define SPMVB200_DEFINE_ELL_ADAPTER(NAME, KIND)                                                              \
+    static inline int NAME(spmat* mat, double* x, CONFIG* cfg, double* y) {                                  \
+        (void) cfg;                                                                                          \
+        return spmvb200_cached_spmv(mat, KIND, 1, mat->M, mat->N, mat->MAX_ROW_NZ, (const uint64_t*) 0,      \
+                                    (const uint64_t*) mat->JA, mat->AS, SPMVB200_RL_(mat), x, y,             \
+                                    &ElapsedInternal);                                                       \
+    }
+SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVRowsCSR, SPMVB200_CSR_ROWS)
+SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVWarpPerRowCSR, SPMVB200_CSR_ROWS_WARP)
+SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVAdaptiveCSR, SPMVB200_CSR_ADAPTIVE)
+SPMVB200_DEFINE_ELL_ADAPTER(b200SpMVRowsELL, SPMVB200_ELL_ROWS)
+SPMVB200_DEFINE_ELL_ADAPTER(b200SpMVRowsELLNNTransposed, SPMVB200_ELL_ROWS_NT)
+SPMVB200_DEFINE_ELL_ADAPTER(b200SpMVWarpsPerRowELLNTrasposed, SPMVB200_ELL_ROWS_WARP_NT)
+#endif /* reference headers present */
+
+#endif /* SPMV_B200_H */

@@ -1,0 +1,132 @@
+// common.cuh -- shared helpers for the B200 SpMV engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+namespace spmvb200 {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: 0 = OK, non-zero = failure, message on stderr (reference convention:
+// ERRPRINT, src/include/macros.h:57-58) and kept for spmvb200_last_error().
+// ---------------------------------------------------------------------------------------------
+extern thread_local char g_err[512];
+
+inline int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "\33[31m\33[1m\33[44mspmv_b200: %s\33[0m\n", g_err);
+    return 1;
+}
+
+#define CU_TRY(expr)                                                                                    \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return ::spmvb200::fail("%s -> %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// counter-based hashing (splitmix64 finaliser): every synthetic value is a pure function of
+// (seed, indices) so host and device generators agree bit for bit.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t hash2(uint64_t seed, uint64_t a) { return mix64(mix64(seed) ^ a); }
+__host__ __device__ __forceinline__ uint64_t hash3(uint64_t seed, uint64_t a, uint64_t b) {
+    return mix64(hash2(seed, a) + 0xD1B54A32D192ED03ull * (b + 1));
+}
+// uniform in [0,1) with 53 bits
+__host__ __device__ __forceinline__ double u01(uint64_t h) { return (double) (h >> 11) * (1.0 / 9007199254740992.0); }
+// uniform in (-1,1)
+__host__ __device__ __forceinline__ double usym(uint64_t h) { return 2.0 * u01(h) - 1.0; }
+// uniform integer in [0,n) (n < 2^32) by multiply-shift
+__host__ __device__ __forceinline__ uint64_t urange(uint64_t h, uint64_t n) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(h, n);
+#else
+    return (uint64_t) (((unsigned __int128) h * n) >> 64);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side PTX helpers (sm_100a)
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make the barrier initialisation visible to the async (TMA) proxy
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// L2 eviction policies for cp.async.bulk / ld cache hints
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier.
+// dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+// streaming (read-once) loads: bypass L1 allocation, evict-first in L2
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ double2 ld_stream(const double2* p) { return __ldcs(p); }
+__device__ __forceinline__ uint2 ld_stream(const uint2* p) { return __ldcs(p); }
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
+// x gather: read-only path, normal L1/L2 allocation (we WANT x to stay cached)
+__device__ __forceinline__ double ld_x(const double* x, uint32_t c) { return __ldg(x + c); }
+
+template <int LANES>
+__device__ __forceinline__ double subwarp_sum(double v) {
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off, 32);
+    return v;
+}
+#endif  // __CUDACC__
+
+}  // namespace spmvb200

@@ -1,0 +1,640 @@
+// engine.cu -- the thin C-ABI layer of include/spmv_b200.h: device allocation, H2D upload with
+// on-device 64->32-bit narrowing / ELL transposition, plan building, kernel launch, D2H.
+// Replaces src/commons/cudaUtils.cu (spMatCpyCSR/ELL*, cudaFreeSpmat) and the launch+sync+download
+// code of src/main.cu:192-248 / test/SpMV_test.cu:103-145.  No CPU compute path exists here.
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "../../include/spmv_b200.h"
+#include "engine.h"
+#include "kernels.cuh"
+
+namespace spmvb200 {
+thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+}  // namespace spmvb200
+using namespace spmvb200;
+
+// -------------------------------------------------------------------------------------------------
+static void free_arrays(spmvb200_matrix* m) {
+    if (m->own) {
+        cudaFree(m->irp);
+        cudaFree(m->ja);
+        cudaFree(m->as);
+        cudaFree(m->rl);
+    }
+    cudaFree(m->desc);
+    cudaFree(m->longrec);
+    cudaFree(m->partial);
+    cudaFree(m->ticket);
+    cudaFree(m->d_x);
+    cudaFree(m->d_y);
+    cudaFree(m->flush);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+}
+
+extern "C" const char* spmvb200_last_error(void) { return g_err; }
+extern "C" int spmvb200_version(void) { return SPMVB200_VERSION; }
+extern "C" unsigned long long spmvb200_launch_count(void) { return g_launches; }
+
+extern "C" int spmvb200_device_count(int* count) {
+    if (!count) return fail("device_count: null argument");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail("cudaGetDeviceCount -> %s (no CUDA device: this engine has no CPU fallback)", cudaGetErrorString(e));
+    }
+    return 0;
+}
+extern "C" int spmvb200_set_device(int device) {
+    CU_TRY(cudaSetDevice(device));
+    return 0;
+}
+extern "C" int spmvb200_device_info(char* name, size_t name_len, int* sm_count, size_t* l2_bytes, size_t* mem_bytes) {
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    CU_TRY(cudaGetDeviceProperties(&p, dev));
+    if (name && name_len) snprintf(name, name_len, "%s", p.name);
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = (size_t) p.l2CacheSize;
+    if (mem_bytes) *mem_bytes = p.totalGlobalMem;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- plumbing
+extern "C" int spmvb200_dmalloc(void** d_ptr, size_t bytes) {
+    if (!d_ptr) return fail("dmalloc: null argument");
+    CU_TRY(cudaMalloc(d_ptr, bytes ? bytes : 16));
+    return 0;
+}
+extern "C" int spmvb200_dfree(void* d_ptr) {
+    CU_TRY(cudaFree(d_ptr));
+    return 0;
+}
+extern "C" int spmvb200_h2d(void* d, const void* h, size_t bytes) {
+    CU_TRY(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int spmvb200_d2h(void* h, const void* d, size_t bytes) {
+    CU_TRY(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int spmvb200_sync(void) {
+    CU_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- CSR plan
+// Greedy row blocking (whole rows, <= TILE non-zeros, <= TILE_ROWS rows); rows longer than TILE are
+// cut into segments that share one LongRec.  Runs on the host over the narrowed row pointer.
+static void build_plan_host(const uint32_t* irp, uint32_t M, std::vector<TileDesc>& tiles, std::vector<LongRec>& longs) {
+    const uint32_t TILE = STREAM_TILE, ROWS = STREAM_TILE_ROWS;
+    tiles.clear();
+    longs.clear();
+    uint32_t start = 0, cur_nnz = 0;
+    auto flush = [&](uint32_t end_row) {
+        if (end_row > start) tiles.push_back({start, irp[start], 0u, 0u});
+        start = end_row;
+        cur_nnz = 0;
+    };
+    for (uint32_t r = 0; r < M; ++r) {
+        const uint32_t len = irp[r + 1] - irp[r];
+        if (len > TILE) {
+            flush(r);
+            const uint32_t nseg = (len + TILE - 1) / TILE;
+            longs.push_back({r, (uint32_t) tiles.size(), nseg, 0u});
+            for (uint32_t s = 0; s < nseg; ++s) tiles.push_back({r | SEG_FLAG, irp[r] + s * TILE, (uint32_t) longs.size() - 1, 0u});
+            start = r + 1;
+            cur_nnz = 0;
+            continue;
+        }
+        if (cur_nnz + len > TILE || r - start == ROWS) flush(r);
+        cur_nnz += len;
+    }
+    flush(M);
+    tiles.push_back({M, irp[M], 0u, 0u});  // sentinel
+}
+
+int spmvb200::finish_csr(spmvb200_matrix* m) {
+    // narrowed row pointer back to the host for the greedy planner
+    std::vector<uint32_t> h_irp((size_t) m->M + 1);
+    CU_TRY(cudaMemcpy(h_irp.data(), m->irp, ((size_t) m->M + 1) * 4, cudaMemcpyDeviceToHost));
+    if (h_irp[m->M] != m->NZ) return fail("CSR row pointer inconsistent: IRP[M]=%u, NZ=%llu", h_irp[m->M], (unsigned long long) m->NZ);
+    std::vector<TileDesc> tiles;
+    std::vector<LongRec> longs;
+    build_plan_host(h_irp.data(), (uint32_t) m->M, tiles, longs);
+    m->ntiles = (uint32_t) tiles.size() - 1;
+    m->nlong = (uint32_t) longs.size();
+    CU_TRY(cudaMalloc(&m->desc, tiles.size() * sizeof(TileDesc)));
+    CU_TRY(cudaMemcpy(m->desc, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMalloc(&m->longrec, std::max<size_t>(1, longs.size()) * sizeof(LongRec)));
+    if (!longs.empty()) CU_TRY(cudaMemcpy(m->longrec, longs.data(), longs.size() * sizeof(LongRec), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMalloc(&m->partial, std::max<size_t>(1, m->ntiles) * sizeof(double)));
+    CU_TRY(cudaMalloc(&m->ticket, std::max<size_t>(1, longs.size()) * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(m->ticket, 0, std::max<size_t>(1, longs.size()) * sizeof(uint32_t)));
+    // sub-warp width of the vector kernel from the mean row length (2 non-zeros per lane and step)
+    const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
+    int lanes = 2;
+    while (lanes < 32 && lanes * 2 < mean) lanes *= 2;
+    m->vec_lanes = lanes;
+    return 0;
+}
+
+static int check_dims(uint64_t M, uint64_t N, uint64_t NZ) {
+    if (M >= 0x7fffffffull || N > 0xffffffffull || NZ >= 0xfffffff0ull)
+        return fail("matrix too large for 32-bit device indices: M=%llu N=%llu NZ=%llu", (unsigned long long) M,
+                    (unsigned long long) N, (unsigned long long) NZ);
+    return 0;
+}
+
+// chunked H2D + narrowing of a 64-bit index array (bounded staging buffer)
+static int upload_narrow(const uint64_t* h_src, uint64_t n, uint64_t sub, uint32_t* d_dst, int* d_overflow) {
+    const uint64_t CH = 1ull << 25;  // 32 Mi elements = 256 MB staging
+    uint64_t* stage = nullptr;
+    if (!n) return 0;
+    CU_TRY(cudaMalloc(&stage, std::min(n, CH) * 8));
+    for (uint64_t o = 0; o < n; o += CH) {
+        const uint64_t c = std::min(CH, n - o);
+        cudaError_t e = cudaMemcpy(stage, h_src + o, c * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(stage);
+            return fail("H2D of index chunk failed: %s", cudaGetErrorString(e));
+        }
+        narrow_u64_kernel<<<1184, 256>>>(stage, d_dst + o, c, sub, d_overflow);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(stage);
+    if (e != cudaSuccess) return fail("index narrowing failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+static int read_overflow(int* d_overflow, const char* what) {
+    int h = 0;
+    CU_TRY(cudaMemcpy(&h, d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h) return fail("%s: an index does not fit 32 bits", what);
+    return 0;
+}
+
+extern "C" int spmvb200_csr_upload(uint64_t M, uint64_t N, const uint64_t* irp, const uint64_t* ja, const double* as,
+                                   uint64_t row_begin, uint64_t row_end, spmvb200_matrix** out) {
+    if (!out) return fail("csr_upload: null output");
+    *out = nullptr;
+    if (!irp || (M && !ja && irp[M]) || row_begin > row_end || row_end > M) return fail("csr_upload: bad arguments");
+    int ndev = 0;
+    if (spmvb200_device_count(&ndev) || ndev == 0) return fail("csr_upload: no CUDA device (no CPU fallback)");
+    const uint64_t rows = row_end - row_begin, n0 = irp[row_begin], nz = irp[row_end] - n0;
+    if (check_dims(rows, N, nz)) return 1;
+    spmvb200_matrix* m = new spmvb200_matrix();
+    m->format = SPMVB200_FMT_CSR;
+    m->M = rows;
+    m->N = N;
+    m->NZ = nz;
+    m->own = 1;
+    int* d_of = nullptr;
+    int rc = 0;
+    do {
+        if ((rc = (cudaMalloc(&d_of, sizeof(int)) != cudaSuccess))) break;
+        cudaMemset(d_of, 0, sizeof(int));
+        if ((rc = (cudaMalloc(&m->irp, (rows + 1) * 4) != cudaSuccess))) break;
+        if ((rc = (cudaMalloc(&m->ja, (nz + PAD) * 4) != cudaSuccess))) break;
+        if ((rc = (cudaMalloc(&m->as, (nz + PAD) * 8) != cudaSuccess))) break;
+        cudaMemset(m->ja + nz, 0, PAD * 4);
+        cudaMemset(m->as + nz, 0, PAD * 8);
+        if ((rc = upload_narrow(irp + row_begin, rows + 1, n0, m->irp, d_of))) break;
+        if ((rc = upload_narrow(ja + n0, nz, 0, m->ja, d_of))) break;
+        if (nz && (rc = (cudaMemcpy(m->as, as + n0, nz * 8, cudaMemcpyHostToDevice) != cudaSuccess))) break;
+        if ((rc = read_overflow(d_of, "csr_upload"))) break;
+        rc = finish_csr(m);
+    } while (0);
+    cudaFree(d_of);
+    if (rc) {
+        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("csr_upload: %s", cudaGetErrorString(cudaGetLastError()));
+        free_arrays(m);
+        delete m;
+        return 1;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" int spmvb200_csr_adopt_device(uint64_t M, uint64_t N, uint64_t NZ, uint32_t* d_irp32, uint32_t* d_ja32,
+                                         double* d_as, int own, spmvb200_matrix** out) {
+    if (!out) return fail("csr_adopt_device: null output");
+    *out = nullptr;
+    if (check_dims(M, N, NZ)) return 1;
+    spmvb200_matrix* m = new spmvb200_matrix();
+    m->format = SPMVB200_FMT_CSR;
+    m->M = M;
+    m->N = N;
+    m->NZ = NZ;
+    m->irp = d_irp32;
+    m->ja = d_ja32;
+    m->as = d_as;
+    m->own = own;
+    if (finish_csr(m)) {
+        m->own = 0;  // the caller keeps ownership on failure
+        free_arrays(m);
+        delete m;
+        return 1;
+    }
+    *out = m;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- ELL
+static uint64_t ell_pitch(int format, uint64_t rows, uint64_t K) {
+    return format == SPMVB200_FMT_ELL_COLMAJOR ? ((rows + 63) / 64) * 64 : ((std::max<uint64_t>(K, 1) + 3) / 4) * 4;
+}
+static int ell_alloc(spmvb200_matrix* m) {
+    const uint64_t slots = m->format == SPMVB200_FMT_ELL_COLMAJOR ? m->pitch * std::max<uint64_t>(m->K, 1) : m->pitch * std::max<uint64_t>(m->M, 1);
+    m->slots = slots;
+    CU_TRY(cudaMalloc(&m->ja, (slots + PAD) * 4));
+    CU_TRY(cudaMalloc(&m->as, (slots + PAD) * 8));
+    CU_TRY(cudaMemset(m->ja, 0, (slots + PAD) * 4));
+    CU_TRY(cudaMemset(m->as, 0, (slots + PAD) * 8));
+    CU_TRY(cudaMalloc(&m->rl, std::max<uint64_t>(m->M, 1) * 4));
+    return 0;
+}
+static void ell_pick_lanes(spmvb200_matrix* m) {
+    int lanes = 1;
+    while (lanes < 32 && (uint64_t) lanes * 4 <= m->K) lanes *= 2;  // ~2-4 slots per lane
+    m->vec_lanes = lanes;
+}
+
+extern "C" int spmvb200_ell_upload(uint64_t M, uint64_t N, uint64_t K, const uint64_t* ja, const double* as,
+                                   const uint64_t* rl, uint64_t row_begin, uint64_t row_end, int format,
+                                   spmvb200_matrix** out) {
+    if (!out) return fail("ell_upload: null output");
+    *out = nullptr;
+    if (format != SPMVB200_FMT_ELL_COLMAJOR && format != SPMVB200_FMT_ELL_ROWMAJOR) return fail("ell_upload: bad format %d", format);
+    if (row_begin > row_end || row_end > M || (M && K && (!ja || !as))) return fail("ell_upload: bad arguments");
+    int ndev = 0;
+    if (spmvb200_device_count(&ndev) || ndev == 0) return fail("ell_upload: no CUDA device (no CPU fallback)");
+    const uint64_t rows = row_end - row_begin;
+    if (check_dims(rows, N, rows * K) || K > 0xffffffffull) return 1;
+    spmvb200_matrix* m = new spmvb200_matrix();
+    m->format = format;
+    m->M = rows;
+    m->N = N;
+    m->K = K;
+    m->own = 1;
+    m->pitch = ell_pitch(format, rows, K);
+    int* d_of = nullptr;
+    uint64_t *st_ja = nullptr, *st_rl = nullptr;
+    double* st_as = nullptr;
+    int rc = 0;
+    do {
+        if ((rc = ell_alloc(m))) break;
+        if ((rc = (cudaMalloc(&d_of, sizeof(int)) != cudaSuccess))) break;
+        cudaMemset(d_of, 0, sizeof(int));
+        if (rl) {
+            if ((rc = upload_narrow(rl + row_begin, rows, 0, m->rl, d_of))) break;
+        }
+        // row chunks of the row-major host arrays -> staging -> layout kernel
+        const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(rows, (1ull << 25) / std::max<uint64_t>(K, 1)));
+        if (rows && K) {
+            if ((rc = (cudaMalloc(&st_ja, chunk_rows * K * 8) != cudaSuccess))) break;
+            if ((rc = (cudaMalloc(&st_as, chunk_rows * K * 8) != cudaSuccess))) break;
+            for (uint64_t r = 0; r < rows && !rc; r += chunk_rows) {
+                const uint64_t cr = std::min(chunk_rows, rows - r);
+                const uint64_t ho = (row_begin + r) * K;
+                if ((rc = (cudaMemcpy(st_ja, ja + ho, cr * K * 8, cudaMemcpyHostToDevice) != cudaSuccess))) break;
+                if ((rc = (cudaMemcpy(st_as, as + ho, cr * K * 8, cudaMemcpyHostToDevice) != cudaSuccess))) break;
+                if (format == SPMVB200_FMT_ELL_COLMAJOR) {
+                    dim3 grid((unsigned) ((cr + 31) / 32), (unsigned) ((K + 31) / 32));
+                    ell_transpose_kernel<<<grid, dim3(32, 8)>>>(st_ja, st_as, (uint32_t) cr, (uint32_t) K, (uint32_t) r, m->pitch, m->ja, m->as, d_of);
+                } else {
+                    ell_repitch_kernel<<<1184, 256>>>(st_ja, st_as, (uint32_t) cr, (uint32_t) K, (uint32_t) r, m->pitch, m->ja, m->as, d_of);
+                }
+                if (!rl) ell_derive_rl_kernel<<<(unsigned) ((cr + 255) / 256), 256>>>(st_as, (uint32_t) cr, (uint32_t) K, (uint32_t) r, m->rl);
+                rc = cudaDeviceSynchronize() != cudaSuccess;
+            }
+            if (rc) break;
+        } else if (rows) {
+            cudaMemset(m->rl, 0, rows * 4);
+        }
+        if ((rc = read_overflow(d_of, "ell_upload"))) break;
+        // NZ = sum of row lengths (host side sum of the narrowed vector; upload time only)
+        std::vector<uint32_t> h_rl(rows);
+        if (rows && (rc = (cudaMemcpy(h_rl.data(), m->rl, rows * 4, cudaMemcpyDeviceToHost) != cudaSuccess))) break;
+        uint64_t nz = 0;
+        for (uint64_t r = 0; r < rows; ++r) {
+            if (h_rl[r] > K) { rc = fail("ell_upload: row length %u > K=%llu at row %llu", h_rl[r], (unsigned long long) K, (unsigned long long) r); break; }
+            nz += h_rl[r];
+        }
+        if (rc) break;
+        m->NZ = nz;
+        ell_pick_lanes(m);
+    } while (0);
+    cudaFree(d_of);
+    cudaFree(st_ja);
+    cudaFree(st_as);
+    cudaFree(st_rl);
+    if (rc) {
+        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("ell_upload: %s", cudaGetErrorString(cudaGetLastError()));
+        free_arrays(m);
+        delete m;
+        return 1;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" int spmvb200_ell_from_csr(const spmvb200_matrix* csr, int format, spmvb200_matrix** out) {
+    if (!out) return fail("ell_from_csr: null output");
+    *out = nullptr;
+    if (!csr || csr->format != SPMVB200_FMT_CSR) return fail("ell_from_csr: source is not a CSR handle");
+    if (format != SPMVB200_FMT_ELL_COLMAJOR && format != SPMVB200_FMT_ELL_ROWMAJOR) return fail("ell_from_csr: bad format %d", format);
+    spmvb200_matrix* m = new spmvb200_matrix();
+    m->format = format;
+    m->M = csr->M;
+    m->N = csr->N;
+    m->NZ = csr->NZ;
+    m->own = 1;
+    uint32_t* d_kmax = nullptr;
+    int rc = 0;
+    do {
+        if ((rc = (cudaMalloc(&d_kmax, 4) != cudaSuccess))) break;
+        cudaMemset(d_kmax, 0, 4);
+        if ((rc = (cudaMalloc(&m->rl, std::max<uint64_t>(m->M, 1) * 4) != cudaSuccess))) break;
+        if (m->M) row_len_from_irp_kernel<<<(unsigned) ((m->M + 255) / 256), 256>>>(csr->irp, (uint32_t) m->M, m->rl, d_kmax);
+        uint32_t kmax = 0;
+        if ((rc = (cudaMemcpy(&kmax, d_kmax, 4, cudaMemcpyDeviceToHost) != cudaSuccess))) break;
+        m->K = kmax;
+        m->pitch = ell_pitch(format, m->M, m->K);
+        uint32_t* keep_rl = m->rl;
+        m->rl = nullptr;
+        rc = ell_alloc(m);  // allocates a fresh rl too
+        if (rc) { cudaFree(keep_rl); break; }
+        cudaFree(m->rl);
+        m->rl = keep_rl;
+        if (m->M && m->K)
+            csr_to_ell_kernel<<<(unsigned) ((m->M + 255) / 256), 256>>>(csr->irp, csr->ja, csr->as, (uint32_t) m->M, (uint32_t) m->K, m->pitch,
+                                                                         format == SPMVB200_FMT_ELL_COLMAJOR, m->ja, m->as);
+        if ((rc = (cudaDeviceSynchronize() != cudaSuccess))) break;
+        ell_pick_lanes(m);
+    } while (0);
+    cudaFree(d_kmax);
+    if (rc) {
+        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("ell_from_csr: %s", cudaGetErrorString(cudaGetLastError()));
+        free_arrays(m);
+        delete m;
+        return 1;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" int spmvb200_free(spmvb200_matrix* m) {
+    if (!m) return 0;
+    free_arrays(m);
+    delete m;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("free: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- queries
+extern "C" int spmvb200_dims(const spmvb200_matrix* m, uint64_t* M, uint64_t* N, uint64_t* NZ, uint64_t* K, int* format) {
+    if (!m) return fail("dims: null handle");
+    if (M) *M = m->M;
+    if (N) *N = m->N;
+    if (NZ) *NZ = m->NZ;
+    if (K) *K = m->K;
+    if (format) *format = m->format;
+    return 0;
+}
+extern "C" uint64_t spmvb200_algorithmic_bytes(const spmvb200_matrix* m) {
+    if (!m) return 0;
+    if (m->format == SPMVB200_FMT_CSR) return 12 * m->NZ + 4 * (m->M + 1) + 8 * m->N + 8 * m->M;
+    return 12 * m->NZ + 4 * m->M + 8 * m->N + 8 * m->M;
+}
+extern "C" uint64_t spmvb200_device_bytes(const spmvb200_matrix* m) {
+    if (!m) return 0;
+    if (m->format == SPMVB200_FMT_CSR)
+        return (m->NZ + PAD) * 12 + (m->M + 1) * 4 + ((uint64_t) m->ntiles + 1) * sizeof(TileDesc) + (uint64_t) m->ntiles * 8 +
+               (uint64_t) m->nlong * (sizeof(LongRec) + 4);
+    return (m->slots + PAD) * 12 + m->M * 4;
+}
+extern "C" int spmvb200_kind_supported(const spmvb200_matrix* m, int kind) {
+    if (!m) return 0;
+    switch (kind) {
+        case SPMVB200_CSR_ROWS:
+        case SPMVB200_CSR_ROWS_WARP:
+        case SPMVB200_CSR_ADAPTIVE: return m->format == SPMVB200_FMT_CSR;
+        case SPMVB200_ELL_ROWS: return m->format == SPMVB200_FMT_ELL_COLMAJOR;
+        case SPMVB200_ELL_ROWS_NT:
+        case SPMVB200_ELL_ROWS_WARP_NT: return m->format == SPMVB200_FMT_ELL_ROWMAJOR;
+        default: return 0;
+    }
+}
+extern "C" const char* spmvb200_kind_name(int kind) {
+    switch (kind) {  // mode strings of src/include/SpMV.h:37-41 (+ the appended mode)
+        case SPMVB200_CSR_ROWS: return "CUDA_CSR_ROWS";
+        case SPMVB200_CSR_ROWS_WARP: return "CUDA_CSR_ROWS_WARP";
+        case SPMVB200_ELL_ROWS: return "CUDA_ELL_ROWS";
+        case SPMVB200_ELL_ROWS_NT: return "CUDA_ELL_ROWS_WARP_NN_TRANSPOSED_1T";
+        case SPMVB200_ELL_ROWS_WARP_NT: return "CUDA_ELL_ROWS_WARP_NN_TRANSPOSED";
+        case SPMVB200_CSR_ADAPTIVE: return "CUDA_CSR_ADAPTIVE";
+        default: return "?";
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- launch
+template <int LANES>
+static void launch_csr_vector(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    constexpr int BLOCK = 256;
+    const uint64_t threads = m->M * LANES;
+    csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->irp, m->ja, m->as, x, y, (uint32_t) m->M);
+}
+template <int LANES>
+static void launch_ell_rowmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    constexpr int BLOCK = 256;
+    const uint64_t threads = m->M * LANES;
+    ell_rowmajor_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) m->M,
+                                                                                                       (uint32_t) m->K, x, y);
+}
+
+static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, cudaStream_t st) {
+    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
+    if (m->M == 0) return 0;
+    switch (kind) {
+        case SPMVB200_CSR_ROWS:
+            csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, false>
+                <<<m->ntiles, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, d_x, d_y, m->partial, m->ticket);
+            break;
+        case SPMVB200_CSR_ADAPTIVE:
+            csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, true>
+                <<<m->ntiles, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, d_x, d_y, m->partial, m->ticket);
+            break;
+        case SPMVB200_CSR_ROWS_WARP:
+            switch (m->vec_lanes) {
+                case 2: launch_csr_vector<2>(m, d_x, d_y, st); break;
+                case 4: launch_csr_vector<4>(m, d_x, d_y, st); break;
+                case 8: launch_csr_vector<8>(m, d_x, d_y, st); break;
+                case 16: launch_csr_vector<16>(m, d_x, d_y, st); break;
+                default: launch_csr_vector<32>(m, d_x, d_y, st); break;
+            }
+            break;
+        case SPMVB200_ELL_ROWS: {
+            constexpr int BLOCK = 256;
+            ell_colmajor_kernel<4, BLOCK><<<(unsigned) ((m->M + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) m->M,
+                                                                                                     (uint32_t) m->K, d_x, d_y);
+            break;
+        }
+        case SPMVB200_ELL_ROWS_NT:
+            switch (m->vec_lanes) {
+                case 1: launch_ell_rowmajor<1>(m, d_x, d_y, st); break;
+                case 2: launch_ell_rowmajor<2>(m, d_x, d_y, st); break;
+                case 4: launch_ell_rowmajor<4>(m, d_x, d_y, st); break;
+                case 8: launch_ell_rowmajor<8>(m, d_x, d_y, st); break;
+                case 16: launch_ell_rowmajor<16>(m, d_x, d_y, st); break;
+                default: launch_ell_rowmajor<32>(m, d_x, d_y, st); break;
+            }
+            break;
+        case SPMVB200_ELL_ROWS_WARP_NT: launch_ell_rowmajor<32>(m, d_x, d_y, st); break;
+    }
+    ++g_launches;
+    CU_TRY(cudaPeekAtLastError());
+    return 0;
+}
+
+static int prefer_smem_once() {
+    static bool done = false;
+    if (done) return 0;
+    // the stream kernel wants 8 x 28 KB of shared memory per SM: ask for the largest carve-out
+    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, false>,
+                                cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, true>,
+                                cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    done = true;
+    return 0;
+}
+
+extern "C" int spmvb200_spmv_device(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, void* stream) {
+    if (!m || !d_x || !d_y) return fail("spmv_device: null argument");
+    if (prefer_smem_once()) return 1;
+    return launch(m, kind, d_x, d_y, (cudaStream_t) stream);
+}
+
+static int ensure_events(spmvb200_matrix* m) {
+    if (!m->ev0) CU_TRY(cudaEventCreate(&m->ev0));
+    if (!m->ev1) CU_TRY(cudaEventCreate(&m->ev1));
+    return 0;
+}
+
+extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms) {
+    if (!m || !x || !y) return fail("spmv_host: null argument");
+    if (prefer_smem_once() || ensure_events(m)) return 1;
+    if (!m->d_x) CU_TRY(cudaMalloc(&m->d_x, std::max<uint64_t>(m->N, 1) * 8));
+    if (!m->d_y) CU_TRY(cudaMalloc(&m->d_y, std::max<uint64_t>(m->M, 1) * 8));
+    CU_TRY(cudaMemcpyAsync(m->d_x, x, m->N * 8, cudaMemcpyHostToDevice, 0));
+    CU_TRY(cudaEventRecord(m->ev0, 0));
+    if (launch(m, kind, m->d_x, m->d_y, 0)) return 1;
+    CU_TRY(cudaEventRecord(m->ev1, 0));
+    CU_TRY(cudaMemcpyAsync(y, m->d_y, m->M * 8, cudaMemcpyDeviceToHost, 0));
+    CU_TRY(cudaStreamSynchronize(0));
+    if (kernel_ms) CU_TRY(cudaEventElapsedTime(kernel_ms, m->ev0, m->ev1));
+    return 0;
+}
+
+extern "C" int spmvb200_time_device(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, int reps, int flush_l2,
+                                    float* times_ms) {
+    if (!m || !d_x || !d_y || reps <= 0 || !times_ms) return fail("time_device: bad arguments");
+    if (prefer_smem_once() || ensure_events(m)) return 1;
+    const size_t FLUSH = 512ull << 20;  // > 126 MB L2
+    if (flush_l2 && !m->flush) CU_TRY(cudaMalloc(&m->flush, FLUSH));
+    for (int i = 0; i < reps; ++i) {
+        if (flush_l2) CU_TRY(cudaMemsetAsync(m->flush, i & 0xff, FLUSH, 0));
+        CU_TRY(cudaEventRecord(m->ev0, 0));
+        if (launch(m, kind, d_x, d_y, 0)) return 1;
+        CU_TRY(cudaEventRecord(m->ev1, 0));
+        CU_TRY(cudaEventSynchronize(m->ev1));
+        CU_TRY(cudaEventElapsedTime(times_ms + i, m->ev0, m->ev1));
+    }
+    return 0;
+}
+
+extern "C" int spmvb200_csr_download(const spmvb200_matrix* m, uint64_t* irp, uint64_t* ja, double* as) {
+    if (!m || m->format != SPMVB200_FMT_CSR) return fail("csr_download: not a CSR handle");
+    uint64_t* tmp = nullptr;
+    const uint64_t n = std::max<uint64_t>(m->NZ, m->M + 1);
+    CU_TRY(cudaMalloc(&tmp, n * 8));
+    int rc = 0;
+    if (irp) {
+        widen_u32_kernel<<<1184, 256>>>(m->irp, tmp, m->M + 1, 0);
+        rc |= cudaMemcpy(irp, tmp, (m->M + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess;
+    }
+    if (ja && m->NZ) {
+        widen_u32_kernel<<<1184, 256>>>(m->ja, tmp, m->NZ, 0);
+        rc |= cudaMemcpy(ja, tmp, m->NZ * 8, cudaMemcpyDeviceToHost) != cudaSuccess;
+    }
+    if (as && m->NZ) rc |= cudaMemcpy(as, m->as, m->NZ * 8, cudaMemcpyDeviceToHost) != cudaSuccess;
+    cudaFree(tmp);
+    if (rc) return fail("csr_download: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- adapter cache
+namespace {
+struct CacheKey {
+    const void* key;
+    int fmt;
+    bool operator<(const CacheKey& o) const { return key != o.key ? key < o.key : fmt < o.fmt; }
+};
+struct CacheVal {
+    spmvb200_matrix* m;
+    const void *ja, *as;
+    uint64_t M, N, K;
+};
+std::map<CacheKey, CacheVal> g_cache;
+std::mutex g_cache_mu;
+}  // namespace
+
+extern "C" int spmvb200_cached_spmv(const void* key, int kind, int is_ell, uint64_t M, uint64_t N, uint64_t K,
+                                    const uint64_t* irp, const uint64_t* ja, const double* as, const uint64_t* rl,
+                                    const double* x, double* y, double* elapsed_internal_s) {
+    int fmt = SPMVB200_FMT_CSR;
+    if (kind == SPMVB200_ELL_ROWS) fmt = SPMVB200_FMT_ELL_COLMAJOR;
+    else if (kind == SPMVB200_ELL_ROWS_NT || kind == SPMVB200_ELL_ROWS_WARP_NT) fmt = SPMVB200_FMT_ELL_ROWMAJOR;
+    if ((fmt == SPMVB200_FMT_CSR) == (is_ell != 0)) return fail("cached_spmv: kind %d does not match the %s input", kind, is_ell ? "ELL" : "CSR");
+    spmvb200_matrix* m = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_cache.find({key, fmt});
+        if (it != g_cache.end() && (it->second.ja != ja || it->second.as != as || it->second.M != M || it->second.N != N || it->second.K != K)) {
+            spmvb200_free(it->second.m);  // the host matrix behind this key changed
+            g_cache.erase(it);
+            it = g_cache.end();
+        }
+        if (it == g_cache.end()) {
+            int rc = is_ell ? spmvb200_ell_upload(M, N, K, ja, as, rl, 0, M, fmt, &m) : spmvb200_csr_upload(M, N, irp, ja, as, 0, M, &m);
+            if (rc) return 1;
+            g_cache[{key, fmt}] = {m, ja, as, M, N, K};
+        } else {
+            m = it->second.m;
+        }
+    }
+    float ms = 0;
+    if (spmvb200_spmv_host(m, kind, x, y, &ms)) return 1;
+    if (elapsed_internal_s) *elapsed_internal_s = (double) ms * 1e-3;
+    return 0;
+}
+
+extern "C" int spmvb200_cache_drop(const void* key) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto it = g_cache.begin(); it != g_cache.end();) {
+        if (!key || it->first.key == key) {
+            spmvb200_free(it->second.m);
+            it = g_cache.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    return 0;
+}

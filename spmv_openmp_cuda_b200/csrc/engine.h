@@ -1,0 +1,40 @@
+// engine.h -- private definition of the opaque handle of include/spmv_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spmvb200 {
+struct TileDesc;
+struct LongRec;
+constexpr uint64_t PAD = 16;  // readable slack after ja/as (vector loads and 16-byte aligned TMA tiles overrun)
+}  // namespace spmvb200
+
+// Device-resident matrix.  Indices are 32 bit, values fp64.
+//   CSR          : irp[M+1], ja[NZ+PAD], as[NZ+PAD]  + row-block plan (desc/longrec/partial/ticket)
+//   ELL colmajor : ja/as[K*pitch+PAD] (slot k of row r at k*pitch+r, pitch = M rounded up to 64), rl[M]
+//   ELL rowmajor : ja/as[M*pitch+PAD] (slot k of row r at r*pitch+k, pitch = K rounded up to 4),  rl[M]
+struct spmvb200_matrix {
+    int format = 0;
+    uint64_t M = 0, N = 0, NZ = 0, K = 0, pitch = 0, slots = 0;
+    uint32_t* irp = nullptr;
+    uint32_t* ja = nullptr;
+    double* as = nullptr;
+    uint32_t* rl = nullptr;
+    int own = 1;
+    // CSR stream plan
+    spmvb200::TileDesc* desc = nullptr;
+    spmvb200::LongRec* longrec = nullptr;
+    double* partial = nullptr;
+    uint32_t* ticket = nullptr;
+    uint32_t ntiles = 0, nlong = 0;
+    int vec_lanes = 32;
+    // host-path scratch
+    double* d_x = nullptr;
+    double* d_y = nullptr;
+    void* flush = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace spmvb200 {
+int finish_csr(spmvb200_matrix* m);  // build the plan once irp/ja/as are on the device
+}

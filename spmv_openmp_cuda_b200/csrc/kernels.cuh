@@ -1,0 +1,384 @@
+// kernels.cuh -- hand-written sm_100a SpMV kernels (fp64 values, 32-bit indices).
+//
+// Replaces the reference's five __global__ kernels (src/SpMV_CUDA.cu:33-135):
+//   csr_stream_kernel   <- cudaSpMVRowsCSR            (thread-per-row semantics, bit-exact with sgemvSerial)
+//                          and the new row-length-adaptive mode (ADAPTIVE=true)
+//   csr_vector_kernel   <- cudaSpMVWarpPerRowCSR      (sub-warp per row, 128-bit loads, shuffle reduction)
+//   ell_colmajor_kernel <- cudaSpMVRowsELL            (pitched column-major ELL, row-length early exit)
+//   ell_rowmajor_kernel <- cudaSpMVRowsELLNNTransposed / cudaSpMVWarpsPerRowELLNTrasposed
+//
+// All are HBM-bound (2 flop per >= 12 bytes): the design goal is bytes in flight and no wasted
+// sectors, not math throughput.  See DESIGN.md for the roofline of each.
+#pragma once
+#include "common.cuh"
+
+namespace spmvb200 {
+
+// ---------------------------------------------------------------------------------------------
+// Row-block plan for the CSR stream kernel.
+//   tile b covers rows [row0[b], row0[b+1]) and non-zeros [nnz0[b], nnz0[b+1]) -- always whole rows,
+//   at most TILE non-zeros and TILE_ROWS rows -- unless bit 31 of row0 is set: then the tile is one
+//   SEGMENT (<= TILE non-zeros) of the long row (row0 & 0x7fffffff); `aux` indexes its LongRec.
+// The array has ntiles+1 entries (sentinel {M, NZ}).
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) TileDesc {
+    uint32_t row0, nnz0, aux, pad;
+};
+struct __align__(16) LongRec {
+    uint32_t row, first_tile, ntiles, pad;
+};
+constexpr uint32_t SEG_FLAG = 0x80000000u;
+
+constexpr int STREAM_TILE = 2048;        // non-zeros per tile (24 KB of values + column ids)
+constexpr int STREAM_BLOCK = 256;        // threads per CTA
+constexpr int STREAM_TILE_ROWS = 512;    // rows per tile (row-pointer slice in shared memory); 8 CTAs/SM fit
+constexpr int STREAM_LONG_T = 16;        // ADAPTIVE: rows longer than this are reduced by a whole warp
+
+__device__ __forceinline__ uint32_t skew(uint32_t i) { return i + (i >> 5); }  // one pad double / 32: kills
+                                                                               // bank conflicts of the per-row walk
+// ---------------------------------------------------------------------------------------------
+// CSR "stream" kernel.  One CTA per tile:
+//   1. thread 0 issues two TMA bulk copies (values, column ids) of the tile's 16-byte aligned
+//      non-zero range into shared memory, completion on an mbarrier; L2 evict-first (read once);
+//      the other threads meanwhile fetch the tile's row-pointer slice.
+//   2. every thread gathers x for TILE/BLOCK elements (independent loads, issued back to back),
+//      multiplies and writes the products back to shared memory (skewed layout).
+//   3. one thread per row adds its products left to right with separate mul/add roundings -- the
+//      summation order of sgemvSerial (src/SpMV_CSR_OMP.c:229-250), hence bit-identical results.
+//      ADAPTIVE: rows longer than STREAM_LONG_T are instead reduced by a whole warp (tree order).
+//   Segment tiles (pieces of a row longer than TILE) block-reduce to one partial; the last
+//   segment to finish (ticket counter) adds the partials in segment order => deterministic.
+// Bytes in flight do not depend on occupancy or registers: 8 resident CTAs x 24 KB per SM.
+// ---------------------------------------------------------------------------------------------
+template <int TILE, int BLOCK, int TILE_ROWS, bool ADAPTIVE>
+__global__ void __launch_bounds__(BLOCK)
+csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__ longrec,
+                  const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
+                  const double* __restrict__ x, double* __restrict__ y, double* __restrict__ partial,
+                  uint32_t* __restrict__ ticket) {
+    constexpr int CAP = TILE + 8;
+    constexpr int EPT = TILE / BLOCK;
+    constexpr int NWARPS = BLOCK / 32;
+    constexpr int MAXLONG = TILE / STREAM_LONG_T;
+    static_assert(TILE % BLOCK == 0, "tile must be a multiple of the block");
+
+    __shared__ __align__(128) double s_val[CAP + CAP / 32 + 2];
+    __shared__ __align__(16) uint32_t s_col[CAP];
+    __shared__ uint32_t s_rp[TILE_ROWS + 1];
+    __shared__ uint32_t s_long[ADAPTIVE ? MAXLONG : 1];
+    __shared__ double s_red[NWARPS];
+    __shared__ uint32_t s_nlong;
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t b = blockIdx.x;
+    const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(desc + b));
+    const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(desc + b + 1));
+    const bool seg = (d0.x & SEG_FLAG) != 0;
+    const uint32_t r0 = d0.x & ~SEG_FLAG;
+    const uint32_t n0 = d0.y, n1 = d1.y;
+    const uint32_t nnz = n1 - n0;
+    const uint32_t a0 = n0 & ~3u;               // 16-byte aligned start (4 x u32, 4 x f64 = 32 B)
+    const uint32_t off = n0 - a0;
+    const uint32_t cnt = ((n1 + 3u) & ~3u) - a0;  // <= TILE + 6
+    const uint32_t nrows = seg ? 0u : (d1.x & ~SEG_FLAG) - r0;
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        if (nnz) {
+            const uint64_t pol = policy_evict_first();
+            mbar_arrive_expect_tx(&s_bar, cnt * 12u);
+            bulk_g2s(s_val, as + a0, cnt * 8u, &s_bar, pol);
+            bulk_g2s(s_col, ja + a0, cnt * 4u, &s_bar, pol);
+        }
+        s_nlong = 0;
+    }
+    if (!seg)
+        for (uint32_t i = tid; i <= nrows; i += BLOCK) s_rp[i] = __ldg(irp + r0 + i) - n0;
+    __syncthreads();
+    if (nnz) mbar_wait(&s_bar, 0);
+
+    // ---- products (element e of the tile sits at shared position off + e)
+    double p[EPT];
+    {
+        uint32_t c[EPT];
+        double v[EPT];
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
+            const uint32_t e = tid + u * BLOCK;
+            const bool ok = e < nnz;
+            c[u] = ok ? s_col[off + e] : 0u;
+            v[u] = ok ? s_val[off + e] : 0.0;
+        }
+        double xv[EPT];
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) xv[u] = (tid + u * BLOCK < nnz) ? ld_x(x, c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) p[u] = __dmul_rn(v[u], xv[u]);
+    }
+
+    if (seg) {  // ---- one piece of a long row: block sum -> partial -> ordered combine by the last arriver
+        double t = 0;
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) t += p[u];
+        t = subwarp_sum<32>(t);
+        if ((tid & 31) == 0) s_red[tid >> 5] = t;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0;
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w) tot += s_red[w];
+            const LongRec rec = longrec[d0.z];
+            partial[b] = tot;
+            __threadfence();
+            const uint32_t done = atomicAdd(ticket + d0.z, 1u);
+            if (done == rec.ntiles - 1) {
+                __threadfence();
+                double acc = 0;
+                for (uint32_t k = 0; k < rec.ntiles; ++k) acc += __ldcg(partial + rec.first_tile + k);
+                y[rec.row] = acc;
+                ticket[d0.z] = 0;  // ready for the next launch
+            }
+        }
+        return;
+    }
+
+    __syncthreads();  // all reads of the TMA-landed values are done: products may overwrite them
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+        const uint32_t e = tid + u * BLOCK;
+        if (e < nnz) s_val[skew(e)] = p[u];
+    }
+    __syncthreads();
+
+    for (uint32_t r = tid; r < nrows; r += BLOCK) {
+        const uint32_t s = s_rp[r], e = s_rp[r + 1];
+        if (ADAPTIVE && e - s > (uint32_t) STREAM_LONG_T) {
+            s_long[atomicAdd(&s_nlong, 1u)] = r;
+            continue;
+        }
+        double acc = 0;
+        for (uint32_t j = s; j < e; ++j) acc = __dadd_rn(acc, s_val[skew(j)]);
+        y[r0 + r] = acc;
+    }
+    if (ADAPTIVE) {
+        __syncthreads();
+        const uint32_t nl = s_nlong, lane = tid & 31;
+        for (uint32_t k = tid >> 5; k < nl; k += NWARPS) {
+            const uint32_t r = s_long[k];
+            const uint32_t s = s_rp[r], e = s_rp[r + 1];
+            double acc = 0;
+            for (uint32_t j = s + lane; j < e; j += 32) acc += s_val[skew(j)];
+            acc = subwarp_sum<32>(acc);
+            if (lane == 0) y[r0 + r] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR "vector" kernel: LANES (2..32, chosen from the mean row length) lanes per row, each lane
+// loads two consecutive non-zeros per step with one 128-bit value load and one 64-bit index load
+// (row starts are peeled to an even index so the loads stay aligned), shuffle-tree reduction.
+// Replaces cudaSpMVWarpPerRowCSR (src/SpMV_CUDA.cu:52-73) and fixes its blockIdx.y defect
+// (SURVEY.md §2.3-1): the row comes from a linear thread id.
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+csr_vector_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
+                  const double* __restrict__ x, double* __restrict__ y, uint32_t M) {
+    const uint32_t gt = blockIdx.x * BLOCK + threadIdx.x;
+    const uint32_t row = gt / LANES, lane = gt % LANES;
+    double acc = 0;
+    if (row < M) {
+        const uint32_t s = __ldg(irp + row), e = __ldg(irp + row + 1);
+        for (uint32_t i = (s & ~1u) + 2 * lane; i < e; i += 2 * LANES) {
+            const double2 v = ld_stream(reinterpret_cast<const double2*>(as + i));
+            const uint2 c = ld_stream(reinterpret_cast<const uint2*>(ja + i));
+            if (i >= s) acc = fma(v.x, ld_x(x, c.x), acc);
+            if (i + 1 < e) acc = fma(v.y, ld_x(x, c.y), acc);
+        }
+    }
+    acc = subwarp_sum<LANES>(acc);
+    if (lane == 0 && row < M) y[row] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column-major pitched ELL, one thread per row: slot k of row r at k*pitch + r, so a warp reads 32
+// consecutive values (256 B) and 32 consecutive column ids (128 B) per slot -- fully coalesced.
+// Row-length early exit: the loop bound is the warp's longest row, shorter rows are predicated
+// off, padding is never fetched by a lane (the reference kernel walks all K slots and gathers
+// x[0] for padding, src/SpMV_CUDA.cu:83-93).  UNROLL independent slots are in flight per thread.
+// Per-row sum is left to right with separate mul/add => bit-identical to sgemvSerial.
+// ---------------------------------------------------------------------------------------------
+template <int UNROLL, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+ell_colmajor_kernel(const double* __restrict__ as, const uint32_t* __restrict__ ja, const uint32_t* __restrict__ rl,
+                    uint64_t pitch, uint32_t M, uint32_t K, const double* __restrict__ x, double* __restrict__ y) {
+    const uint32_t row = blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = row < M;
+    const uint32_t len = live ? (rl ? __ldg(rl + row) : K) : 0u;
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, len);
+    const double* a = as + row;
+    const uint32_t* j = ja + row;
+    double acc = 0;
+    uint32_t k = 0;
+    for (; k + UNROLL <= wmax; k += UNROLL) {
+        double v[UNROLL];
+        uint32_t c[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const bool ok = k + u < len;
+            v[u] = ok ? ld_stream(a + (uint64_t) (k + u) * pitch) : 0.0;
+            c[u] = ok ? ld_stream(j + (uint64_t) (k + u) * pitch) : 0u;
+        }
+        double xv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) xv[u] = (k + u < len) ? ld_x(x, c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (k + u < len) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+    }
+    for (; k < wmax; ++k) {
+        if (k < len) {
+            const double v = ld_stream(a + (uint64_t) k * pitch);
+            const uint32_t c = ld_stream(j + (uint64_t) k * pitch);
+            acc = __dadd_rn(acc, __dmul_rn(v, ld_x(x, c)));
+        }
+    }
+    if (live) y[row] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-major pitched ELL (pitch a multiple of 4 slots => rows 32-byte aligned): LANES lanes per
+// row, two slots per lane and step (128-bit value / 64-bit index loads), loop bounded by the row
+// length, shuffle reduction.  LANES = 32 is the reference's warp-per-row mapping
+// (cudaSpMVWarpsPerRowELLNTrasposed, src/SpMV_CUDA.cu:116-135); smaller LANES (picked from K) serve
+// the thread-per-row entry point cudaSpMVRowsELLNNTransposed (src/SpMV_CUDA.cu:99-115) without its
+// lane-stride-pitch access pattern.
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+ell_rowmajor_kernel(const double* __restrict__ as, const uint32_t* __restrict__ ja, const uint32_t* __restrict__ rl,
+                    uint64_t pitch, uint32_t M, uint32_t K, const double* __restrict__ x, double* __restrict__ y) {
+    const uint32_t gt = blockIdx.x * BLOCK + threadIdx.x;
+    const uint32_t row = gt / LANES, lane = gt % LANES;
+    double acc = 0;
+    if (row < M) {
+        const uint32_t len = rl ? __ldg(rl + row) : K;
+        const uint64_t base = (uint64_t) row * pitch;
+        for (uint32_t k = 2 * lane; k < len; k += 2 * LANES) {
+            const double2 v = ld_stream(reinterpret_cast<const double2*>(as + base + k));
+            const uint2 c = ld_stream(reinterpret_cast<const uint2*>(ja + base + k));
+            acc = fma(v.x, ld_x(x, c.x), acc);
+            if (k + 1 < len) acc = fma(v.y, ld_x(x, c.y), acc);
+        }
+    }
+    acc = subwarp_sum<LANES>(acc);
+    if (lane == 0 && row < M) y[row] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// upload-side helpers (run once per matrix, not on the hot path)
+// ---------------------------------------------------------------------------------------------
+// 64-bit -> 32-bit index narrowing with optional rebase; flags values that do not fit
+__global__ void narrow_u64_kernel(const uint64_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t n,
+                                  uint64_t sub, int* __restrict__ overflow) {
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t v = src[i] - sub;
+        if (v > 0xffffffffull) *overflow = 1;
+        dst[i] = (uint32_t) v;
+    }
+}
+
+// row-major (rows x K, 64-bit ids) host layout chunk -> column-major pitched device layout.
+// 32 x 32 tiles through shared memory: coalesced on both sides.
+__global__ void ell_transpose_kernel(const uint64_t* __restrict__ ja_rm, const double* __restrict__ as_rm,
+                                     uint32_t rows, uint32_t K, uint32_t row_off, uint64_t pitch,
+                                     uint32_t* __restrict__ ja_cm, double* __restrict__ as_cm, int* __restrict__ overflow) {
+    __shared__ double t_as[32][33];
+    __shared__ uint32_t t_ja[32][33];
+    const uint32_t r_base = blockIdx.x * 32, k_base = blockIdx.y * 32;
+    for (uint32_t i = threadIdx.y; i < 32; i += blockDim.y) {
+        const uint32_t r = r_base + i, k = k_base + threadIdx.x;
+        double v = 0;
+        uint32_t c = 0;
+        if (r < rows && k < K) {
+            v = as_rm[(uint64_t) r * K + k];
+            const uint64_t cc = ja_rm[(uint64_t) r * K + k];
+            if (cc > 0xffffffffull) *overflow = 1;
+            c = (uint32_t) cc;
+        }
+        t_as[i][threadIdx.x] = v;
+        t_ja[i][threadIdx.x] = c;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.y; i < 32; i += blockDim.y) {
+        const uint32_t k = k_base + i, r = r_base + threadIdx.x;
+        if (r < rows && k < K) {
+            as_cm[(uint64_t) k * pitch + row_off + r] = t_as[threadIdx.x][i];
+            ja_cm[(uint64_t) k * pitch + row_off + r] = t_ja[threadIdx.x][i];
+        }
+    }
+}
+
+// row-major chunk -> row-major pitched narrow layout
+__global__ void ell_repitch_kernel(const uint64_t* __restrict__ ja_rm, const double* __restrict__ as_rm, uint32_t rows,
+                                   uint32_t K, uint32_t row_off, uint64_t pitch, uint32_t* __restrict__ ja_o,
+                                   double* __restrict__ as_o, int* __restrict__ overflow) {
+    const uint64_t n = (uint64_t) rows * K, stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t r = i / K, k = i % K;
+        const uint64_t cc = ja_rm[i];
+        if (cc > 0xffffffffull) *overflow = 1;
+        as_o[(row_off + r) * pitch + k] = as_rm[i];
+        ja_o[(row_off + r) * pitch + k] = (uint32_t) cc;
+    }
+}
+
+// effective row lengths of a row-major host-layout chunk when the caller has no RL vector:
+// index of the last slot with AS != 0, plus one (trailing zero slots add nothing to the sum)
+__global__ void ell_derive_rl_kernel(const double* __restrict__ as_rm, uint32_t rows, uint32_t K, uint32_t row_off,
+                                     uint32_t* __restrict__ rl) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    uint32_t len = 0;
+    for (uint32_t k = 0; k < K; ++k)
+        if (as_rm[(uint64_t) r * K + k] != 0.0) len = k + 1;
+    rl[row_off + r] = len;
+}
+
+__global__ void row_len_from_irp_kernel(const uint32_t* __restrict__ irp, uint32_t M, uint32_t* __restrict__ rl,
+                                        uint32_t* __restrict__ kmax) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t len = 0;
+    if (r < M) {
+        len = irp[r + 1] - irp[r];
+        if (rl) rl[r] = len;
+    }
+    len = __reduce_max_sync(0xffffffffu, len);
+    if ((threadIdx.x & 31) == 0 && len) atomicMax(kmax, len);
+}
+
+// CSR -> ELL (either layout) on the device; padding slots get AS = 0, JA = 0 like the reference
+// (src/lib/parser.c:245-252)
+__global__ void csr_to_ell_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja,
+                                  const double* __restrict__ as, uint32_t M, uint32_t K, uint64_t pitch, int colmajor,
+                                  uint32_t* __restrict__ eja, double* __restrict__ eas) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const uint32_t s = irp[r], len = irp[r + 1] - s;
+    for (uint32_t k = 0; k < K; ++k) {
+        const uint64_t o = colmajor ? (uint64_t) k * pitch + r : (uint64_t) r * pitch + k;
+        eas[o] = k < len ? as[s + k] : 0.0;
+        eja[o] = k < len ? ja[s + k] : 0u;
+    }
+}
+
+__global__ void widen_u32_kernel(const uint32_t* __restrict__ src, uint64_t* __restrict__ dst, uint64_t n, uint64_t add) {
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (uint64_t) src[i] + add;
+}
+
+}  // namespace spmvb200

@@ -1,0 +1,299 @@
+"""Host-side mirror of the reference's GPU interface, on top of the C ABI (include/spmv_b200.h).
+
+Names, argument order and error behaviour follow the reference so that the parity tests read like
+its harness (test/SpMV_test.cu):
+
+  reference (C / CUDA)                                   here
+  ---------------------------------------------------    ------------------------------------------
+  spmat  (src/include/sparseMatrix.h:25-42)              Spmat           (host arrays, 64-bit ids)
+  CONFIG (src/include/config.h:21-32)                    Config
+  spMatCpyCSR / spMatCpyELL (src/commons/cudaUtils.cu)   spMatCpyCSR / spMatCpyELL -> DeviceSpmat
+  cudaFreeSpmat (src/include/cudaUtils.h:70-78)          cudaFreeSpmat
+  f<<<grid,block>>>(dMat,dVect,Conf,dOutV)               f(dMat, dVect, Conf, dOutV)  with f one of
+  SpmvCUDA_CSRFuncs / SpmvCUDA_ELLFuncs (SpMV.h:130-142) the same-named functions / tables below
+  SPMV_INTERF f(mat,x,&Conf,y) (SpMV.h:63-64)            b200SpMV*(mat, x, Conf, y)  (host buffers)
+
+Return convention: like the reference, functions return 0 (EXIT_SUCCESS); failures raise
+SpmvB200Error carrying the library's diagnostic (the C layer itself returns non-zero + stderr).
+There is no CPU fallback anywhere in this package.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import (CSR_ADAPTIVE, CSR_ROWS, CSR_ROWS_WARP, ELL_ROWS, ELL_ROWS_NT, ELL_ROWS_WARP_NT, FMT_CSR,
+                   FMT_ELL_COLMAJOR, FMT_ELL_ROWMAJOR, SpmvB200Error, check, lib, ptr)
+
+EXIT_SUCCESS = 0
+
+# compute-mode strings, src/include/SpMV.h:37-41 (+ the appended adaptive mode)
+CUDA_CSR_ROWS = "CUDA_CSR_ROWS"
+CUDA_CSR_ROWS_WARP = "CUDA_CSR_ROWS_WARP"
+CUDA_ELL_ROWS = "CUDA_ELL_ROWS"
+CUDA_ELL_ROWS_WARP = "CUDA_ELL_ROWS_WARP"
+CUDA_ELL_ROWS_WARP_NT = "CUDA_ELL_ROWS_WARP_NN_TRANSPOSED"
+CUDA_CSR_ADAPTIVE = "CUDA_CSR_ADAPTIVE"
+
+
+class Spmat:
+    """Host sparse matrix with the reference's field names (src/include/sparseMatrix.h:25-42).
+    CSR: IRP[M+1], JA[NZ], AS[NZ] (+RL[M]).  ELL: JA/AS row-major M x MAX_ROW_NZ (+RL[M]), IRP None."""
+
+    def __init__(self, M, N, NZ, JA, AS, IRP=None, RL=None, MAX_ROW_NZ=0):
+        self.M, self.N, self.NZ, self.MAX_ROW_NZ = int(M), int(N), int(NZ), int(MAX_ROW_NZ)
+        self.JA = np.ascontiguousarray(JA, dtype=np.uint64)
+        self.AS = np.ascontiguousarray(AS, dtype=np.float64)
+        self.IRP = None if IRP is None else np.ascontiguousarray(IRP, dtype=np.uint64)
+        self.RL = None if RL is None else np.ascontiguousarray(RL, dtype=np.uint64)
+
+    @classmethod
+    def csr(cls, N, IRP, JA, AS, RL=None):
+        IRP = np.ascontiguousarray(IRP, dtype=np.uint64)
+        M = len(IRP) - 1
+        if RL is None:
+            RL = np.diff(IRP)
+        return cls(M, N, int(IRP[-1]), JA, AS, IRP=IRP, RL=RL, MAX_ROW_NZ=int(np.max(np.diff(IRP))) if M else 0)
+
+    @classmethod
+    def ell(cls, M, N, K, JA, AS, RL=None, NZ=None):
+        if NZ is None:
+            NZ = int(np.sum(RL)) if RL is not None else int(np.count_nonzero(AS))
+        return cls(M, N, NZ, JA, AS, IRP=None, RL=RL, MAX_ROW_NZ=K)
+
+
+class Config:
+    """CONFIG, src/include/config.h:21-32.  gridSize/blockSize are accepted and ignored by the engine
+    (it chooses its own launch geometry)."""
+
+    def __init__(self, gridRows=8, gridCols=8, threadNum=0, gridSize=None, blockSize=None, sharedMemSize=0):
+        self.gridRows, self.gridCols, self.threadNum = gridRows, gridCols, threadNum
+        self.gridSize, self.blockSize, self.sharedMemSize = gridSize, blockSize, sharedMemSize
+
+
+class DeviceSpmat:
+    """Device-resident matrix: owns one opaque spmvb200_matrix handle."""
+
+    def __init__(self, handle):
+        self._h = handle
+        M, N, NZ, K, fmt = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+        check(lib().spmvb200_dims(handle, C.byref(M), C.byref(N), C.byref(NZ), C.byref(K), C.byref(fmt)), "dims")
+        self.M, self.N, self.NZ, self.MAX_ROW_NZ, self.format = M.value, N.value, NZ.value, K.value, fmt.value
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise SpmvB200Error("matrix handle already freed")
+        return self._h
+
+    @property
+    def algorithmic_bytes(self):
+        return int(lib().spmvb200_algorithmic_bytes(self.handle))
+
+    @property
+    def device_bytes(self):
+        return int(lib().spmvb200_device_bytes(self.handle))
+
+    def supports(self, kind):
+        return bool(lib().spmvb200_kind_supported(self.handle, kind))
+
+    def to_ell(self, fmt=FMT_ELL_COLMAJOR):
+        out = C.c_void_p()
+        check(lib().spmvb200_ell_from_csr(self.handle, fmt, C.byref(out)), "ell_from_csr")
+        return DeviceSpmat(out.value)
+
+    def download_csr(self):
+        irp = np.empty(self.M + 1, dtype=np.uint64)
+        ja = np.empty(self.NZ, dtype=np.uint64)
+        as_ = np.empty(self.NZ, dtype=np.float64)
+        check(lib().spmvb200_csr_download(self.handle, ptr(irp), ptr(ja), ptr(as_)), "csr_download")
+        return irp, ja, as_
+
+    def free(self):
+        if self._h:
+            h, self._h = self._h, None
+            check(lib().spmvb200_free(h), "free")
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class DeviceVector:
+    """fp64 device vector allocated through the C ABI (cudaMalloc)."""
+
+    def __init__(self, n):
+        self.n = int(n)
+        p = C.c_void_p()
+        check(lib().spmvb200_dmalloc(C.byref(p), max(self.n, 1) * 8), "dmalloc")
+        self._p = p.value
+
+    @classmethod
+    def from_host(cls, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        v = cls(len(a))
+        if len(a):
+            check(lib().spmvb200_h2d(v._p, ptr(a), a.nbytes), "h2d")
+        return v
+
+    def data_ptr(self):
+        return self._p
+
+    def to_host(self, out=None):
+        out = np.empty(self.n, dtype=np.float64) if out is None else out
+        if self.n:
+            check(lib().spmvb200_d2h(ptr(out), self._p, self.n * 8), "d2h")
+        return out
+
+    def fill_bytes(self, byte):
+        a = np.frombuffer(bytes([byte]) * (self.n * 8), dtype=np.float64)
+        if self.n:
+            check(lib().spmvb200_h2d(self._p, ptr(a), a.nbytes), "h2d")
+
+    def free(self):
+        if self._p:
+            p, self._p = self._p, None
+            lib().spmvb200_dfree(p)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+# ---------------------------------------------------------------------------------------- upload
+def spMatCpyCSR(mat, row_begin=0, row_end=None):
+    """Host CSR -> device (replaces spMatCpyCSR, src/commons/cudaUtils.cu:20-55).  A row range uploads
+    one GPU's slice of a row-block partition."""
+    capi.require_device()
+    row_end = mat.M if row_end is None else row_end
+    out = C.c_void_p()
+    check(lib().spmvb200_csr_upload(mat.M, mat.N, ptr(mat.IRP), ptr(mat.JA), ptr(mat.AS), row_begin, row_end,
+                                    C.byref(out)), "spMatCpyCSR")
+    return DeviceSpmat(out.value)
+
+
+def spMatCpyELL(mat, row_begin=0, row_end=None, use_rowlens=True):
+    """Row-major host ELL -> pitched COLUMN-major device ELL; the transposition the reference does on
+    the host (ellTranspose, src/commons/sparseUtils.c:145-185) happens on the device
+    (replaces spMatCpyELL, src/commons/cudaUtils.cu:56-98)."""
+    return _ell_upload(mat, FMT_ELL_COLMAJOR, row_begin, row_end, use_rowlens)
+
+
+def spMatCpyELLNNPitched(mat, row_begin=0, row_end=None, use_rowlens=True):
+    """Row-major host ELL -> row-major device ELL (replaces spMatCpyELLNNPitched,
+    src/commons/cudaUtils.cu:100-140, and spMatCpyELL on the non-transposed matrix)."""
+    return _ell_upload(mat, FMT_ELL_ROWMAJOR, row_begin, row_end, use_rowlens)
+
+
+def _ell_upload(mat, fmt, row_begin, row_end, use_rowlens):
+    capi.require_device()
+    row_end = mat.M if row_end is None else row_end
+    out = C.c_void_p()
+    rl = mat.RL if use_rowlens else None
+    check(lib().spmvb200_ell_upload(mat.M, mat.N, mat.MAX_ROW_NZ, ptr(mat.JA), ptr(mat.AS), ptr(rl), row_begin,
+                                    row_end, fmt, C.byref(out)), "spMatCpyELL")
+    return DeviceSpmat(out.value)
+
+
+def cudaFreeSpmat(dmat):
+    dmat.free()
+    return EXIT_SUCCESS
+
+
+# ---------------------------------------------------------------------------------------- kernels
+def _launch(kind, m, v, cfg, outV, stream=None):
+    check(lib().spmvb200_spmv_device(m.handle, kind, ptr(v), ptr(outV), stream), capi.lib().spmvb200_kind_name(kind).decode())
+    return EXIT_SUCCESS
+
+
+def cudaSpMVRowsCSR(m, v, cfg, outV, stream=None):
+    """src/SpMV_CUDA.cu:33-49 -> TMA-staged CSR stream kernel, bit-identical to sgemvSerial."""
+    return _launch(CSR_ROWS, m, v, cfg, outV, stream)
+
+
+def cudaSpMVWarpPerRowCSR(m, v, cfg, outV, stream=None):
+    """src/SpMV_CUDA.cu:52-73 -> sub-warp-per-row vector kernel (128-bit loads, shuffle reduction)."""
+    return _launch(CSR_ROWS_WARP, m, v, cfg, outV, stream)
+
+
+def cudaSpMVAdaptiveCSR(m, v, cfg, outV, stream=None):
+    """new mode: row-length adaptive stream kernel (long rows reduced by warps / split across CTAs)."""
+    return _launch(CSR_ADAPTIVE, m, v, cfg, outV, stream)
+
+
+def cudaSpMVRowsELL(m, v, cfg, outV, stream=None):
+    """src/SpMV_CUDA.cu:79-96 -> column-major pitched ELL, row-length early exit."""
+    return _launch(ELL_ROWS, m, v, cfg, outV, stream)
+
+
+def cudaSpMVRowsELLNNTransposed(m, v, cfg, outV, stream=None):
+    """src/SpMV_CUDA.cu:99-115 -> row-major ELL, sub-warp per row sized from K."""
+    return _launch(ELL_ROWS_NT, m, v, cfg, outV, stream)
+
+
+def cudaSpMVWarpsPerRowELLNTrasposed(m, v, cfg, outV, stream=None):
+    """src/SpMV_CUDA.cu:116-135 -> row-major ELL, one warp per row."""
+    return _launch(ELL_ROWS_WARP_NT, m, v, cfg, outV, stream)
+
+
+# function tables, src/include/SpMV.h:130-142 (the adaptive mode appended)
+SpmvCUDA_CSRFuncs = [cudaSpMVRowsCSR, cudaSpMVWarpPerRowCSR, cudaSpMVAdaptiveCSR]
+SpmvCUDA_CSRFuncs_WarpPerRowIdx = 1
+SpmvCUDA_ELLFuncs = [cudaSpMVRowsELL, cudaSpMVRowsELLNNTransposed, cudaSpMVWarpsPerRowELLNTrasposed]
+SpmvCUDA_ELLFuncs_NN_TraposedImpl = 1
+SpmvCUDA_ELLFuncs_WarpPerRowIdx = 2
+
+KIND_OF = {cudaSpMVRowsCSR: CSR_ROWS, cudaSpMVWarpPerRowCSR: CSR_ROWS_WARP, cudaSpMVAdaptiveCSR: CSR_ADAPTIVE,
+           cudaSpMVRowsELL: ELL_ROWS, cudaSpMVRowsELLNNTransposed: ELL_ROWS_NT,
+           cudaSpMVWarpsPerRowELLNTrasposed: ELL_ROWS_WARP_NT}
+MODE_OF = {CUDA_CSR_ROWS: CSR_ROWS, CUDA_CSR_ROWS_WARP: CSR_ROWS_WARP, CUDA_ELL_ROWS: ELL_ROWS,
+           CUDA_ELL_ROWS_WARP_NT: ELL_ROWS_WARP_NT, CUDA_CSR_ADAPTIVE: CSR_ADAPTIVE}
+
+
+def time_kernel(kind, m, v, outV, reps=25, flush_l2=False):
+    """CUDA-event time (ms) of `reps` launches -- the timing loop of testSpMVImplCuda
+    (test/SpMV_test.cu:103-145) with events instead of a host stopwatch."""
+    t = np.zeros(reps, dtype=np.float32)
+    check(lib().spmvb200_time_device(m.handle, kind, ptr(v), ptr(outV), reps, int(flush_l2), ptr(t)), "time_device")
+    return t
+
+
+def spmv_host(kind, m, x, y):
+    """x, y host buffers (numpy or pinned torch tensors): H2D x, kernel, D2H y.  Returns kernel ms."""
+    ms = C.c_float(0)
+    check(lib().spmvb200_spmv_host(m.handle, kind, ptr(x), ptr(y), C.byref(ms)), "spmv_host")
+    return ms.value
+
+
+# ---------------------------------------------------------------------------------------- SPMV_INTERF adapters
+def _host_adapter(kind, is_ell):
+    def f(mat, x, cfg, y):
+        el = C.c_double(0)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert isinstance(y, np.ndarray) and y.dtype == np.float64 and y.flags.c_contiguous and len(y) == mat.M
+        rl = mat.RL
+        check(lib().spmvb200_cached_spmv(id(mat), kind, int(is_ell), mat.M, mat.N, mat.MAX_ROW_NZ if is_ell else 0,
+                                         ptr(mat.IRP), ptr(mat.JA), ptr(mat.AS), ptr(rl), ptr(x), ptr(y), C.byref(el)),
+              "b200SpMV")
+        f.ElapsedInternal = el.value
+        return EXIT_SUCCESS
+    f.ElapsedInternal = 0.0
+    return f
+
+
+b200SpMVRowsCSR = _host_adapter(CSR_ROWS, False)
+b200SpMVWarpPerRowCSR = _host_adapter(CSR_ROWS_WARP, False)
+b200SpMVAdaptiveCSR = _host_adapter(CSR_ADAPTIVE, False)
+b200SpMVRowsELL = _host_adapter(ELL_ROWS, True)
+b200SpMVRowsELLNNTransposed = _host_adapter(ELL_ROWS_NT, True)
+b200SpMVWarpsPerRowELLNTrasposed = _host_adapter(ELL_ROWS_WARP_NT, True)
+SpmvB200CSRFuncs = [b200SpMVRowsCSR, b200SpMVWarpPerRowCSR, b200SpMVAdaptiveCSR]
+SpmvB200ELLFuncs = [b200SpMVRowsELL, b200SpMVRowsELLNNTransposed, b200SpMVWarpsPerRowELLNTrasposed]
+
+
+def cache_drop(mat=None):
+    check(lib().spmvb200_cache_drop(None if mat is None else id(mat)), "cache_drop")

@@ -1,0 +1,112 @@
+"""CPU-only checks of the product boundary: the C-ABI library builds/loads, exports every symbol
+include/spmv_b200.h declares, fails loudly without a GPU, and the host generators are deterministic.
+No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import spmv_openmp_cuda_b200 as sp
+    sp.capi.lib()
+    return sp
+
+
+def test_header_symbols_all_exported(sp):
+    hdr = open(os.path.join(ROOT, "include", "spmv_b200.h")).read()
+    hdr = hdr.split("reference-typed adapters")[0]
+    declared = set(re.findall(r"\b(spmvb200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    L = C.CDLL(sp.capi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(sp.capi.EXPORTS), declared ^ set(sp.capi.EXPORTS)
+
+
+def test_version_and_kind_names(sp):
+    L = sp.capi.lib()
+    assert L.spmvb200_version() == 100
+    names = [L.spmvb200_kind_name(k).decode() for k in range(6)]
+    assert names[0] == "CUDA_CSR_ROWS" and names[1] == "CUDA_CSR_ROWS_WARP" and names[2] == "CUDA_ELL_ROWS"
+    assert names[4] == "CUDA_ELL_ROWS_WARP_NN_TRANSPOSED"  # src/include/SpMV.h:41
+
+
+def test_tables_mirror_reference(sp):
+    # src/include/SpMV.h:130-142
+    assert [f.__name__ for f in sp.SpmvCUDA_CSRFuncs[:2]] == ["cudaSpMVRowsCSR", "cudaSpMVWarpPerRowCSR"]
+    assert [f.__name__ for f in sp.SpmvCUDA_ELLFuncs] == ["cudaSpMVRowsELL", "cudaSpMVRowsELLNNTransposed",
+                                                          "cudaSpMVWarpsPerRowELLNTrasposed"]
+    assert sp.SpmvCUDA_CSRFuncs_WarpPerRowIdx == 1 and sp.SpmvCUDA_ELLFuncs_WarpPerRowIdx == 2
+
+
+def test_no_cpu_fallback(sp):
+    """Without a device the product path must raise, never compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    g = load_golden("lap2d_8")
+    mat = sp.Spmat.csr(int(g["N"]), g["irp"], g["ja"], g["as_"])
+    with pytest.raises(sp.SpmvB200Error):
+        sp.spMatCpyCSR(mat)
+    with pytest.raises(sp.SpmvB200Error):
+        sp.b200SpMVRowsCSR(mat, g["x"], sp.Config(), np.zeros(mat.M))
+    with pytest.raises(sp.SpmvB200Error):
+        sp.synth.device_csr(sp.synth.lap2d(8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "spmv_openmp_cuda_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_host_generators_match_reference_parser(sp):
+    """The 5-point generator reproduces, entry for entry, what the reference's Matrix Market reader
+    built for the same matrix (golden fixture written by tests/golden/make_golden.py)."""
+    for n, name in ((8, "lap2d_8"), (33, "lap2d_33")):
+        g = load_golden(name)
+        m = sp.synth.host_csr(sp.synth.lap2d(n))
+        np.testing.assert_array_equal(m.IRP, g["irp"])
+        np.testing.assert_array_equal(m.JA, g["ja"])
+        np.testing.assert_array_equal(m.AS, g["as_"])
+        e = sp.synth.csr_to_ell_host(m)
+        np.testing.assert_array_equal(e.JA, g["ell_ja"])
+        np.testing.assert_array_equal(e.AS, g["ell_as"])
+
+
+def test_generators_row_ranges_and_shapes(sp):
+    s = sp.synth
+    full = s.host_csr(s.banded(4096, 32, 300))
+    assert full.NZ == 4096 * 32
+    ja = full.JA.reshape(4096, 32).astype(np.int64)
+    assert np.all(np.diff(ja, axis=1) > 0)  # sorted, distinct
+    rows = np.arange(4096)[:, None]
+    assert np.all(np.abs(ja - rows) <= 300) and ja.min() >= 0 and ja.max() < 4096
+    part = s.host_csr(s.banded(4096, 32, 300), 1000, 1500)
+    np.testing.assert_array_equal(part.JA, full.JA[1000 * 32:1500 * 32])
+    np.testing.assert_array_equal(part.AS, full.AS[1000 * 32:1500 * 32])
+    st = s.host_csr(s.stencil27(7, 6, 5))
+    assert st.NZ == (3 * 7 - 2) * (3 * 6 - 2) * (3 * 5 - 2) and st.MAX_ROW_NZ == 27
+    mx = s.host_csr(s.mixed(20000, 48, 0.05))
+    rl = np.diff(mx.IRP)
+    assert set(rl.tolist()) == {4, 48} and 0.03 < (rl == 48).mean() < 0.07
+    for r in (0, 7, 19999):
+        c = mx.JA[int(mx.IRP[r]):int(mx.IRP[r + 1])].astype(np.int64)
+        assert np.all(np.diff(c) > 0)
+    rm = s.rmat_host_csr(9, 8)
+    assert rm.M == 512 and rm.NZ <= 8 * 512 and rm.NZ > 2000
+    for r in range(0, 512, 37):
+        c = rm.JA[int(rm.IRP[r]):int(rm.IRP[r + 1])].astype(np.int64)
+        assert np.all(np.diff(c) > 0)
+    x1, x2 = s.host_vector(100), s.host_vector(40, begin=60)
+    np.testing.assert_array_equal(x1[60:], x2)
+    assert np.all(np.abs(x1) < 3e-5) and np.all(np.isfinite(x1))

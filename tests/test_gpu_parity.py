@@ -1,0 +1,233 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle / golden fixtures.
+
+Tolerances (stated, as BASELINE.json's north_star asks):
+  * cudaSpMVRowsCSR and cudaSpMVRowsELL replacements sum each row left to right with separate
+    mul/add roundings => BIT-IDENTICAL to sgemvSerial (src/SpMV_CSR_OMP.c:229-250);
+  * tree-reduced kinds: |y_i - yref_i| <= 1e-12 * sum_j |a_ij x_j|   (TAU), NaN => fail;
+  * every kind also passes the reference's own check |y - yref| <= 7e-4 (src/commons/utils.c:362-393).
+Output vectors are pre-filled with a NaN pattern so stale results can never pass.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+TAU = 1e-12
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import spmv_openmp_cuda_b200 as sp
+    sp.capi.require_device()
+    return sp
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import oracle
+    return oracle
+
+
+EXACT = {"cudaSpMVRowsCSR", "cudaSpMVRowsELL"}
+
+
+def run_all_kinds(sp, orc, mat, x, y_ref, ell=None, kinds="all"):
+    """The reference harness flow (test/SpMV_test.cu:273-343): upload, run every table entry, compare."""
+    cfg = sp.Config()
+    dx = sp.DeviceVector.from_host(x)
+    dy = sp.DeviceVector(mat.M)
+    ell = ell if ell is not None else sp.synth.csr_to_ell_host(mat)
+    d_csr = sp.spMatCpyCSR(mat)
+    d_ell = sp.spMatCpyELL(ell)
+    d_rm = sp.spMatCpyELLNNPitched(ell)
+    runs = [(f, d_csr) for f in sp.SpmvCUDA_CSRFuncs] + \
+           [(sp.cudaSpMVRowsELL, d_ell), (sp.cudaSpMVRowsELLNNTransposed, d_rm), (sp.cudaSpMVWarpsPerRowELLNTrasposed, d_rm)]
+    for f, dm in runs:
+        dy.fill_bytes(0xFF)
+        assert f(dm, dx, cfg, dy) == 0
+        y = dy.to_host()
+        assert np.all(np.isfinite(y)), f.__name__
+        failed, dmax = orc.double_vectors_diff(y_ref, y)
+        assert not failed, (f.__name__, dmax)
+        bad, worst = orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=TAU)
+        assert bad == 0, (f.__name__, bad, worst)
+        if f.__name__ in EXACT:
+            np.testing.assert_array_equal(y, y_ref, err_msg=f.__name__)
+    for dm in (d_csr, d_ell, d_rm):
+        sp.cudaFreeSpmat(dm)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fixtures_all_kinds(sp, orc, name):
+    g = load_golden(name)
+    mat = sp.Spmat.csr(int(g["N"]), g["irp"], g["ja"], g["as_"], RL=g["rl"])
+    ell = sp.Spmat.ell(int(g["M"]), int(g["N"]), int(g["K"]), g["ell_ja"], g["ell_as"], RL=g["rl"], NZ=int(g["NZ"]))
+    run_all_kinds(sp, orc, mat, g["x"], g["y_sgemvSerial"], ell=ell)
+
+
+@pytest.mark.parametrize("name", ["lap2d_33", "rect_empty_rows", "skew_long_row"])
+def test_ell_without_rowlens(sp, orc, name):
+    """A driver built without -DROWLENS has no RL vector: lengths are derived on the device."""
+    g = load_golden(name)
+    ell = sp.Spmat.ell(int(g["M"]), int(g["N"]), int(g["K"]), g["ell_ja"], g["ell_as"], RL=None, NZ=int(g["NZ"]))
+    dx, dy = sp.DeviceVector.from_host(g["x"]), sp.DeviceVector(int(g["M"]))
+    for up, f in ((sp.spMatCpyELL, sp.cudaSpMVRowsELL), (sp.spMatCpyELLNNPitched, sp.cudaSpMVWarpsPerRowELLNTrasposed)):
+        dm = up(ell, use_rowlens=False)
+        dy.fill_bytes(0xFF)
+        f(dm, dx, sp.Config(), dy)
+        y = dy.to_host()
+        bad, worst = orc.strict_diff_csr(g["irp"], g["ja"], g["as_"], g["x"], g["y_sgemvSerial"], y, tau=TAU)
+        assert bad == 0, worst
+
+
+def _oracle_y(orc, mat, x):
+    return orc.sgemv_serial(mat.IRP, mat.JA, mat.AS, x)
+
+
+@pytest.mark.parametrize("builder", [
+    lambda s: s.host_csr(s.lap2d(64)),
+    lambda s: s.host_csr(s.stencil27(20, 18, 16)),
+    lambda s: s.host_csr(s.banded(30000, 32, 2000)),
+    lambda s: s.host_csr(s.mixed(40000, 48, 0.03)),
+    lambda s: s.rmat_host_csr(13, 16),
+])
+def test_scaled_down_baseline_configs(sp, orc, builder):
+    mat = builder(sp.synth)
+    x = sp.synth.host_vector(mat.N)
+    run_all_kinds(sp, orc, mat, x, _oracle_y(orc, mat, x))
+
+
+def test_edge_cases(sp, orc):
+    rng = np.random.default_rng(7)
+
+    def rand_csr(M, N, lens):
+        irp = np.zeros(M + 1, dtype=np.uint64)
+        irp[1:] = np.cumsum(lens)
+        ja = np.concatenate([np.sort(rng.choice(N, k, replace=False)) for k in lens] + [np.zeros(0, int)]).astype(np.uint64)
+        return sp.Spmat.csr(N, irp, ja, rng.uniform(-1, 1, int(irp[-1])))
+
+    cases = {
+        "all_rows_empty": rand_csr(100, 50, np.zeros(100, int)),
+        "one_by_one": rand_csr(1, 1, np.array([1])),
+        "rows_longer_than_a_tile": rand_csr(6, 20000, np.array([3, 9000, 0, 2048, 2049, 17000])),
+        "many_short_then_long": rand_csr(3000, 6000, np.r_[np.ones(2999, int), 5000]),
+        "tile_boundary_rows": rand_csr(1200, 4096, np.r_[np.full(400, 5), np.full(400, 0), np.full(400, 31)]),
+        "single_column": rand_csr(777, 1, rng.integers(0, 2, 777)),
+    }
+    for name, mat in cases.items():
+        x = rng.uniform(-1, 1, mat.N)
+        y_ref = _oracle_y(orc, mat, x)
+        if mat.MAX_ROW_NZ * mat.M < 3_000_000:
+            run_all_kinds(sp, orc, mat, x, y_ref)
+        else:  # ELL would be huge (the reference caps it too, config.h:69): CSR kinds only
+            dx, dy, dm = sp.DeviceVector.from_host(x), sp.DeviceVector(mat.M), sp.spMatCpyCSR(mat)
+            for f in sp.SpmvCUDA_CSRFuncs:
+                dy.fill_bytes(0xFF)
+                f(dm, dx, sp.Config(), dy)
+                bad, worst = orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, dy.to_host(), tau=TAU)
+                assert bad == 0, (name, f.__name__, worst)
+
+
+def test_long_row_split_is_deterministic(sp):
+    """Rows split across CTAs are combined in segment order by the last arriver: run-to-run identical."""
+    mat = sp.synth.rmat_host_csr(14, 16)
+    x = sp.synth.host_vector(mat.N)
+    dx, dy, dm = sp.DeviceVector.from_host(x), sp.DeviceVector(mat.M), sp.spMatCpyCSR(mat)
+    for f in (sp.cudaSpMVRowsCSR, sp.cudaSpMVAdaptiveCSR):
+        outs = []
+        for _ in range(5):
+            dy.fill_bytes(0xFF)
+            f(dm, dx, sp.Config(), dy)
+            outs.append(dy.to_host())
+        for o in outs[1:]:
+            np.testing.assert_array_equal(o, outs[0])
+
+
+def test_host_adapters_spmv_interf(sp, orc):
+    """SPMV_INTERF-shaped calls with host buffers (src/include/SpMV.h:63-64), the flow of
+    testSpMVImplOMP (test/SpMV_test.cu:67-101): repeated calls, result compared every time."""
+    mat = sp.synth.host_csr(sp.synth.stencil27(16))
+    ell = sp.synth.csr_to_ell_host(mat)
+    x = sp.synth.host_vector(mat.N)
+    y_ref = _oracle_y(orc, mat, x)
+    for f, m in [(f, mat) for f in sp.SpmvB200CSRFuncs] + [(f, ell) for f in sp.SpmvB200ELLFuncs]:
+        for _ in range(3):
+            y = np.full(mat.M, np.nan)
+            assert f(m, x, sp.Config(), y) == 0
+            assert not orc.double_vectors_diff(y_ref, y)[0]
+            assert orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=TAU)[0] == 0
+            assert f.ElapsedInternal > 0
+    sp.cache_drop()
+
+
+def test_row_block_partition_slices(sp, orc):
+    """Row-block partition: per-slice handles produce the slices of y."""
+    mat = sp.synth.host_csr(sp.synth.banded(50000, 32, 3000))
+    x = sp.synth.host_vector(mat.N)
+    y_ref = _oracle_y(orc, mat, x)
+    dx = sp.DeviceVector.from_host(x)
+    bounds = [0, 12500, 25000, 37500, 50000]
+    y = np.empty(mat.M)
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        dm, dy = sp.spMatCpyCSR(mat, a, b), sp.DeviceVector(b - a)
+        sp.cudaSpMVRowsCSR(dm, dx, sp.Config(), dy)
+        y[a:b] = dy.to_host()
+    np.testing.assert_array_equal(y, y_ref)
+
+
+def test_device_generators_match_host(sp):
+    s = sp.synth
+    for spec in (s.lap2d(50), s.stencil27(9, 8, 7), s.banded(20000, 32, 500), s.mixed(30000, 32, 0.1)):
+        h = s.host_csr(spec)
+        d = s.device_csr(spec)
+        irp, ja, as_ = d.download_csr()
+        np.testing.assert_array_equal(irp, h.IRP)
+        np.testing.assert_array_equal(ja, h.JA)
+        np.testing.assert_array_equal(as_, h.AS)
+    h = s.host_csr(s.banded(20000, 32, 500), 5000, 9000)
+    irp, ja, as_ = s.device_csr(s.banded(20000, 32, 500), 5000, 9000).download_csr()
+    np.testing.assert_array_equal(ja, h.JA)
+    np.testing.assert_array_equal(as_, h.AS)
+    h = s.rmat_host_csr(12, 16)
+    irp, ja, as_ = s.rmat_device_csr(12, 16).download_csr()
+    np.testing.assert_array_equal(irp, h.IRP)
+    np.testing.assert_array_equal(ja, h.JA)
+    np.testing.assert_array_equal(as_, h.AS)
+    n = 1000
+    dv = sp.DeviceVector(n)
+    s.device_vector_fill(dv, n)
+    np.testing.assert_array_equal(dv.to_host(), s.host_vector(n))
+
+
+def test_full_size_cfg2_properties(sp, orc):
+    """BASELINE cfg2 at full size (27-point 128^3, 55.7 M nnz), size-independent checks:
+    A*1 = 27 - rowlen exactly; linearity; sampled row blocks against the oracle."""
+    s = sp.synth
+    spec = s.stencil27(128)
+    d_csr = s.device_csr(spec)
+    assert d_csr.NZ == (3 * 128 - 2) ** 3
+    d_ell = d_csr.to_ell(sp.FMT_ELL_COLMAJOR)
+    d_rm = d_csr.to_ell(sp.FMT_ELL_ROWMAJOR)
+    M = d_csr.M
+    ones = sp.DeviceVector.from_host(np.ones(M))
+    dy = sp.DeviceVector(M)
+    irp, _, _ = d_csr.download_csr()
+    expect = 27.0 - np.diff(irp).astype(np.float64)
+    for f, dm in ((sp.cudaSpMVRowsCSR, d_csr), (sp.cudaSpMVWarpPerRowCSR, d_csr), (sp.cudaSpMVAdaptiveCSR, d_csr),
+                  (sp.cudaSpMVRowsELL, d_ell), (sp.cudaSpMVRowsELLNNTransposed, d_rm), (sp.cudaSpMVWarpsPerRowELLNTrasposed, d_rm)):
+        dy.fill_bytes(0xFF)
+        f(dm, ones, sp.Config(), dy)
+        np.testing.assert_array_equal(dy.to_host(), expect, err_msg=f.__name__)
+    x = s.host_vector(M)
+    dx = sp.DeviceVector.from_host(x)
+    sp.cudaSpMVRowsELL(d_ell, dx, sp.Config(), dy)
+    y = dy.to_host()
+    sp.cudaSpMVRowsCSR(d_csr, dx, sp.Config(), dy)
+    np.testing.assert_array_equal(dy.to_host(), y)  # two exact kinds agree bit for bit
+    for a in (0, 1_000_000, M - 50_000):  # sampled row blocks vs the oracle
+        h = s.host_csr(spec, a, a + 50_000)
+        np.testing.assert_array_equal(y[a:a + 50_000], orc.sgemv_serial(h.IRP, h.JA, h.AS, x))
+    d2 = sp.DeviceVector.from_host(2.0 * x)  # linearity: A(2x) = 2 A x exactly (power of two)
+    sp.cudaSpMVRowsELL(d_ell, d2, sp.Config(), dy)
+    np.testing.assert_array_equal(dy.to_host(), 2.0 * y)
