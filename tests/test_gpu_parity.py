@@ -30,6 +30,7 @@ def orc():
 
 
 EXACT = {"cudaSpMVRowsCSR", "cudaSpMVRowsELL"}
+STREAM_TILE = 2048  # csrc/kernels.cuh
 
 
 def run_all_kinds(sp, orc, mat, x, y_ref, ell=None, kinds="all"):
@@ -53,7 +54,10 @@ def run_all_kinds(sp, orc, mat, x, y_ref, ell=None, kinds="all"):
         bad, worst = orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=TAU)
         assert bad == 0, (f.__name__, bad, worst)
         if f.__name__ in EXACT:
-            np.testing.assert_array_equal(y, y_ref, err_msg=f.__name__)
+            # rows longer than one tile (2048 nnz) are split across CTAs by the CSR kernel and summed
+            # in segment order: deterministic, within TAU, but not the serial order
+            exact = np.ones(mat.M, dtype=bool) if f.__name__ == "cudaSpMVRowsELL" else (np.diff(mat.IRP) <= STREAM_TILE)
+            np.testing.assert_array_equal(y[exact], y_ref[exact], err_msg=f.__name__)
     for dm in (d_csr, d_ell, d_rm):
         sp.cudaFreeSpmat(dm)
 
