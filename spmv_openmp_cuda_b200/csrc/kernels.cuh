@@ -30,39 +30,40 @@ struct __align__(16) LongRec {
 constexpr uint32_t SEG_FLAG = 0x80000000u;
 
 constexpr int STREAM_TILE = 2048;        // non-zeros per tile (24 KB of values + column ids)
-constexpr int STREAM_BLOCK = 256;        // threads per CTA
+constexpr int STREAM_BLOCK = 128;        // threads per CTA
 constexpr int STREAM_TILE_ROWS = 512;    // rows per tile (row-pointer slice in shared memory); 8 CTAs/SM fit
-constexpr int STREAM_LONG_T = 16;        // ADAPTIVE: rows longer than this are reduced by a whole warp
+constexpr int STREAM_LONG_T = 64;        // ADAPTIVE: rows longer than this are reduced by a whole warp
 
-__device__ __forceinline__ uint32_t skew(uint32_t i) { return i + (i >> 5); }  // one pad double / 32: kills
-                                                                               // bank conflicts of the per-row walk
 // ---------------------------------------------------------------------------------------------
 // CSR "stream" kernel.  One CTA per tile:
 //   1. thread 0 issues two TMA bulk copies (values, column ids) of the tile's 16-byte aligned
 //      non-zero range into shared memory, completion on an mbarrier; L2 evict-first (read once);
 //      the other threads meanwhile fetch the tile's row-pointer slice.
-//   2. every thread gathers x for TILE/BLOCK elements (independent loads, issued back to back),
-//      multiplies and writes the products back to shared memory (skewed layout).
-//   3. one thread per row adds its products left to right with separate mul/add roundings -- the
-//      summation order of sgemvSerial (src/SpMV_CSR_OMP.c:229-250), hence bit-identical results.
-//      ADAPTIVE: rows longer than STREAM_LONG_T are instead reduced by a whole warp (tree order).
+//   2. one thread per row walks its row in shared memory: value and column id come from the staged
+//      tile, x from global memory (read-only path, L1/L2 resident), products are added left to
+//      right with separate mul/add roundings -- the summation order of sgemvSerial
+//      (src/SpMV_CSR_OMP.c:229-250), hence bit-identical results.  Adjacent lanes own adjacent rows,
+//      so for stencil-like matrices a warp's x gather touches one or two 128-byte lines.
+//      ADAPTIVE: rows longer than STREAM_LONG_T are instead handled by a whole warp (lane-strided
+//      walk, shuffle tree), and even-length rows are walked from a per-lane rotated start so that
+//      equal-length rows do not collide on shared-memory banks (order differs => tolerance, not
+//      bit-exact).
 //   Segment tiles (pieces of a row longer than TILE) block-reduce to one partial; the last
 //   segment to finish (ticket counter) adds the partials in segment order => deterministic.
-// Bytes in flight do not depend on occupancy or registers: 8 resident CTAs x 24 KB per SM.
+// The matrix stream never touches L1 or registers before it is consumed: bytes in flight are
+// 8 resident CTAs x 24 KB per SM, independent of occupancy and register count.
 // ---------------------------------------------------------------------------------------------
 template <int TILE, int BLOCK, int TILE_ROWS, bool ADAPTIVE>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 8)
 csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__ longrec,
                   const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
                   const double* __restrict__ x, double* __restrict__ y, double* __restrict__ partial,
                   uint32_t* __restrict__ ticket) {
     constexpr int CAP = TILE + 8;
-    constexpr int EPT = TILE / BLOCK;
     constexpr int NWARPS = BLOCK / 32;
     constexpr int MAXLONG = TILE / STREAM_LONG_T;
-    static_assert(TILE % BLOCK == 0, "tile must be a multiple of the block");
 
-    __shared__ __align__(128) double s_val[CAP + CAP / 32 + 2];
+    __shared__ __align__(128) double s_val[CAP];
     __shared__ __align__(16) uint32_t s_col[CAP];
     __shared__ uint32_t s_rp[TILE_ROWS + 1];
     __shared__ uint32_t s_long[ADAPTIVE ? MAXLONG : 1];
@@ -79,7 +80,6 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
     const uint32_t n0 = d0.y, n1 = d1.y;
     const uint32_t nnz = n1 - n0;
     const uint32_t a0 = n0 & ~3u;               // 16-byte aligned start (4 x u32, 4 x f64 = 32 B)
-    const uint32_t off = n0 - a0;
     const uint32_t cnt = ((n1 + 3u) & ~3u) - a0;  // <= TILE + 6
     const uint32_t nrows = seg ? 0u : (d1.x & ~SEG_FLAG) - r0;
 
@@ -94,34 +94,16 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
         }
         s_nlong = 0;
     }
+    // row pointers as positions inside the staged tile (which starts at non-zero a0)
     if (!seg)
-        for (uint32_t i = tid; i <= nrows; i += BLOCK) s_rp[i] = __ldg(irp + r0 + i) - n0;
+        for (uint32_t i = tid; i <= nrows; i += BLOCK) s_rp[i] = __ldg(irp + r0 + i) - a0;
     __syncthreads();
     if (nnz) mbar_wait(&s_bar, 0);
 
-    // ---- products (element e of the tile sits at shared position off + e)
-    double p[EPT];
-    {
-        uint32_t c[EPT];
-        double v[EPT];
-#pragma unroll
-        for (int u = 0; u < EPT; ++u) {
-            const uint32_t e = tid + u * BLOCK;
-            const bool ok = e < nnz;
-            c[u] = ok ? s_col[off + e] : 0u;
-            v[u] = ok ? s_val[off + e] : 0.0;
-        }
-        double xv[EPT];
-#pragma unroll
-        for (int u = 0; u < EPT; ++u) xv[u] = (tid + u * BLOCK < nnz) ? ld_x(x, c[u]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < EPT; ++u) p[u] = __dmul_rn(v[u], xv[u]);
-    }
-
     if (seg) {  // ---- one piece of a long row: block sum -> partial -> ordered combine by the last arriver
         double t = 0;
-#pragma unroll
-        for (int u = 0; u < EPT; ++u) t += p[u];
+        const uint32_t lo = n0 - a0, hi = n1 - a0;
+        for (uint32_t j = lo + tid; j < hi; j += BLOCK) t = fma(s_val[j], ld_x(x, s_col[j]), t);
         t = subwarp_sum<32>(t);
         if ((tid & 31) == 0) s_red[tid >> 5] = t;
         __syncthreads();
@@ -144,22 +126,25 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
         return;
     }
 
-    __syncthreads();  // all reads of the TMA-landed values are done: products may overwrite them
-#pragma unroll
-    for (int u = 0; u < EPT; ++u) {
-        const uint32_t e = tid + u * BLOCK;
-        if (e < nnz) s_val[skew(e)] = p[u];
-    }
-    __syncthreads();
-
     for (uint32_t r = tid; r < nrows; r += BLOCK) {
         const uint32_t s = s_rp[r], e = s_rp[r + 1];
-        if (ADAPTIVE && e - s > (uint32_t) STREAM_LONG_T) {
-            s_long[atomicAdd(&s_nlong, 1u)] = r;
-            continue;
-        }
+        const uint32_t len = e - s;
         double acc = 0;
-        for (uint32_t j = s; j < e; ++j) acc = __dadd_rn(acc, s_val[skew(j)]);
+        if (ADAPTIVE) {
+            if (len > (uint32_t) STREAM_LONG_T) {
+                s_long[atomicAdd(&s_nlong, 1u)] = r;
+                continue;
+            }
+            uint32_t j = (len & 1u) ? 0u : (tid & 31u) % (len ? len : 1u);  // rotated start for even lengths
+#pragma unroll 4
+            for (uint32_t k = 0; k < len; ++k) {
+                acc = fma(s_val[s + j], ld_x(x, s_col[s + j]), acc);
+                if (++j == len) j = 0;
+            }
+        } else {
+#pragma unroll 4
+            for (uint32_t j = s; j < e; ++j) acc = __dadd_rn(acc, __dmul_rn(s_val[j], ld_x(x, s_col[j])));
+        }
         y[r0 + r] = acc;
     }
     if (ADAPTIVE) {
@@ -169,7 +154,7 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
             const uint32_t r = s_long[k];
             const uint32_t s = s_rp[r], e = s_rp[r + 1];
             double acc = 0;
-            for (uint32_t j = s + lane; j < e; j += 32) acc += s_val[skew(j)];
+            for (uint32_t j = s + lane; j < e; j += 32) acc = fma(s_val[j], ld_x(x, s_col[j]), acc);
             acc = subwarp_sum<32>(acc);
             if (lane == 0) y[r0 + r] = acc;
         }
