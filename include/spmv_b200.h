@@ -102,6 +102,10 @@ uint64_t spmvb200_device_bytes(const spmvb200_matrix* m);
 /* 1 if `kind` can run on this handle's format */
 int spmvb200_kind_supported(const spmvb200_matrix* m, int kind);
 const char* spmvb200_kind_name(int kind); /* the reference's mode string, e.g. "CUDA_CSR_ROWS" */
+/* SPMVB200_CSR_ADAPTIVE times its candidate kernels (stream with 8 CTAs/SM, stream with a large L1,
+ * vector with 2..32 lanes per row) on the handle's first adaptive launch and keeps the fastest;
+ * this returns the winner's name ("" before that first launch). */
+int spmvb200_adaptive_choice(const spmvb200_matrix* m, char* name, size_t len);
 
 /* ------------------------------------------------------------------ compute
  * Device-resident SpMV: y[0..rows) = A[row_begin..row_end) * x, d_x has N doubles, d_y has

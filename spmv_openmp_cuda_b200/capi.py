@@ -41,6 +41,7 @@ _SIGS = {
     "spmvb200_device_bytes": (_u64, [_vp]),
     "spmvb200_kind_supported": (C.c_int, [_vp, C.c_int]),
     "spmvb200_kind_name": (C.c_char_p, [C.c_int]),
+    "spmvb200_adaptive_choice": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "spmvb200_spmv_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "spmvb200_spmv_host": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(C.c_float)]),
     "spmvb200_time_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),

@@ -3,6 +3,7 @@
 // Replaces src/commons/cudaUtils.cu (spMatCpyCSR/ELL*, cudaFreeSpmat) and the launch+sync+download
 // code of src/main.cu:192-248 / test/SpMV_test.cu:103-145.  No CPU compute path exists here.
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -29,6 +30,7 @@ static void free_arrays(spmvb200_matrix* m) {
     cudaFree(m->longrec);
     cudaFree(m->partial);
     cudaFree(m->ticket);
+    cudaFree(m->seg_tiles);
     cudaFree(m->d_x);
     cudaFree(m->d_y);
     cudaFree(m->flush);
@@ -137,10 +139,17 @@ int spmvb200::finish_csr(spmvb200_matrix* m) {
     CU_TRY(cudaMalloc(&m->partial, std::max<size_t>(1, m->ntiles) * sizeof(double)));
     CU_TRY(cudaMalloc(&m->ticket, std::max<size_t>(1, longs.size()) * sizeof(uint32_t)));
     CU_TRY(cudaMemset(m->ticket, 0, std::max<size_t>(1, longs.size()) * sizeof(uint32_t)));
+    std::vector<uint32_t> segs;
+    for (size_t t = 0; t + 1 < tiles.size(); ++t)
+        if (tiles[t].row0 & SEG_FLAG) segs.push_back((uint32_t) t);
+    m->nseg = (uint32_t) segs.size();
+    CU_TRY(cudaMalloc(&m->seg_tiles, std::max<size_t>(1, segs.size()) * sizeof(uint32_t)));
+    if (!segs.empty()) CU_TRY(cudaMemcpy(m->seg_tiles, segs.data(), segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     // sub-warp width of the vector kernel from the mean row length (2 non-zeros per lane and step)
     const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
     int lanes = 2;
     while (lanes < 32 && lanes * 2 < mean) lanes *= 2;
+    if (const char* e = getenv("SPMVB200_VEC_LANES")) lanes = atoi(e);  // developer knob
     m->vec_lanes = lanes;
     return 0;
 }
@@ -447,11 +456,75 @@ extern "C" const char* spmvb200_kind_name(int kind) {
 
 // ------------------------------------------------------------------------------------------------- launch
 template <int LANES>
-static void launch_csr_vector(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+static void launch_csr_vector_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
     constexpr int BLOCK = 256;
     const uint64_t threads = m->M * LANES;
-    csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->irp, m->ja, m->as, x, y, (uint32_t) m->M);
+    csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->irp, m->ja, m->as, x, y, (uint32_t) m->M,
+                                                                                                     (uint32_t) STREAM_TILE);
 }
+// vector kernel for rows up to one tile + the long-row kernel for the rest (same stream, back to back)
+static void launch_csr_vector(const spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st) {
+    switch (lanes) {
+        case 2: launch_csr_vector_t<2>(m, x, y, st); break;
+        case 4: launch_csr_vector_t<4>(m, x, y, st); break;
+        case 8: launch_csr_vector_t<8>(m, x, y, st); break;
+        case 16: launch_csr_vector_t<16>(m, x, y, st); break;
+        default: launch_csr_vector_t<32>(m, x, y, st); break;
+    }
+    if (m->nseg) csr_longrow_kernel<128><<<m->nseg, 128, 0, st>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+}
+template <bool ADAPT, int VARIANT>
+static void launch_csr_stream(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, ADAPT, VARIANT>
+        <<<m->ntiles, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, x, y, m->partial, m->ticket);
+}
+
+// ---- SPMVB200_CSR_ADAPTIVE: candidates; the fastest on this matrix is picked at first use
+static const int N_CAND = 7;
+static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32"};
+static void launch_candidate(const spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st) {
+    switch (c) {
+        case 0: launch_csr_stream<true, 0>(m, x, y, st); break;
+        case 1: launch_csr_stream<true, 1>(m, x, y, st); break;
+        default: launch_csr_vector(m, 2 << (c - 2), x, y, st); break;
+    }
+}
+static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
+    // d_x / d_y are the caller's vectors: y is overwritten by every candidate with the same result
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    int best = 0;
+    float best_ms = 1e30f;
+    const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
+    for (int c = 0; c < N_CAND; ++c) {
+        m->tuned_ms[c] = -1.f;
+        if (c >= 2 && ((2 << (c - 2)) > 4 * mean + 2 || (double) (2 << (c - 2)) * 64 < mean)) continue;  // hopeless widths
+        launch_candidate(m, c, d_x, d_y, st);
+        float ms_min = 1e30f;
+        for (int rep = 0; rep < 2; ++rep) {
+            CU_TRY(cudaEventRecord(e0, st));
+            launch_candidate(m, c, d_x, d_y, st);
+            CU_TRY(cudaEventRecord(e1, st));
+            CU_TRY(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            ms_min = std::min(ms_min, ms);
+        }
+        m->tuned_ms[c] = ms_min;
+        if (ms_min < best_ms) { best_ms = ms_min; best = c; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    m->tuned = best;
+    if (getenv("SPMVB200_VERBOSE")) {
+        fprintf(stderr, "spmv_b200: adaptive tuning M=%llu NZ=%llu ->", (unsigned long long) m->M, (unsigned long long) m->NZ);
+        for (int c = 0; c < N_CAND; ++c) fprintf(stderr, " %s=%.3fms%s", CAND_NAME[c], m->tuned_ms[c], c == best ? "*" : "");
+        fprintf(stderr, "\n");
+    }
+    return 0;
+}
+
 template <int LANES>
 static void launch_ell_rowmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
     constexpr int BLOCK = 256;
@@ -464,23 +537,12 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
     if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
     if (m->M == 0) return 0;
     switch (kind) {
-        case SPMVB200_CSR_ROWS:
-            csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, false>
-                <<<m->ntiles, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, d_x, d_y, m->partial, m->ticket);
-            break;
+        case SPMVB200_CSR_ROWS: launch_csr_stream<false, 0>(m, d_x, d_y, st); break;
         case SPMVB200_CSR_ADAPTIVE:
-            csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, true>
-                <<<m->ntiles, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, d_x, d_y, m->partial, m->ticket);
+            if (m->tuned < 0 && tune_adaptive(m, d_x, d_y, st)) return 1;
+            launch_candidate(m, m->tuned, d_x, d_y, st);
             break;
-        case SPMVB200_CSR_ROWS_WARP:
-            switch (m->vec_lanes) {
-                case 2: launch_csr_vector<2>(m, d_x, d_y, st); break;
-                case 4: launch_csr_vector<4>(m, d_x, d_y, st); break;
-                case 8: launch_csr_vector<8>(m, d_x, d_y, st); break;
-                case 16: launch_csr_vector<16>(m, d_x, d_y, st); break;
-                default: launch_csr_vector<32>(m, d_x, d_y, st); break;
-            }
-            break;
+        case SPMVB200_CSR_ROWS_WARP: launch_csr_vector(m, m->vec_lanes, d_x, d_y, st); break;
         case SPMVB200_ELL_ROWS: {
             constexpr int BLOCK = 256;
             ell_colmajor_kernel<4, BLOCK><<<(unsigned) ((m->M + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) m->M,
@@ -507,11 +569,16 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
 static int prefer_smem_once() {
     static bool done = false;
     if (done) return 0;
-    // the stream kernel wants 8 x 28 KB of shared memory per SM: ask for the largest carve-out
-    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, false>,
+    // streaming variant: 8 CTAs x 27 KB of shared memory per SM => largest carve-out.
+    // gather variant (VARIANT=1): half the shared memory, the rest stays L1 for the x gathers.
+    int carve1 = 50;
+    if (const char* e = getenv("SPMVB200_CARVEOUT")) carve1 = atoi(e);  // developer knob
+    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, false, 0>,
                                 cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, true>,
+    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, true, 0>,
                                 cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, true, 1>,
+                                cudaFuncAttributePreferredSharedMemoryCarveout, carve1));
     done = true;
     return 0;
 }
@@ -557,6 +624,12 @@ extern "C" int spmvb200_time_device(spmvb200_matrix* m, int kind, const double* 
         CU_TRY(cudaEventSynchronize(m->ev1));
         CU_TRY(cudaEventElapsedTime(times_ms + i, m->ev0, m->ev1));
     }
+    return 0;
+}
+
+extern "C" int spmvb200_adaptive_choice(const spmvb200_matrix* m, char* name, size_t len) {
+    if (!m || !name || !len) return fail("adaptive_choice: bad arguments");
+    snprintf(name, len, "%s", m->tuned >= 0 ? CAND_NAME[m->tuned] : "");
     return 0;
 }
 

@@ -26,8 +26,12 @@ struct spmvb200_matrix {
     spmvb200::LongRec* longrec = nullptr;
     double* partial = nullptr;
     uint32_t* ticket = nullptr;
-    uint32_t ntiles = 0, nlong = 0;
+    uint32_t* seg_tiles = nullptr;  // indices of the segment tiles (rows longer than one tile)
+    uint32_t ntiles = 0, nlong = 0, nseg = 0;
     int vec_lanes = 32;
+    // SPMVB200_CSR_ADAPTIVE: candidate chosen by the first-use tuning run (-1 = not tuned yet)
+    int tuned = -1;
+    float tuned_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // host-path scratch
     double* d_x = nullptr;
     double* d_y = nullptr;

@@ -53,7 +53,7 @@ constexpr int STREAM_LONG_T = 64;        // ADAPTIVE: rows longer than this are 
 // The matrix stream never touches L1 or registers before it is consumed: bytes in flight are
 // 8 resident CTAs x 24 KB per SM, independent of occupancy and register count.
 // ---------------------------------------------------------------------------------------------
-template <int TILE, int BLOCK, int TILE_ROWS, bool ADAPTIVE>
+template <int TILE, int BLOCK, int TILE_ROWS, bool ADAPTIVE, int VARIANT>
 __global__ void __launch_bounds__(BLOCK, 8)
 csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__ longrec,
                   const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
@@ -171,21 +171,57 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
 template <int LANES, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 csr_vector_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
-                  const double* __restrict__ x, double* __restrict__ y, uint32_t M) {
+                  const double* __restrict__ x, double* __restrict__ y, uint32_t M, uint32_t max_len) {
     const uint32_t gt = blockIdx.x * BLOCK + threadIdx.x;
     const uint32_t row = gt / LANES, lane = gt % LANES;
     double acc = 0;
-    if (row < M) {
+    bool mine = row < M;
+    if (mine) {
         const uint32_t s = __ldg(irp + row), e = __ldg(irp + row + 1);
-        for (uint32_t i = (s & ~1u) + 2 * lane; i < e; i += 2 * LANES) {
-            const double2 v = ld_stream(reinterpret_cast<const double2*>(as + i));
-            const uint2 c = ld_stream(reinterpret_cast<const uint2*>(ja + i));
-            if (i >= s) acc = fma(v.x, ld_x(x, c.x), acc);
-            if (i + 1 < e) acc = fma(v.y, ld_x(x, c.y), acc);
-        }
+        mine = e - s <= max_len;  // longer rows belong to csr_longrow_kernel (same launch sequence)
+        if (mine)
+            for (uint32_t i = (s & ~1u) + 2 * lane; i < e; i += 2 * LANES) {
+                const double2 v = ld_stream(reinterpret_cast<const double2*>(as + i));
+                const uint2 c = ld_stream(reinterpret_cast<const uint2*>(ja + i));
+                if (i >= s) acc = fma(v.x, ld_x(x, c.x), acc);
+                if (i + 1 < e) acc = fma(v.y, ld_x(x, c.y), acc);
+            }
     }
     acc = subwarp_sum<LANES>(acc);
-    if (lane == 0 && row < M) y[row] = acc;
+    if (lane == 0 && mine) y[row] = acc;
+}
+
+// Rows longer than one tile, for the vector kernel: one CTA per <= TILE-non-zero segment (the plan's
+// segment tiles), direct coalesced loads, block sum, ordered combine by the last segment to finish.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+csr_longrow_kernel(const uint32_t* __restrict__ seg_tiles, const TileDesc* __restrict__ desc, const LongRec* __restrict__ longrec,
+                   const uint32_t* __restrict__ ja, const double* __restrict__ as, const double* __restrict__ x,
+                   double* __restrict__ y, double* __restrict__ partial, uint32_t* __restrict__ ticket) {
+    __shared__ double s_red[BLOCK / 32];
+    const uint32_t tid = threadIdx.x, b = seg_tiles[blockIdx.x];
+    const uint32_t n0 = desc[b].nnz0, n1 = desc[b + 1].nnz0, rec_id = desc[b].aux;
+    double t = 0;
+    for (uint32_t j = n0 + tid; j < n1; j += BLOCK) t = fma(ld_stream(as + j), ld_x(x, ld_stream(ja + j)), t);
+    t = subwarp_sum<32>(t);
+    if ((tid & 31) == 0) s_red[tid >> 5] = t;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0;
+#pragma unroll
+        for (int w = 0; w < BLOCK / 32; ++w) tot += s_red[w];
+        const LongRec rec = longrec[rec_id];
+        partial[b] = tot;
+        __threadfence();
+        const uint32_t done = atomicAdd(ticket + rec_id, 1u);
+        if (done == rec.ntiles - 1) {
+            __threadfence();
+            double acc = 0;
+            for (uint32_t k = 0; k < rec.ntiles; ++k) acc += __ldcg(partial + rec.first_tile + k);
+            y[rec.row] = acc;
+            ticket[rec_id] = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -94,6 +94,12 @@ class DeviceSpmat:
     def device_bytes(self):
         return int(lib().spmvb200_device_bytes(self.handle))
 
+    @property
+    def adaptive_choice(self):
+        buf = C.create_string_buffer(64)
+        check(lib().spmvb200_adaptive_choice(self.handle, buf, 64), "adaptive_choice")
+        return buf.value.decode()
+
     def supports(self, kind):
         return bool(lib().spmvb200_kind_supported(self.handle, kind))
 

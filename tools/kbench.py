@@ -33,7 +33,9 @@ def bench(label, dm, kinds, reps, flush):
         sp.time_kernel(kind, dm, dx, dy, reps=3, flush_l2=False)
         t = sp.time_kernel(kind, dm, dx, dy, reps=reps, flush_l2=flush)
         tmin, tmean = float(t.min()), float(t.mean())
-        print("%-28s %-10s flush=%d  min %8.3f us  mean %8.3f us  %8.1f GB/s (mean)  frac %.3f  %7.1f GFLOP/s   [M=%d NZ=%d bytes=%.1f MB]" % (
+        if kind == sp.CSR_ADAPTIVE:
+            name = name + "[" + dm.adaptive_choice + "]"
+        print("%-28s %-24s flush=%d  min %8.3f us  mean %8.3f us  %8.1f GB/s (mean)  frac %.3f  %7.1f GFLOP/s   [M=%d NZ=%d bytes=%.1f MB]" % (
             label, name, flush, tmin * 1e3, tmean * 1e3, B / tmean / 1e6, B / tmean / 1e6 / PEAK, 2 * dm.NZ / tmean / 1e6, dm.M, dm.NZ, B / 1e6), flush=True)
 
 
