@@ -33,6 +33,9 @@ sys.path.insert(0, ROOT)
 # kernels use schedule(runtime); plain "static" crashes its ompGetRuntimeSchedule (ompGetICV.c:43)
 os.environ.setdefault("OMP_SCHEDULE", "nonmonotonic:static")
 os.environ.setdefault("OMP_PROC_BIND", "close")
+if "reference" in sys.argv and "LOCAL_RANK" in os.environ:
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU reference arm (rank 0 only) uses all host cores
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 METRIC = "SpMV GFLOP/s (2*nnz/t), fp64"
 UNIT = "GFLOP/s"
@@ -236,11 +239,13 @@ def main():
         dm = synth.device_csr(spec, r0, r1)
         kind, kname = sp.CSR_ROWS, "csr_stream_kernel"
     Ncols = dm.N
-    nnz_total = torch.tensor([dm.NZ], dtype=torch.int64, device="cuda")
-    bytes_local = dm.algorithmic_bytes
+    tot = torch.tensor([dm.NZ, dm.M], dtype=torch.int64, device="cuda")
     if world > 1:
-        dist.all_reduce(nnz_total)
-    nnz_total = int(nnz_total.item())
+        dist.all_reduce(tot)
+    nnz_total, rows_total = int(tot[0].item()), int(tot[1].item())
+    # algorithmic bytes of the GLOBAL SpMV, split evenly: x is counted once for the whole job
+    rowmeta = 4 * rows_total if args.workload == "cfg2" else 4 * (rows_total + 1)
+    bytes_local = (12 * nnz_total + rowmeta + 8 * Ncols + 8 * rows_total) // nr
 
     x = torch.empty(Ncols, dtype=torch.float64, device="cuda")
     y = torch.empty(dm.M, dtype=torch.float64, device="cuda")
@@ -339,7 +344,7 @@ def main():
         "gpu_launches": launches, "gpu_launches_e2e": e2e_launch,
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_local),
-                     "note": "per GPU; algorithmic bytes = 12*nnz + 4*M + 8*N + 8*M (DESIGN.md)"},
+                     "note": "per GPU = global algorithmic bytes / n_gpus; global = 12*nnz + 4*M(+1 for CSR) + 8*N + 8*M (DESIGN.md)"},
         "parity": parity,
     }
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")

@@ -1,0 +1,42 @@
+"""The C drop-in, end to end on the GPU: tests/integration/b200_harness (built in the container against the
+REAL reference headers and oracle/_ref/libspmv_ref.so) parses a Matrix Market file with the reference's reader,
+computes the oracle with the reference's sgemvSerial, runs the b200SpMV* SPMV_INTERF adapters of
+include/spmv_b200.h and compares with the reference's doubleVectorsDiff after every repetition."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+HARNESS = os.path.join(ROOT, "tests", "integration", "_build", "b200_harness")
+
+
+def _write_mtx(path, M, N, rows, cols, vals):
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (M, N, len(rows)))
+        for r, c, v in zip(rows, cols, vals):
+            f.write("%d %d %.17g\n" % (r + 1, c + 1, v))
+
+
+@pytest.mark.parametrize("case", ["lap2d_150", "skewed"])
+def test_reference_side_harness(tmp_path, case):
+    if not os.path.exists(HARNESS):
+        pytest.skip("harness not built (needs /root/reference at build time)")
+    import spmv_openmp_cuda_b200 as sp
+    sp.capi.require_device()
+    if case == "lap2d_150":
+        m = sp.synth.host_csr(sp.synth.lap2d(150))
+    else:
+        m = sp.synth.rmat_host_csr(12, 12)
+    rows = np.repeat(np.arange(m.M), np.diff(m.IRP).astype(np.int64))
+    p = str(tmp_path / (case + ".mtx"))
+    _write_mtx(p, m.M, m.N, rows, m.JA, m.AS)
+    env = dict(os.environ, OMP_SCHEDULE="nonmonotonic:static")
+    out = subprocess.run([HARNESS, p], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "B200_HARNESS_OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+    # the reference's log format (test/SpMV_test.cu:93-96) so scripts/parseLog.py keeps working
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("threadNum:")]
+    assert len(lines) == 6 and all("timeInternalAvg:" in ln for ln in lines)
