@@ -16,7 +16,7 @@ HARNESS = os.path.join(ROOT, "tests", "integration", "_build", "b200_harness")
 
 def _write_mtx(path, M, N, rows, cols, vals):
     with open(path, "w") as f:
-        f.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (M, N, len(rows)))
+        f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (M, N, len(rows)))
         for r, c, v in zip(rows, cols, vals):
             f.write("%d %d %.17g\n" % (r + 1, c + 1, v))
 

@@ -19,7 +19,7 @@ B = os.path.join(ROOT, "tests", "integration", "_build")
 def write_mtx(path, m):
     rows = np.repeat(np.arange(m.M), np.diff(m.IRP).astype(np.int64)) + 1
     with open(path, "w") as f:
-        f.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (m.M, m.N, m.NZ))
+        f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (m.M, m.N, m.NZ))
         np.savetxt(f, np.column_stack([rows, m.JA.astype(np.int64) + 1, m.AS]), fmt="%d %d %.17g")
 
 
