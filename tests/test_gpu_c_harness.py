@@ -67,5 +67,5 @@ def test_unmodified_reference_harness_runs_dropin_kernels(tmp_path, case):
     env = dict(os.environ, OMP_SCHEDULE="nonmonotonic:static", GRID_ROWS="8", GRID_COLS="4")
     out = subprocess.run([REF_B200, p, xv], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    cuda_lines = [ln for ln in out.stdout.splitlines() if ln.startswith("cudaBlockSize:")]
+    cuda_lines = [ln for ln in out.stdout.replace("\x1b[0m", "").splitlines() if ln.startswith("cudaBlockSize:")]
     assert len(cuda_lines) == 5, out.stdout[-2000:]  # 2 CSR + 3 ELL kernels (src/include/SpMV.h:130-140)

@@ -37,7 +37,7 @@ def main():
                 out = subprocess.run([os.path.join(B, exe), p, xv], capture_output=True, text=True, env=env)
                 print("=== %s  %s  M=%d NZ=%d  rc=%d" % (exe, name, m.M, m.NZ, out.returncode))
                 lab = ""
-                for ln in out.stdout.splitlines():
+                for ln in out.stdout.replace("\x1b[0m", "").splitlines():
                     if "@computing" in ln:
                         lab = ln.replace("\x1b[1m\x1b[92m", "").replace("\x1b[0m", "").split("func:")[1].split(" at:")[0].strip()
                     if ln.startswith("cudaBlockSize:") or ln.startswith("threadNum:"):
