@@ -19,6 +19,17 @@ static unsigned long long g_launches = 0;
 using namespace spmvb200;
 
 // -------------------------------------------------------------------------------------------------
+static void destroy_pipe(HostPipe* p) {
+    if (!p) return;
+    for (auto e : p->x_ready) cudaEventDestroy(e);
+    for (auto e : p->k_start) cudaEventDestroy(e);
+    for (auto e : p->k_end) cudaEventDestroy(e);
+    if (p->s_up) cudaStreamDestroy(p->s_up);
+    if (p->s_comp) cudaStreamDestroy(p->s_comp);
+    if (p->s_down) cudaStreamDestroy(p->s_down);
+    delete p;
+}
+
 static void free_arrays(spmvb200_matrix* m) {
     if (m->own) {
         cudaFree(m->irp);
@@ -36,6 +47,8 @@ static void free_arrays(spmvb200_matrix* m) {
     cudaFree(m->flush);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
+    destroy_pipe(m->pipe);
+    m->pipe = nullptr;
 }
 
 extern "C" const char* spmvb200_last_error(void) { return g_err; }
@@ -132,6 +145,9 @@ int spmvb200::finish_csr(spmvb200_matrix* m) {
     build_plan_host(h_irp.data(), (uint32_t) m->M, tiles, longs);
     m->ntiles = (uint32_t) tiles.size() - 1;
     m->nlong = (uint32_t) longs.size();
+    m->h_tile_row0.resize(tiles.size());
+    m->h_tile_nnz0.resize(tiles.size());
+    for (size_t t = 0; t < tiles.size(); ++t) { m->h_tile_row0[t] = tiles[t].row0; m->h_tile_nnz0[t] = tiles[t].nnz0; }
     CU_TRY(cudaMalloc(&m->desc, tiles.size() * sizeof(TileDesc)));
     CU_TRY(cudaMemcpy(m->desc, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
     CU_TRY(cudaMalloc(&m->longrec, std::max<size_t>(1, longs.size()) * sizeof(LongRec)));
@@ -455,28 +471,39 @@ extern "C" const char* spmvb200_kind_name(int kind) {
 }
 
 // ------------------------------------------------------------------------------------------------- launch
+// rows [r0, r1) (whole matrix: 0, M); y is always indexed by the handle's row number
 template <int LANES>
-static void launch_csr_vector_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+static void launch_csr_vector_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
     constexpr int BLOCK = 256;
-    const uint64_t threads = m->M * LANES;
-    csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->irp, m->ja, m->as, x, y, (uint32_t) m->M,
+    const uint64_t threads = (r1 - r0) * LANES;
+    if (!threads) return;
+    csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->irp, m->ja, m->as, x, y, (uint32_t) r0, (uint32_t) r1,
                                                                                                      (uint32_t) STREAM_TILE);
 }
 // vector kernel for rows up to one tile + the long-row kernel for the rest (same stream, back to back)
-static void launch_csr_vector(const spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st) {
+static void launch_csr_vector(const spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
     switch (lanes) {
-        case 2: launch_csr_vector_t<2>(m, x, y, st); break;
-        case 4: launch_csr_vector_t<4>(m, x, y, st); break;
-        case 8: launch_csr_vector_t<8>(m, x, y, st); break;
-        case 16: launch_csr_vector_t<16>(m, x, y, st); break;
-        default: launch_csr_vector_t<32>(m, x, y, st); break;
+        case 2: launch_csr_vector_t<2>(m, x, y, st, r0, r1); break;
+        case 4: launch_csr_vector_t<4>(m, x, y, st, r0, r1); break;
+        case 8: launch_csr_vector_t<8>(m, x, y, st, r0, r1); break;
+        case 16: launch_csr_vector_t<16>(m, x, y, st, r0, r1); break;
+        default: launch_csr_vector_t<32>(m, x, y, st, r0, r1); break;
     }
-    if (m->nseg) csr_longrow_kernel<128><<<m->nseg, 128, 0, st>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+    if (m->nseg && r1 == m->M)
+        csr_longrow_kernel<128><<<m->nseg, 128, 0, st>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
 }
+// tiles [t0, t1) (whole matrix: 0, ntiles)
 template <bool ADAPT, int VARIANT>
-static void launch_csr_stream(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+static void launch_csr_stream(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint32_t t0, uint32_t t1) {
+    if (t1 <= t0) return;
     csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, ADAPT, VARIANT>
-        <<<m->ntiles, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, x, y, m->partial, m->ticket);
+        <<<t1 - t0, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, x, y, m->partial, m->ticket, t0);
+}
+static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
+    constexpr int BLOCK = 256;
+    if (r1 <= r0) return;
+    ell_colmajor_kernel<4, BLOCK><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1,
+                                                                                                 (uint32_t) m->K, x, y);
 }
 
 // ---- SPMVB200_CSR_ADAPTIVE: candidates; the fastest on this matrix is picked at first use
@@ -484,9 +511,9 @@ static const int N_CAND = 7;
 static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32"};
 static void launch_candidate(const spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st) {
     switch (c) {
-        case 0: launch_csr_stream<true, 0>(m, x, y, st); break;
-        case 1: launch_csr_stream<true, 1>(m, x, y, st); break;
-        default: launch_csr_vector(m, 2 << (c - 2), x, y, st); break;
+        case 0: launch_csr_stream<true, 0>(m, x, y, st, 0, m->ntiles); break;
+        case 1: launch_csr_stream<true, 1>(m, x, y, st, 0, m->ntiles); break;
+        default: launch_csr_vector(m, 2 << (c - 2), x, y, st, 0, m->M); break;
     }
 }
 static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
@@ -537,18 +564,13 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
     if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
     if (m->M == 0) return 0;
     switch (kind) {
-        case SPMVB200_CSR_ROWS: launch_csr_stream<false, 0>(m, d_x, d_y, st); break;
+        case SPMVB200_CSR_ROWS: launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles); break;
         case SPMVB200_CSR_ADAPTIVE:
             if (m->tuned < 0 && tune_adaptive(m, d_x, d_y, st)) return 1;
             launch_candidate(m, m->tuned, d_x, d_y, st);
             break;
-        case SPMVB200_CSR_ROWS_WARP: launch_csr_vector(m, m->vec_lanes, d_x, d_y, st); break;
-        case SPMVB200_ELL_ROWS: {
-            constexpr int BLOCK = 256;
-            ell_colmajor_kernel<4, BLOCK><<<(unsigned) ((m->M + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) m->M,
-                                                                                                     (uint32_t) m->K, d_x, d_y);
-            break;
-        }
+        case SPMVB200_CSR_ROWS_WARP: launch_csr_vector(m, m->vec_lanes, d_x, d_y, st, 0, m->M); break;
+        case SPMVB200_ELL_ROWS: launch_ell_colmajor(m, d_x, d_y, st, 0, m->M); break;
         case SPMVB200_ELL_ROWS_NT:
             switch (m->vec_lanes) {
                 case 1: launch_ell_rowmajor<1>(m, d_x, d_y, st); break;
@@ -595,18 +617,177 @@ static int ensure_events(spmvb200_matrix* m) {
     return 0;
 }
 
+// ---- pipelined host path --------------------------------------------------------------------------
+// which kernel a (kind, handle) pair runs chunk-wise: 0/1 stream variants (+10 exact), 2.. vector lanes, 100 ELL column-major
+static int pipe_candidate(const spmvb200_matrix* m, int kind) {
+    switch (kind) {
+        case SPMVB200_CSR_ROWS: return 10;
+        case SPMVB200_CSR_ADAPTIVE: return (m->tuned >= 2 && m->nseg) ? -1 : m->tuned;  // long rows finish in a separate launch
+        case SPMVB200_CSR_ROWS_WARP: return m->nseg ? -1 : 20 + m->vec_lanes;
+        case SPMVB200_ELL_ROWS: return 100;
+        default: return -1;
+    }
+}
+static void launch_chunk(const spmvb200_matrix* m, const HostPipe* p, int k, const double* x, double* y) {
+    const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
+    const int c = p->cand;
+    if (c == 100) launch_ell_colmajor(m, x, y, p->s_comp, r0, r1);
+    else if (c == 10) launch_csr_stream<false, 0>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
+    else if (c == 0) launch_csr_stream<true, 0>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
+    else if (c == 1) launch_csr_stream<true, 1>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
+    else if (c >= 20) launch_csr_vector(m, c - 20, x, y, p->s_comp, r0, r1);
+    else launch_csr_vector(m, 2 << (c - 2), x, y, p->s_comp, r0, r1);
+}
+static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
+    destroy_pipe(m->pipe);  // rebuilt only when another kind is used through the host path
+    m->pipe = nullptr;
+    HostPipe* p = new HostPipe();
+    m->pipe = p;
+    p->kind = kind;
+    p->cand = cand;
+    int nch = 4;  // measured on B200/PCIe5: 1 chunk 0.74 ms, 2: 0.63, 4: 0.54, 8: 0.59, 16: 0.70 per call (cfg2)
+    if (const char* e = getenv("SPMVB200_HOST_CHUNKS")) nch = std::max(1, atoi(e));
+    if (m->M < 65536 || cand < 0) nch = 1;
+    const bool stream = (cand == 0 || cand == 1 || cand == 10);
+    if (stream) nch = (int) std::max<uint32_t>(1, std::min<uint32_t>(nch, m->ntiles));
+    p->nch = nch;
+    p->row_b.assign(nch + 1, m->M);
+    p->tile_b.assign(nch + 1, m->ntiles);
+    p->row_b[0] = 0;
+    p->tile_b[0] = 0;
+    for (int k = 1; k < nch; ++k) {
+        if (stream) {
+            uint32_t t = (uint32_t) ((uint64_t) m->ntiles * k / nch);
+            // never cut inside the segment run of a long row: its y entry is written by whichever segment finishes last
+            while (t < m->ntiles && t > 0 && (m->h_tile_row0[t] & SEG_FLAG) && (m->h_tile_row0[t - 1] & SEG_FLAG) &&
+                   (m->h_tile_row0[t] == m->h_tile_row0[t - 1]))
+                ++t;
+            t = std::max(t, p->tile_b[k - 1]);
+            p->tile_b[k] = t;
+            p->row_b[k] = m->h_tile_row0[t] & ~SEG_FLAG;
+        } else {
+            p->row_b[k] = std::max<uint64_t>(p->row_b[k - 1], (m->M * k / nch) & ~255ull);
+        }
+    }
+    // x pieces: piece k ends right after the largest column id row chunks 0..k read, so that chunk k can start
+    // the moment "its" piece has landed (banded / stencil matrices: pieces ~ equal; unstructured: piece 0 = all of x)
+    p->x_b.assign(nch + 1, m->N);
+    p->x_b[0] = 0;
+    if (nch > 1) {
+        uint32_t* d_cm = nullptr;
+        CU_TRY(cudaMalloc(&d_cm, nch * 4));
+        CU_TRY(cudaMemset(d_cm, 0, nch * 4));
+        for (int k = 0; k < nch; ++k) {
+            if (m->format == SPMVB200_FMT_CSR) {
+                uint64_t n0, n1;
+                if (stream) { n0 = m->h_tile_nnz0[p->tile_b[k]]; n1 = m->h_tile_nnz0[p->tile_b[k + 1]]; }
+                else {
+                    uint32_t h[2] = {0, 0};
+                    CU_TRY(cudaMemcpy(&h[0], m->irp + p->row_b[k], 4, cudaMemcpyDeviceToHost));
+                    CU_TRY(cudaMemcpy(&h[1], m->irp + p->row_b[k + 1], 4, cudaMemcpyDeviceToHost));
+                    n0 = h[0]; n1 = h[1];
+                }
+                if (n1 > n0) colmax_flat_kernel<<<592, 256>>>(m->ja, n0, n1, d_cm + k);
+            } else if (p->row_b[k + 1] > p->row_b[k]) {
+                const uint32_t r0 = (uint32_t) p->row_b[k], r1 = (uint32_t) p->row_b[k + 1];
+                colmax_ell_cm_kernel<<<(r1 - r0 + 255) / 256, 256>>>(m->ja, m->rl, m->pitch, r0, r1, d_cm + k);
+            }
+        }
+        std::vector<uint32_t> h_cm(nch);
+        cudaError_t e = cudaMemcpy(h_cm.data(), d_cm, nch * 4, cudaMemcpyDeviceToHost);
+        cudaFree(d_cm);
+        if (e != cudaSuccess) return fail("host-path plan: %s", cudaGetErrorString(e));
+        for (int k = 0; k < nch; ++k) {
+            const uint64_t need = std::min<uint64_t>(m->N, ((uint64_t) h_cm[k] + 1 + 511) & ~511ull);  // 4 KB granules
+            p->x_b[k + 1] = std::max(p->x_b[k], k + 1 == nch ? m->N : need);
+        }
+    }
+    p->npieces = nch;
+    CU_TRY(cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking));
+    p->x_ready.resize(nch);
+    p->k_start.resize(nch);
+    p->k_end.resize(nch);
+    for (auto& ev : p->x_ready) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : p->k_start) CU_TRY(cudaEventCreate(&ev));
+    for (auto& ev : p->k_end) CU_TRY(cudaEventCreate(&ev));
+    return 0;
+}
+
 extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms) {
     if (!m || !x || !y) return fail("spmv_host: null argument");
+    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
     if (prefer_smem_once() || ensure_events(m)) return 1;
     if (!m->d_x) CU_TRY(cudaMalloc(&m->d_x, std::max<uint64_t>(m->N, 1) * 8));
     if (!m->d_y) CU_TRY(cudaMalloc(&m->d_y, std::max<uint64_t>(m->M, 1) * 8));
-    CU_TRY(cudaMemcpyAsync(m->d_x, x, m->N * 8, cudaMemcpyHostToDevice, 0));
-    CU_TRY(cudaEventRecord(m->ev0, 0));
-    if (launch(m, kind, m->d_x, m->d_y, 0)) return 1;
-    CU_TRY(cudaEventRecord(m->ev1, 0));
-    CU_TRY(cudaMemcpyAsync(y, m->d_y, m->M * 8, cudaMemcpyDeviceToHost, 0));
-    CU_TRY(cudaStreamSynchronize(0));
-    if (kernel_ms) CU_TRY(cudaEventElapsedTime(kernel_ms, m->ev0, m->ev1));
+    const bool untuned = kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0;
+    int cand = untuned ? -1 : pipe_candidate(m, kind);
+    if (!untuned && (!m->pipe || m->pipe->kind != kind || m->pipe->cand != cand))
+        if (build_pipe(m, kind, cand)) return 1;
+    if (untuned || m->pipe->nch <= 1) {  // plain path: x up, one launch, y down (also the adaptive mode's tuning call)
+        CU_TRY(cudaMemcpyAsync(m->d_x, x, m->N * 8, cudaMemcpyHostToDevice, 0));
+        CU_TRY(cudaEventRecord(m->ev0, 0));
+        if (launch(m, kind, m->d_x, m->d_y, 0)) return 1;
+        CU_TRY(cudaEventRecord(m->ev1, 0));
+        CU_TRY(cudaMemcpyAsync(y, m->d_y, m->M * 8, cudaMemcpyDeviceToHost, 0));
+        CU_TRY(cudaStreamSynchronize(0));
+        if (kernel_ms) CU_TRY(cudaEventElapsedTime(kernel_ms, m->ev0, m->ev1));
+        return 0;
+    }
+    HostPipe* p = m->pipe;
+    const bool dbg = getenv("SPMVB200_PIPE_DEBUG") != nullptr;
+    std::vector<cudaEvent_t> dbg_up, dbg_down;
+    cudaEvent_t dbg0 = nullptr;
+    if (dbg) {
+        cudaEventCreate(&dbg0);
+        cudaEventRecord(dbg0, p->s_up);
+    }
+    for (int j = 0; j < p->nch; ++j) {
+        const uint64_t o = p->x_b[j], n = p->x_b[j + 1] - o;
+        if (n) CU_TRY(cudaMemcpyAsync(m->d_x + o, x + o, n * 8, cudaMemcpyHostToDevice, p->s_up));
+        CU_TRY(cudaEventRecord(p->x_ready[j], p->s_up));
+        if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, p->s_up); dbg_up.push_back(e); }
+    }
+    for (int k = 0; k < p->nch; ++k) {
+        CU_TRY(cudaStreamWaitEvent(p->s_comp, p->x_ready[k], 0));
+        CU_TRY(cudaEventRecord(p->k_start[k], p->s_comp));
+        launch_chunk(m, p, k, m->d_x, m->d_y);
+        ++g_launches;
+        CU_TRY(cudaEventRecord(p->k_end[k], p->s_comp));
+        const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
+        if (r1 > r0) {
+            CU_TRY(cudaStreamWaitEvent(p->s_down, p->k_end[k], 0));
+            CU_TRY(cudaMemcpyAsync(y + r0, m->d_y + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, p->s_down));
+            if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, p->s_down); dbg_down.push_back(e); }
+        }
+    }
+    CU_TRY(cudaPeekAtLastError());
+    CU_TRY(cudaStreamSynchronize(p->s_comp));
+    CU_TRY(cudaStreamSynchronize(p->s_down));
+    CU_TRY(cudaStreamSynchronize(p->s_up));
+    if (dbg) {
+        float ms;
+        fprintf(stderr, "pipe: x piece bounds=");
+        for (int k = 0; k <= p->nch; ++k) fprintf(stderr, "%llu ", (unsigned long long) p->x_b[k]);
+        fprintf(stderr, "\n  up done at:");
+        for (auto e : dbg_up) { cudaEventElapsedTime(&ms, dbg0, e); fprintf(stderr, " %.3f", ms); cudaEventDestroy(e); }
+        fprintf(stderr, "\n  kernels [start,end]:");
+        for (int k = 0; k < p->nch; ++k) { float a, b; cudaEventElapsedTime(&a, dbg0, p->k_start[k]); cudaEventElapsedTime(&b, dbg0, p->k_end[k]); fprintf(stderr, " [%.3f,%.3f]", a, b); }
+        fprintf(stderr, "\n  down done at:");
+        for (auto e : dbg_down) { cudaEventElapsedTime(&ms, dbg0, e); fprintf(stderr, " %.3f", ms); cudaEventDestroy(e); }
+        fprintf(stderr, "\n");
+        cudaEventDestroy(dbg0);
+    }
+    if (kernel_ms) {
+        float tot = 0;
+        for (int k = 0; k < p->nch; ++k) {
+            float ms = 0;
+            CU_TRY(cudaEventElapsedTime(&ms, p->k_start[k], p->k_end[k]));
+            tot += ms;
+        }
+        *kernel_ms = tot;
+    }
     return 0;
 }
 

@@ -3,9 +3,21 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace spmvb200 {
 struct TileDesc;
 struct LongRec;
+// Plan of the pipelined host path (spmvb200_spmv_host): x goes up in pieces, row chunks start as soon as the
+// pieces they read have landed, y chunks go down while later chunks compute (three streams, full-duplex PCIe).
+struct HostPipe {
+    int kind = -1, cand = -1, nch = 0, npieces = 0;
+    std::vector<uint64_t> row_b;   // nch+1 row bounds
+    std::vector<uint32_t> tile_b;  // nch+1 tile bounds (CSR stream kernel)
+    std::vector<uint64_t> x_b;     // nch+1 bounds of the x pieces: chunk k reads only x[0, x_b[k+1])
+    cudaStream_t s_up = nullptr, s_comp = nullptr, s_down = nullptr;
+    std::vector<cudaEvent_t> x_ready, k_start, k_end;
+};
 constexpr uint64_t PAD = 16;  // readable slack after ja/as (vector loads and 16-byte aligned TMA tiles overrun)
 }  // namespace spmvb200
 
@@ -32,6 +44,8 @@ struct spmvb200_matrix {
     // SPMVB200_CSR_ADAPTIVE: candidate chosen by the first-use tuning run (-1 = not tuned yet)
     int tuned = -1;
     float tuned_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<uint32_t> h_tile_row0, h_tile_nnz0;  // host copy of the tile plan (chunking of the host path)
+    spmvb200::HostPipe* pipe = nullptr;
     // host-path scratch
     double* d_x = nullptr;
     double* d_y = nullptr;

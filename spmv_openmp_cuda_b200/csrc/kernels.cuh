@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(BLOCK, 8)
 csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__ longrec,
                   const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
                   const double* __restrict__ x, double* __restrict__ y, double* __restrict__ partial,
-                  uint32_t* __restrict__ ticket) {
+                  uint32_t* __restrict__ ticket, uint32_t tile_base) {
     constexpr int CAP = TILE + 8;
     constexpr int NWARPS = BLOCK / 32;
     constexpr int MAXLONG = TILE / STREAM_LONG_T;
@@ -72,7 +72,7 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
     __shared__ __align__(8) uint64_t s_bar;
 
     const uint32_t tid = threadIdx.x;
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = blockIdx.x + tile_base;  // tile_base > 0: a row chunk of the pipelined host path
     const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(desc + b));
     const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(desc + b + 1));
     const bool seg = (d0.x & SEG_FLAG) != 0;
@@ -171,9 +171,9 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
 template <int LANES, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 csr_vector_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
-                  const double* __restrict__ x, double* __restrict__ y, uint32_t M, uint32_t max_len) {
+                  const double* __restrict__ x, double* __restrict__ y, uint32_t row_begin, uint32_t M, uint32_t max_len) {
     const uint32_t gt = blockIdx.x * BLOCK + threadIdx.x;
-    const uint32_t row = gt / LANES, lane = gt % LANES;
+    const uint32_t row = row_begin + gt / LANES, lane = gt % LANES;
     double acc = 0;
     bool mine = row < M;
     if (mine) {
@@ -235,8 +235,8 @@ csr_longrow_kernel(const uint32_t* __restrict__ seg_tiles, const TileDesc* __res
 template <int UNROLL, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 ell_colmajor_kernel(const double* __restrict__ as, const uint32_t* __restrict__ ja, const uint32_t* __restrict__ rl,
-                    uint64_t pitch, uint32_t M, uint32_t K, const double* __restrict__ x, double* __restrict__ y) {
-    const uint32_t row = blockIdx.x * BLOCK + threadIdx.x;
+                    uint64_t pitch, uint32_t row_begin, uint32_t M, uint32_t K, const double* __restrict__ x, double* __restrict__ y) {
+    const uint32_t row = row_begin + blockIdx.x * BLOCK + threadIdx.x;  // rows [row_begin, M)
     const bool live = row < M;
     const uint32_t len = live ? (rl ? __ldg(rl + row) : K) : 0u;
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, len);
@@ -395,6 +395,27 @@ __global__ void csr_to_ell_kernel(const uint32_t* __restrict__ irp, const uint32
         eas[o] = k < len ? as[s + k] : 0.0;
         eja[o] = k < len ? ja[s + k] : 0u;
     }
+}
+
+// largest column id in a range of a column-id array / in the valid slots of a row range of a column-major ELL
+// (plan of the pipelined host path: which x pieces a row chunk needs)
+__global__ void colmax_flat_kernel(const uint32_t* __restrict__ ja, uint64_t n0, uint64_t n1, uint32_t* __restrict__ out) {
+    uint32_t mx = 0;
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i = n0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += stride) mx = max(mx, ja[i]);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
+}
+__global__ void colmax_ell_cm_kernel(const uint32_t* __restrict__ ja, const uint32_t* __restrict__ rl, uint64_t pitch, uint32_t r0,
+                                     uint32_t r1, uint32_t* __restrict__ out) {
+    const uint32_t r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t mx = 0;
+    if (r < r1) {
+        const uint32_t len = rl[r];
+        for (uint32_t k = 0; k < len; ++k) mx = max(mx, ja[(uint64_t) k * pitch + r]);
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
 }
 
 __global__ void widen_u32_kernel(const uint32_t* __restrict__ src, uint64_t* __restrict__ dst, uint64_t n, uint64_t add) {

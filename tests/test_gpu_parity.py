@@ -165,6 +165,31 @@ def test_host_adapters_spmv_interf(sp, orc):
     sp.cache_drop()
 
 
+@pytest.mark.parametrize("builder", [
+    lambda s: s.host_csr(s.stencil27(48)),              # 110 592 rows: chunked pipeline, banded column spans
+    lambda s: s.host_csr(s.banded(200000, 32, 3000)),
+    lambda s: s.rmat_host_csr(17, 16),                  # rows longer than a tile inside the chunked CSR path
+    lambda s: s.host_csr(s.mixed(150000, 48, 0.02)),    # uniform columns: every chunk needs all of x
+])
+def test_pipelined_host_path(sp, orc, builder):
+    """spmvb200_spmv_host on matrices large enough for the chunked path: x pieces up, row chunks, y chunks down."""
+    mat = builder(sp.synth)
+    ell = sp.synth.csr_to_ell_host(mat) if mat.MAX_ROW_NZ * mat.M < 2e7 else None
+    x = sp.synth.host_vector(mat.N)
+    y_ref = _oracle_y(orc, mat, x)
+    short = np.diff(mat.IRP) <= STREAM_TILE
+    runs = [(f, mat) for f in sp.SpmvB200CSRFuncs] + ([(sp.b200SpMVRowsELL, ell)] if ell is not None else [])
+    for f, m in runs:
+        for rep in range(3):
+            y = np.full(mat.M, np.nan)
+            assert f(m, x, sp.Config(), y) == 0
+            assert orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=TAU)[0] == 0, (f, rep)
+            if f in (sp.b200SpMVRowsCSR, sp.b200SpMVRowsELL):
+                np.testing.assert_array_equal(y[short], y_ref[short])
+            assert f.ElapsedInternal > 0
+    sp.cache_drop()
+
+
 def test_row_block_partition_slices(sp, orc):
     """Row-block partition: per-slice handles produce the slices of y."""
     mat = sp.synth.host_csr(sp.synth.banded(50000, 32, 3000))
