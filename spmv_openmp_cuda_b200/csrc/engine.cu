@@ -42,6 +42,8 @@ static void free_arrays(spmvb200_matrix* m) {
     cudaFree(m->partial);
     cudaFree(m->ticket);
     cudaFree(m->seg_tiles);
+    cudaFree(m->span_b);
+    cudaFree(m->mid_rows);
     cudaFree(m->d_x);
     cudaFree(m->d_y);
     cudaFree(m->flush);
@@ -161,6 +163,36 @@ int spmvb200::finish_csr(spmvb200_matrix* m) {
     m->nseg = (uint32_t) segs.size();
     CU_TRY(cudaMalloc(&m->seg_tiles, std::max<size_t>(1, segs.size()) * sizeof(uint32_t)));
     if (!segs.empty()) CU_TRY(cudaMemcpy(m->seg_tiles, segs.data(), segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    {   // rows the vector kernels hand to csr_midrow_kernel
+        std::vector<uint32_t> mid;
+        for (uint32_t r = 0; r < m->M; ++r) {
+            const uint32_t len = h_irp[r + 1] - h_irp[r];
+            if (len > (uint32_t) VEC_MID && len <= (uint32_t) STREAM_TILE) mid.push_back(r);
+        }
+        m->nmid = (uint32_t) mid.size();
+        CU_TRY(cudaMalloc(&m->mid_rows, std::max<size_t>(1, mid.size()) * 4));
+        if (!mid.empty()) CU_TRY(cudaMemcpy(m->mid_rows, mid.data(), mid.size() * 4, cudaMemcpyHostToDevice));
+    }
+    {   // contiguous nnz-balanced row spans for the persistent vector kernel: SPANS_PER_SM big CTAs per SM
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int per_sm = 2;
+        if (const char* e = getenv("SPMVB200_SPANS_PER_SM")) per_sm = std::max(1, atoi(e));
+        const uint32_t ns = (uint32_t) std::min<uint64_t>((uint64_t) sms * per_sm, std::max<uint64_t>(1, m->M));
+        std::vector<uint32_t> sb(ns + 1);
+        for (uint32_t k = 0; k <= ns; ++k) {
+            const uint64_t target = (uint64_t) m->NZ * k / ns;
+            sb[k] = (uint32_t) (std::lower_bound(h_irp.begin(), h_irp.end(), (uint32_t) target) - h_irp.begin());
+            if (sb[k] > m->M) sb[k] = (uint32_t) m->M;
+            if (k && sb[k] < sb[k - 1]) sb[k] = sb[k - 1];
+        }
+        sb[0] = 0;
+        sb[ns] = (uint32_t) m->M;
+        m->nspans = ns;
+        CU_TRY(cudaMalloc(&m->span_b, (ns + 1) * 4));
+        CU_TRY(cudaMemcpy(m->span_b, sb.data(), (ns + 1) * 4, cudaMemcpyHostToDevice));
+    }
     // sub-warp width of the vector kernel from the mean row length (2 non-zeros per lane and step)
     const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
     int lanes = 2;
@@ -471,14 +503,20 @@ extern "C" const char* spmvb200_kind_name(int kind) {
 }
 
 // ------------------------------------------------------------------------------------------------- launch
+// rows the vector kernels skip: medium rows (one CTA each) and rows longer than a tile (one CTA per segment)
+static void launch_vector_tail(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    if (m->nmid) csr_midrow_kernel<128><<<m->nmid, 128, 0, st>>>(m->mid_rows, m->irp, m->ja, m->as, x, y);
+    if (m->nseg) csr_longrow_kernel<128><<<m->nseg, 128, 0, st>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+}
 // rows [r0, r1) (whole matrix: 0, M); y is always indexed by the handle's row number
 template <int LANES>
 static void launch_csr_vector_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
     constexpr int BLOCK = 256;
     const uint64_t threads = (r1 - r0) * LANES;
     if (!threads) return;
-    csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->irp, m->ja, m->as, x, y, (uint32_t) r0, (uint32_t) r1,
-                                                                                                     (uint32_t) STREAM_TILE);
+    // whole-matrix launches leave rows longer than VEC_MID to the per-row CTAs below; row-chunk launches keep them
+    csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(
+        m->irp, m->ja, m->as, x, y, (uint32_t) r0, (uint32_t) r1, (uint32_t) ((r0 == 0 && r1 == m->M) ? VEC_MID : STREAM_TILE));
 }
 // vector kernel for rows up to one tile + the long-row kernel for the rest (same stream, back to back)
 static void launch_csr_vector(const spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
@@ -489,8 +527,21 @@ static void launch_csr_vector(const spmvb200_matrix* m, int lanes, const double*
         case 16: launch_csr_vector_t<16>(m, x, y, st, r0, r1); break;
         default: launch_csr_vector_t<32>(m, x, y, st, r0, r1); break;
     }
-    if (m->nseg && r1 == m->M)
-        csr_longrow_kernel<128><<<m->nseg, 128, 0, st>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+    if (r0 == 0 && r1 == m->M) launch_vector_tail(m, x, y, st);
+}
+template <int LANES>
+static void launch_csr_vspan_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    csr_vector_span_kernel<LANES, 1024><<<m->nspans, 1024, 0, st>>>(m->span_b, m->irp, m->ja, m->as, x, y, (uint32_t) VEC_MID);
+}
+static void launch_csr_vspan(const spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st) {
+    switch (lanes) {
+        case 2: launch_csr_vspan_t<2>(m, x, y, st); break;
+        case 4: launch_csr_vspan_t<4>(m, x, y, st); break;
+        case 8: launch_csr_vspan_t<8>(m, x, y, st); break;
+        case 16: launch_csr_vspan_t<16>(m, x, y, st); break;
+        default: launch_csr_vspan_t<32>(m, x, y, st); break;
+    }
+    launch_vector_tail(m, x, y, st);
 }
 // tiles [t0, t1) (whole matrix: 0, ntiles)
 template <bool ADAPT, int VARIANT>
@@ -507,14 +558,15 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
 }
 
 // ---- SPMVB200_CSR_ADAPTIVE: candidates; the fastest on this matrix is picked at first use
-static const int N_CAND = 7;
-static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32"};
+static const int N_CAND = 12;
+static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32",
+                                        "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32"};
+static int cand_lanes(int c) { return c < 2 ? 0 : 2 << ((c - 2) % 5); }
 static void launch_candidate(const spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st) {
-    switch (c) {
-        case 0: launch_csr_stream<true, 0>(m, x, y, st, 0, m->ntiles); break;
-        case 1: launch_csr_stream<true, 1>(m, x, y, st, 0, m->ntiles); break;
-        default: launch_csr_vector(m, 2 << (c - 2), x, y, st, 0, m->M); break;
-    }
+    if (c == 0) launch_csr_stream<true, 0>(m, x, y, st, 0, m->ntiles);
+    else if (c == 1) launch_csr_stream<true, 1>(m, x, y, st, 0, m->ntiles);
+    else if (c < 7) launch_csr_vector(m, cand_lanes(c), x, y, st, 0, m->M);
+    else launch_csr_vspan(m, cand_lanes(c), x, y, st);
 }
 static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
     // d_x / d_y are the caller's vectors: y is overwritten by every candidate with the same result
@@ -526,7 +578,8 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
     const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
     for (int c = 0; c < N_CAND; ++c) {
         m->tuned_ms[c] = -1.f;
-        if (c >= 2 && ((2 << (c - 2)) > 4 * mean + 2 || (double) (2 << (c - 2)) * 64 < mean)) continue;  // hopeless widths
+        if (c >= 2 && (cand_lanes(c) > 4 * mean + 2 || (double) cand_lanes(c) * 64 < mean)) continue;  // hopeless widths
+        if (const char* e = getenv("SPMVB200_FORCE_CAND")) if (atoi(e) != c) continue;  // developer knob
         launch_candidate(m, c, d_x, d_y, st);
         float ms_min = 1e30f;
         for (int rep = 0; rep < 2; ++rep) {
@@ -622,7 +675,7 @@ static int ensure_events(spmvb200_matrix* m) {
 static int pipe_candidate(const spmvb200_matrix* m, int kind) {
     switch (kind) {
         case SPMVB200_CSR_ROWS: return 10;
-        case SPMVB200_CSR_ADAPTIVE: return (m->tuned >= 2 && m->nseg) ? -1 : m->tuned;  // long rows finish in a separate launch
+        case SPMVB200_CSR_ADAPTIVE: return ((m->tuned >= 2 && m->nseg) || m->tuned >= 7) ? -1 : m->tuned;  // long rows / spans: one launch
         case SPMVB200_CSR_ROWS_WARP: return m->nseg ? -1 : 20 + m->vec_lanes;
         case SPMVB200_ELL_ROWS: return 100;
         default: return -1;

@@ -38,12 +38,16 @@ struct spmvb200_matrix {
     spmvb200::LongRec* longrec = nullptr;
     double* partial = nullptr;
     uint32_t* ticket = nullptr;
+    uint32_t* span_b = nullptr;     // nnz-balanced contiguous row spans, one per persistent CTA (vector-span kernel)
+    uint32_t nspans = 0;
+    uint32_t* mid_rows = nullptr;   // rows with VEC_MID < len <= TILE (vector kernels give them a CTA each)
+    uint32_t nmid = 0;
     uint32_t* seg_tiles = nullptr;  // indices of the segment tiles (rows longer than one tile)
     uint32_t ntiles = 0, nlong = 0, nseg = 0;
     int vec_lanes = 32;
     // SPMVB200_CSR_ADAPTIVE: candidate chosen by the first-use tuning run (-1 = not tuned yet)
     int tuned = -1;
-    float tuned_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float tuned_ms[16] = {0};
     std::vector<uint32_t> h_tile_row0, h_tile_nnz0;  // host copy of the tile plan (chunking of the host path)
     spmvb200::HostPipe* pipe = nullptr;
     // host-path scratch

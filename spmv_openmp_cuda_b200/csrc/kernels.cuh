@@ -32,7 +32,8 @@ constexpr uint32_t SEG_FLAG = 0x80000000u;
 constexpr int STREAM_TILE = 2048;        // non-zeros per tile (24 KB of values + column ids)
 constexpr int STREAM_BLOCK = 128;        // threads per CTA
 constexpr int STREAM_TILE_ROWS = 512;    // rows per tile (row-pointer slice in shared memory); 8 CTAs/SM fit
-constexpr int STREAM_LONG_T = 64;        // ADAPTIVE: rows longer than this are reduced by a whole warp
+constexpr int STREAM_LONG_T = 64;
+constexpr int VEC_MID = 256;             // vector kernels: longer rows get a CTA of their own (csr_midrow_kernel)        // ADAPTIVE: rows longer than this are reduced by a whole warp
 
 // ---------------------------------------------------------------------------------------------
 // CSR "stream" kernel.  One CTA per tile:
@@ -189,6 +190,37 @@ csr_vector_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__
     }
     acc = subwarp_sum<LANES>(acc);
     if (lane == 0 && mine) y[row] = acc;
+}
+
+// Same row algorithm, but each CTA owns a CONTIGUOUS, nnz-balanced span of rows (span_b) and walks it front to
+// back with all its threads: with one or two big CTAs per SM the x window an SM touches slides slowly, so the
+// gathers of banded / locally-coupled matrices hit the 228 KB L1 instead of going to L2 (whose sector rate is what
+// bounds random gathers on B200).
+template <int LANES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+csr_vector_span_kernel(const uint32_t* __restrict__ span_b, const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja,
+                       const double* __restrict__ as, const double* __restrict__ x, double* __restrict__ y, uint32_t max_len) {
+    constexpr uint32_t ROWS = BLOCK / LANES;
+    const uint32_t r_end = span_b[blockIdx.x + 1];
+    const uint32_t sub = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+    for (uint32_t r0 = span_b[blockIdx.x]; r0 < r_end; r0 += ROWS) {
+        const uint32_t row = r0 + sub;
+        double acc = 0;
+        bool mine = row < r_end;
+        if (mine) {
+            const uint32_t s = __ldg(irp + row), e = __ldg(irp + row + 1);
+            mine = e - s <= max_len;
+            if (mine)
+                for (uint32_t i = (s & ~1u) + 2 * lane; i < e; i += 2 * LANES) {
+                    const double2 v = ld_stream(reinterpret_cast<const double2*>(as + i));
+                    const uint2 c = ld_stream(reinterpret_cast<const uint2*>(ja + i));
+                    if (i >= s) acc = fma(v.x, ld_x(x, c.x), acc);
+                    if (i + 1 < e) acc = fma(v.y, ld_x(x, c.y), acc);
+                }
+        }
+        acc = subwarp_sum<LANES>(acc);
+        if (lane == 0 && mine) y[row] = acc;
+    }
 }
 
 // Rows longer than one tile, for the vector kernel: one CTA per <= TILE-non-zero segment (the plan's
@@ -394,6 +426,33 @@ __global__ void csr_to_ell_kernel(const uint32_t* __restrict__ irp, const uint32
         const uint64_t o = colmajor ? (uint64_t) k * pitch + r : (uint64_t) r * pitch + k;
         eas[o] = k < len ? as[s + k] : 0.0;
         eja[o] = k < len ? ja[s + k] : 0u;
+    }
+}
+
+// Rows of medium length (VEC_MID < len <= TILE) for the vector kernels: one CTA per listed row, so that a sub-warp
+// of the vector kernel never iterates over more than VEC_MID non-zeros while its neighbours idle.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+csr_midrow_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja,
+                  const double* __restrict__ as, const double* __restrict__ x, double* __restrict__ y) {
+    __shared__ double s_red[BLOCK / 32];
+    const uint32_t tid = threadIdx.x, row = rows[blockIdx.x];
+    const uint32_t s = __ldg(irp + row), e = __ldg(irp + row + 1);
+    double t = 0;
+    for (uint32_t i = (s & ~1u) + 2 * tid; i < e; i += 2 * BLOCK) {
+        const double2 v = ld_stream(reinterpret_cast<const double2*>(as + i));
+        const uint2 c = ld_stream(reinterpret_cast<const uint2*>(ja + i));
+        if (i >= s) t = fma(v.x, ld_x(x, c.x), t);
+        if (i + 1 < e) t = fma(v.y, ld_x(x, c.y), t);
+    }
+    t = subwarp_sum<32>(t);
+    if ((tid & 31) == 0) s_red[tid >> 5] = t;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0;
+#pragma unroll
+        for (int w = 0; w < BLOCK / 32; ++w) tot += s_red[w];
+        y[row] = tot;
     }
 }
 

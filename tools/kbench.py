@@ -71,8 +71,10 @@ def main():
                 bench("cfg4 banded 2^25 w=%d" % hw, d, CSR_KINDS, max(5, reps // 5), False)
                 d.free()
         elif w == "cfg4s":
-            d = synth.device_csr(synth.banded(1 << 22, 32, 1 << 15))
-            bench("cfg4s banded 2^22 w=2^15", d, CSR_KINDS, reps, False)
+            for hw in (1 << 15, 1 << 12):
+                d = synth.device_csr(synth.banded(1 << 22, 32, hw))
+                bench("cfg4s banded 2^22 w=%d" % hw, d, CSR_KINDS, reps, False)
+                d.free()
         elif w == "cfg5":
             for kmax, p in ((32, 0.0), (32, 0.02), (32, 0.15), (32, 1.0)):
                 d = synth.device_csr(synth.mixed(1 << 23, kmax, p))
