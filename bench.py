@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (default: min(steps, 200))")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--half-width", type=int, default=1 << 15, help="cfg4: band half width w")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -186,11 +187,12 @@ def main():
         def slab_spec():
             return synth.stencil27(128, 128, 128)
     else:
-        wl_name = "cfg4: CSR fp64 SpMV, random banded 2^25 rows x 32 nnz/row (w=2^15), row-block partitioned, kernel cudaSpMVRowsCSR"
+        wl_name = ("cfg4: CSR fp64 SpMV, random banded 2^25 rows x 32 nnz/row (half width w=%d), row-block partitioned, "
+                   "kernel: adaptive CSR mode" % args.half_width)
         scaling = "strong"
 
         def slab_spec():
-            return synth.banded(1 << 21, 32, 1 << 15)  # bounded CPU sample: 2^21 rows of the same generator
+            return synth.banded(1 << 21, 32, args.half_width)  # bounded CPU sample: 2^21 rows of the same generator
 
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
     if args.impl == "reference":
@@ -233,11 +235,11 @@ def main():
         d_csr.free()
         kind, kname = sp.ELL_ROWS, "ell_colmajor_kernel"
     else:
-        spec = synth.banded(1 << 25, 32, 1 << 15)
+        spec = synth.banded(1 << 25, 32, args.half_width)
         Mtot = 1 << 25
         r0, r1 = rank * Mtot // nr, (rank + 1) * Mtot // nr
         dm = synth.device_csr(spec, r0, r1)
-        kind, kname = sp.CSR_ROWS, "csr_stream_kernel"
+        kind, kname = sp.CSR_ADAPTIVE, "csr_adaptive"
     Ncols = dm.N
     tot = torch.tensor([dm.NZ, dm.M], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -264,6 +266,8 @@ def main():
     for _ in range(args.warmup):
         step()
     sync_all()
+    if kind == sp.CSR_ADAPTIVE:
+        kname = "csr_adaptive[%s]" % dm.adaptive_choice
     launches0 = lib.spmvb200_launch_count()
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
