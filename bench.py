@@ -159,6 +159,17 @@ def cpu_reference(spec_fn, steps, warmup, label):
 
 
 # ------------------------------------------------------------------------------------------ main
+def emit(obj):
+    """The one JSON line, on the real stdout (fd 1 is pointed at stderr while the benchmark runs so that
+    library banners such as 'NCCL version ...' cannot pollute it)."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,6 +181,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--half-width", type=int, default=1 << 15, help="cfg4: band half width w")
+    ap.add_argument("--x-dist", default="allgather", choices=["allgather", "bcast"],
+                    help="N>1 e2e: every rank uploads its slice of x then NCCL all-gather (default), or rank 0 uploads all of x then NCCL broadcast")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -200,7 +213,7 @@ def main():
             return 0
         steps = min(args.steps, 50)
         value, ms, info = cpu_reference(slab_spec, steps, min(args.warmup, 5), args.workload)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": steps,
+        emit(({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": steps,
                           "warmup": min(args.warmup, 5), "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": wl_name, "note": "reference OpenMP CPU implementation on the host cores"},
@@ -293,14 +306,20 @@ def main():
     hy = torch.empty(dm.M, dtype=torch.float64).pin_memory()
     hx.copy_(x.cpu())
     e2e_ms = None
+    xs0, xs1 = rank * Ncols // nr, (rank + 1) * Ncols // nr  # this rank's slice of x (square matrix: its own rows)
+    even = Ncols % nr == 0
 
     def e2e_step():
         if world == 1:
             capi.check(lib.spmvb200_spmv_host(dm.handle, kind, hx.data_ptr(), hy.data_ptr(), None), "spmv_host")
         else:
-            if rank == 0:
-                x.copy_(hx, non_blocking=True)
-            dist.broadcast(x, src=0)
+            if args.x_dist == "allgather" and even:
+                x[xs0:xs1].copy_(hx[xs0:xs1], non_blocking=True)      # every rank: its slice over its own PCIe link
+                dist.all_gather_into_tensor(x, x[xs0:xs1])             # replicate over NVLink / NVSwitch
+            else:
+                if rank == 0:
+                    x.copy_(hx, non_blocking=True)
+                dist.broadcast(x, src=0)
             step()
             hy.copy_(y, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -343,8 +362,10 @@ def main():
         "hbm_gbs": achieved * nr, "clocks": clocks,
         "e2e": {"value": 2.0 * nnz_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "wall_ms_per_step": wall / e2e_steps,
                 "steps": e2e_steps, "h2d_bytes_per_step": int(Ncols * 8), "d2h_bytes_per_step": int(dm.M * 8 * nr),
-                "path": "spmvb200_spmv_host (pinned host x -> device, kernel, y -> pinned host)" if world == 1 else
-                        "rank0 H2D x, NCCL broadcast, spmvb200_spmv_device, per-rank D2H of its y slice"},
+                "path": "spmvb200_spmv_host (pinned host x -> device in pieces, row chunks, y chunks -> pinned host)" if world == 1 else
+                        ("per-rank H2D of its x slice, NCCL all-gather, spmvb200_spmv_device, per-rank D2H of its y slice"
+                         if args.x_dist == "allgather" and even else
+                         "rank0 H2D x, NCCL broadcast, spmvb200_spmv_device, per-rank D2H of its y slice")},
         "gpu_launches": launches, "gpu_launches_e2e": e2e_launch,
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_local),
@@ -364,7 +385,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "unavailable", "sample": repr(e)}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

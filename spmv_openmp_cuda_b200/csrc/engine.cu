@@ -505,8 +505,14 @@ extern "C" const char* spmvb200_kind_name(int kind) {
 // ------------------------------------------------------------------------------------------------- launch
 // rows the vector kernels skip: medium rows (one CTA each) and rows longer than a tile (one CTA per segment)
 static void launch_vector_tail(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
-    if (m->nmid) csr_midrow_kernel<128><<<m->nmid, 128, 0, st>>>(m->mid_rows, m->irp, m->ja, m->as, x, y);
-    if (m->nseg) csr_longrow_kernel<128><<<m->nseg, 128, 0, st>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+    if (m->nmid) {
+        csr_midrow_kernel<128><<<m->nmid, 128, 0, st>>>(m->mid_rows, m->irp, m->ja, m->as, x, y);
+        ++g_launches;
+    }
+    if (m->nseg) {
+        csr_longrow_kernel<128><<<m->nseg, 128, 0, st>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+        ++g_launches;
+    }
 }
 // rows [r0, r1) (whole matrix: 0, M); y is always indexed by the handle's row number
 template <int LANES>
@@ -517,6 +523,7 @@ static void launch_csr_vector_t(const spmvb200_matrix* m, const double* x, doubl
     // whole-matrix launches leave rows longer than VEC_MID to the per-row CTAs below; row-chunk launches keep them
     csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(
         m->irp, m->ja, m->as, x, y, (uint32_t) r0, (uint32_t) r1, (uint32_t) ((r0 == 0 && r1 == m->M) ? VEC_MID : STREAM_TILE));
+    ++g_launches;
 }
 // vector kernel for rows up to one tile + the long-row kernel for the rest (same stream, back to back)
 static void launch_csr_vector(const spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
@@ -532,6 +539,7 @@ static void launch_csr_vector(const spmvb200_matrix* m, int lanes, const double*
 template <int LANES>
 static void launch_csr_vspan_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
     csr_vector_span_kernel<LANES, 1024><<<m->nspans, 1024, 0, st>>>(m->span_b, m->irp, m->ja, m->as, x, y, (uint32_t) VEC_MID);
+    ++g_launches;
 }
 static void launch_csr_vspan(const spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st) {
     switch (lanes) {
@@ -549,12 +557,14 @@ static void launch_csr_stream(const spmvb200_matrix* m, const double* x, double*
     if (t1 <= t0) return;
     csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, ADAPT, VARIANT>
         <<<t1 - t0, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, x, y, m->partial, m->ticket, t0);
+    ++g_launches;
 }
 static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
     constexpr int BLOCK = 256;
     if (r1 <= r0) return;
     ell_colmajor_kernel<4, BLOCK><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1,
                                                                                                  (uint32_t) m->K, x, y);
+    ++g_launches;
 }
 
 // ---- SPMVB200_CSR_ADAPTIVE: candidates; the fastest on this matrix is picked at first use
@@ -611,6 +621,7 @@ static void launch_ell_rowmajor(const spmvb200_matrix* m, const double* x, doubl
     const uint64_t threads = m->M * LANES;
     ell_rowmajor_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) m->M,
                                                                                                        (uint32_t) m->K, x, y);
+    ++g_launches;
 }
 
 static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, cudaStream_t st) {
@@ -636,7 +647,6 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
             break;
         case SPMVB200_ELL_ROWS_WARP_NT: launch_ell_rowmajor<32>(m, d_x, d_y, st); break;
     }
-    ++g_launches;
     CU_TRY(cudaPeekAtLastError());
     return 0;
 }
@@ -806,7 +816,6 @@ extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x,
         CU_TRY(cudaStreamWaitEvent(p->s_comp, p->x_ready[k], 0));
         CU_TRY(cudaEventRecord(p->k_start[k], p->s_comp));
         launch_chunk(m, p, k, m->d_x, m->d_y);
-        ++g_launches;
         CU_TRY(cudaEventRecord(p->k_end[k], p->s_comp));
         const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
         if (r1 > r0) {
