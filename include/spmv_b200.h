@@ -38,14 +38,17 @@ typedef enum {
     SPMVB200_ELL_ROWS_NT       = 3, /* replaces cudaSpMVRowsELLNNTransposed     src/SpMV_CUDA.cu:99-115  */
     SPMVB200_ELL_ROWS_WARP_NT  = 4, /* replaces cudaSpMVWarpsPerRowELLNTrasposed src/SpMV_CUDA.cu:116-135 */
     SPMVB200_CSR_ADAPTIVE      = 5, /* new: row-length driven split (short rows streamed, long rows shared) */
-    SPMVB200_KIND_COUNT        = 6
+    SPMVB200_SELL_ROWS         = 6, /* new: sliced ELL (SELL-32-sigma), thread per row, no global padding */
+    SPMVB200_KIND_COUNT        = 7
 } spmvb200_kind;
 
 /* Storage formats a handle can hold. */
 typedef enum {
     SPMVB200_FMT_CSR          = 0,
     SPMVB200_FMT_ELL_COLMAJOR = 1, /* pitched, column-major: slot k of row r at k*pitch + r */
-    SPMVB200_FMT_ELL_ROWMAJOR = 2  /* pitched, row-major:    slot k of row r at r*pitch + k */
+    SPMVB200_FMT_ELL_ROWMAJOR = 2, /* pitched, row-major:    slot k of row r at r*pitch + k */
+    SPMVB200_FMT_SELL         = 3  /* sliced ELL: rows sorted by length inside windows of sigma rows, slices of 32 rows stored
+                                      column-major and padded only to the slice's longest row */
 } spmvb200_format;
 
 typedef struct spmvb200_matrix spmvb200_matrix; /* opaque, device resident */
@@ -89,13 +92,19 @@ int spmvb200_csr_adopt_device(uint64_t M, uint64_t N, uint64_t NZ, uint32_t* d_i
 /* Build an ELL handle (either layout) on the device from a CSR handle. */
 int spmvb200_ell_from_csr(const spmvb200_matrix* csr, int format, spmvb200_matrix** out);
 
+/* Build a SELL-32-sigma handle on the device from a CSR handle (sigma: sorting window in rows, a multiple of 32;
+ * 0 = default 16384).  The successor of the ELL early-exit kernel for matrices with mixed short/long rows
+ * (BASELINE.json configs[4]; the reference author's notes discuss SELL-C-sigma): coalesced like ELL, padding bounded
+ * by the length spread inside a window instead of the global maximum. */
+int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma, spmvb200_matrix** out);
+
 /* Replaces cudaFreeSpmat (src/include/cudaUtils.h:70-78). */
 int spmvb200_free(spmvb200_matrix* m);
 
 /* ------------------------------------------------------------------ queries */
 int spmvb200_dims(const spmvb200_matrix* m, uint64_t* M, uint64_t* N, uint64_t* NZ, uint64_t* K, int* format);
 /* algorithmic bytes of one SpMV with this handle:
- *   CSR: 12*NZ + 4*(M+1) + 8*N + 8*M      ELL: 12*NZ + 4*M + 8*N + 8*M  */
+ *   CSR: 12*NZ + 4*(M+1) + 8*N + 8*M      ELL: 12*NZ + 4*M + 8*N + 8*M      SELL: 12*NZ + 8*M + 8*N + 8*M  */
 uint64_t spmvb200_algorithmic_bytes(const spmvb200_matrix* m);
 /* bytes of device memory the handle's arrays occupy (includes ELL padding and the plan) */
 uint64_t spmvb200_device_bytes(const spmvb200_matrix* m);
@@ -214,6 +223,7 @@ int spmvb200_csr_download(const spmvb200_matrix* m, uint64_t* irp, uint64_t* ja,
 SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVRowsCSR, SPMVB200_CSR_ROWS)
 SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVWarpPerRowCSR, SPMVB200_CSR_ROWS_WARP)
 SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVAdaptiveCSR, SPMVB200_CSR_ADAPTIVE)
+SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVRowsSELL, SPMVB200_SELL_ROWS) /* CSR in, SELL-32-sigma built on the device */
 SPMVB200_DEFINE_ELL_ADAPTER(b200SpMVRowsELL, SPMVB200_ELL_ROWS)
 SPMVB200_DEFINE_ELL_ADAPTER(b200SpMVRowsELLNNTransposed, SPMVB200_ELL_ROWS_NT)
 SPMVB200_DEFINE_ELL_ADAPTER(b200SpMVWarpsPerRowELLNTrasposed, SPMVB200_ELL_ROWS_WARP_NT)

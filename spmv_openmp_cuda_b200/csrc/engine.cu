@@ -2,6 +2,8 @@
 // on-device 64->32-bit narrowing / ELL transposition, plan building, kernel launch, D2H.
 // Replaces src/commons/cudaUtils.cu (spMatCpyCSR/ELL*, cudaFreeSpmat) and the launch+sync+download
 // code of src/main.cu:192-248 / test/SpMV_test.cu:103-145.  No CPU compute path exists here.
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <cstdlib>
 #include <map>
@@ -36,6 +38,7 @@ static void free_arrays(spmvb200_matrix* m) {
         cudaFree(m->ja);
         cudaFree(m->as);
         cudaFree(m->rl);
+        cudaFree(m->perm);
     }
     cudaFree(m->desc);
     cudaFree(m->longrec);
@@ -447,6 +450,73 @@ extern "C" int spmvb200_ell_from_csr(const spmvb200_matrix* csr, int format, spm
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------- SELL-32-sigma
+extern "C" int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma, spmvb200_matrix** out) {
+    if (!out) return fail("sell_from_csr: null output");
+    *out = nullptr;
+    if (!csr || csr->format != SPMVB200_FMT_CSR) return fail("sell_from_csr: source is not a CSR handle");
+    if (sigma == 0) sigma = 16384;
+    if (sigma % 32) return fail("sell_from_csr: sigma must be a multiple of 32");
+    spmvb200_matrix* m = new spmvb200_matrix();
+    m->format = SPMVB200_FMT_SELL;
+    m->M = csr->M;
+    m->N = csr->N;
+    m->NZ = csr->NZ;
+    m->own = 1;
+    m->Mpad = ((csr->M + 31) / 32) * 32;
+    const uint32_t Mpad = (uint32_t) m->Mpad, nsl = Mpad / 32;
+    uint64_t *k0 = nullptr, *k1 = nullptr, *slots = nullptr, *slots_scan = nullptr;
+    uint32_t* v0 = nullptr;
+    void* tmp = nullptr;
+    int rc = 0;
+    do {
+        if (Mpad == 0) { rc = fail("sell_from_csr: empty matrix"); break; }
+        if ((rc = cudaMalloc(&k0, (size_t) Mpad * 8) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&k1, (size_t) Mpad * 8) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&v0, (size_t) Mpad * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->perm, (size_t) Mpad * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->rl, (size_t) Mpad * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->irp, ((size_t) nsl + 1) * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&slots, ((size_t) nsl + 1) * 8) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&slots_scan, ((size_t) nsl + 1) * 8) != cudaSuccess)) break;
+        sell_keys_kernel<<<(Mpad + 255) / 256, 256>>>(csr->irp, (uint32_t) csr->M, Mpad, sigma, k0, v0);
+        size_t b1 = 0, b2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, v0, m->perm, (int) Mpad);
+        cub::DeviceScan::ExclusiveSum(nullptr, b2, slots, slots_scan, (int) nsl + 1);
+        if ((rc = cudaMalloc(&tmp, std::max(b1, b2) + 16) != cudaSuccess)) break;
+        if ((rc = cub::DeviceRadixSort::SortPairs(tmp, b1, k0, k1, v0, m->perm, (int) Mpad) != cudaSuccess)) break;
+        cudaMemset(slots, 0, ((size_t) nsl + 1) * 8);
+        sell_slices_kernel<<<(Mpad + 255) / 256, 256>>>(k1, Mpad, m->rl, slots);
+        if ((rc = cub::DeviceScan::ExclusiveSum(tmp, b2, slots, slots_scan, (int) nsl + 1) != cudaSuccess)) break;
+        uint64_t total = 0;
+        if ((rc = cudaMemcpy(&total, slots_scan + nsl, 8, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        if (total >= 0xfffffff0ull) { rc = fail("sell_from_csr: %llu slots do not fit 32-bit offsets", (unsigned long long) total); break; }
+        m->slots = total;
+        narrow_u64_kernel<<<592, 256>>>(slots_scan, m->irp, (uint64_t) nsl + 1, 0, (int*) slots);  // slots[] reused as overflow flag sink
+        if ((rc = cudaMalloc(&m->ja, (total + PAD) * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->as, (total + PAD) * 8) != cudaSuccess)) break;
+        cudaMemset(m->ja + total, 0, PAD * 4);
+        cudaMemset(m->as + total, 0, PAD * 8);
+        sell_fill_kernel<<<(Mpad + 255) / 256, 256>>>(csr->irp, csr->ja, csr->as, m->perm, m->irp, Mpad, m->ja, m->as);
+        if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
+        m->K = sigma;  // reported through spmvb200_dims as K
+    } while (0);
+    cudaFree(k0);
+    cudaFree(k1);
+    cudaFree(v0);
+    cudaFree(slots);
+    cudaFree(slots_scan);
+    cudaFree(tmp);
+    if (rc) {
+        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("sell_from_csr: %s", cudaGetErrorString(cudaGetLastError()));
+        free_arrays(m);
+        delete m;
+        return 1;
+    }
+    *out = m;
+    return 0;
+}
+
 extern "C" int spmvb200_free(spmvb200_matrix* m) {
     if (!m) return 0;
     free_arrays(m);
@@ -469,6 +539,7 @@ extern "C" int spmvb200_dims(const spmvb200_matrix* m, uint64_t* M, uint64_t* N,
 extern "C" uint64_t spmvb200_algorithmic_bytes(const spmvb200_matrix* m) {
     if (!m) return 0;
     if (m->format == SPMVB200_FMT_CSR) return 12 * m->NZ + 4 * (m->M + 1) + 8 * m->N + 8 * m->M;
+    if (m->format == SPMVB200_FMT_SELL) return 12 * m->NZ + 8 * m->M + 8 * m->N + 8 * m->M;  // row length + permutation per row
     return 12 * m->NZ + 4 * m->M + 8 * m->N + 8 * m->M;
 }
 extern "C" uint64_t spmvb200_device_bytes(const spmvb200_matrix* m) {
@@ -476,6 +547,7 @@ extern "C" uint64_t spmvb200_device_bytes(const spmvb200_matrix* m) {
     if (m->format == SPMVB200_FMT_CSR)
         return (m->NZ + PAD) * 12 + (m->M + 1) * 4 + ((uint64_t) m->ntiles + 1) * sizeof(TileDesc) + (uint64_t) m->ntiles * 8 +
                (uint64_t) m->nlong * (sizeof(LongRec) + 4);
+    if (m->format == SPMVB200_FMT_SELL) return (m->slots + PAD) * 12 + m->Mpad * 8 + (m->Mpad / 32 + 1) * 4;
     return (m->slots + PAD) * 12 + m->M * 4;
 }
 extern "C" int spmvb200_kind_supported(const spmvb200_matrix* m, int kind) {
@@ -485,6 +557,7 @@ extern "C" int spmvb200_kind_supported(const spmvb200_matrix* m, int kind) {
         case SPMVB200_CSR_ROWS_WARP:
         case SPMVB200_CSR_ADAPTIVE: return m->format == SPMVB200_FMT_CSR;
         case SPMVB200_ELL_ROWS: return m->format == SPMVB200_FMT_ELL_COLMAJOR;
+        case SPMVB200_SELL_ROWS: return m->format == SPMVB200_FMT_SELL;
         case SPMVB200_ELL_ROWS_NT:
         case SPMVB200_ELL_ROWS_WARP_NT: return m->format == SPMVB200_FMT_ELL_ROWMAJOR;
         default: return 0;
@@ -498,6 +571,7 @@ extern "C" const char* spmvb200_kind_name(int kind) {
         case SPMVB200_ELL_ROWS_NT: return "CUDA_ELL_ROWS_WARP_NN_TRANSPOSED_1T";
         case SPMVB200_ELL_ROWS_WARP_NT: return "CUDA_ELL_ROWS_WARP_NN_TRANSPOSED";
         case SPMVB200_CSR_ADAPTIVE: return "CUDA_CSR_ADAPTIVE";
+        case SPMVB200_SELL_ROWS: return "CUDA_SELL_ROWS";
         default: return "?";
     }
 }
@@ -562,7 +636,8 @@ static void launch_csr_stream(const spmvb200_matrix* m, const double* x, double*
 static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
     constexpr int BLOCK = 256;
     if (r1 <= r0) return;
-    ell_colmajor_kernel<4, BLOCK><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1,
+    static const bool no_exit = getenv("SPMVB200_ELL_NO_EARLY_EXIT") != nullptr;  // developer knob: walk all K slots like the reference
+    ell_colmajor_kernel<4, BLOCK><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1,
                                                                                                  (uint32_t) m->K, x, y);
     ++g_launches;
 }
@@ -635,6 +710,10 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
             break;
         case SPMVB200_CSR_ROWS_WARP: launch_csr_vector(m, m->vec_lanes, d_x, d_y, st, 0, m->M); break;
         case SPMVB200_ELL_ROWS: launch_ell_colmajor(m, d_x, d_y, st, 0, m->M); break;
+        case SPMVB200_SELL_ROWS:
+            sell_kernel<4, 256><<<(unsigned) ((m->Mpad + 255) / 256), 256, 0, st>>>(m->irp, m->perm, m->rl, m->as, m->ja, (uint32_t) m->Mpad, d_x, d_y);
+            ++g_launches;
+            break;
         case SPMVB200_ELL_ROWS_NT:
             switch (m->vec_lanes) {
                 case 1: launch_ell_rowmajor<1>(m, d_x, d_y, st); break;
@@ -918,7 +997,8 @@ extern "C" int spmvb200_cached_spmv(const void* key, int kind, int is_ell, uint6
     int fmt = SPMVB200_FMT_CSR;
     if (kind == SPMVB200_ELL_ROWS) fmt = SPMVB200_FMT_ELL_COLMAJOR;
     else if (kind == SPMVB200_ELL_ROWS_NT || kind == SPMVB200_ELL_ROWS_WARP_NT) fmt = SPMVB200_FMT_ELL_ROWMAJOR;
-    if ((fmt == SPMVB200_FMT_CSR) == (is_ell != 0)) return fail("cached_spmv: kind %d does not match the %s input", kind, is_ell ? "ELL" : "CSR");
+    else if (kind == SPMVB200_SELL_ROWS) fmt = SPMVB200_FMT_SELL;  // built on the device from the CSR input
+    if ((fmt == SPMVB200_FMT_CSR || fmt == SPMVB200_FMT_SELL) == (is_ell != 0)) return fail("cached_spmv: kind %d does not match the %s input", kind, is_ell ? "ELL" : "CSR");
     spmvb200_matrix* m = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -931,6 +1011,13 @@ extern "C" int spmvb200_cached_spmv(const void* key, int kind, int is_ell, uint6
         if (it == g_cache.end()) {
             int rc = is_ell ? spmvb200_ell_upload(M, N, K, ja, as, rl, 0, M, fmt, &m) : spmvb200_csr_upload(M, N, irp, ja, as, 0, M, &m);
             if (rc) return 1;
+            if (fmt == SPMVB200_FMT_SELL) {
+                spmvb200_matrix* sell = nullptr;
+                rc = spmvb200_sell_from_csr(m, 0, &sell);
+                spmvb200_free(m);
+                if (rc) return 1;
+                m = sell;
+            }
             g_cache[{key, fmt}] = {m, ja, as, M, N, K};
         } else {
             m = it->second.m;

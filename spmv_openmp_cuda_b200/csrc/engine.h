@@ -32,6 +32,9 @@ struct spmvb200_matrix {
     uint32_t* ja = nullptr;
     double* as = nullptr;
     uint32_t* rl = nullptr;
+    // SELL: irp = slice_ptr[nslices+1], rl = row lengths in sorted order, perm = sorted position -> row (0xffffffff = padding)
+    uint32_t* perm = nullptr;
+    uint64_t Mpad = 0;
     int own = 1;
     // CSR stream plan
     spmvb200::TileDesc* desc = nullptr;

@@ -303,6 +303,81 @@ ell_colmajor_kernel(const double* __restrict__ as, const uint32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// SELL-32-sigma: rows are sorted by decreasing length inside windows of sigma rows (perm), cut into slices of 32
+// consecutive sorted rows, each slice stored column-major (slot k of lane l at slice_ptr + 32k + l) and padded only
+// to its own longest row.  One thread per row, a warp per slice: fully coalesced 256 B / 128 B loads per slot, loop
+// bound = the slice length (warp uniform), per-lane predicate at the row length.  Left-to-right sum with separate
+// mul/add => bit-identical to sgemvSerial.  y is written through the permutation (scatter inside one window).
+// ---------------------------------------------------------------------------------------------
+template <int UNROLL, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+sell_kernel(const uint32_t* __restrict__ slice_ptr, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ rl_sorted,
+            const double* __restrict__ as, const uint32_t* __restrict__ ja, uint32_t Mpad, const double* __restrict__ x,
+            double* __restrict__ y) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= Mpad) return;  // Mpad is a multiple of 32: whole warps leave together
+    const uint32_t len = __ldg(rl_sorted + i);
+    const uint32_t sp0 = __ldg(slice_ptr + (i >> 5)), sp1 = __ldg(slice_ptr + (i >> 5) + 1);
+    const uint32_t wmax = (sp1 - sp0) >> 5;
+    const double* a = as + sp0 + (i & 31);
+    const uint32_t* j = ja + sp0 + (i & 31);
+    double acc = 0;
+    uint32_t k = 0;
+    for (; k + UNROLL <= wmax; k += UNROLL) {
+        double v[UNROLL];
+        uint32_t c[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const bool ok = k + u < len;
+            v[u] = ok ? ld_stream(a + (k + u) * 32) : 0.0;
+            c[u] = ok ? ld_stream(j + (k + u) * 32) : 0u;
+        }
+        double xv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) xv[u] = (k + u < len) ? ld_x(x, c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (k + u < len) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+    }
+    for (; k < wmax; ++k)
+        if (k < len) acc = __dadd_rn(acc, __dmul_rn(ld_stream(a + k * 32), ld_x(x, ld_stream(j + k * 32))));
+    const uint32_t row = __ldg(perm + i);
+    if (row != 0xffffffffu) y[row] = acc;
+}
+
+// SELL construction (device): sort keys, slice lengths, fill
+__global__ void sell_keys_kernel(const uint32_t* __restrict__ irp, uint32_t M, uint32_t Mpad, uint32_t sigma, uint64_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= Mpad) return;
+    const uint32_t len = r < M ? irp[r + 1] - irp[r] : 0u;
+    keys[r] = ((uint64_t) (r / sigma) << 32) | (uint64_t) (0xffffffffu - len);  // ascending sort = descending length per window
+    vals[r] = r < M ? r : 0xffffffffu;
+}
+__global__ void sell_slices_kernel(const uint64_t* __restrict__ keys_sorted, uint32_t Mpad, uint32_t* __restrict__ rl_sorted,
+                                   uint64_t* __restrict__ slice_slots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Mpad) return;
+    const uint32_t len = 0xffffffffu - (uint32_t) (keys_sorted[i] & 0xffffffffull);
+    rl_sorted[i] = len;
+    if ((i & 31) == 0) slice_slots[i >> 5] = (uint64_t) len * 32;  // first row of a slice is its longest
+}
+__global__ void sell_fill_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
+                                 const uint32_t* __restrict__ perm, const uint32_t* __restrict__ slice_ptr, uint32_t Mpad,
+                                 uint32_t* __restrict__ sja, double* __restrict__ sas) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Mpad) return;
+    const uint32_t row = perm[i];
+    const uint32_t sp0 = slice_ptr[i >> 5], wmax = (slice_ptr[(i >> 5) + 1] - sp0) >> 5;
+    const uint32_t s = row != 0xffffffffu ? irp[row] : 0u, len = row != 0xffffffffu ? irp[row + 1] - s : 0u;
+    for (uint32_t k = 0; k < wmax; ++k) {
+        const uint32_t o = sp0 + k * 32 + (i & 31);
+        sas[o] = k < len ? as[s + k] : 0.0;
+        sja[o] = k < len ? ja[s + k] : 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row-major pitched ELL (pitch a multiple of 4 slots => rows 32-byte aligned): LANES lanes per
 // row, two slots per lane and step (128-bit value / 64-bit index loads), loop bounded by the row
 // length, shuffle reduction.  LANES = 32 is the reference's warp-per-row mapping

@@ -23,7 +23,7 @@ import numpy as np
 
 from . import capi
 from .capi import (CSR_ADAPTIVE, CSR_ROWS, CSR_ROWS_WARP, ELL_ROWS, ELL_ROWS_NT, ELL_ROWS_WARP_NT, FMT_CSR,
-                   FMT_ELL_COLMAJOR, FMT_ELL_ROWMAJOR, SpmvB200Error, check, lib, ptr)
+                   FMT_ELL_COLMAJOR, FMT_ELL_ROWMAJOR, FMT_SELL, SELL_ROWS, SpmvB200Error, check, lib, ptr)
 
 EXIT_SUCCESS = 0
 
@@ -106,6 +106,12 @@ class DeviceSpmat:
     def to_ell(self, fmt=FMT_ELL_COLMAJOR):
         out = C.c_void_p()
         check(lib().spmvb200_ell_from_csr(self.handle, fmt, C.byref(out)), "ell_from_csr")
+        return DeviceSpmat(out.value)
+
+    def to_sell(self, sigma=0):
+        """SELL-32-sigma copy of a CSR handle (rows sorted by length inside windows of sigma rows)."""
+        out = C.c_void_p()
+        check(lib().spmvb200_sell_from_csr(self.handle, sigma, C.byref(out)), "sell_from_csr")
         return DeviceSpmat(out.value)
 
     def download_csr(self):
@@ -236,6 +242,11 @@ def cudaSpMVRowsELL(m, v, cfg, outV, stream=None):
     return _launch(ELL_ROWS, m, v, cfg, outV, stream)
 
 
+def cudaSpMVRowsSELL(m, v, cfg, outV, stream=None):
+    """new mode: sliced ELL (SELL-32-sigma), thread per row, bit-identical to sgemvSerial."""
+    return _launch(SELL_ROWS, m, v, cfg, outV, stream)
+
+
 def cudaSpMVRowsELLNNTransposed(m, v, cfg, outV, stream=None):
     """src/SpMV_CUDA.cu:99-115 -> row-major ELL, sub-warp per row sized from K."""
     return _launch(ELL_ROWS_NT, m, v, cfg, outV, stream)
@@ -247,14 +258,14 @@ def cudaSpMVWarpsPerRowELLNTrasposed(m, v, cfg, outV, stream=None):
 
 
 # function tables, src/include/SpMV.h:130-142 (the adaptive mode appended)
-SpmvCUDA_CSRFuncs = [cudaSpMVRowsCSR, cudaSpMVWarpPerRowCSR, cudaSpMVAdaptiveCSR]
+SpmvCUDA_CSRFuncs = [cudaSpMVRowsCSR, cudaSpMVWarpPerRowCSR, cudaSpMVAdaptiveCSR]  # SELL needs its own handle: see to_sell()
 SpmvCUDA_CSRFuncs_WarpPerRowIdx = 1
 SpmvCUDA_ELLFuncs = [cudaSpMVRowsELL, cudaSpMVRowsELLNNTransposed, cudaSpMVWarpsPerRowELLNTrasposed]
 SpmvCUDA_ELLFuncs_NN_TraposedImpl = 1
 SpmvCUDA_ELLFuncs_WarpPerRowIdx = 2
 
 KIND_OF = {cudaSpMVRowsCSR: CSR_ROWS, cudaSpMVWarpPerRowCSR: CSR_ROWS_WARP, cudaSpMVAdaptiveCSR: CSR_ADAPTIVE,
-           cudaSpMVRowsELL: ELL_ROWS, cudaSpMVRowsELLNNTransposed: ELL_ROWS_NT,
+           cudaSpMVRowsSELL: SELL_ROWS, cudaSpMVRowsELL: ELL_ROWS, cudaSpMVRowsELLNNTransposed: ELL_ROWS_NT,
            cudaSpMVWarpsPerRowELLNTrasposed: ELL_ROWS_WARP_NT}
 MODE_OF = {CUDA_CSR_ROWS: CSR_ROWS, CUDA_CSR_ROWS_WARP: CSR_ROWS_WARP, CUDA_ELL_ROWS: ELL_ROWS,
            CUDA_ELL_ROWS_WARP_NT: ELL_ROWS_WARP_NT, CUDA_CSR_ADAPTIVE: CSR_ADAPTIVE}
@@ -294,10 +305,11 @@ def _host_adapter(kind, is_ell):
 b200SpMVRowsCSR = _host_adapter(CSR_ROWS, False)
 b200SpMVWarpPerRowCSR = _host_adapter(CSR_ROWS_WARP, False)
 b200SpMVAdaptiveCSR = _host_adapter(CSR_ADAPTIVE, False)
+b200SpMVRowsSELL = _host_adapter(SELL_ROWS, False)
 b200SpMVRowsELL = _host_adapter(ELL_ROWS, True)
 b200SpMVRowsELLNNTransposed = _host_adapter(ELL_ROWS_NT, True)
 b200SpMVWarpsPerRowELLNTrasposed = _host_adapter(ELL_ROWS_WARP_NT, True)
-SpmvB200CSRFuncs = [b200SpMVRowsCSR, b200SpMVWarpPerRowCSR, b200SpMVAdaptiveCSR]
+SpmvB200CSRFuncs = [b200SpMVRowsCSR, b200SpMVWarpPerRowCSR, b200SpMVAdaptiveCSR, b200SpMVRowsSELL]
 SpmvB200ELLFuncs = [b200SpMVRowsELL, b200SpMVRowsELLNNTransposed, b200SpMVWarpsPerRowELLNTrasposed]
 
 

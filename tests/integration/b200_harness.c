@@ -69,12 +69,13 @@ int main(int argc, char** argv) {
     printf("SpMV_OMP_test.c\tAVG_TIMES_ITERATION:%d\tsparse matrix: %lux%lu-%luNNZ-%ld=MAX_ROW_NZ\n", AVG_TIMES_ITERATION, csr->M,
            csr->N, csr->NZ, (long) ell->MAX_ROW_NZ);
 
-    static const SPMV_INTERF csr_funcs[] = {&b200SpMVRowsCSR, &b200SpMVWarpPerRowCSR, &b200SpMVAdaptiveCSR};
-    static const char* csr_names[] = {"B200 CSR 0 (b200SpMVRowsCSR)", "B200 CSR 1 (b200SpMVWarpPerRowCSR)", "B200 CSR 2 (b200SpMVAdaptiveCSR)"};
+    static const SPMV_INTERF csr_funcs[] = {&b200SpMVRowsCSR, &b200SpMVWarpPerRowCSR, &b200SpMVAdaptiveCSR, &b200SpMVRowsSELL};
+    static const char* csr_names[] = {"B200 CSR 0 (b200SpMVRowsCSR)", "B200 CSR 1 (b200SpMVWarpPerRowCSR)", "B200 CSR 2 (b200SpMVAdaptiveCSR)",
+                                      "B200 CSR 3 (b200SpMVRowsSELL)"};
     static const SPMV_INTERF ell_funcs[] = {&b200SpMVRowsELL, &b200SpMVRowsELLNNTransposed, &b200SpMVWarpsPerRowELLNTrasposed};
     static const char* ell_names[] = {"B200 ELL 0 (b200SpMVRowsELL)", "B200 ELL 1 (b200SpMVRowsELLNNTransposed)",
                                       "B200 ELL 2 (b200SpMVWarpsPerRowELLNTrasposed)"};
-    for (unsigned f = 0; f < 3; f++)
+    for (unsigned f = 0; f < 4; f++)
         if (run_impl(csr_names[f], csr_funcs[f], csr, x, y, oracle_y, csr->M)) goto _free;
     for (unsigned f = 0; f < 3; f++)
         if (run_impl(ell_names[f], ell_funcs[f], ell, x, y, oracle_y, csr->M)) goto _free;

@@ -39,7 +39,7 @@ def test_reference_side_harness(tmp_path, case):
     assert out.returncode == 0 and "B200_HARNESS_OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
     # the reference's log format (test/SpMV_test.cu:93-96) so scripts/parseLog.py keeps working
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("threadNum:")]
-    assert len(lines) == 6 and all("timeInternalAvg:" in ln for ln in lines)
+    assert len(lines) == 7 and all("timeInternalAvg:" in ln for ln in lines)
 
 
 REF_B200 = os.path.join(ROOT, "tests", "integration", "_build", "ref_harness_b200")

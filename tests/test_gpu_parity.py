@@ -29,7 +29,7 @@ def orc():
     return oracle
 
 
-EXACT = {"cudaSpMVRowsCSR", "cudaSpMVRowsELL"}
+EXACT = {"cudaSpMVRowsCSR", "cudaSpMVRowsELL", "cudaSpMVRowsSELL"}
 STREAM_TILE = 2048  # csrc/kernels.cuh
 
 
@@ -42,8 +42,11 @@ def run_all_kinds(sp, orc, mat, x, y_ref, ell=None, kinds="all"):
     d_csr = sp.spMatCpyCSR(mat)
     d_ell = sp.spMatCpyELL(ell)
     d_rm = sp.spMatCpyELLNNPitched(ell)
+    d_sell = d_csr.to_sell(64)       # tiny sorting window: slices straddle every length class
+    d_sell2 = d_csr.to_sell()        # default window
     runs = [(f, d_csr) for f in sp.SpmvCUDA_CSRFuncs] + \
-           [(sp.cudaSpMVRowsELL, d_ell), (sp.cudaSpMVRowsELLNNTransposed, d_rm), (sp.cudaSpMVWarpsPerRowELLNTrasposed, d_rm)]
+           [(sp.cudaSpMVRowsELL, d_ell), (sp.cudaSpMVRowsELLNNTransposed, d_rm), (sp.cudaSpMVWarpsPerRowELLNTrasposed, d_rm),
+            (sp.cudaSpMVRowsSELL, d_sell), (sp.cudaSpMVRowsSELL, d_sell2)]
     for f, dm in runs:
         dy.fill_bytes(0xFF)
         assert f(dm, dx, cfg, dy) == 0
@@ -56,9 +59,9 @@ def run_all_kinds(sp, orc, mat, x, y_ref, ell=None, kinds="all"):
         if f.__name__ in EXACT:
             # rows longer than one tile (2048 nnz) are split across CTAs by the CSR kernel and summed
             # in segment order: deterministic, within TAU, but not the serial order
-            exact = np.ones(mat.M, dtype=bool) if f.__name__ == "cudaSpMVRowsELL" else (np.diff(mat.IRP) <= STREAM_TILE)
+            exact = np.ones(mat.M, dtype=bool) if f.__name__ != "cudaSpMVRowsCSR" else (np.diff(mat.IRP) <= STREAM_TILE)
             np.testing.assert_array_equal(y[exact], y_ref[exact], err_msg=f.__name__)
-    for dm in (d_csr, d_ell, d_rm):
+    for dm in (d_csr, d_ell, d_rm, d_sell, d_sell2):
         sp.cudaFreeSpmat(dm)
 
 
@@ -126,9 +129,10 @@ def test_edge_cases(sp, orc):
             run_all_kinds(sp, orc, mat, x, y_ref)
         else:  # ELL would be huge (the reference caps it too, config.h:69): CSR kinds only
             dx, dy, dm = sp.DeviceVector.from_host(x), sp.DeviceVector(mat.M), sp.spMatCpyCSR(mat)
-            for f in sp.SpmvCUDA_CSRFuncs:
+            dsell = dm.to_sell(32)
+            for f in sp.SpmvCUDA_CSRFuncs + [sp.cudaSpMVRowsSELL]:
                 dy.fill_bytes(0xFF)
-                f(dm, dx, sp.Config(), dy)
+                f(dsell if f is sp.cudaSpMVRowsSELL else dm, dx, sp.Config(), dy)
                 bad, worst = orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, dy.to_host(), tau=TAU)
                 assert bad == 0, (name, f.__name__, worst)
 
@@ -184,7 +188,7 @@ def test_pipelined_host_path(sp, orc, builder):
             y = np.full(mat.M, np.nan)
             assert f(m, x, sp.Config(), y) == 0
             assert orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=TAU)[0] == 0, (f, rep)
-            if f in (sp.b200SpMVRowsCSR, sp.b200SpMVRowsELL):
+            if f in (sp.b200SpMVRowsCSR, sp.b200SpMVRowsELL, sp.b200SpMVRowsSELL):
                 np.testing.assert_array_equal(y[short], y_ref[short])
             assert f.ElapsedInternal > 0
     sp.cache_drop()
