@@ -3,6 +3,7 @@
 // Replaces src/commons/cudaUtils.cu (spMatCpyCSR/ELL*, cudaFreeSpmat) and the launch+sync+download
 // code of src/main.cu:192-248 / test/SpMV_test.cu:103-145.  No CPU compute path exists here.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -13,6 +14,7 @@
 #include "../../include/spmv_b200.h"
 #include "engine.h"
 #include "kernels.cuh"
+#include "plan.cuh"
 
 namespace spmvb200 {
 thread_local char g_err[512] = "";
@@ -110,91 +112,95 @@ extern "C" int spmvb200_sync(void) {
 }
 
 // ------------------------------------------------------------------------------------------------- CSR plan
-// Greedy row blocking (whole rows, <= TILE non-zeros, <= TILE_ROWS rows); rows longer than TILE are
-// cut into segments that share one LongRec.  Runs on the host over the narrowed row pointer.
-static void build_plan_host(const uint32_t* irp, uint32_t M, std::vector<TileDesc>& tiles, std::vector<LongRec>& longs) {
-    const uint32_t TILE = STREAM_TILE, ROWS = STREAM_TILE_ROWS;
-    tiles.clear();
-    longs.clear();
-    uint32_t start = 0, cur_nnz = 0;
-    auto flush = [&](uint32_t end_row) {
-        if (end_row > start) tiles.push_back({start, irp[start], 0u, 0u});
-        start = end_row;
-        cur_nnz = 0;
-    };
-    for (uint32_t r = 0; r < M; ++r) {
-        const uint32_t len = irp[r + 1] - irp[r];
-        if (len > TILE) {
-            flush(r);
-            const uint32_t nseg = (len + TILE - 1) / TILE;
-            longs.push_back({r, (uint32_t) tiles.size(), nseg, 0u});
-            for (uint32_t s = 0; s < nseg; ++s) tiles.push_back({r | SEG_FLAG, irp[r] + s * TILE, (uint32_t) longs.size() - 1, 0u});
-            start = r + 1;
-            cur_nnz = 0;
-            continue;
-        }
-        if (cur_nnz + len > TILE || r - start == ROWS) flush(r);
-        cur_nnz += len;
-    }
-    flush(M);
-    tiles.push_back({M, irp[M], 0u, 0u});  // sentinel
+static int scan_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, size_t n) {
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int) n);
+    if (e != cudaSuccess) return fail("plan scan: %s", cudaGetErrorString(e));
+    return 0;
 }
 
+// Builds, entirely on the device (plan.cuh), the row-block tiles of the stream kernel, the long-row records and
+// segment list, the medium-row list and the contiguous spans of the vector kernels.
 int spmvb200::finish_csr(spmvb200_matrix* m) {
-    // narrowed row pointer back to the host for the greedy planner
-    std::vector<uint32_t> h_irp((size_t) m->M + 1);
-    CU_TRY(cudaMemcpy(h_irp.data(), m->irp, ((size_t) m->M + 1) * 4, cudaMemcpyDeviceToHost));
-    if (h_irp[m->M] != m->NZ) return fail("CSR row pointer inconsistent: IRP[M]=%u, NZ=%llu", h_irp[m->M], (unsigned long long) m->NZ);
-    std::vector<TileDesc> tiles;
-    std::vector<LongRec> longs;
-    build_plan_host(h_irp.data(), (uint32_t) m->M, tiles, longs);
-    m->ntiles = (uint32_t) tiles.size() - 1;
-    m->nlong = (uint32_t) longs.size();
-    m->h_tile_row0.resize(tiles.size());
-    m->h_tile_nnz0.resize(tiles.size());
-    for (size_t t = 0; t < tiles.size(); ++t) { m->h_tile_row0[t] = tiles[t].row0; m->h_tile_nnz0[t] = tiles[t].nnz0; }
-    CU_TRY(cudaMalloc(&m->desc, tiles.size() * sizeof(TileDesc)));
-    CU_TRY(cudaMemcpy(m->desc, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
-    CU_TRY(cudaMalloc(&m->longrec, std::max<size_t>(1, longs.size()) * sizeof(LongRec)));
-    if (!longs.empty()) CU_TRY(cudaMemcpy(m->longrec, longs.data(), longs.size() * sizeof(LongRec), cudaMemcpyHostToDevice));
-    CU_TRY(cudaMalloc(&m->partial, std::max<size_t>(1, m->ntiles) * sizeof(double)));
-    CU_TRY(cudaMalloc(&m->ticket, std::max<size_t>(1, longs.size()) * sizeof(uint32_t)));
-    CU_TRY(cudaMemset(m->ticket, 0, std::max<size_t>(1, longs.size()) * sizeof(uint32_t)));
-    std::vector<uint32_t> segs;
-    for (size_t t = 0; t + 1 < tiles.size(); ++t)
-        if (tiles[t].row0 & SEG_FLAG) segs.push_back((uint32_t) t);
-    m->nseg = (uint32_t) segs.size();
-    CU_TRY(cudaMalloc(&m->seg_tiles, std::max<size_t>(1, segs.size()) * sizeof(uint32_t)));
-    if (!segs.empty()) CU_TRY(cudaMemcpy(m->seg_tiles, segs.data(), segs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    {   // rows the vector kernels hand to csr_midrow_kernel
-        std::vector<uint32_t> mid;
-        for (uint32_t r = 0; r < m->M; ++r) {
-            const uint32_t len = h_irp[r + 1] - h_irp[r];
-            if (len > (uint32_t) VEC_MID && len <= (uint32_t) STREAM_TILE) mid.push_back(r);
+    const uint32_t M = (uint32_t) m->M;
+    const size_t n1 = (size_t) M + 1;
+    uint32_t last = 0;
+    CU_TRY(cudaMemcpy(&last, m->irp + M, 4, cudaMemcpyDeviceToHost));
+    if (last != m->NZ) return fail("CSR row pointer inconsistent: IRP[M]=%u, NZ=%llu", last, (unsigned long long) m->NZ);
+    uint32_t *cnt = nullptr, *idx = nullptr, *d_num = nullptr;  // cnt: tiles_at | long_at | segs_at ; idx: their scans
+    void* tmp = nullptr;
+    uint32_t *h_r0 = nullptr, *h_n0 = nullptr;
+    int rc = 0;
+    do {
+        if ((rc = cudaMalloc(&cnt, 3 * n1 * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&idx, 3 * n1 * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&d_num, 16) != cudaSuccess)) break;
+        size_t b_scan = 0, b_sel = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, b_scan, cnt, idx, (int) n1);
+        thrust::counting_iterator<uint32_t> rows_it(0);
+        MidRowPred pred{m->irp};
+        cub::DeviceSelect::If(nullptr, b_sel, rows_it, cnt, d_num, (int) M, pred);
+        const size_t tmp_bytes = std::max(b_scan, b_sel) + 16;
+        if ((rc = cudaMalloc(&tmp, tmp_bytes) != cudaSuccess)) break;
+        uint32_t lmax = 0;
+        if (M) {
+            cudaMemset(d_num, 0, 4);
+            row_len_from_irp_kernel<<<(M + 255) / 256, 256>>>(m->irp, M, nullptr, d_num);
+            if ((rc = cudaMemcpy(&lmax, d_num, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
         }
-        m->nmid = (uint32_t) mid.size();
-        CU_TRY(cudaMalloc(&m->mid_rows, std::max<size_t>(1, mid.size()) * 4));
-        if (!mid.empty()) CU_TRY(cudaMemcpy(m->mid_rows, mid.data(), mid.size() * 4, cudaMemcpyHostToDevice));
-    }
-    {   // contiguous nnz-balanced row spans for the persistent vector kernel: SPANS_PER_SM big CTAs per SM
-        int dev = 0, sms = 148;
+        const uint32_t special = std::max<uint32_t>(1, std::min<uint32_t>(PLAN_SPECIAL_MAX, lmax));
+        plan_count_kernel<<<(unsigned) ((n1 + 255) / 256), 256>>>(m->irp, M, special, cnt, cnt + n1, cnt + 2 * n1);
+        for (int a = 0; a < 3 && !rc; ++a) rc = scan_u32(tmp, tmp_bytes, cnt + a * n1, idx + a * n1, n1);
+        if (rc) break;
+        uint32_t tot[3];
+        for (int a = 0; a < 3; ++a)
+            if ((rc = cudaMemcpy(&tot[a], idx + a * n1 + M, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        if (rc) break;
+        m->ntiles = tot[0];
+        m->nlong = tot[1];
+        m->nseg = tot[2];
+        if ((rc = cudaMalloc(&m->desc, ((size_t) m->ntiles + 1) * sizeof(TileDesc)) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->longrec, std::max<size_t>(1, m->nlong) * sizeof(LongRec)) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->seg_tiles, std::max<size_t>(1, m->nseg) * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->partial, std::max<size_t>(1, m->ntiles) * sizeof(double)) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->ticket, std::max<size_t>(1, m->nlong) * 4) != cudaSuccess)) break;
+        cudaMemset(m->ticket, 0, std::max<size_t>(1, m->nlong) * 4);
+        plan_scatter_kernel<<<(unsigned) ((n1 + 255) / 256), 256>>>(m->irp, M, (uint32_t) m->NZ, cnt, idx, idx + n1, idx + 2 * n1, m->ntiles, m->desc,
+                                                                   m->longrec, m->seg_tiles);
+        // rows the vector kernels hand to csr_midrow_kernel (cnt is free again: reuse it as the output list)
+        if (M) {
+            if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
+            if ((rc = cub::DeviceSelect::If(tmp, b_sel, rows_it, cnt, d_num, (int) M, pred) != cudaSuccess)) break;
+            if ((rc = cudaMemcpy(&m->nmid, d_num, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        }
+        if ((rc = cudaMalloc(&m->mid_rows, std::max<size_t>(1, m->nmid) * 4) != cudaSuccess)) break;
+        if (m->nmid && (rc = cudaMemcpy(m->mid_rows, cnt, (size_t) m->nmid * 4, cudaMemcpyDeviceToDevice) != cudaSuccess)) break;
+        // contiguous nnz-balanced row spans for the persistent vector kernel: SPANS_PER_SM big CTAs per SM
+        int dev = 0, sms = 148, per_sm = 2;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int per_sm = 2;
         if (const char* e = getenv("SPMVB200_SPANS_PER_SM")) per_sm = std::max(1, atoi(e));
-        const uint32_t ns = (uint32_t) std::min<uint64_t>((uint64_t) sms * per_sm, std::max<uint64_t>(1, m->M));
-        std::vector<uint32_t> sb(ns + 1);
-        for (uint32_t k = 0; k <= ns; ++k) {
-            const uint64_t target = (uint64_t) m->NZ * k / ns;
-            sb[k] = (uint32_t) (std::lower_bound(h_irp.begin(), h_irp.end(), (uint32_t) target) - h_irp.begin());
-            if (sb[k] > m->M) sb[k] = (uint32_t) m->M;
-            if (k && sb[k] < sb[k - 1]) sb[k] = sb[k - 1];
-        }
-        sb[0] = 0;
-        sb[ns] = (uint32_t) m->M;
-        m->nspans = ns;
-        CU_TRY(cudaMalloc(&m->span_b, (ns + 1) * 4));
-        CU_TRY(cudaMemcpy(m->span_b, sb.data(), (ns + 1) * 4, cudaMemcpyHostToDevice));
+        m->nspans = (uint32_t) std::min<uint64_t>((uint64_t) sms * per_sm, std::max<uint64_t>(1, m->M));
+        if ((rc = cudaMalloc(&m->span_b, ((size_t) m->nspans + 1) * 4) != cudaSuccess)) break;
+        plan_spans_kernel<<<(m->nspans + 1 + 255) / 256, 256>>>(m->irp, M, m->NZ, m->nspans, m->span_b);
+        // host copy of the tile bounds (chunking of the pipelined host path): two flat arrays
+        const uint32_t nt1 = m->ntiles + 1;
+        if ((rc = cudaMalloc(&h_r0, (size_t) nt1 * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&h_n0, (size_t) nt1 * 4) != cudaSuccess)) break;
+        plan_split_desc_kernel<<<(nt1 + 255) / 256, 256>>>(m->desc, nt1, h_r0, h_n0);
+        m->h_tile_row0.resize(nt1);
+        m->h_tile_nnz0.resize(nt1);
+        if ((rc = cudaMemcpy(m->h_tile_row0.data(), h_r0, (size_t) nt1 * 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        if ((rc = cudaMemcpy(m->h_tile_nnz0.data(), h_n0, (size_t) nt1 * 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+    } while (0);
+    cudaFree(cnt);
+    cudaFree(idx);
+    cudaFree(d_num);
+    cudaFree(tmp);
+    cudaFree(h_r0);
+    cudaFree(h_n0);
+    if (rc) {
+        if (cudaPeekAtLastError() != cudaSuccess || !g_err[0]) fail("CSR plan: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
     }
     // sub-warp width of the vector kernel from the mean row length (2 non-zeros per lane and step)
     const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;

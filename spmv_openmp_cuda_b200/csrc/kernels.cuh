@@ -127,26 +127,81 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
         return;
     }
 
-    for (uint32_t r = tid; r < nrows; r += BLOCK) {
-        const uint32_t s = s_rp[r], e = s_rp[r + 1];
-        const uint32_t len = e - s;
-        double acc = 0;
-        if (ADAPTIVE) {
-            if (len > (uint32_t) STREAM_LONG_T) {
-                s_long[atomicAdd(&s_nlong, 1u)] = r;
-                continue;
-            }
-            uint32_t j = (len & 1u) ? 0u : (tid & 31u) % (len ? len : 1u);  // rotated start for even lengths
+    constexpr int RI = TILE_ROWS / BLOCK;
+    static_assert(TILE_ROWS % BLOCK == 0, "tile rows must be a multiple of the block");
+    if (nrows <= (uint32_t) BLOCK) {
+        // ---- at most one row per thread: walk it with 4 independent gathers in flight
+        if (tid < nrows) {
+            const uint32_t s = s_rp[tid], e = s_rp[tid + 1], len = e - s;
+            double acc = 0;
+            bool mine = true;
+            if (ADAPTIVE) {
+                if (len > (uint32_t) STREAM_LONG_T) {  // a whole warp takes this row below
+                    s_long[atomicAdd(&s_nlong, 1u)] = tid;
+                    mine = false;
+                } else {
+                    uint32_t j = (len & 1u) ? 0u : (tid & 31u) % (len ? len : 1u);  // rotated start for even lengths (bank conflicts)
 #pragma unroll 4
-            for (uint32_t k = 0; k < len; ++k) {
-                acc = fma(s_val[s + j], ld_x(x, s_col[s + j]), acc);
-                if (++j == len) j = 0;
-            }
-        } else {
+                    for (uint32_t k = 0; k < len; ++k) {
+                        acc = fma(s_val[s + j], ld_x(x, s_col[s + j]), acc);
+                        if (++j == len) j = 0;
+                    }
+                }
+            } else {
 #pragma unroll 4
-            for (uint32_t j = s; j < e; ++j) acc = __dadd_rn(acc, __dmul_rn(s_val[j], ld_x(x, s_col[j])));
+                for (uint32_t j = s; j < e; ++j) acc = __dadd_rn(acc, __dmul_rn(s_val[j], ld_x(x, s_col[j])));
+            }
+            if (mine) y[r0 + tid] = acc;
         }
-        y[r0 + r] = acc;
+    } else {
+        // ---- short-row tile (hundreds of rows): RI rows per thread INTERLEAVED (rows tid, tid+BLOCK, ...).  Their
+        // shared-memory reads and x gathers are independent, so RI gathers are in flight per thread instead of one
+        // exposed gather latency per row.
+        uint32_t rs[RI], rlen[RI], rot[RI];
+        double acc[RI];
+        uint32_t maxlen = 0;
+#pragma unroll
+        for (int q = 0; q < RI; ++q) {
+            const uint32_t r = tid + q * BLOCK;
+            acc[q] = 0;
+            rs[q] = 0;
+            rlen[q] = 0;
+            rot[q] = 0;
+            if (r < nrows) {
+                rs[q] = s_rp[r];
+                rlen[q] = s_rp[r + 1] - rs[q];
+                if (ADAPTIVE) {
+                    if (rlen[q] > (uint32_t) STREAM_LONG_T) {
+                        s_long[atomicAdd(&s_nlong, 1u)] = r;
+                        rlen[q] = 0;
+                    } else if (!(rlen[q] & 1u) && rlen[q]) {
+                        rot[q] = (tid & 31u) % rlen[q];
+                    }
+                }
+            }
+            maxlen = max(maxlen, rlen[q]);
+        }
+#pragma unroll 2
+        for (uint32_t k = 0; k < maxlen; ++k) {
+#pragma unroll
+            for (int q = 0; q < RI; ++q) {
+                if (k < rlen[q]) {
+                    uint32_t j = k;
+                    if (ADAPTIVE) {
+                        j = k + rot[q];
+                        if (j >= rlen[q]) j -= rlen[q];
+                    }
+                    const double v = s_val[rs[q] + j];
+                    const double xv = ld_x(x, s_col[rs[q] + j]);
+                    acc[q] = ADAPTIVE ? fma(v, xv, acc[q]) : __dadd_rn(acc[q], __dmul_rn(v, xv));
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RI; ++q) {
+            const uint32_t r = tid + q * BLOCK;
+            if (r < nrows && !(ADAPTIVE && s_rp[r + 1] - s_rp[r] > (uint32_t) STREAM_LONG_T)) y[r0 + r] = acc[q];
+        }
     }
     if (ADAPTIVE) {
         __syncthreads();
