@@ -39,7 +39,8 @@ typedef enum {
     SPMVB200_ELL_ROWS_WARP_NT  = 4, /* replaces cudaSpMVWarpsPerRowELLNTrasposed src/SpMV_CUDA.cu:116-135 */
     SPMVB200_CSR_ADAPTIVE      = 5, /* new: row-length driven split (short rows streamed, long rows shared) */
     SPMVB200_SELL_ROWS         = 6, /* new: sliced ELL (SELL-32-sigma), thread per row, no global padding */
-    SPMVB200_KIND_COUNT        = 7
+    SPMVB200_XWIN_ROWS         = 7, /* new: x-window CSR -- x gathered from shared-memory windows, thread per row */
+    SPMVB200_KIND_COUNT        = 8
 } spmvb200_kind;
 
 /* Storage formats a handle can hold. */
@@ -47,8 +48,10 @@ typedef enum {
     SPMVB200_FMT_CSR          = 0,
     SPMVB200_FMT_ELL_COLMAJOR = 1, /* pitched, column-major: slot k of row r at k*pitch + r */
     SPMVB200_FMT_ELL_ROWMAJOR = 2, /* pitched, row-major:    slot k of row r at r*pitch + k */
-    SPMVB200_FMT_SELL         = 3  /* sliced ELL: rows sorted by length inside windows of sigma rows, slices of 32 rows stored
+    SPMVB200_FMT_SELL         = 3, /* sliced ELL: rows sorted by length inside windows of sigma rows, slices of 32 rows stored
                                       column-major and padded only to the slice's longest row */
+    SPMVB200_FMT_XWIN         = 4  /* x-window CSR: row blocks x column windows, jagged slot-major groups of 32 rows, 16-bit
+                                      window-local column ids; the kernel stages each x window in shared memory */
 } spmvb200_format;
 
 typedef struct spmvb200_matrix spmvb200_matrix; /* opaque, device resident */
@@ -97,6 +100,17 @@ int spmvb200_ell_from_csr(const spmvb200_matrix* csr, int format, spmvb200_matri
  * (BASELINE.json configs[4]; the reference author's notes discuss SELL-C-sigma): coalesced like ELL, padding bounded
  * by the length spread inside a window instead of the global maximum. */
 int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma, spmvb200_matrix** out);
+
+/* Build an x-window CSR handle on the device from a CSR handle.  For matrices whose rows touch a column range too wide
+ * for L1 but local enough that a block of rows_per_block rows needs only a few windows of window_cols columns (banded,
+ * stencil, FEM-like: BASELINE.json configs[3]), the x gather is then served from shared memory instead of L2 -- on B200 the
+ * L2 sector request rate (~1 per clock per SM) caps a gather-from-L2 SpMV at ~0.5 of the HBM roofline.
+ * rows_per_block: power of two in [512, 4096] (0 = 2048); window_cols: even, <= 65536 (0 = 8192).  Fails if a row has more
+ * than 255 non-zeros inside one window.  Column-sorted rows give results bit-identical to sgemvSerial. */
+int spmvb200_xwin_from_csr(const spmvb200_matrix* csr, uint32_t rows_per_block, uint32_t window_cols, spmvb200_matrix** out);
+/* geometry of an x-window handle; moved_bytes = everything one SpMV reads/writes including the x windows (from L2) */
+int spmvb200_xwin_info(const spmvb200_matrix* m, uint32_t* rows_per_block, uint32_t* window_cols, uint32_t* ntiles,
+                       uint32_t* ring, uint64_t* moved_bytes);
 
 /* Replaces cudaFreeSpmat (src/include/cudaUtils.h:70-78). */
 int spmvb200_free(spmvb200_matrix* m);
@@ -224,6 +238,7 @@ SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVRowsCSR, SPMVB200_CSR_ROWS)
 SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVWarpPerRowCSR, SPMVB200_CSR_ROWS_WARP)
 SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVAdaptiveCSR, SPMVB200_CSR_ADAPTIVE)
 SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVRowsSELL, SPMVB200_SELL_ROWS) /* CSR in, SELL-32-sigma built on the device */
+SPMVB200_DEFINE_CSR_ADAPTER(b200SpMVRowsXWIN, SPMVB200_XWIN_ROWS) /* CSR in, x-window CSR built on the device */
 SPMVB200_DEFINE_ELL_ADAPTER(b200SpMVRowsELL, SPMVB200_ELL_ROWS)
 SPMVB200_DEFINE_ELL_ADAPTER(b200SpMVRowsELLNNTransposed, SPMVB200_ELL_ROWS_NT)
 SPMVB200_DEFINE_ELL_ADAPTER(b200SpMVWarpsPerRowELLNTrasposed, SPMVB200_ELL_ROWS_WARP_NT)

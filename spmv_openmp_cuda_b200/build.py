@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libspmv_b200.so")
 SOURCES = ["engine.cu", "synth.cu"]
-DEPS = SOURCES + ["kernels.cuh", "plan.cuh", "common.cuh", "engine.h", os.path.join("..", "..", "include", "spmv_b200.h")]
+DEPS = SOURCES + ["kernels.cuh", "plan.cuh", "xwin.cuh", "common.cuh", "engine.h", os.path.join("..", "..", "include", "spmv_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp,-O2", "--shared", "-lgomp"]
 
@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DSPMVB200_XW_DEBUG"] if os.environ.get("SPMVB200_XW_DEBUG_BUILD") else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     subprocess.check_call(cmd)
     return LIB

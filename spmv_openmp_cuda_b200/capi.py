@@ -9,8 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libspmv_b200.so")
 
 # kernel selectors / formats (include/spmv_b200.h)
-CSR_ROWS, CSR_ROWS_WARP, ELL_ROWS, ELL_ROWS_NT, ELL_ROWS_WARP_NT, CSR_ADAPTIVE, SELL_ROWS = range(7)
-FMT_CSR, FMT_ELL_COLMAJOR, FMT_ELL_ROWMAJOR, FMT_SELL = range(4)
+CSR_ROWS, CSR_ROWS_WARP, ELL_ROWS, ELL_ROWS_NT, ELL_ROWS_WARP_NT, CSR_ADAPTIVE, SELL_ROWS, XWIN_ROWS = range(8)
+FMT_CSR, FMT_ELL_COLMAJOR, FMT_ELL_ROWMAJOR, FMT_SELL, FMT_XWIN = range(5)
 
 
 class SpmvB200Error(RuntimeError):
@@ -36,6 +36,8 @@ _SIGS = {
     "spmvb200_csr_adopt_device": (C.c_int, [_u64, _u64, _u64, _vp, _vp, _vp, C.c_int, C.POINTER(_vp)]),
     "spmvb200_ell_from_csr": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "spmvb200_sell_from_csr": (C.c_int, [_vp, C.c_uint32, C.POINTER(_vp)]),
+    "spmvb200_xwin_from_csr": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
+    "spmvb200_xwin_info": (C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(_u64)]),
     "spmvb200_free": (C.c_int, [_vp]),
     "spmvb200_dims": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(C.c_int)]),
     "spmvb200_algorithmic_bytes": (_u64, [_vp]),

@@ -15,6 +15,7 @@
 #include "engine.h"
 #include "kernels.cuh"
 #include "plan.cuh"
+#include "xwin.cuh"
 
 namespace spmvb200 {
 thread_local char g_err[512] = "";
@@ -42,6 +43,11 @@ static void free_arrays(spmvb200_matrix* m) {
         cudaFree(m->rl);
         cudaFree(m->perm);
     }
+    cudaFree(m->xw_rb_tile0);
+    cudaFree(m->xw_tile_win);
+    cudaFree(m->xw_grp_off);
+    cudaFree(m->xw_cnt);
+    cudaFree(m->xw_col);
     cudaFree(m->desc);
     cudaFree(m->longrec);
     cudaFree(m->partial);
@@ -523,6 +529,139 @@ extern "C" int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------- x-window CSR
+// (xwin.cuh) built on the device from a CSR handle: mark (row block, window) pairs -> scan -> tile list ->
+// per-row counts -> scan -> jagged slot-major fill.
+extern "C" int spmvb200_xwin_from_csr(const spmvb200_matrix* csr, uint32_t rows_per_block, uint32_t window_cols,
+                                      spmvb200_matrix** out) {
+    if (!out) return fail("xwin_from_csr: null output");
+    *out = nullptr;
+    if (!csr || csr->format != SPMVB200_FMT_CSR) return fail("xwin_from_csr: source is not a CSR handle");
+    uint32_t R = rows_per_block ? rows_per_block : 2048, W = window_cols ? window_cols : 8192;
+    if (const char* e = getenv("SPMVB200_XW_R")) R = (uint32_t) atoi(e);  // developer knobs
+    if (const char* e = getenv("SPMVB200_XW_W")) W = (uint32_t) atoi(e);
+    if (R < 512 || R > 4096 || (R & (R - 1))) return fail("xwin_from_csr: rows_per_block must be a power of two in [512, 4096] (got %u)", R);
+    if (W < 64 || W > 65536 || (W & 1)) return fail("xwin_from_csr: window_cols must be even and in [64, 65536] (got %u)", W);
+    if (csr->M == 0) return fail("xwin_from_csr: empty matrix");
+    const uint32_t M = (uint32_t) csr->M, G = R / 32;
+    const uint32_t nrb = (M + R - 1) / R;
+    const uint64_t nwin = (std::max<uint64_t>(csr->N, 1) + W - 1) / W;
+    const uint32_t nwords = (uint32_t) ((nwin + 31) / 32);
+    const uint64_t nbits_words = (uint64_t) nrb * nwords;
+    if (nbits_words > (1ull << 28)) return fail("xwin_from_csr: %u row blocks x %llu windows is too sparse a tiling for this format", nrb, (unsigned long long) nwin);
+    spmvb200_matrix* m = new spmvb200_matrix();
+    m->format = SPMVB200_FMT_XWIN;
+    m->M = csr->M;
+    m->N = csr->N;
+    m->NZ = csr->NZ;
+    m->own = 1;
+    m->xw_R = R;
+    m->xw_W = W;
+    m->xw_nrb = nrb;
+    m->K = W;
+    uint32_t *bitmap = nullptr, *pc = nullptr, *scan = nullptr, *tile_rb = nullptr, *grp_cnt = nullptr;
+    int* d_flags = nullptr;  // [0] unsorted rows seen, [1] more than 255 entries of one row in one window
+    void* tmp = nullptr;
+    int rc = 0;
+    do {
+        if ((rc = cudaMalloc(&bitmap, nbits_words * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&pc, (nbits_words + 1) * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&scan, (nbits_words + 1) * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&d_flags, 8) != cudaSuccess)) break;
+        cudaMemset(bitmap, 0, nbits_words * 4);
+        cudaMemset(d_flags, 0, 8);
+        xw_mark_kernel<<<(M + 255) / 256, 256>>>(csr->irp, csr->ja, M, R, W, nwords, bitmap, d_flags);
+        xw_popc_kernel<<<(unsigned) ((nbits_words + 1 + 255) / 256), 256>>>(bitmap, nbits_words, pc);
+        size_t b1 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, b1, pc, scan, (int) (nbits_words + 1));
+        if ((rc = cudaMalloc(&tmp, b1 + 16) != cudaSuccess)) break;
+        if ((rc = cub::DeviceScan::ExclusiveSum(tmp, b1, pc, scan, (int) (nbits_words + 1)) != cudaSuccess)) break;
+        uint32_t ntiles = 0;
+        int h_flags[2] = {0, 0};
+        if ((rc = cudaMemcpy(&ntiles, scan + nbits_words, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        if ((rc = cudaMemcpy(h_flags, d_flags, 8, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        m->xw_ntiles = ntiles;
+        m->xw_sorted = !h_flags[0];
+        const uint64_t ngroups = (uint64_t) ntiles * G;
+        if (ngroups >= 0x7fffffffull) { rc = fail("xwin_from_csr: %llu (tile, group) pairs: tiling too fine", (unsigned long long) ngroups); break; }
+        if ((rc = cudaMalloc(&m->xw_rb_tile0, ((size_t) nrb + 1) * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->xw_tile_win, std::max<size_t>(1, ntiles) * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&tile_rb, std::max<size_t>(1, ntiles) * 4) != cudaSuccess)) break;
+        xw_tiles_kernel<<<(unsigned) ((nbits_words + 1 + 255) / 256), 256>>>(bitmap, scan, nrb, nwords, m->xw_rb_tile0, m->xw_tile_win, tile_rb);
+        if ((rc = cudaMalloc(&m->xw_cnt, std::max<size_t>(1, (size_t) ntiles * R)) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&grp_cnt, (ngroups + 1) * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->xw_grp_off, (ngroups + 1) * 4) != cudaSuccess)) break;
+        const unsigned cblocks = (unsigned) (((ngroups + 1) * 32 + 255) / 256);
+        if (m->xw_sorted)
+            xw_count_kernel<true><<<cblocks, 256>>>(csr->irp, csr->ja, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, grp_cnt, d_flags + 1);
+        else
+            xw_count_kernel<false><<<cblocks, 256>>>(csr->irp, csr->ja, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, grp_cnt, d_flags + 1);
+        size_t b2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, b2, grp_cnt, m->xw_grp_off, (int) (ngroups + 1));
+        if (b2 > b1) {
+            cudaFree(tmp);
+            tmp = nullptr;
+            if ((rc = cudaMalloc(&tmp, b2 + 16) != cudaSuccess)) break;
+        }
+        if ((rc = cub::DeviceScan::ExclusiveSum(tmp, b2, grp_cnt, m->xw_grp_off, (int) (ngroups + 1)) != cudaSuccess)) break;
+        uint32_t total = 0;
+        if ((rc = cudaMemcpy(&total, m->xw_grp_off + ngroups, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        if ((rc = cudaMemcpy(h_flags, d_flags, 8, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        if (h_flags[1]) { rc = fail("xwin_from_csr: a row has more than 255 non-zeros inside one %u-column window (format limit)", W); break; }
+        if (total != csr->NZ) { rc = fail("xwin_from_csr: internal count mismatch (%u entries placed, NZ=%llu)", total, (unsigned long long) csr->NZ); break; }
+        if ((rc = cudaMalloc(&m->xw_col, (m->NZ + PAD) * 2) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->as, (m->NZ + PAD) * 8) != cudaSuccess)) break;
+        cudaMemset(m->xw_col + m->NZ, 0, PAD * 2);
+        cudaMemset(m->as + m->NZ, 0, PAD * 8);
+        if (ngroups) {
+            const unsigned fblocks = (unsigned) ((ngroups * 32 + 255) / 256);
+            if (m->xw_sorted)
+                xw_fill_kernel<true><<<fblocks, 256>>>(csr->irp, csr->ja, csr->as, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, m->xw_grp_off, m->xw_col, m->as);
+            else
+                xw_fill_kernel<false><<<fblocks, 256>>>(csr->irp, csr->ja, csr->as, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, m->xw_grp_off, m->xw_col, m->as);
+        }
+        if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
+        // ring depth: as many windows as fit next to the barriers in the 227 KB a CTA may use
+        uint32_t nbuf = (uint32_t) std::min<uint64_t>(XW_MAX_NBUF, (232448 - 256) / ((uint64_t) W * 8));
+        if (const char* e = getenv("SPMVB200_XW_NBUF")) nbuf = std::min<uint32_t>(nbuf, (uint32_t) std::max(1, atoi(e)));
+        if (nbuf < 2) { rc = fail("xwin_from_csr: window of %u columns leaves no room for double buffering", W); break; }
+        m->xw_nbuf = std::min<uint32_t>(nbuf, 4);
+        m->xw_nw = R >= 1024 ? 32 : 16;
+        if (const char* e = getenv("SPMVB200_XW_NW")) m->xw_nw = (uint32_t) atoi(e);
+        if ((m->xw_nw != 16 && m->xw_nw != 32) || R / (32 * m->xw_nw) < 1 || R / (32 * m->xw_nw) > (m->xw_nw == 32 ? 4u : 8u)) { rc = fail("xwin_from_csr: no kernel for R=%u with %u warps", R, m->xw_nw); break; }
+    } while (0);
+    cudaFree(bitmap);
+    cudaFree(pc);
+    cudaFree(scan);
+    cudaFree(tile_rb);
+    cudaFree(grp_cnt);
+    cudaFree(d_flags);
+    cudaFree(tmp);
+    if (rc) {
+        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("xwin_from_csr: %s", cudaGetErrorString(cudaGetLastError()));
+        free_arrays(m);
+        delete m;
+        return 1;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" int spmvb200_xwin_info(const spmvb200_matrix* m, uint32_t* rows_per_block, uint32_t* window_cols, uint32_t* ntiles,
+                                  uint32_t* ring, uint64_t* moved_bytes) {
+    if (!m || m->format != SPMVB200_FMT_XWIN) return fail("xwin_info: not an x-window handle");
+    if (rows_per_block) *rows_per_block = m->xw_R;
+    if (window_cols) *window_cols = m->xw_W;
+    if (ntiles) *ntiles = m->xw_ntiles;
+    if (ring) *ring = m->xw_nbuf;
+    // what one SpMV reads and writes: entries, per-row counts, group offsets, tile list, y -- and the x windows (from L2)
+    if (moved_bytes)
+        *moved_bytes = 10 * m->NZ + (uint64_t) m->xw_ntiles * m->xw_R + (uint64_t) m->xw_ntiles * (m->xw_R / 32) * 4 + (uint64_t) m->xw_ntiles * 4 +
+                       8 * m->M + (uint64_t) m->xw_ntiles * m->xw_W * 8;
+    return 0;
+}
+
 extern "C" int spmvb200_free(spmvb200_matrix* m) {
     if (!m) return 0;
     free_arrays(m);
@@ -544,7 +683,7 @@ extern "C" int spmvb200_dims(const spmvb200_matrix* m, uint64_t* M, uint64_t* N,
 }
 extern "C" uint64_t spmvb200_algorithmic_bytes(const spmvb200_matrix* m) {
     if (!m) return 0;
-    if (m->format == SPMVB200_FMT_CSR) return 12 * m->NZ + 4 * (m->M + 1) + 8 * m->N + 8 * m->M;
+    if (m->format == SPMVB200_FMT_CSR || m->format == SPMVB200_FMT_XWIN) return 12 * m->NZ + 4 * (m->M + 1) + 8 * m->N + 8 * m->M;
     if (m->format == SPMVB200_FMT_SELL) return 12 * m->NZ + 8 * m->M + 8 * m->N + 8 * m->M;  // row length + permutation per row
     return 12 * m->NZ + 4 * m->M + 8 * m->N + 8 * m->M;
 }
@@ -554,6 +693,9 @@ extern "C" uint64_t spmvb200_device_bytes(const spmvb200_matrix* m) {
         return (m->NZ + PAD) * 12 + (m->M + 1) * 4 + ((uint64_t) m->ntiles + 1) * sizeof(TileDesc) + (uint64_t) m->ntiles * 8 +
                (uint64_t) m->nlong * (sizeof(LongRec) + 4);
     if (m->format == SPMVB200_FMT_SELL) return (m->slots + PAD) * 12 + m->Mpad * 8 + (m->Mpad / 32 + 1) * 4;
+    if (m->format == SPMVB200_FMT_XWIN)
+        return (m->NZ + PAD) * 10 + (uint64_t) m->xw_ntiles * m->xw_R + ((uint64_t) m->xw_ntiles * (m->xw_R / 32) + 1) * 4 +
+               (uint64_t) m->xw_ntiles * 4 + ((uint64_t) m->xw_nrb + 1) * 4;
     return (m->slots + PAD) * 12 + m->M * 4;
 }
 extern "C" int spmvb200_kind_supported(const spmvb200_matrix* m, int kind) {
@@ -564,6 +706,7 @@ extern "C" int spmvb200_kind_supported(const spmvb200_matrix* m, int kind) {
         case SPMVB200_CSR_ADAPTIVE: return m->format == SPMVB200_FMT_CSR;
         case SPMVB200_ELL_ROWS: return m->format == SPMVB200_FMT_ELL_COLMAJOR;
         case SPMVB200_SELL_ROWS: return m->format == SPMVB200_FMT_SELL;
+        case SPMVB200_XWIN_ROWS: return m->format == SPMVB200_FMT_XWIN;
         case SPMVB200_ELL_ROWS_NT:
         case SPMVB200_ELL_ROWS_WARP_NT: return m->format == SPMVB200_FMT_ELL_ROWMAJOR;
         default: return 0;
@@ -578,6 +721,7 @@ extern "C" const char* spmvb200_kind_name(int kind) {
         case SPMVB200_ELL_ROWS_WARP_NT: return "CUDA_ELL_ROWS_WARP_NN_TRANSPOSED";
         case SPMVB200_CSR_ADAPTIVE: return "CUDA_CSR_ADAPTIVE";
         case SPMVB200_SELL_ROWS: return "CUDA_SELL_ROWS";
+        case SPMVB200_XWIN_ROWS: return "CUDA_CSR_XWINDOW_ROWS";
         default: return "?";
     }
 }
@@ -646,6 +790,48 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
     ell_colmajor_kernel<4, BLOCK><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1,
                                                                                                  (uint32_t) m->K, x, y);
     ++g_launches;
+}
+
+
+// ---- x-window CSR: one CTA per row block, NW warps, ring of x windows in shared memory
+template <int NW, int ACC, int U, int DBG>
+static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    const size_t smem = (size_t) m->xw_nbuf * m->xw_W * 8 + XW_MAX_NBUF * 12;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CU_TRY(cudaFuncSetAttribute(xwin_kernel<NW, ACC, U, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured = smem;
+    }
+    xwin_kernel<NW, ACC, U, DBG><<<m->xw_nrb, 32 * NW, smem, st>>>(m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
+                                                                   (uint32_t) m->M, (uint32_t) m->N, m->xw_W, m->xw_nbuf, ((uintptr_t) x & 15) == 0);
+    ++g_launches;
+    return 0;
+}
+// (warps, row groups per warp, slots per load batch): 2*U*ACC loads in flight per lane
+static int launch_xwin(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    const uint32_t acc = m->xw_R / (32 * m->xw_nw);
+    static const int u_env = getenv("SPMVB200_XW_U") ? atoi(getenv("SPMVB200_XW_U")) : 0;  // developer knobs
+#ifdef SPMVB200_XW_DEBUG
+    static const int dbg = getenv("SPMVB200_XW_DBG") ? atoi(getenv("SPMVB200_XW_DBG")) : 0;
+    if (m->xw_nw == 32 && acc == 2 && dbg == 1) return launch_xwin_t<32, 2, 4, 1>(m, x, y, st);
+    if (m->xw_nw == 32 && acc == 2 && dbg == 2) return launch_xwin_t<32, 2, 4, 2>(m, x, y, st);
+    if (m->xw_nw == 32 && acc == 2 && dbg == 3) return launch_xwin_t<32, 2, 4, 3>(m, x, y, st);
+#endif
+#define XW_CASE(NW, ACC, UDEF, UALT, UALT2)                                                     \
+    if (m->xw_nw == NW && acc == ACC) {                                                         \
+        if (u_env == UALT) return launch_xwin_t<NW, ACC, UALT, 0>(m, x, y, st);                 \
+        if (u_env == UALT2) return launch_xwin_t<NW, ACC, UALT2, 0>(m, x, y, st);               \
+        return launch_xwin_t<NW, ACC, UDEF, 0>(m, x, y, st);                                    \
+    }
+    XW_CASE(32, 1, 4, 8, 6)
+    XW_CASE(32, 2, 4, 3, 5)
+    XW_CASE(32, 4, 2, 1, 3)
+    XW_CASE(16, 1, 8, 4, 16)
+    XW_CASE(16, 2, 8, 4, 6)
+    XW_CASE(16, 4, 4, 2, 3)
+    XW_CASE(16, 8, 2, 1, 3)
+#undef XW_CASE
+    return fail("x-window kernel: no instantiation for R=%u, %u warps", m->xw_R, m->xw_nw);
 }
 
 // ---- SPMVB200_CSR_ADAPTIVE: candidates; the fastest on this matrix is picked at first use
@@ -719,6 +905,9 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
         case SPMVB200_SELL_ROWS:
             sell_kernel<4, 256><<<(unsigned) ((m->Mpad + 255) / 256), 256, 0, st>>>(m->irp, m->perm, m->rl, m->as, m->ja, (uint32_t) m->Mpad, d_x, d_y);
             ++g_launches;
+            break;
+        case SPMVB200_XWIN_ROWS:
+            if (launch_xwin(m, d_x, d_y, st)) return 1;
             break;
         case SPMVB200_ELL_ROWS_NT:
             switch (m->vec_lanes) {
@@ -1004,7 +1193,8 @@ extern "C" int spmvb200_cached_spmv(const void* key, int kind, int is_ell, uint6
     if (kind == SPMVB200_ELL_ROWS) fmt = SPMVB200_FMT_ELL_COLMAJOR;
     else if (kind == SPMVB200_ELL_ROWS_NT || kind == SPMVB200_ELL_ROWS_WARP_NT) fmt = SPMVB200_FMT_ELL_ROWMAJOR;
     else if (kind == SPMVB200_SELL_ROWS) fmt = SPMVB200_FMT_SELL;  // built on the device from the CSR input
-    if ((fmt == SPMVB200_FMT_CSR || fmt == SPMVB200_FMT_SELL) == (is_ell != 0)) return fail("cached_spmv: kind %d does not match the %s input", kind, is_ell ? "ELL" : "CSR");
+    else if (kind == SPMVB200_XWIN_ROWS) fmt = SPMVB200_FMT_XWIN;  // likewise
+    if ((fmt == SPMVB200_FMT_CSR || fmt == SPMVB200_FMT_SELL || fmt == SPMVB200_FMT_XWIN) == (is_ell != 0)) return fail("cached_spmv: kind %d does not match the %s input", kind, is_ell ? "ELL" : "CSR");
     spmvb200_matrix* m = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -1017,12 +1207,12 @@ extern "C" int spmvb200_cached_spmv(const void* key, int kind, int is_ell, uint6
         if (it == g_cache.end()) {
             int rc = is_ell ? spmvb200_ell_upload(M, N, K, ja, as, rl, 0, M, fmt, &m) : spmvb200_csr_upload(M, N, irp, ja, as, 0, M, &m);
             if (rc) return 1;
-            if (fmt == SPMVB200_FMT_SELL) {
-                spmvb200_matrix* sell = nullptr;
-                rc = spmvb200_sell_from_csr(m, 0, &sell);
+            if (fmt == SPMVB200_FMT_SELL || fmt == SPMVB200_FMT_XWIN) {
+                spmvb200_matrix* conv = nullptr;
+                rc = fmt == SPMVB200_FMT_SELL ? spmvb200_sell_from_csr(m, 0, &conv) : spmvb200_xwin_from_csr(m, 0, 0, &conv);
                 spmvb200_free(m);
                 if (rc) return 1;
-                m = sell;
+                m = conv;
             }
             g_cache[{key, fmt}] = {m, ja, as, M, N, K};
         } else {

@@ -35,6 +35,13 @@ struct spmvb200_matrix {
     // SELL: irp = slice_ptr[nslices+1], rl = row lengths in sorted order, perm = sorted position -> row (0xffffffff = padding)
     uint32_t* perm = nullptr;
     uint64_t Mpad = 0;
+    // x-window CSR (xwin.cuh): row blocks of xw_R rows x windows of xw_W columns; as = values in tile order
+    uint32_t xw_R = 0, xw_W = 0, xw_nrb = 0, xw_ntiles = 0, xw_nbuf = 0, xw_nw = 0, xw_sorted = 1;
+    uint32_t* xw_rb_tile0 = nullptr;  // [nrb+1] first tile of a row block
+    uint32_t* xw_tile_win = nullptr;  // [ntiles] window id
+    uint32_t* xw_grp_off = nullptr;   // [ntiles*R/32+1] first entry of a (tile, 32-row group)
+    uint8_t* xw_cnt = nullptr;        // [ntiles*R] entries of a row inside a tile
+    uint16_t* xw_col = nullptr;       // [NZ+PAD] window-local column ids
     int own = 1;
     // CSR stream plan
     spmvb200::TileDesc* desc = nullptr;

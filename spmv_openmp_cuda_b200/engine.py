@@ -23,7 +23,7 @@ import numpy as np
 
 from . import capi
 from .capi import (CSR_ADAPTIVE, CSR_ROWS, CSR_ROWS_WARP, ELL_ROWS, ELL_ROWS_NT, ELL_ROWS_WARP_NT, FMT_CSR,
-                   FMT_ELL_COLMAJOR, FMT_ELL_ROWMAJOR, FMT_SELL, SELL_ROWS, SpmvB200Error, check, lib, ptr)
+                   FMT_ELL_COLMAJOR, FMT_ELL_ROWMAJOR, FMT_SELL, FMT_XWIN, SELL_ROWS, XWIN_ROWS, SpmvB200Error, check, lib, ptr)
 
 EXIT_SUCCESS = 0
 
@@ -113,6 +113,18 @@ class DeviceSpmat:
         out = C.c_void_p()
         check(lib().spmvb200_sell_from_csr(self.handle, sigma, C.byref(out)), "sell_from_csr")
         return DeviceSpmat(out.value)
+
+    def to_xwin(self, rows_per_block=0, window_cols=0):
+        """x-window copy of a CSR handle: row blocks x column windows, x gathered from shared memory (csrc/xwin.cuh)."""
+        out = C.c_void_p()
+        check(lib().spmvb200_xwin_from_csr(self.handle, rows_per_block, window_cols, C.byref(out)), "xwin_from_csr")
+        return DeviceSpmat(out.value)
+
+    @property
+    def xwin_info(self):
+        R, W, nt, ring, moved = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+        check(lib().spmvb200_xwin_info(self.handle, C.byref(R), C.byref(W), C.byref(nt), C.byref(ring), C.byref(moved)), "xwin_info")
+        return dict(rows_per_block=R.value, window_cols=W.value, ntiles=nt.value, ring=ring.value, moved_bytes=moved.value)
 
     def download_csr(self):
         irp = np.empty(self.M + 1, dtype=np.uint64)
@@ -247,6 +259,11 @@ def cudaSpMVRowsSELL(m, v, cfg, outV, stream=None):
     return _launch(SELL_ROWS, m, v, cfg, outV, stream)
 
 
+def cudaSpMVRowsXWIN(m, v, cfg, outV, stream=None):
+    """new mode: x-window CSR (x gathered from shared-memory windows), bit-identical to sgemvSerial for sorted rows."""
+    return _launch(XWIN_ROWS, m, v, cfg, outV, stream)
+
+
 def cudaSpMVRowsELLNNTransposed(m, v, cfg, outV, stream=None):
     """src/SpMV_CUDA.cu:99-115 -> row-major ELL, sub-warp per row sized from K."""
     return _launch(ELL_ROWS_NT, m, v, cfg, outV, stream)
@@ -265,7 +282,7 @@ SpmvCUDA_ELLFuncs_NN_TraposedImpl = 1
 SpmvCUDA_ELLFuncs_WarpPerRowIdx = 2
 
 KIND_OF = {cudaSpMVRowsCSR: CSR_ROWS, cudaSpMVWarpPerRowCSR: CSR_ROWS_WARP, cudaSpMVAdaptiveCSR: CSR_ADAPTIVE,
-           cudaSpMVRowsSELL: SELL_ROWS, cudaSpMVRowsELL: ELL_ROWS, cudaSpMVRowsELLNNTransposed: ELL_ROWS_NT,
+           cudaSpMVRowsSELL: SELL_ROWS, cudaSpMVRowsXWIN: XWIN_ROWS, cudaSpMVRowsELL: ELL_ROWS, cudaSpMVRowsELLNNTransposed: ELL_ROWS_NT,
            cudaSpMVWarpsPerRowELLNTrasposed: ELL_ROWS_WARP_NT}
 MODE_OF = {CUDA_CSR_ROWS: CSR_ROWS, CUDA_CSR_ROWS_WARP: CSR_ROWS_WARP, CUDA_ELL_ROWS: ELL_ROWS,
            CUDA_ELL_ROWS_WARP_NT: ELL_ROWS_WARP_NT, CUDA_CSR_ADAPTIVE: CSR_ADAPTIVE}
@@ -306,10 +323,11 @@ b200SpMVRowsCSR = _host_adapter(CSR_ROWS, False)
 b200SpMVWarpPerRowCSR = _host_adapter(CSR_ROWS_WARP, False)
 b200SpMVAdaptiveCSR = _host_adapter(CSR_ADAPTIVE, False)
 b200SpMVRowsSELL = _host_adapter(SELL_ROWS, False)
+b200SpMVRowsXWIN = _host_adapter(XWIN_ROWS, False)
 b200SpMVRowsELL = _host_adapter(ELL_ROWS, True)
 b200SpMVRowsELLNNTransposed = _host_adapter(ELL_ROWS_NT, True)
 b200SpMVWarpsPerRowELLNTrasposed = _host_adapter(ELL_ROWS_WARP_NT, True)
-SpmvB200CSRFuncs = [b200SpMVRowsCSR, b200SpMVWarpPerRowCSR, b200SpMVAdaptiveCSR, b200SpMVRowsSELL]
+SpmvB200CSRFuncs = [b200SpMVRowsCSR, b200SpMVWarpPerRowCSR, b200SpMVAdaptiveCSR, b200SpMVRowsSELL, b200SpMVRowsXWIN]
 SpmvB200ELLFuncs = [b200SpMVRowsELL, b200SpMVRowsELLNNTransposed, b200SpMVWarpsPerRowELLNTrasposed]
 
 

@@ -29,7 +29,7 @@ def orc():
     return oracle
 
 
-EXACT = {"cudaSpMVRowsCSR", "cudaSpMVRowsELL", "cudaSpMVRowsSELL"}
+EXACT = {"cudaSpMVRowsCSR", "cudaSpMVRowsELL", "cudaSpMVRowsSELL", "cudaSpMVRowsXWIN"}
 STREAM_TILE = 2048  # csrc/kernels.cuh
 
 
@@ -44,9 +44,16 @@ def run_all_kinds(sp, orc, mat, x, y_ref, ell=None, kinds="all"):
     d_rm = sp.spMatCpyELLNNPitched(ell)
     d_sell = d_csr.to_sell(64)       # tiny sorting window: slices straddle every length class
     d_sell2 = d_csr.to_sell()        # default window
+    # x-window CSR: 64-column windows never overflow the 255-per-(row, window) limit and give many tiles per row block;
+    # the default geometry (4096 x 8192) applies when no row is longer than 255
+    d_xw = [d_csr.to_xwin(512, 64), d_csr.to_xwin(1024, 200)] if mat.M else []
+    if mat.M and mat.MAX_ROW_NZ <= 255:
+        d_xw.append(d_csr.to_xwin())
     runs = [(f, d_csr) for f in sp.SpmvCUDA_CSRFuncs] + \
            [(sp.cudaSpMVRowsELL, d_ell), (sp.cudaSpMVRowsELLNNTransposed, d_rm), (sp.cudaSpMVWarpsPerRowELLNTrasposed, d_rm),
-            (sp.cudaSpMVRowsSELL, d_sell), (sp.cudaSpMVRowsSELL, d_sell2)]
+            (sp.cudaSpMVRowsSELL, d_sell), (sp.cudaSpMVRowsSELL, d_sell2)] + [(sp.cudaSpMVRowsXWIN, d) for d in d_xw]
+    sorted_rows = all(np.all(np.diff(mat.JA[int(a):int(b)].astype(np.int64)) >= 0) for a, b in zip(mat.IRP[:-1], mat.IRP[1:])) \
+        if mat.M <= 5000 else True  # generators emit sorted rows; fixtures are small enough to check
     for f, dm in runs:
         dy.fill_bytes(0xFF)
         assert f(dm, dx, cfg, dy) == 0
@@ -60,8 +67,10 @@ def run_all_kinds(sp, orc, mat, x, y_ref, ell=None, kinds="all"):
             # rows longer than one tile (2048 nnz) are split across CTAs by the CSR kernel and summed
             # in segment order: deterministic, within TAU, but not the serial order
             exact = np.ones(mat.M, dtype=bool) if f.__name__ != "cudaSpMVRowsCSR" else (np.diff(mat.IRP) <= STREAM_TILE)
+            if f.__name__ == "cudaSpMVRowsXWIN" and not sorted_rows:
+                continue  # windows are visited in column order: bit-identical only for column-sorted rows
             np.testing.assert_array_equal(y[exact], y_ref[exact], err_msg=f.__name__)
-    for dm in (d_csr, d_ell, d_rm, d_sell, d_sell2):
+    for dm in [d_csr, d_ell, d_rm, d_sell, d_sell2] + d_xw:
         sp.cudaFreeSpmat(dm)
 
 
@@ -130,11 +139,48 @@ def test_edge_cases(sp, orc):
         else:  # ELL would be huge (the reference caps it too, config.h:69): CSR kinds only
             dx, dy, dm = sp.DeviceVector.from_host(x), sp.DeviceVector(mat.M), sp.spMatCpyCSR(mat)
             dsell = dm.to_sell(32)
-            for f in sp.SpmvCUDA_CSRFuncs + [sp.cudaSpMVRowsSELL]:
+            dxw = dm.to_xwin(512, 128)
+            for f in sp.SpmvCUDA_CSRFuncs + [sp.cudaSpMVRowsSELL, sp.cudaSpMVRowsXWIN]:
                 dy.fill_bytes(0xFF)
-                f(dsell if f is sp.cudaSpMVRowsSELL else dm, dx, sp.Config(), dy)
+                f(dsell if f is sp.cudaSpMVRowsSELL else dxw if f is sp.cudaSpMVRowsXWIN else dm, dx, sp.Config(), dy)
                 bad, worst = orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, dy.to_host(), tau=TAU)
                 assert bad == 0, (name, f.__name__, worst)
+
+
+def test_xwin_limits_fail_loudly(sp):
+    """More than 255 non-zeros of one row inside one window, or a bad geometry: an error, never a wrong answer."""
+    irp = np.array([0, 300, 301], dtype=np.uint64)
+    ja = np.r_[np.arange(300), 5].astype(np.uint64)
+    dm = sp.spMatCpyCSR(sp.Spmat.csr(1000, irp, ja, np.ones(301)))
+    with pytest.raises(sp.SpmvB200Error, match="255"):
+        dm.to_xwin(512, 1000)
+    for R, W in ((500, 64), (512, 63), (16384, 64), (512, 70000)):
+        with pytest.raises(sp.SpmvB200Error):
+            dm.to_xwin(R, W)
+    ok = dm.to_xwin(512, 128)  # 128-column windows: at most 128 per (row, window)
+    dx, dy = sp.DeviceVector.from_host(np.ones(1000)), sp.DeviceVector(2)
+    sp.cudaSpMVRowsXWIN(ok, dx, sp.Config(), dy)
+    np.testing.assert_array_equal(dy.to_host(), [300.0, 1.0])
+    with pytest.raises(sp.SpmvB200Error):
+        sp.cudaSpMVRowsXWIN(dm, dx, sp.Config(), dy)  # CSR handle, x-window kind
+
+
+def test_xwin_unaligned_x_and_odd_windows(sp, orc):
+    """x that is not 16-byte aligned (the producer warp copies the windows itself) and N that leaves an odd last window."""
+    mat = sp.synth.host_csr(sp.synth.banded(20001, 32, 700))
+    x = sp.synth.host_vector(mat.N)
+    y_ref = _oracle_y(orc, mat, x)
+    dm = sp.spMatCpyCSR(mat)
+    big = sp.DeviceVector(mat.N + 1)
+    sp.capi.check(sp.capi.lib().spmvb200_h2d(big.data_ptr() + 8, sp.capi.ptr(x), x.nbytes), "h2d")
+    dy = sp.DeviceVector(mat.M)
+    for R, W in ((512, 1000), (1024, 4096), (4096, 8192), (2048, 350)):
+        dxw = dm.to_xwin(R, W)
+        for xp in (big.data_ptr() + 8, sp.DeviceVector.from_host(x)):
+            dy.fill_bytes(0xFF)
+            sp.cudaSpMVRowsXWIN(dxw, xp, sp.Config(), dy)
+            np.testing.assert_array_equal(dy.to_host(), y_ref)
+        dxw.free()
 
 
 def test_long_row_split_is_deterministic(sp):
@@ -182,13 +228,14 @@ def test_pipelined_host_path(sp, orc, builder):
     x = sp.synth.host_vector(mat.N)
     y_ref = _oracle_y(orc, mat, x)
     short = np.diff(mat.IRP) <= STREAM_TILE
-    runs = [(f, mat) for f in sp.SpmvB200CSRFuncs] + ([(sp.b200SpMVRowsELL, ell)] if ell is not None else [])
+    runs = [(f, mat) for f in sp.SpmvB200CSRFuncs if not (f is sp.b200SpMVRowsXWIN and mat.MAX_ROW_NZ > 255)] + \
+           ([(sp.b200SpMVRowsELL, ell)] if ell is not None else [])
     for f, m in runs:
         for rep in range(3):
             y = np.full(mat.M, np.nan)
             assert f(m, x, sp.Config(), y) == 0
             assert orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=TAU)[0] == 0, (f, rep)
-            if f in (sp.b200SpMVRowsCSR, sp.b200SpMVRowsELL, sp.b200SpMVRowsSELL):
+            if f in (sp.b200SpMVRowsCSR, sp.b200SpMVRowsELL, sp.b200SpMVRowsSELL, sp.b200SpMVRowsXWIN):
                 np.testing.assert_array_equal(y[short], y_ref[short])
             assert f.ElapsedInternal > 0
     sp.cache_drop()

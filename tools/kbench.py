@@ -39,6 +39,24 @@ def bench(label, dm, kinds, reps, flush):
             label, name, flush, tmin * 1e3, tmean * 1e3, B / tmean / 1e6, B / tmean / 1e6 / PEAK, 2 * dm.NZ / tmean / 1e6, dm.M, dm.NZ, B / 1e6), flush=True)
 
 
+def bench_xwin(label, d, geoms, reps, flush=False):
+    """x-window copies of a CSR handle at several (rows per block, window columns) geometries."""
+    for R, W in geoms:
+        try:
+            xw = d.to_xwin(R, W)
+        except sp.SpmvB200Error as e:
+            print("%-28s xwin R=%d W=%d: %s" % (label, R, W, e), flush=True)
+            continue
+        info = xw.xwin_info
+        bench(label, xw, [("xwin R=%d W=%d x%d" % (R, W, info["ring"]), sp.XWIN_ROWS)], reps, flush)
+        print("#   tiles=%d (%.2f per row block), moved %.1f MB of which x windows %.1f MB" % (
+            info["ntiles"], info["ntiles"] / ((d.M + R - 1) // R), info["moved_bytes"] / 1e6, info["ntiles"] * W * 8 / 1e6), flush=True)
+        xw.free()
+
+
+XW_GEOMS = [(4096, 8192), (2048, 8192), (8192, 8192), (4096, 4096), (4096, 12288), (2048, 4096), (1024, 4096)]
+
+
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     reps = 25
@@ -52,11 +70,14 @@ def main():
             d = synth.device_csr(synth.lap2d(1024))
             bench("cfg1 lap2d 1024^2", d, CSR_KINDS, reps, True)
             bench("cfg1 lap2d 1024^2", d, CSR_KINDS, reps, False)
+            bench_xwin("cfg1 lap2d 1024^2", d, [(1024, 4096), (1024, 2048), (2048, 4096), (512, 2048)], reps, True)
+            bench_xwin("cfg1 lap2d 1024^2", d, [(1024, 4096), (1024, 2048), (2048, 4096), (512, 2048)], reps, False)
             e = d.to_ell(sp.FMT_ELL_COLMAJOR)
             bench("cfg1 lap2d ELL", e, [("ell_rows", sp.ELL_ROWS)], reps, True)
         elif w == "cfg2":
             d = synth.device_csr(synth.stencil27(128))
             bench("cfg2 stencil27 128^3 CSR", d, CSR_KINDS, reps, False)
+            bench_xwin("cfg2 stencil27 128^3", d, XW_GEOMS, reps)
             e = d.to_ell(sp.FMT_ELL_COLMAJOR)
             bench("cfg2 stencil27 128^3 ELL", e, [("ell_rows", sp.ELL_ROWS)], reps, False)
             e.free()
@@ -69,11 +90,13 @@ def main():
             for hw in (1 << 15, 1 << 12):
                 d = synth.device_csr(synth.banded(1 << 25, 32, hw))
                 bench("cfg4 banded 2^25 w=%d" % hw, d, CSR_KINDS, max(5, reps // 5), False)
+                bench_xwin("cfg4 banded 2^25 w=%d" % hw, d, XW_GEOMS[:3], max(5, reps // 5))
                 d.free()
         elif w == "cfg4s":
             for hw in (1 << 15, 1 << 12):
                 d = synth.device_csr(synth.banded(1 << 22, 32, hw))
                 bench("cfg4s banded 2^22 w=%d" % hw, d, CSR_KINDS, reps, False)
+                bench_xwin("cfg4s banded 2^22 w=%d" % hw, d, XW_GEOMS, reps)
                 d.free()
         elif w == "cfg5":
             for kmax, p in ((32, 0.0), (32, 0.02), (32, 0.15), (32, 1.0)):
