@@ -13,13 +13,14 @@ namespace spmvb200 {
 // ERRPRINT, src/include/macros.h:57-58) and kept for spmvb200_last_error().
 // ---------------------------------------------------------------------------------------------
 extern thread_local char g_err[512];
+extern thread_local int g_quiet;  // set while probing an optional format: the message is kept but not printed
 
 inline int fail(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
-    fprintf(stderr, "\33[31m\33[1m\33[44mspmv_b200: %s\33[0m\n", g_err);
+    if (!g_quiet) fprintf(stderr, "\33[31m\33[1m\33[44mspmv_b200: %s\33[0m\n", g_err);
     return 1;
 }
 

@@ -19,6 +19,7 @@
 
 namespace spmvb200 {
 thread_local char g_err[512] = "";
+thread_local int g_quiet = 0;
 static unsigned long long g_launches = 0;
 }  // namespace spmvb200
 using namespace spmvb200;
@@ -36,6 +37,10 @@ static void destroy_pipe(HostPipe* p) {
 }
 
 static void free_arrays(spmvb200_matrix* m) {
+    if (m->xw_child) {
+        spmvb200_free(m->xw_child);
+        m->xw_child = nullptr;
+    }
     if (m->own) {
         cudaFree(m->irp);
         cudaFree(m->ja);
@@ -44,6 +49,7 @@ static void free_arrays(spmvb200_matrix* m) {
         cudaFree(m->perm);
     }
     cudaFree(m->xw_rb_tile0);
+    cudaFree(m->xw_cta_rb);
     cudaFree(m->xw_tile_win);
     cudaFree(m->xw_grp_off);
     cudaFree(m->xw_cnt);
@@ -589,7 +595,7 @@ extern "C" int spmvb200_xwin_from_csr(const spmvb200_matrix* csr, uint32_t rows_
         if ((rc = cudaMalloc(&m->xw_tile_win, std::max<size_t>(1, ntiles) * 4) != cudaSuccess)) break;
         if ((rc = cudaMalloc(&tile_rb, std::max<size_t>(1, ntiles) * 4) != cudaSuccess)) break;
         xw_tiles_kernel<<<(unsigned) ((nbits_words + 1 + 255) / 256), 256>>>(bitmap, scan, nrb, nwords, m->xw_rb_tile0, m->xw_tile_win, tile_rb);
-        if ((rc = cudaMalloc(&m->xw_cnt, std::max<size_t>(1, (size_t) ntiles * R)) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&m->xw_cnt, std::max<size_t>(1, (size_t) ntiles * R) * 2) != cudaSuccess)) break;
         if ((rc = cudaMalloc(&grp_cnt, (ngroups + 1) * 4) != cudaSuccess)) break;
         if ((rc = cudaMalloc(&m->xw_grp_off, (ngroups + 1) * 4) != cudaSuccess)) break;
         const unsigned cblocks = (unsigned) (((ngroups + 1) * 32 + 255) / 256);
@@ -621,9 +627,22 @@ extern "C" int spmvb200_xwin_from_csr(const spmvb200_matrix* csr, uint32_t rows_
             else
                 xw_fill_kernel<false><<<fblocks, 256>>>(csr->irp, csr->ja, csr->as, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, m->xw_grp_off, m->xw_col, m->as);
         }
+        {   // persistent CTAs: one per SM (or per row block if there are fewer), contiguous row blocks balanced by non-zeros
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            m->xw_ncta = std::min<uint32_t>(nrb, (uint32_t) sms);
+            if (const char* e = getenv("SPMVB200_XW_NCTA")) {  // developer knob: force persistent CTAs of this count
+                m->xw_ncta = std::min<uint32_t>(nrb, (uint32_t) std::max(1, atoi(e)));
+                m->xw_mode = 1;
+            }
+            if (const char* e = getenv("SPMVB200_XW_MODE")) m->xw_mode = atoi(e);
+            if ((rc = cudaMalloc(&m->xw_cta_rb, ((size_t) m->xw_ncta + 1) * 4) != cudaSuccess)) break;
+            xw_cta_split_kernel<<<(m->xw_ncta + 1 + 255) / 256, 256>>>(m->xw_rb_tile0, m->xw_grp_off, G, nrb, m->NZ, m->xw_ncta, m->xw_cta_rb);
+        }
         if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
         // ring depth: as many windows as fit next to the barriers in the 227 KB a CTA may use
-        uint32_t nbuf = (uint32_t) std::min<uint64_t>(XW_MAX_NBUF, (232448 - 256) / ((uint64_t) W * 8));
+        uint32_t nbuf = (uint32_t) std::min<uint64_t>(XW_MAX_NBUF, (232448 - 256) / (((uint64_t) W + 2) * 8));
         if (const char* e = getenv("SPMVB200_XW_NBUF")) nbuf = std::min<uint32_t>(nbuf, (uint32_t) std::max(1, atoi(e)));
         if (nbuf < 2) { rc = fail("xwin_from_csr: window of %u columns leaves no room for double buffering", W); break; }
         m->xw_nbuf = std::min<uint32_t>(nbuf, 4);
@@ -657,7 +676,7 @@ extern "C" int spmvb200_xwin_info(const spmvb200_matrix* m, uint32_t* rows_per_b
     if (ring) *ring = m->xw_nbuf;
     // what one SpMV reads and writes: entries, per-row counts, group offsets, tile list, y -- and the x windows (from L2)
     if (moved_bytes)
-        *moved_bytes = 10 * m->NZ + (uint64_t) m->xw_ntiles * m->xw_R + (uint64_t) m->xw_ntiles * (m->xw_R / 32) * 4 + (uint64_t) m->xw_ntiles * 4 +
+        *moved_bytes = 10 * m->NZ + (uint64_t) m->xw_ntiles * m->xw_R * 2 + (uint64_t) m->xw_ntiles * (m->xw_R / 32) * 4 + (uint64_t) m->xw_ntiles * 4 +
                        8 * m->M + (uint64_t) m->xw_ntiles * m->xw_W * 8;
     return 0;
 }
@@ -694,7 +713,7 @@ extern "C" uint64_t spmvb200_device_bytes(const spmvb200_matrix* m) {
                (uint64_t) m->nlong * (sizeof(LongRec) + 4);
     if (m->format == SPMVB200_FMT_SELL) return (m->slots + PAD) * 12 + m->Mpad * 8 + (m->Mpad / 32 + 1) * 4;
     if (m->format == SPMVB200_FMT_XWIN)
-        return (m->NZ + PAD) * 10 + (uint64_t) m->xw_ntiles * m->xw_R + ((uint64_t) m->xw_ntiles * (m->xw_R / 32) + 1) * 4 +
+        return (m->NZ + PAD) * 10 + (uint64_t) m->xw_ntiles * m->xw_R * 2 + ((uint64_t) m->xw_ntiles * (m->xw_R / 32) + 1) * 4 +
                (uint64_t) m->xw_ntiles * 4 + ((uint64_t) m->xw_nrb + 1) * 4;
     return (m->slots + PAD) * 12 + m->M * 4;
 }
@@ -794,56 +813,83 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
 
 
 // ---- x-window CSR: one CTA per row block, NW warps, ring of x windows in shared memory
-template <int NW, int ACC, int U, int DBG>
+template <int NW, int ACC, int UMAX>
 static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
-    const size_t smem = (size_t) m->xw_nbuf * m->xw_W * 8 + XW_MAX_NBUF * 12;
+    const size_t smem = (size_t) m->xw_nbuf * (m->xw_W + 2) * 8 + XW_MAX_NBUF * 12;
     static size_t configured = 0;
     if (smem > configured) {
-        CU_TRY(cudaFuncSetAttribute(xwin_kernel<NW, ACC, U, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CU_TRY(cudaFuncSetAttribute(xwin_kernel<NW, ACC, UMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         configured = smem;
     }
-    xwin_kernel<NW, ACC, U, DBG><<<m->xw_nrb, 32 * NW, smem, st>>>(m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
-                                                                   (uint32_t) m->M, (uint32_t) m->N, m->xw_W, m->xw_nbuf, ((uintptr_t) x & 15) == 0);
+    const bool persist = m->xw_mode == 1;
+    xwin_kernel<NW, ACC, UMAX><<<persist ? m->xw_ncta : m->xw_nrb, 32 * NW, smem, st>>>(persist ? m->xw_cta_rb : nullptr, m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
+                                                                 (uint32_t) m->M, (uint32_t) m->N, m->xw_W, m->xw_nbuf, ((uintptr_t) x & 15) == 0);
     ++g_launches;
     return 0;
 }
-// (warps, row groups per warp, slots per load batch): 2*U*ACC loads in flight per lane
+// (warps, row groups per warp, largest batch in slots): up to 2*UMAX*ACC loads in flight per lane
 static int launch_xwin(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
     const uint32_t acc = m->xw_R / (32 * m->xw_nw);
-    static const int u_env = getenv("SPMVB200_XW_U") ? atoi(getenv("SPMVB200_XW_U")) : 0;  // developer knobs
-#ifdef SPMVB200_XW_DEBUG
-    static const int dbg = getenv("SPMVB200_XW_DBG") ? atoi(getenv("SPMVB200_XW_DBG")) : 0;
-    if (m->xw_nw == 32 && acc == 2 && dbg == 1) return launch_xwin_t<32, 2, 4, 1>(m, x, y, st);
-    if (m->xw_nw == 32 && acc == 2 && dbg == 2) return launch_xwin_t<32, 2, 4, 2>(m, x, y, st);
-    if (m->xw_nw == 32 && acc == 2 && dbg == 3) return launch_xwin_t<32, 2, 4, 3>(m, x, y, st);
-#endif
-#define XW_CASE(NW, ACC, UDEF, UALT, UALT2)                                                     \
-    if (m->xw_nw == NW && acc == ACC) {                                                         \
-        if (u_env == UALT) return launch_xwin_t<NW, ACC, UALT, 0>(m, x, y, st);                 \
-        if (u_env == UALT2) return launch_xwin_t<NW, ACC, UALT2, 0>(m, x, y, st);               \
-        return launch_xwin_t<NW, ACC, UDEF, 0>(m, x, y, st);                                    \
+    static const int u_env = getenv("SPMVB200_XW_U") ? atoi(getenv("SPMVB200_XW_U")) : 0;  // developer knob
+#define XW_CASE(NW, ACC, UDEF, UALT, UALT2)                                                  \
+    if (m->xw_nw == NW && acc == ACC) {                                                      \
+        if (u_env == UALT) return launch_xwin_t<NW, ACC, UALT>(m, x, y, st);                 \
+        if (u_env == UALT2) return launch_xwin_t<NW, ACC, UALT2>(m, x, y, st);               \
+        return launch_xwin_t<NW, ACC, UDEF>(m, x, y, st);                                    \
     }
-    XW_CASE(32, 1, 4, 8, 6)
-    XW_CASE(32, 2, 4, 3, 5)
-    XW_CASE(32, 4, 2, 1, 3)
-    XW_CASE(16, 1, 8, 4, 16)
-    XW_CASE(16, 2, 8, 4, 6)
-    XW_CASE(16, 4, 4, 2, 3)
-    XW_CASE(16, 8, 2, 1, 3)
+    XW_CASE(32, 1, 8, 6, 4)
+    XW_CASE(32, 2, 5, 4, 6)
+    XW_CASE(32, 4, 3, 2, 4)
+    XW_CASE(16, 1, 8, 6, 4)
+    XW_CASE(16, 2, 8, 6, 4)
+    XW_CASE(16, 4, 6, 4, 8)
+    XW_CASE(16, 8, 3, 4, 2)
 #undef XW_CASE
     return fail("x-window kernel: no instantiation for R=%u, %u warps", m->xw_R, m->xw_nw);
 }
 
+// first use of an x-window handle: one CTA per row block, or persistent CTAs?  (Persistent wins when a row block has few
+// tiles -- no pipeline refill per row block; per-row-block wins on wide bands, where concurrent CTAs then share windows.)
+static int tune_xwin(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, float* best_ms_out) {
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    int best = 0;
+    for (int mode = 0; mode < 2; ++mode) {
+        m->xw_mode = mode;
+        if (launch_xwin(m, x, y, st)) return 1;
+        float ms_min = 1e30f;
+        for (int rep = 0; rep < 2; ++rep) {
+            CU_TRY(cudaEventRecord(e0, st));
+            if (launch_xwin(m, x, y, st)) return 1;
+            CU_TRY(cudaEventRecord(e1, st));
+            CU_TRY(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            ms_min = std::min(ms_min, ms);
+        }
+        if (ms_min < best_ms) { best_ms = ms_min; best = mode; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    m->xw_mode = best;
+    if (best_ms_out) *best_ms_out = best_ms;
+    return 0;
+}
+
 // ---- SPMVB200_CSR_ADAPTIVE: candidates; the fastest on this matrix is picked at first use
-static const int N_CAND = 12;
+static const int N_CAND = 13;
+static const int CAND_XWIN = 12;  // x-window copy (built during tuning when the tile census says it can pay off)
 static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32",
-                                        "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32"};
+                                        "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32", "xwindow"};
 static int cand_lanes(int c) { return c < 2 ? 0 : 2 << ((c - 2) % 5); }
 static void launch_candidate(const spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st) {
     if (c == 0) launch_csr_stream<true, 0>(m, x, y, st, 0, m->ntiles);
     else if (c == 1) launch_csr_stream<true, 1>(m, x, y, st, 0, m->ntiles);
     else if (c < 7) launch_csr_vector(m, cand_lanes(c), x, y, st, 0, m->M);
-    else launch_csr_vspan(m, cand_lanes(c), x, y, st);
+    else if (c < CAND_XWIN) launch_csr_vspan(m, cand_lanes(c), x, y, st);
+    else launch_xwin(m->xw_child, x, y, st);
 }
 static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
     // d_x / d_y are the caller's vectors: y is overwritten by every candidate with the same result
@@ -853,7 +899,8 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
     int best = 0;
     float best_ms = 1e30f;
     const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
-    for (int c = 0; c < N_CAND; ++c) {
+    m->tuned_ms[CAND_XWIN] = -1.f;
+    for (int c = 0; c < CAND_XWIN; ++c) {
         m->tuned_ms[c] = -1.f;
         if (c >= 2 && (cand_lanes(c) > 4 * mean + 2 || (double) cand_lanes(c) * 64 < mean)) continue;  // hopeless widths
         if (const char* e = getenv("SPMVB200_FORCE_CAND")) if (atoi(e) != c) continue;  // developer knob
@@ -873,6 +920,27 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    // x-window copy: costs a second copy of the matrix (10.x B per non-zero), so it is only built when the matrix is big
+    // enough to matter, and kept only if it beats everything else by 5 %
+    const char* force = getenv("SPMVB200_FORCE_CAND");
+    if (!getenv("SPMVB200_NO_XWINDOW") && m->NZ >= (1u << 20) && (!force || atoi(force) == CAND_XWIN)) {
+        g_quiet = 1;  // "does not fit this format" is an expected answer here, not an error to print
+        spmvb200_matrix* xw = nullptr;
+        const int rc = spmvb200_xwin_from_csr(m, 0, 0, &xw);
+        g_quiet = 0;
+        if (!rc) {
+            uint64_t moved = 0;
+            spmvb200_xwin_info(xw, nullptr, nullptr, nullptr, nullptr, &moved);
+            float ms = -1.f;
+            // window traffic (L2 -> shared memory) above ~1.5x the matrix stream cannot win: skip the timing
+            if (moved <= 25 * m->NZ && !tune_xwin(xw, d_x, d_y, st, &ms)) {
+                m->tuned_ms[CAND_XWIN] = ms;
+                if (ms < 0.95f * best_ms || force) { best_ms = ms; best = CAND_XWIN; }
+            }
+            if (best == CAND_XWIN) m->xw_child = xw; else spmvb200_free(xw);
+        }
+        g_err[0] = 0;
+    }
     m->tuned = best;
     if (getenv("SPMVB200_VERBOSE")) {
         fprintf(stderr, "spmv_b200: adaptive tuning M=%llu NZ=%llu ->", (unsigned long long) m->M, (unsigned long long) m->NZ);
@@ -907,6 +975,7 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
             ++g_launches;
             break;
         case SPMVB200_XWIN_ROWS:
+            if (m->xw_mode < 0 && tune_xwin(m, d_x, d_y, st, nullptr)) return 1;
             if (launch_xwin(m, d_x, d_y, st)) return 1;
             break;
         case SPMVB200_ELL_ROWS_NT:

@@ -37,10 +37,14 @@ struct spmvb200_matrix {
     uint64_t Mpad = 0;
     // x-window CSR (xwin.cuh): row blocks of xw_R rows x windows of xw_W columns; as = values in tile order
     uint32_t xw_R = 0, xw_W = 0, xw_nrb = 0, xw_ntiles = 0, xw_nbuf = 0, xw_nw = 0, xw_sorted = 1;
+    uint32_t* xw_cta_rb = nullptr;    // [xw_ncta+1] row blocks of a persistent CTA (balanced by non-zeros)
+    uint32_t xw_ncta = 0;
+    int xw_mode = -1;                 // -1 not tuned yet, 0 one CTA per row block, 1 persistent CTAs (xw_cta_rb); first-use timing
+    spmvb200_matrix* xw_child = nullptr;  // CSR handle: x-window copy built by the adaptive mode's tuning run
     uint32_t* xw_rb_tile0 = nullptr;  // [nrb+1] first tile of a row block
     uint32_t* xw_tile_win = nullptr;  // [ntiles] window id
     uint32_t* xw_grp_off = nullptr;   // [ntiles*R/32+1] first entry of a (tile, 32-row group)
-    uint8_t* xw_cnt = nullptr;        // [ntiles*R] entries of a row inside a tile
+    uint16_t* xw_cnt = nullptr;       // [ntiles*R] entries of a row inside a tile | its place in the group's sorted order << 8
     uint16_t* xw_col = nullptr;       // [NZ+PAD] window-local column ids
     int own = 1;
     // CSR stream plan

@@ -9,12 +9,16 @@
 //   window     w = columns [w*W, (w+1)*W)               W*8 bytes of x, staged by ONE TMA bulk copy
 //   tile       (b, w) with at least one non-zero        tiles of a row block are stored in ascending window order
 //
-// Inside a tile the rows are cut into groups of 32 (a warp, lane = row) and each group is stored JAGGED slot-major:
-// first the 1st non-zero (in this window) of every row that has one, then the 2nd of every row that has two, ...
-// with no padding at all.  Lane l finds "its" entry of slot k at  off + popc(ballot(cnt > k) & lanemask_lt)  and the
-// warp's loads are always contiguous (<= 256 B of values, <= 64 B of 16-bit window-local column ids).
-// Per row and tile the format spends one byte (cnt), per group and tile four (offset): 10.1-10.4 B per non-zero
-// instead of CSR's 12 -- the kernel moves fewer bytes than the "algorithmic" 12*nnz it is scored against.
+// Inside a tile the rows are cut into groups of 32 (a warp, lane = row) and each group is stored JAGGED slot-major and
+// SORTED: slot k holds the k-th non-zero (in this window) of every row that has one, rows ordered by decreasing count,
+// with no padding at all.  A row's place p in that order is stored with its count (one u16 per row and tile), so the
+// rows active in slot k are exactly the places [0, n_k) and lane l finds its entry at  (group base + S_k) + p_l  with
+// S_k = n_0 + ... + n_{k-1} warp-uniform: per slot the kernel spends ONE ballot + popc and advances two per-lane
+// pointers -- no per-slot rank, no 64-bit address rebuild (the SpMV is instruction-issue bound long before it is HBM
+// bound if every non-zero costs a rank computation: measured 1.9 warp instructions per non-zero, 58 % issue
+// utilisation at 0.6 of the roofline for the unsorted layout).  The warp's loads stay contiguous (<= 256 B of values,
+// <= 64 B of 16-bit window-local column ids); lanes keep their own rows (sums stay in registers across tiles).
+// Per row and tile the format spends two bytes, per group and tile four: 10.3-10.7 B per non-zero instead of CSR's 12.
 //
 // Kernel: NW warps.  The row block's x windows stream through a ring of NBUF shared-memory buffers (one mbarrier per
 // slot for "landed", one counter per slot for "every warp has left", no CTA-wide barrier in the loop); lanes keep their
@@ -37,57 +41,50 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 
 constexpr int XW_MAX_NBUF = 8;
 
-// One slot of one 32-row group, load half: lanes with cnt > k fetch their entry of the jagged slot
-//   idx = off + popc(ballot(cnt > k) & lanemask_lt),  off += popc(ballot)
-// with the two loads predicated (no branch, no zero fill).  Written in PTX so that the batch of U x ACC of these is
-// emitted back to back (asm volatile keeps program order) ahead of the first use: 11 instructions per slot and group.
-__device__ __forceinline__ void xw_slot_load(double& v, uint32_t& cc, uint32_t& off, const double* __restrict__ val,
-                                             const uint16_t* __restrict__ col, uint32_t c, uint32_t k, uint32_t lt) {
+// One slot of one 32-row group, load half.  Lanes with cnt > k fetch their entry through their own pointers, which
+// then advance by the slot's population n_k = popc(ballot(cnt > k)).  Inactive lanes keep v = 0 and cc = W (the index
+// of a zero kept behind every x window), so the consume half needs no predicate.  PTX so that a batch of these is
+// emitted back to back ahead of the first use (asm volatile keeps program order).
+__device__ __forceinline__ void xw_slot_load(double& v, uint32_t& cc, const double*& pv, const uint16_t*& pc, uint32_t c, uint32_t k,
+                                             uint32_t W) {
     asm volatile(
         "{\n"
         ".reg .pred q;\n"
-        ".reg .b32 m, r;\n"
-        ".reg .b64 pa, pb;\n"
-        "setp.gt.u32 q, %5, %6;\n"
+        ".reg .b32 m;\n"
+        "setp.gt.u32 q, %4, %5;\n"
         "vote.sync.ballot.b32 m, q, 0xffffffff;\n"
-        "and.b32 r, m, %7;\n"
-        "popc.b32 r, r;\n"
-        "add.u32 r, r, %2;\n"
         "popc.b32 m, m;\n"
-        "add.u32 %2, %2, m;\n"
-        "mad.wide.u32 pa, r, 8, %3;\n"
-        "mad.wide.u32 pb, r, 2, %4;\n"
         "mov.f64 %0, 0d0000000000000000;\n"
-        "@q ld.global.cs.f64 %0, [pa];\n"
-        "@q ld.global.cs.u16 %1, [pb];\n"
+        "mov.b32 %1, %6;\n"
+        "@q ld.global.cs.f64 %0, [%2];\n"
+        "@q ld.global.cs.u16 %1, [%3];\n"
+        "mad.wide.u32 %2, m, 8, %2;\n"
+        "mad.wide.u32 %3, m, 2, %3;\n"
         "}\n"
-        : "+d"(v), "+r"(cc), "+r"(off)
-        : "l"(val), "l"(col), "r"(c), "r"(k), "r"(lt)
+        : "=d"(v), "=r"(cc), "+l"(pv), "+l"(pc)
+        : "r"(c), "r"(k), "r"(W)
         : "memory");
 }
 // consume half: acc += v * xw[cc] with separate mul / add roundings (the order and rounding of sgemvSerial,
-// src/SpMV_CSR_OMP.c:229-250).  Lanes with cnt <= k add (+0) * (+0): exact, since a running sum that starts at +0 is
-// never -0; this keeps the two fp64 instructions unpredicated (ptxas turns predicated fp64 math into selects).
-__device__ __forceinline__ void xw_slot_fma(double& acc, double v, uint32_t cc, uint32_t c, uint32_t k, uint32_t xw_saddr) {
+// src/SpMV_CSR_OMP.c:229-250).  Inactive lanes add (+0) * (+0): exact, since a running sum that starts at +0 is never -0.
+__device__ __forceinline__ void xw_slot_fma(double& acc, double v, uint32_t cc, uint32_t xw_saddr) {
     asm volatile(
         "{\n"
-        ".reg .pred q;\n"
         ".reg .f64 x, p;\n"
         ".reg .b32 sa;\n"
-        "setp.gt.u32 q, %3, %4;\n"
-        "mad.lo.u32 sa, %2, 8, %5;\n"
-        "mov.f64 x, 0d0000000000000000;\n"
-        "@q ld.shared.f64 x, [sa];\n"
+        "mad.lo.u32 sa, %2, 8, %3;\n"
+        "ld.shared.f64 x, [sa];\n"
         "mul.rn.f64 p, %1, x;\n"
         "add.rn.f64 %0, %0, p;\n"
         "}\n"
         : "+d"(acc)
-        : "d"(v), "r"(cc), "r"(c), "r"(k), "r"(xw_saddr)
+        : "d"(v), "r"(cc), "r"(xw_saddr)
         : "memory");
 }
 
-// x window of tile t -> ring slot s.  Called by one whole warp.  Aligned x: lane 0 issues one TMA bulk copy that
-// completes on full[s]; otherwise (caller's x not 16-byte aligned) the warp copies the window itself.
+// x window of tile t -> ring slot s (slots are W+2 doubles apart: index W holds the zero inactive lanes read).
+// Called by one whole warp.  Aligned x: lane 0 issues one TMA bulk copy that completes on full[s]; otherwise
+// (caller's x not 16-byte aligned) the warp copies the window itself.
 __device__ __forceinline__ void xw_load_window(const double* __restrict__ x, uint32_t win, uint32_t W, uint32_t N, double* dst, uint64_t* bar,
                                                int x_aligned, uint32_t lane, uint64_t pol) {
     const uint64_t base = (uint64_t) win * W;
@@ -107,113 +104,174 @@ __device__ __forceinline__ void xw_load_window(const double* __restrict__ x, uin
     }
 }
 
+// U slots of all ACC groups: loads first (2*U*ACC independent loads per lane in flight), then the gathers and sums.
+// The first batch of a tile waits for the tile's x window only AFTER its loads are out: window and matrix latencies
+// overlap.
+template <int ACC, int U>
+__device__ __forceinline__ void xw_batch(double (&acc)[ACC], const double* (&pv)[ACC], const uint16_t* (&pc)[ACC], const uint32_t (&c)[ACC],
+                                         uint32_t k0, uint32_t W, uint32_t xw, uint64_t* bar, uint32_t ph) {
+    double v[U][ACC];
+    uint32_t cc[U][ACC];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int a = 0; a < ACC; ++a) xw_slot_load(v[u][a], cc[u][a], pv[a], pc[a], c[a], k0 + u, W);
+    if (k0 == 0) mbar_wait(bar, ph);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int a = 0; a < ACC; ++a) xw_slot_fma(acc[a], v[u][a], cc[u][a], xw);
+}
+
 // No producer warp and no CTA-wide barrier in the loop: every warp counts itself out of a ring slot (shared-memory
 // atomic, acq_rel); the LAST warp to leave slot s refills it with the window of tile t + nbuf.
 // Latency: the matrix stream lands in registers (shared memory belongs to the x windows).  A warp issues the loads of
-// U slots x ACC groups (2*U*ACC independent loads per lane) before it consumes the first, and fetches the next tile's
+// a batch of up to UMAX slots x ACC groups before it consumes the first -- the batch size is chosen per tile from the
+// warp's longest row in that tile (switch over fully unrolled bodies), so that short tiles neither execute
+// predicated-off slots nor leave a lone tail slot exposed to a full memory round trip -- and fetches the next tile's
 // counts/offsets while it works on the current tile.
-// DBG (developer builds only): bit 0 = no x windows (no TMA, no waits), bit 1 = no shared-memory gather.
-template <int NW, int ACC, int U, int DBG = 0>
+// CTA i owns the contiguous row blocks [cta_rb[i], cta_rb[i+1]) and runs their tiles as ONE sequence: tile ids are
+// global and consecutive across row blocks, so the window ring and the metadata prefetch keep going at a row-block
+// boundary; only the sums are written out and reset there.  One row block per CTA is the plain launch.
+template <int NW, int ACC, int UMAX>
 __global__ void __launch_bounds__(32 * NW, 1)
-xwin_kernel(const uint32_t* __restrict__ rb_tile0, const uint32_t* __restrict__ tile_win, const uint32_t* __restrict__ grp_off,
-            const uint8_t* __restrict__ cnt, const uint16_t* __restrict__ col, const double* __restrict__ val,
-            const double* __restrict__ x, double* __restrict__ y, uint32_t M, uint32_t N, uint32_t W, uint32_t nbuf, int x_aligned) {
+xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb_tile0, const uint32_t* __restrict__ tile_win,
+            const uint32_t* __restrict__ grp_off, const uint16_t* __restrict__ cp, const uint16_t* __restrict__ col,
+            const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y, uint32_t M, uint32_t N, uint32_t W,
+            uint32_t nbuf, int x_aligned) {
     constexpr uint32_t R = 32u * NW * ACC, G = NW * ACC;
     extern __shared__ __align__(128) unsigned char xw_smem[];
-    double* xs = reinterpret_cast<double*>(xw_smem);                       // nbuf windows of W doubles
-    uint64_t* full = reinterpret_cast<uint64_t*>(xs + (size_t) nbuf * W);  // [nbuf] window landed
-    uint32_t* done = reinterpret_cast<uint32_t*>(full + XW_MAX_NBUF);      // [nbuf] warps that have left the slot (monotonic)
+    double* xs = reinterpret_cast<double*>(xw_smem);                              // nbuf windows of W (+2) doubles
+    const uint32_t WS = W + 2;                                                    // slot stride; xs[s*WS + W] = 0
+    uint64_t* full = reinterpret_cast<uint64_t*>(xs + (size_t) nbuf * WS);        // [nbuf] window landed
+    uint32_t* done = reinterpret_cast<uint32_t*>(full + XW_MAX_NBUF);             // [nbuf] warps that have left the slot (monotonic)
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t b = blockIdx.x;
-    const uint32_t t0 = __ldg(rb_tile0 + b), t1 = __ldg(rb_tile0 + b + 1);
+    uint32_t rb = cta_rb ? __ldg(cta_rb + blockIdx.x) : blockIdx.x;  // no split table: one row block per CTA
+    const uint32_t rb1 = cta_rb ? __ldg(cta_rb + blockIdx.x + 1) : blockIdx.x + 1;
+    if (rb >= rb1) return;
+    const uint32_t T0 = __ldg(rb_tile0 + rb), T1 = __ldg(rb_tile0 + rb1);  // this CTA's tiles
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < nbuf; ++s) {
             mbar_init(full + s, 1);
             done[s] = 0;
+            xs[(size_t) s * WS + W] = 0.0;
+            xs[(size_t) s * WS + W + 1] = 0.0;
         }
         mbar_fence_init();
     }
     __syncthreads();
     const uint64_t pol = policy_evict_last();
-    if (!(DBG & 1) && warp == 0)
-        for (uint32_t i = 0; i < nbuf && t0 + i < t1; ++i)
-            xw_load_window(x, __ldg(tile_win + t0 + i), W, N, xs + (size_t) i * W, full + i, x_aligned, lane, pol);
+    if (warp == 0)
+        for (uint32_t i = 0; i < nbuf && T0 + i < T1; ++i)
+            xw_load_window(x, __ldg(tile_win + T0 + i), W, N, xs + (size_t) i * WS, full + i, x_aligned, lane, pol);
 
-    // warp owns row groups g = a*NW + warp (a < ACC), lane = row inside the group
+    // warp owns row groups g = a*NW + warp (a < ACC) of every row block, lane = row inside the group
+    const uint32_t myrow = warp * 32u + lane;  // + rb*R + a*NW*32
     double acc[ACC];
-    uint32_t c_nx[ACC], off_nx[ACC];
+    uint32_t cp_nx[ACC], off_nx[ACC];
 #pragma unroll
     for (int a = 0; a < ACC; ++a) {
         acc[a] = 0.0;
-        c_nx[a] = 0;
+        cp_nx[a] = 0;
         off_nx[a] = 0;
-        if (t0 < t1) {
-            const uint32_t g = a * NW + warp;
-            c_nx[a] = __ldg(cnt + (size_t) t0 * R + g * 32u + lane);
-            off_nx[a] = __ldg(grp_off + (size_t) t0 * G + g);
+        if (T0 < T1) {
+            cp_nx[a] = __ldg(cp + (size_t) T0 * R + a * NW * 32u + myrow);
+            off_nx[a] = __ldg(grp_off + (size_t) T0 * G + a * NW + warp);
         }
     }
-    const uint32_t lt = lanemask_lt();
-    uint32_t s = 0, ph = 0;
-    for (uint32_t t = t0; t < t1; ++t) {
-        uint32_t c[ACC], off[ACC], kmax = 0;
+    uint32_t t_end = __ldg(rb_tile0 + rb + 1);
+    // row blocks without tiles at the start of the range
+    while (t_end == T0 && rb < rb1) {
 #pragma unroll
         for (int a = 0; a < ACC; ++a) {
-            c[a] = c_nx[a];
-            off[a] = off_nx[a];
+            const uint32_t row = rb * R + a * NW * 32u + myrow;
+            if (row < M) y[row] = 0.0;
+        }
+        if (++rb < rb1) t_end = __ldg(rb_tile0 + rb + 1);
+    }
+    uint32_t s = 0, ph = 0;
+#pragma unroll 1
+    for (uint32_t t = T0; t < T1; ++t) {
+        uint32_t c[ACC], kmax = 0;
+        const double* pv[ACC];
+        const uint16_t* pc[ACC];
+#pragma unroll
+        for (int a = 0; a < ACC; ++a) {
+            c[a] = cp_nx[a] & 0xffu;                               // entries of my row in this tile
+            const uint32_t first = off_nx[a] + (cp_nx[a] >> 8);    // group base + my place in the sorted order
+            pv[a] = val + first;
+            pc[a] = col + first;
             kmax = max(kmax, c[a]);
         }
-        if (t + 1 < t1) {  // next tile's metadata: in flight while this tile is processed
+        if (t + 1 < T1) {  // next tile's metadata (possibly the next row block's): in flight while this tile is processed
 #pragma unroll
             for (int a = 0; a < ACC; ++a) {
-                const uint32_t g = a * NW + warp;
-                c_nx[a] = __ldg(cnt + (size_t) (t + 1) * R + g * 32u + lane);
-                off_nx[a] = __ldg(grp_off + (size_t) (t + 1) * G + g);
+                cp_nx[a] = __ldg(cp + (size_t) (t + 1) * R + a * NW * 32u + myrow);
+                off_nx[a] = __ldg(grp_off + (size_t) (t + 1) * G + a * NW + warp);
             }
         }
         kmax = __reduce_max_sync(0xffffffffu, kmax);
-        if (!(DBG & 1)) mbar_wait(full + s, ph);
-        const uint32_t xw = smem_u32(xs + (size_t) s * W);
-        double v[U][ACC];
-        uint32_t cc[U][ACC];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int a = 0; a < ACC; ++a) { v[u][a] = 0.0; cc[u][a] = 0u; }
+        const uint32_t xw = smem_u32(xs + (size_t) s * WS);
+        if (kmax == 0) mbar_wait(full + s, ph);  // nothing of this warp's rows here: still keep step with the ring
+        uint32_t k0 = 0;
 #pragma unroll 1
-        for (uint32_t k0 = 0; k0 < kmax; k0 += U) {  // U slots x ACC groups in flight before the first use; slots past a row's count are predicated off
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int a = 0; a < ACC; ++a) xw_slot_load(v[u][a], cc[u][a], off[a], val, col, c[a], k0 + u, lt);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int a = 0; a < ACC; ++a) {
-                    if (DBG & 2) acc[a] += v[u][a] * (double) cc[u][a];
-                    else xw_slot_fma(acc[a], v[u][a], cc[u][a], c[a], k0 + u, xw);
+        while (k0 < kmax) {
+            const uint32_t rem = kmax - k0;
+            if (rem >= (uint32_t) UMAX) {
+                xw_batch<ACC, UMAX>(acc, pv, pc, c, k0, W, xw, full + s, ph);
+                k0 += UMAX;
+            } else {
+                switch (rem) {  // exact tail (or whole short tile) in one batch
+                    case 1: xw_batch<ACC, 1>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
+                    case 2: xw_batch<ACC, (UMAX > 2 ? 2 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
+                    case 3: xw_batch<ACC, (UMAX > 3 ? 3 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
+                    case 4: xw_batch<ACC, (UMAX > 4 ? 4 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
+                    case 5: xw_batch<ACC, (UMAX > 5 ? 5 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
+                    case 6: xw_batch<ACC, (UMAX > 6 ? 6 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
+                    default: xw_batch<ACC, (UMAX > 7 ? 7 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
                 }
-        }
-        if (!(DBG & 1)) {
-            __syncwarp();
-            uint32_t last = 0;
-            if (lane == 0) {
-                uint32_t prev;
-                asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(prev) : "r"(smem_u32(done + s)) : "memory");
-                last = ((prev + 1u) % NW) == 0u;
+                k0 = kmax;
             }
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last && t + nbuf < t1)
-                xw_load_window(x, __ldg(tile_win + t + nbuf), W, N, xs + (size_t) s * W, full + s, x_aligned, lane, pol);
         }
+        __syncwarp();
+        uint32_t last = 0;
+        if (lane == 0) {
+            uint32_t prev;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(prev) : "r"(smem_u32(done + s)) : "memory");
+            last = ((prev + 1u) % NW) == 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && t + nbuf < T1)
+            xw_load_window(x, __ldg(tile_win + t + nbuf), W, N, xs + (size_t) s * WS, full + s, x_aligned, lane, pol);
         if (++s == nbuf) { s = 0; ph ^= 1u; }
-    }
+        while (t + 1 == t_end && rb < rb1) {  // row block finished (and any tile-less row blocks after it)
 #pragma unroll
-    for (int a = 0; a < ACC; ++a) {
-        const uint32_t row = b * R + (a * NW + warp) * 32u + lane;
-        if (row < M) y[row] = acc[a];
+            for (int a = 0; a < ACC; ++a) {
+                const uint32_t row = rb * R + a * NW * 32u + myrow;
+                if (row < M) y[row] = acc[a];
+                acc[a] = 0.0;
+            }
+            if (++rb < rb1) t_end = __ldg(rb_tile0 + rb + 1);
+        }
     }
+}
+
+// row blocks per persistent CTA, balanced by non-zeros: CTA i starts at the first row block whose first entry index
+// reaches i * NZ / ncta  (grp_off[rb_tile0[rb] * G] = entries before row block rb)
+__global__ void xw_cta_split_kernel(const uint32_t* __restrict__ rb_tile0, const uint32_t* __restrict__ grp_off, uint32_t G, uint32_t nrb,
+                                    uint64_t NZ, uint32_t ncta, uint32_t* __restrict__ cta_rb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > ncta) return;
+    if (i == 0) { cta_rb[0] = 0; return; }
+    if (i == ncta) { cta_rb[ncta] = nrb; return; }
+    const uint64_t target = NZ * i / ncta;
+    uint32_t lo = 0, hi = nrb;
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if ((uint64_t) grp_off[(size_t) rb_tile0[mid] * G] < target) lo = mid + 1; else hi = mid;
+    }
+    cta_rb[i] = lo;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,11 +325,12 @@ __device__ __forceinline__ uint32_t xw_lower_bound(const uint32_t* __restrict__ 
     }
     return s;
 }
-// one warp per (tile, 32-row group): per-row entry count inside the tile's window, group total
+// one warp per (tile, 32-row group): per-row entry count inside the tile's window, the row's place in the group's
+// order by decreasing count (ties by lane), group total
 template <bool SORTED>
 __global__ void xw_count_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, uint32_t M, uint32_t R, uint32_t W,
                                 const uint32_t* __restrict__ tile_win, const uint32_t* __restrict__ tile_rb, uint64_t ngroups,
-                                uint8_t* __restrict__ cnt, uint32_t* __restrict__ grp_cnt, int* __restrict__ overflow) {
+                                uint16_t* __restrict__ cp, uint32_t* __restrict__ grp_cnt, int* __restrict__ overflow) {
     const uint64_t wg = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31, G = R / 32;
     if (wg > ngroups) return;
@@ -290,15 +349,20 @@ __global__ void xw_count_kernel(const uint32_t* __restrict__ irp, const uint32_t
         }
     }
     if (c > 255u) { *overflow = 1; c = 255u; }
-    cnt[(size_t) t * R + g * 32 + lane] = (uint8_t) c;
+    uint32_t place = 0;
+    for (uint32_t j = 0; j < 32; ++j) {
+        const uint32_t cj = __shfl_sync(0xffffffffu, c, j);
+        place += (cj > c) || (cj == c && j < lane);
+    }
+    cp[(size_t) t * R + g * 32 + lane] = (uint16_t) (c | (place << 8));
     const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0) grp_cnt[wg] = tot;
 }
-// one warp per (tile, group): jagged slot-major fill (the layout xwin_kernel reads)
+// one warp per (tile, group): jagged, sorted, slot-major fill (the layout xwin_kernel reads)
 template <bool SORTED>
 __global__ void xw_fill_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as, uint32_t M,
                                uint32_t R, uint32_t W, const uint32_t* __restrict__ tile_win, const uint32_t* __restrict__ tile_rb,
-                               uint64_t ngroups, const uint8_t* __restrict__ cnt, const uint32_t* __restrict__ grp_off,
+                               uint64_t ngroups, const uint16_t* __restrict__ cp, const uint32_t* __restrict__ grp_off,
                                uint16_t* __restrict__ col, double* __restrict__ val) {
     const uint64_t wg = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31, G = R / 32;
@@ -306,7 +370,7 @@ __global__ void xw_fill_kernel(const uint32_t* __restrict__ irp, const uint32_t*
     const uint32_t t = (uint32_t) (wg / G), g = (uint32_t) (wg % G);
     const uint32_t row = tile_rb[t] * R + g * 32 + lane;
     const uint64_t lo_c = (uint64_t) tile_win[t] * W, hi_c = lo_c + W;
-    const uint32_t c = cnt[(size_t) t * R + g * 32 + lane];
+    const uint32_t cpv = cp[(size_t) t * R + g * 32 + lane], c = cpv & 0xffu, place = cpv >> 8;
     uint32_t j = 0, e = 0;
     if (row < M && c) {
         j = irp[row];
@@ -314,13 +378,13 @@ __global__ void xw_fill_kernel(const uint32_t* __restrict__ irp, const uint32_t*
         if (SORTED) j = xw_lower_bound(ja, j, e, lo_c);
     }
     uint32_t off = grp_off[wg];
-    const uint32_t kmax = __reduce_max_sync(0xffffffffu, c), lt = lanemask_lt();
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, c);
     for (uint32_t k = 0; k < kmax; ++k) {
         const bool on = c > k;
         const uint32_t m = __ballot_sync(0xffffffffu, on);
         if (on) {
             if (!SORTED) while (j < e && !(ja[j] >= lo_c && ja[j] < hi_c)) ++j;
-            const uint32_t idx = off + __popc(m & lt);
+            const uint32_t idx = off + place;  // rows with more than k entries are exactly the places [0, popc(m))
             val[idx] = as[j];
             col[idx] = (uint16_t) ((uint64_t) ja[j] - lo_c);
             ++j;
