@@ -146,8 +146,9 @@ int spmvb200_spmv_device(spmvb200_matrix* m, int kind, const double* d_x, double
 int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms);
 
 /* Repeat the kernel `reps` times on device-resident vectors and return per-repetition CUDA-event
- * times in ms (times_ms[reps]); with flush_l2 != 0 a buffer larger than L2 is overwritten between
- * repetitions, outside the timed region.  Mirrors the timing loop of testSpMVImplCuda
+ * times in ms (times_ms[reps]); with flush_l2 != 0 a buffer larger than L2 is read (1: leaves clean lines) or
+ * overwritten (2: leaves dirty lines, whose write-back the timed kernel then pays for) between repetitions, outside
+ * the timed region.  Mirrors the timing loop of testSpMVImplCuda
  * (test/SpMV_test.cu:103-145) with events instead of a host stopwatch. */
 int spmvb200_time_device(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, int reps, int flush_l2,
                          float* times_ms);

@@ -159,6 +159,7 @@ int spmvb200::finish_csr(spmvb200_matrix* m) {
             row_len_from_irp_kernel<<<(M + 255) / 256, 256>>>(m->irp, M, nullptr, d_num);
             if ((rc = cudaMemcpy(&lmax, d_num, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
         }
+        m->lmax = lmax;
         const uint32_t special = std::max<uint32_t>(1, std::min<uint32_t>(PLAN_SPECIAL_MAX, lmax));
         plan_count_kernel<<<(unsigned) ((n1 + 255) / 256), 256>>>(m->irp, M, special, cnt, cnt + n1, cnt + 2 * n1);
         for (int a = 0; a < 3 && !rc; ++a) rc = scan_u32(tmp, tmp_bytes, cnt + a * n1, idx + a * n1, n1);
@@ -539,8 +540,10 @@ extern "C" int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma
 // ------------------------------------------------------------------------------------------------- x-window CSR
 // (xwin.cuh) built on the device from a CSR handle: mark (row block, window) pairs -> scan -> tile list ->
 // per-row counts -> scan -> jagged slot-major fill.
-extern "C" int spmvb200_xwin_from_csr(const spmvb200_matrix* csr, uint32_t rows_per_block, uint32_t window_cols,
-                                      spmvb200_matrix** out) {
+// max_window_ratio > 0: give up right after the tile census (before anything big is allocated) when the x windows one SpMV
+// would stage exceed that many bytes per non-zero -- the adaptive mode's way of asking "is this matrix local enough?"
+static int xwin_build(const spmvb200_matrix* csr, uint32_t rows_per_block, uint32_t window_cols, double max_window_ratio,
+                      spmvb200_matrix** out) {
     if (!out) return fail("xwin_from_csr: null output");
     *out = nullptr;
     if (!csr || csr->format != SPMVB200_FMT_CSR) return fail("xwin_from_csr: source is not a CSR handle");
@@ -589,6 +592,11 @@ extern "C" int spmvb200_xwin_from_csr(const spmvb200_matrix* csr, uint32_t rows_
         if ((rc = cudaMemcpy(h_flags, d_flags, 8, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
         m->xw_ntiles = ntiles;
         m->xw_sorted = !h_flags[0];
+        if (max_window_ratio > 0 && (double) ntiles * W * 8 > max_window_ratio * (double) std::max<uint64_t>(csr->NZ, 1)) {
+            rc = fail("xwin_from_csr: %u tiles of %u columns: %.1f bytes of x windows per non-zero, not local enough", ntiles, W,
+                      (double) ntiles * W * 8 / (double) std::max<uint64_t>(csr->NZ, 1));
+            break;
+        }
         const uint64_t ngroups = (uint64_t) ntiles * G;
         if (ngroups >= 0x7fffffffull) { rc = fail("xwin_from_csr: %llu (tile, group) pairs: tiling too fine", (unsigned long long) ngroups); break; }
         if ((rc = cudaMalloc(&m->xw_rb_tile0, ((size_t) nrb + 1) * 4) != cudaSuccess)) break;
@@ -665,6 +673,11 @@ extern "C" int spmvb200_xwin_from_csr(const spmvb200_matrix* csr, uint32_t rows_
     }
     *out = m;
     return 0;
+}
+
+extern "C" int spmvb200_xwin_from_csr(const spmvb200_matrix* csr, uint32_t rows_per_block, uint32_t window_cols,
+                                      spmvb200_matrix** out) {
+    return xwin_build(csr, rows_per_block, window_cols, 0.0, out);
 }
 
 extern "C" int spmvb200_xwin_info(const spmvb200_matrix* m, uint32_t* rows_per_block, uint32_t* window_cols, uint32_t* ntiles,
@@ -878,18 +891,25 @@ static int tune_xwin(spmvb200_matrix* m, const double* x, double* y, cudaStream_
     return 0;
 }
 
+static void launch_sell(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    sell_kernel<4, 256><<<(unsigned) ((m->Mpad + 255) / 256), 256, 0, st>>>(m->irp, m->perm, m->rl, m->as, m->ja, (uint32_t) m->Mpad, x, y);
+    ++g_launches;
+}
+
 // ---- SPMVB200_CSR_ADAPTIVE: candidates; the fastest on this matrix is picked at first use
-static const int N_CAND = 13;
+static const int N_CAND = 14;
 static const int CAND_XWIN = 12;  // x-window copy (built during tuning when the tile census says it can pay off)
+static const int CAND_SELL = 13;  // SELL-32-sigma copy (matrices without long rows: thread per row, coalesced, no shuffles)
 static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32",
-                                        "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32", "xwindow"};
+                                        "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32", "xwindow", "sell"};
 static int cand_lanes(int c) { return c < 2 ? 0 : 2 << ((c - 2) % 5); }
 static void launch_candidate(const spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st) {
     if (c == 0) launch_csr_stream<true, 0>(m, x, y, st, 0, m->ntiles);
     else if (c == 1) launch_csr_stream<true, 1>(m, x, y, st, 0, m->ntiles);
     else if (c < 7) launch_csr_vector(m, cand_lanes(c), x, y, st, 0, m->M);
     else if (c < CAND_XWIN) launch_csr_vspan(m, cand_lanes(c), x, y, st);
-    else launch_xwin(m->xw_child, x, y, st);
+    else if (c == CAND_XWIN) launch_xwin(m->xw_child, x, y, st);
+    else launch_sell(m->xw_child, x, y, st);
 }
 static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
     // d_x / d_y are the caller's vectors: y is overwritten by every candidate with the same result
@@ -899,7 +919,7 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
     int best = 0;
     float best_ms = 1e30f;
     const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
-    m->tuned_ms[CAND_XWIN] = -1.f;
+    m->tuned_ms[CAND_XWIN] = m->tuned_ms[CAND_SELL] = -1.f;
     for (int c = 0; c < CAND_XWIN; ++c) {
         m->tuned_ms[c] = -1.f;
         if (c >= 2 && (cand_lanes(c) > 4 * mean + 2 || (double) cand_lanes(c) * 64 < mean)) continue;  // hopeless widths
@@ -926,18 +946,53 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
     if (!getenv("SPMVB200_NO_XWINDOW") && m->NZ >= (1u << 20) && (!force || atoi(force) == CAND_XWIN)) {
         g_quiet = 1;  // "does not fit this format" is an expected answer here, not an error to print
         spmvb200_matrix* xw = nullptr;
-        const int rc = spmvb200_xwin_from_csr(m, 0, 0, &xw);
+        // window traffic (L2 -> shared memory) above ~1.5x the matrix stream cannot win: stop at the tile census
+        const int rc = xwin_build(m, 0, 0, 15.0, &xw);
         g_quiet = 0;
         if (!rc) {
-            uint64_t moved = 0;
-            spmvb200_xwin_info(xw, nullptr, nullptr, nullptr, nullptr, &moved);
             float ms = -1.f;
-            // window traffic (L2 -> shared memory) above ~1.5x the matrix stream cannot win: skip the timing
-            if (moved <= 25 * m->NZ && !tune_xwin(xw, d_x, d_y, st, &ms)) {
+            if (!tune_xwin(xw, d_x, d_y, st, &ms)) {
                 m->tuned_ms[CAND_XWIN] = ms;
                 if (ms < 0.95f * best_ms || force) { best_ms = ms; best = CAND_XWIN; }
             }
             if (best == CAND_XWIN) m->xw_child = xw; else spmvb200_free(xw);
+        }
+        g_err[0] = 0;
+    }
+    // SELL-32-sigma copy: only without long rows (a thread walks its whole row) and when the slices stay nearly padding-free
+    if (!getenv("SPMVB200_NO_SELL") && m->NZ >= (1u << 20) && m->lmax <= 512 && (!force || atoi(force) == CAND_SELL)) {
+        g_quiet = 1;
+        spmvb200_matrix* sell = nullptr;
+        const int rc = spmvb200_sell_from_csr(m, 0, &sell);
+        g_quiet = 0;
+        if (!rc) {
+            float ms_min = 1e30f;
+            if (sell->slots <= m->NZ + m->NZ / 4) {
+                cudaEvent_t s0, s1;
+                CU_TRY(cudaEventCreate(&s0));
+                CU_TRY(cudaEventCreate(&s1));
+                launch_sell(sell, d_x, d_y, st);
+                for (int rep = 0; rep < 2; ++rep) {
+                    CU_TRY(cudaEventRecord(s0, st));
+                    launch_sell(sell, d_x, d_y, st);
+                    CU_TRY(cudaEventRecord(s1, st));
+                    CU_TRY(cudaEventSynchronize(s1));
+                    float ms = 0;
+                    CU_TRY(cudaEventElapsedTime(&ms, s0, s1));
+                    ms_min = std::min(ms_min, ms);
+                }
+                cudaEventDestroy(s0);
+                cudaEventDestroy(s1);
+                m->tuned_ms[CAND_SELL] = ms_min;
+            }
+            if (ms_min < 0.95f * best_ms || (force && ms_min < 1e30f)) {
+                if (m->xw_child) spmvb200_free(m->xw_child);
+                m->xw_child = sell;
+                best_ms = ms_min;
+                best = CAND_SELL;
+            } else {
+                spmvb200_free(sell);
+            }
         }
         g_err[0] = 0;
     }
@@ -970,10 +1025,7 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
             break;
         case SPMVB200_CSR_ROWS_WARP: launch_csr_vector(m, m->vec_lanes, d_x, d_y, st, 0, m->M); break;
         case SPMVB200_ELL_ROWS: launch_ell_colmajor(m, d_x, d_y, st, 0, m->M); break;
-        case SPMVB200_SELL_ROWS:
-            sell_kernel<4, 256><<<(unsigned) ((m->Mpad + 255) / 256), 256, 0, st>>>(m->irp, m->perm, m->rl, m->as, m->ja, (uint32_t) m->Mpad, d_x, d_y);
-            ++g_launches;
-            break;
+        case SPMVB200_SELL_ROWS: launch_sell(m, d_x, d_y, st); break;
         case SPMVB200_XWIN_ROWS:
             if (m->xw_mode < 0 && tune_xwin(m, d_x, d_y, st, nullptr)) return 1;
             if (launch_xwin(m, d_x, d_y, st)) return 1;
@@ -1196,14 +1248,30 @@ extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x,
     return 0;
 }
 
+// L2 flush by READING a buffer larger than L2: leaves the cache full of CLEAN lines.  (A memset leaves it full of dirty
+// lines, whose write-back the next kernel's fills then pay for -- up to one extra byte written per byte read.)
+__global__ void flush_read_kernel(const uint4* __restrict__ p, size_t n, uint4* __restrict__ sink) {
+    uint4 a = make_uint4(0, 0, 0, 0);
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint4 v = p[i];
+        a.x ^= v.x; a.y ^= v.y; a.z ^= v.z; a.w ^= v.w;
+    }
+    if ((a.x ^ a.y ^ a.z ^ a.w) == 0x9e3779b9u) *sink = a;  // never true for a zeroed buffer: keeps the loads alive
+}
+
 extern "C" int spmvb200_time_device(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, int reps, int flush_l2,
                                     float* times_ms) {
     if (!m || !d_x || !d_y || reps <= 0 || !times_ms) return fail("time_device: bad arguments");
     if (prefer_smem_once() || ensure_events(m)) return 1;
     const size_t FLUSH = 512ull << 20;  // > 126 MB L2
-    if (flush_l2 && !m->flush) CU_TRY(cudaMalloc(&m->flush, FLUSH));
+    if (flush_l2 && !m->flush) {
+        CU_TRY(cudaMalloc(&m->flush, FLUSH));
+        CU_TRY(cudaMemset(m->flush, 0, FLUSH));
+    }
     for (int i = 0; i < reps; ++i) {
-        if (flush_l2) CU_TRY(cudaMemsetAsync(m->flush, i & 0xff, FLUSH, 0));
+        if (flush_l2 == 2) CU_TRY(cudaMemsetAsync(m->flush, 0, FLUSH, 0));  // dirty flush (what round 1 first measured with)
+        else if (flush_l2) flush_read_kernel<<<1184, 512>>>((const uint4*) m->flush, FLUSH / 16, (uint4*) m->flush);
         CU_TRY(cudaEventRecord(m->ev0, 0));
         if (launch(m, kind, d_x, d_y, 0)) return 1;
         CU_TRY(cudaEventRecord(m->ev1, 0));

@@ -40,7 +40,8 @@ struct spmvb200_matrix {
     uint32_t* xw_cta_rb = nullptr;    // [xw_ncta+1] row blocks of a persistent CTA (balanced by non-zeros)
     uint32_t xw_ncta = 0;
     int xw_mode = -1;                 // -1 not tuned yet, 0 one CTA per row block, 1 persistent CTAs (xw_cta_rb); first-use timing
-    spmvb200_matrix* xw_child = nullptr;  // CSR handle: x-window copy built by the adaptive mode's tuning run
+    spmvb200_matrix* xw_child = nullptr;  // CSR handle: x-window or SELL copy built (and kept, if it won) by the adaptive mode's tuning run
+    uint32_t lmax = 0;                    // CSR: longest row
     uint32_t* xw_rb_tile0 = nullptr;  // [nrb+1] first tile of a row block
     uint32_t* xw_tile_win = nullptr;  // [ntiles] window id
     uint32_t* xw_grp_off = nullptr;   // [ntiles*R/32+1] first entry of a (tile, 32-row group)

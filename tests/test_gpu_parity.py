@@ -183,6 +183,24 @@ def test_xwin_unaligned_x_and_odd_windows(sp, orc):
         dxw.free()
 
 
+@pytest.mark.parametrize("cand,name", [(12, "xwindow"), (13, "sell")])
+def test_adaptive_child_formats(sp, orc, cand, name, monkeypatch):
+    """The adaptive mode's tuning run may build an x-window or SELL copy of the matrix; force each and check the result."""
+    monkeypatch.setenv("SPMVB200_FORCE_CAND", str(cand))
+    mat = sp.synth.host_csr(sp.synth.banded(70000, 32, 20000))  # 2.2 M nnz: above the size threshold for child formats
+    x = sp.synth.host_vector(mat.N)
+    y_ref = _oracle_y(orc, mat, x)
+    dm, dx, dy = sp.spMatCpyCSR(mat), sp.DeviceVector.from_host(x), sp.DeviceVector(mat.M)
+    for _ in range(3):
+        dy.fill_bytes(0xFF)
+        sp.cudaSpMVAdaptiveCSR(dm, dx, sp.Config(), dy)
+        np.testing.assert_array_equal(dy.to_host(), y_ref)  # both child kernels sum in the serial order
+    assert dm.adaptive_choice == name
+    dy.fill_bytes(0xFF)
+    sp.cudaSpMVRowsCSR(dm, dx, sp.Config(), dy)  # the CSR kinds still work on the same handle
+    np.testing.assert_array_equal(dy.to_host(), y_ref)
+
+
 def test_long_row_split_is_deterministic(sp):
     """Rows split across CTAs are combined in segment order by the last arriver: run-to-run identical."""
     mat = sp.synth.rmat_host_csr(14, 16)

@@ -68,8 +68,9 @@ def main():
         t0 = time.time()
         if w == "cfg1":
             d = synth.device_csr(synth.lap2d(1024))
-            bench("cfg1 lap2d 1024^2", d, CSR_KINDS, reps, True)
-            bench("cfg1 lap2d 1024^2", d, CSR_KINDS, reps, False)
+            bench("cfg1 lap2d 1024^2", d, CSR_KINDS, reps, 1)   # L2 flushed by reading (clean lines)
+            bench("cfg1 lap2d 1024^2", d, CSR_KINDS, reps, 2)   # L2 flushed by a memset (dirty lines: write-back inside the timed kernel)
+            bench("cfg1 lap2d 1024^2", d, CSR_KINDS, reps, 0)
             bench_xwin("cfg1 lap2d 1024^2", d, [(1024, 4096), (1024, 2048), (2048, 4096), (512, 2048)], reps, True)
             bench_xwin("cfg1 lap2d 1024^2", d, [(1024, 4096), (1024, 2048), (2048, 4096), (512, 2048)], reps, False)
             e = d.to_ell(sp.FMT_ELL_COLMAJOR)
@@ -86,6 +87,11 @@ def main():
         elif w == "cfg3":
             d = synth.rmat_device_csr(22, 16)
             bench("cfg3 rmat s22 ef16", d, CSR_KINDS, reps, False)
+            for sigma in (1024, 16384, 1 << 18):
+                e = d.to_sell(sigma)
+                bench("cfg3 rmat s22 ef16 SELL s=%d" % sigma, e, [("sell_rows", sp.SELL_ROWS)], reps, False)
+                print("#   SELL slots / nnz = %.3f" % ((e.device_bytes - e.M * 8) / 12 / max(d.NZ, 1)), flush=True)
+                e.free()
         elif w == "cfg4":
             for hw in (1 << 15, 1 << 12):
                 d = synth.device_csr(synth.banded(1 << 25, 32, hw))
@@ -105,6 +111,9 @@ def main():
                 bench("cfg5 mixed K=%d p=%.2f pad=%.1f" % (kmax, p, pad), d, CSR_KINDS, reps, False)
                 e = d.to_ell(sp.FMT_ELL_COLMAJOR)
                 bench("cfg5 mixed K=%d p=%.2f ELL" % (kmax, p), e, [("ell_rows", sp.ELL_ROWS)], reps, False)
+                e.free()
+                e = d.to_sell()
+                bench("cfg5 mixed K=%d p=%.2f SELL" % (kmax, p), e, [("sell_rows", sp.SELL_ROWS)], reps, False)
                 d.free(); e.free()
         print("# %s done in %.1f s" % (w, time.time() - t0), flush=True)
 
