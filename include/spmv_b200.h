@@ -122,6 +122,10 @@ int spmvb200_dims(const spmvb200_matrix* m, uint64_t* M, uint64_t* N, uint64_t* 
 uint64_t spmvb200_algorithmic_bytes(const spmvb200_matrix* m);
 /* bytes of device memory the handle's arrays occupy (includes ELL padding and the plan) */
 uint64_t spmvb200_device_bytes(const spmvb200_matrix* m);
+/* width of the column ids the handle's kernel reads: 32, or 16 when the engine found a narrower lossless encoding
+ * (x-window CSR: window-local ids; column-major ELL: offsets from the row index when max(col-row) - min(col-row) < 2^16,
+ * true of every stencil / banded matrix).  The algorithmic bytes above always count 32-bit ids. */
+int spmvb200_index_bits(const spmvb200_matrix* m);
 /* 1 if `kind` can run on this handle's format */
 int spmvb200_kind_supported(const spmvb200_matrix* m, int kind);
 const char* spmvb200_kind_name(int kind); /* the reference's mode string, e.g. "CUDA_CSR_ROWS" */

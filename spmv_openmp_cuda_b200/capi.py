@@ -42,6 +42,7 @@ _SIGS = {
     "spmvb200_dims": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(C.c_int)]),
     "spmvb200_algorithmic_bytes": (_u64, [_vp]),
     "spmvb200_device_bytes": (_u64, [_vp]),
+    "spmvb200_index_bits": (C.c_int, [_vp]),
     "spmvb200_kind_supported": (C.c_int, [_vp, C.c_int]),
     "spmvb200_kind_name": (C.c_char_p, [C.c_int]),
     "spmvb200_adaptive_choice": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),

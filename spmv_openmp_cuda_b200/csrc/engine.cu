@@ -46,6 +46,7 @@ static void free_arrays(spmvb200_matrix* m) {
         cudaFree(m->ja);
         cudaFree(m->as);
         cudaFree(m->rl);
+        cudaFree(m->ja16);
         cudaFree(m->perm);
     }
     cudaFree(m->xw_rb_tile0);
@@ -339,6 +340,27 @@ static int ell_alloc(spmvb200_matrix* m) {
     CU_TRY(cudaMalloc(&m->rl, std::max<uint64_t>(m->M, 1) * 4));
     return 0;
 }
+// column-major ELL: if every valid column id is within a 2^16 range of its row index, keep 16-bit offsets as well
+static int ell_try_idx16(spmvb200_matrix* m) {
+    if (m->format != SPMVB200_FMT_ELL_COLMAJOR || !m->M || !m->K || getenv("SPMVB200_ELL_NO_IDX16")) return 0;
+    long long* d_rng = nullptr;
+    CU_TRY(cudaMalloc(&d_rng, 16));
+    const long long init[2] = {(1ll << 62), -(1ll << 62)};
+    CU_TRY(cudaMemcpy(d_rng, init, 16, cudaMemcpyHostToDevice));
+    ell_delta_range_kernel<<<(unsigned) ((m->M + 255) / 256), 256>>>(m->ja, m->rl, m->pitch, (uint32_t) m->M, d_rng, d_rng + 1);
+    long long h[2];
+    cudaError_t e = cudaMemcpy(h, d_rng, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d_rng);
+    if (e != cudaSuccess) return fail("ELL index range: %s", cudaGetErrorString(e));
+    if (h[0] > h[1] || h[1] - h[0] > 65535 || h[0] < -(1ll << 30) || h[0] > (1ll << 30)) return 0;  // empty, or too wide
+    m->ja16_base = (int32_t) h[0];
+    CU_TRY(cudaMalloc(&m->ja16, (m->slots + PAD) * 2));
+    CU_TRY(cudaMemset(m->ja16 + m->slots, 0, PAD * 2));
+    ell_make_idx16_kernel<<<(unsigned) ((m->M + 255) / 256), 256>>>(m->ja, m->rl, m->pitch, (uint32_t) m->M, (uint32_t) m->K, m->ja16_base, m->ja16);
+    CU_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
 static void ell_pick_lanes(spmvb200_matrix* m) {
     int lanes = 1;
     while (lanes < 32 && (uint64_t) lanes * 4 <= m->K) lanes *= 2;  // ~2-4 slots per lane
@@ -409,6 +431,7 @@ extern "C" int spmvb200_ell_upload(uint64_t M, uint64_t N, uint64_t K, const uin
         if (rc) break;
         m->NZ = nz;
         ell_pick_lanes(m);
+        if ((rc = ell_try_idx16(m))) break;
     } while (0);
     cudaFree(d_of);
     cudaFree(st_ja);
@@ -457,6 +480,7 @@ extern "C" int spmvb200_ell_from_csr(const spmvb200_matrix* csr, int format, spm
                                                                          format == SPMVB200_FMT_ELL_COLMAJOR, m->ja, m->as);
         if ((rc = (cudaDeviceSynchronize() != cudaSuccess))) break;
         ell_pick_lanes(m);
+        if ((rc = ell_try_idx16(m))) break;
     } while (0);
     cudaFree(d_kmax);
     if (rc) {
@@ -728,7 +752,13 @@ extern "C" uint64_t spmvb200_device_bytes(const spmvb200_matrix* m) {
     if (m->format == SPMVB200_FMT_XWIN)
         return (m->NZ + PAD) * 10 + (uint64_t) m->xw_ntiles * m->xw_R * 2 + ((uint64_t) m->xw_ntiles * (m->xw_R / 32) + 1) * 4 +
                (uint64_t) m->xw_ntiles * 4 + ((uint64_t) m->xw_nrb + 1) * 4;
-    return (m->slots + PAD) * 12 + m->M * 4;
+    return (m->slots + PAD) * (m->ja16 ? 14 : 12) + m->M * 4;
+}
+extern "C" int spmvb200_index_bits(const spmvb200_matrix* m) {
+    if (!m) return 0;
+    if (m->format == SPMVB200_FMT_XWIN) return 16;
+    if (m->format == SPMVB200_FMT_ELL_COLMAJOR && m->ja16 && !getenv("SPMVB200_ELL_NO_EARLY_EXIT")) return 16;
+    return 32;
 }
 extern "C" int spmvb200_kind_supported(const spmvb200_matrix* m, int kind) {
     if (!m) return 0;
@@ -819,8 +849,12 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
     constexpr int BLOCK = 256;
     if (r1 <= r0) return;
     static const bool no_exit = getenv("SPMVB200_ELL_NO_EARLY_EXIT") != nullptr;  // developer knob: walk all K slots like the reference
-    ell_colmajor_kernel<4, BLOCK><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1,
-                                                                                                 (uint32_t) m->K, x, y);
+    if (m->ja16 && !no_exit)
+        ell_colmajor_kernel<4, BLOCK, true><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1,
+                                                                                                           (uint32_t) m->K, m->ja16_base, x, y);
+    else
+        ell_colmajor_kernel<4, BLOCK, false><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0,
+                                                                                                            (uint32_t) r1, (uint32_t) m->K, 0, x, y);
     ++g_launches;
 }
 

@@ -32,6 +32,8 @@ struct spmvb200_matrix {
     uint32_t* ja = nullptr;
     double* as = nullptr;
     uint32_t* rl = nullptr;
+    uint16_t* ja16 = nullptr;  // column-major ELL: 16-bit column offsets from (row + ja16_base), when the matrix allows it
+    int32_t ja16_base = 0;
     // SELL: irp = slice_ptr[nslices+1], rl = row lengths in sorted order, perm = sorted position -> row (0xffffffff = padding)
     uint32_t* perm = nullptr;
     uint64_t Mpad = 0;

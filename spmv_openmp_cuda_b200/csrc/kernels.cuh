@@ -10,6 +10,8 @@
 // All are HBM-bound (2 flop per >= 12 bytes): the design goal is bytes in flight and no wasted
 // sectors, not math throughput.  See DESIGN.md for the roofline of each.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace spmvb200 {
@@ -319,16 +321,21 @@ csr_longrow_kernel(const uint32_t* __restrict__ seg_tiles, const TileDesc* __res
 // x[0] for padding, src/SpMV_CUDA.cu:83-93).  UNROLL independent slots are in flight per thread.
 // Per-row sum is left to right with separate mul/add => bit-identical to sgemvSerial.
 // ---------------------------------------------------------------------------------------------
-template <int UNROLL, int BLOCK>
+// IDX16: the column ids are stored as 16-bit offsets from (row + base) -- possible whenever max(col - row) - min(col - row)
+// < 2^16 over the whole handle (every stencil / banded matrix of BASELINE.json): 10 instead of 12 bytes per non-zero.
+__device__ __forceinline__ uint32_t ld_stream(const uint16_t* p) { return (uint32_t) __ldcs(reinterpret_cast<const unsigned short*>(p)); }
+template <int UNROLL, int BLOCK, bool IDX16>
 __global__ void __launch_bounds__(BLOCK)
-ell_colmajor_kernel(const double* __restrict__ as, const uint32_t* __restrict__ ja, const uint32_t* __restrict__ rl,
-                    uint64_t pitch, uint32_t row_begin, uint32_t M, uint32_t K, const double* __restrict__ x, double* __restrict__ y) {
+ell_colmajor_kernel(const double* __restrict__ as, const void* __restrict__ ja_any, const uint32_t* __restrict__ rl,
+                    uint64_t pitch, uint32_t row_begin, uint32_t M, uint32_t K, int32_t base, const double* __restrict__ x, double* __restrict__ y) {
+    using idx_t = typename std::conditional<IDX16, uint16_t, uint32_t>::type;
     const uint32_t row = row_begin + blockIdx.x * BLOCK + threadIdx.x;  // rows [row_begin, M)
     const bool live = row < M;
     const uint32_t len = live ? (rl ? __ldg(rl + row) : K) : 0u;
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, len);
     const double* a = as + row;
-    const uint32_t* j = ja + row;
+    const idx_t* j = reinterpret_cast<const idx_t*>(ja_any) + row;
+    const uint32_t cbase = IDX16 ? (uint32_t) ((int32_t) row + base) : 0u;
     double acc = 0;
     uint32_t k = 0;
     for (; k + UNROLL <= wmax; k += UNROLL) {
@@ -338,7 +345,7 @@ ell_colmajor_kernel(const double* __restrict__ as, const uint32_t* __restrict__ 
         for (int u = 0; u < UNROLL; ++u) {
             const bool ok = k + u < len;
             v[u] = ok ? ld_stream(a + (uint64_t) (k + u) * pitch) : 0.0;
-            c[u] = ok ? ld_stream(j + (uint64_t) (k + u) * pitch) : 0u;
+            c[u] = ok ? ld_stream(j + (uint64_t) (k + u) * pitch) + cbase : 0u;
         }
         double xv[UNROLL];
 #pragma unroll
@@ -350,11 +357,41 @@ ell_colmajor_kernel(const double* __restrict__ as, const uint32_t* __restrict__ 
     for (; k < wmax; ++k) {
         if (k < len) {
             const double v = ld_stream(a + (uint64_t) k * pitch);
-            const uint32_t c = ld_stream(j + (uint64_t) k * pitch);
+            const uint32_t c = ld_stream(j + (uint64_t) k * pitch) + cbase;
             acc = __dadd_rn(acc, __dmul_rn(v, ld_x(x, c)));
         }
     }
     if (live) y[row] = acc;
+}
+// range of (col - row) over the valid slots of a column-major ELL, then the 16-bit offsets themselves
+__global__ void ell_delta_range_kernel(const uint32_t* __restrict__ ja, const uint32_t* __restrict__ rl, uint64_t pitch, uint32_t M,
+                                       long long* __restrict__ mn, long long* __restrict__ mx) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    long long lo = (1ll << 62), hi = -(1ll << 62);
+    if (r < M) {
+        const uint32_t len = rl[r];
+        for (uint32_t k = 0; k < len; ++k) {
+            const long long d = (long long) ja[(uint64_t) k * pitch + r] - (long long) r;
+            lo = min(lo, d);
+            hi = max(hi, d);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomicMin(mn, lo);
+        atomicMax(mx, hi);
+    }
+}
+__global__ void ell_make_idx16_kernel(const uint32_t* __restrict__ ja, const uint32_t* __restrict__ rl, uint64_t pitch, uint32_t M, uint32_t K,
+                                      int32_t base, uint16_t* __restrict__ ja16) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const uint32_t len = rl[r];
+    for (uint32_t k = 0; k < K; ++k)
+        ja16[(uint64_t) k * pitch + r] = k < len ? (uint16_t) ((long long) ja[(uint64_t) k * pitch + r] - (long long) r - base) : (uint16_t) 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -26,13 +26,13 @@
 // roundings => bit-identical to sgemvSerial (src/SpMV_CSR_OMP.c:229-250) when the CSR rows are column-sorted.
 #pragma once
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace spmvb200 {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_stream(const uint16_t* p) { return (uint32_t) __ldcs(reinterpret_cast<const unsigned short*>(p)); }
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

@@ -100,6 +100,10 @@ class DeviceSpmat:
         check(lib().spmvb200_adaptive_choice(self.handle, buf, 64), "adaptive_choice")
         return buf.value.decode()
 
+    @property
+    def index_bits(self):
+        return int(lib().spmvb200_index_bits(self.handle))
+
     def supports(self, kind):
         return bool(lib().spmvb200_kind_supported(self.handle, kind))
 
