@@ -142,6 +142,37 @@ int spmvb200_adaptive_choice(const spmvb200_matrix* m, char* name, size_t len);
  * -- the engine picks its own launch geometry. */
 int spmvb200_spmv_device(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, void* stream);
 
+/* Same launch, with FUSED OUTPUT DELIVERY for x <- y iterations over the GPUs of one box: besides
+ * d_y, the kernel that computes row r stores it to dst[p][r + row_offset] for every destination p whose range
+ * [lo[p], hi[p]) contains the global index r + row_offset.  Destinations are device-visible pointers -- typically the next
+ * iteration's x on the other GPUs, mapped with spmvb200_ipc_open -- so the all-gather (for banded matrices: the halo
+ * exchange) happens as posted NVLink stores while the SpMV is still running, not as a collective after it.  The ELL
+ * column-major and x-window kernels deliver from their epilogue; other kinds add one pass over y.  A cross-GPU barrier
+ * (spmvb200_peer_barrier) must separate an iteration's deliveries from the next iteration's reads. */
+typedef struct {
+    int      n;          /* destinations, 0..8 */
+    double*  dst[8];
+    uint64_t lo[8], hi[8];
+    uint64_t row_offset; /* global index of the handle's row 0 */
+} spmvb200_push;
+int spmvb200_spmv_device_push(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, const spmvb200_push* push, void* stream);
+
+/* Peer-memory plumbing for one-process-per-GPU jobs: export a cudaMalloc'ed buffer as a 64-byte CUDA IPC handle, map
+ * another process's handle (peer access is enabled on first use), unmap. */
+int spmvb200_ipc_export(void* d_ptr, unsigned char handle[64]);
+int spmvb200_ipc_open(const unsigned char handle[64], void** d_ptr);
+int spmvb200_ipc_close(void* d_ptr);
+/* Barrier across the n GPUs of a box, as a one-block kernel on `stream`: d_flags[q] is GPU q's flag array (n zero-initialised
+ * uint32_t; the local one for q == rank, peer-mapped otherwise); epoch must grow by one per use.  Every GPU's earlier work on
+ * its stream (including stores to peer memory) is visible to the others' later work. */
+int spmvb200_peer_barrier(uint32_t* const* d_flags, int n, int rank, uint32_t epoch, void* stream);
+
+/* Iterated SpMV on one GPU (square matrices): x <- A x, `iters` times, ping-pong between d_a (holds x on entry) and d_b; the
+ * result is in d_b if iters is odd, else in d_a.  use_graph != 0 captures the launch pair in a CUDA graph (no launch latency
+ * between consecutive SpMVs).  *total_ms (may be NULL) = CUDA-event time of all iterations.  Synchronises before returning. */
+int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a, double* d_b, int iters, int use_graph, void* stream,
+                            float* total_ms);
+
 /* Host-buffer SpMV with the semantics of the reference's SPMV_INTERF
  *   int f(spmat* mat, double* x, CONFIG* cfg, double* y)        src/include/SpMV.h:63-64
  * x (N doubles) is copied to the device, the kernel runs, y (rows doubles) is copied back; the call
@@ -205,6 +236,10 @@ int spmvb200_synth_rmat_csr_device(int scale, uint64_t n_edges, uint64_t seed, s
 /* x_i = U(-1,1) * scale, hashed from (seed, i) */
 int spmvb200_synth_vector_host(uint64_t seed, uint64_t begin, uint64_t end, double scale, double* x);
 int spmvb200_synth_vector_device(uint64_t seed, uint64_t begin, uint64_t end, double scale, double* d_x);
+
+/* smallest / largest column id a CSR handle references: the part of x its rows read (halo planning of the multi-GPU iteration;
+ * both 0 for a handle without non-zeros) */
+int spmvb200_col_range(const spmvb200_matrix* m, uint64_t* col_min, uint64_t* col_max);
 
 /* copy a handle's narrow CSR arrays back to the host (tests / CPU baseline on device-built matrices) */
 int spmvb200_csr_download(const spmvb200_matrix* m, uint64_t* irp, uint64_t* ja, double* as);

@@ -17,6 +17,11 @@ class SpmvB200Error(RuntimeError):
     pass
 
 
+class Push(C.Structure):
+    """spmvb200_push: extra destinations of an SpMV's output rows (include/spmv_b200.h)."""
+    _fields_ = [("n", C.c_int), ("dst", C.c_void_p * 8), ("lo", C.c_uint64 * 8), ("hi", C.c_uint64 * 8), ("row_offset", C.c_uint64)]
+
+
 class Synth(C.Structure):
     _fields_ = [("kind", C.c_int), ("seed", C.c_uint64), ("p0", C.c_uint64), ("p1", C.c_uint64), ("p2", C.c_uint64),
                 ("p3", C.c_uint64)]
@@ -47,6 +52,12 @@ _SIGS = {
     "spmvb200_kind_name": (C.c_char_p, [C.c_int]),
     "spmvb200_adaptive_choice": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "spmvb200_spmv_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "spmvb200_spmv_device_push": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(Push), _vp]),
+    "spmvb200_ipc_export": (C.c_int, [_vp, _vp]),
+    "spmvb200_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "spmvb200_ipc_close": (C.c_int, [_vp]),
+    "spmvb200_peer_barrier": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint32, _vp]),
+    "spmvb200_iterate_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_float)]),
     "spmvb200_spmv_host": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(C.c_float)]),
     "spmvb200_time_device": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "spmvb200_cached_spmv": (C.c_int, [_vp, C.c_int, C.c_int, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double)]),
@@ -65,6 +76,7 @@ _SIGS = {
     "spmvb200_synth_rmat_csr_device": (C.c_int, [C.c_int, _u64, _u64, C.POINTER(_vp)]),
     "spmvb200_synth_vector_host": (C.c_int, [_u64, _u64, _u64, C.c_double, _vp]),
     "spmvb200_synth_vector_device": (C.c_int, [_u64, _u64, _u64, C.c_double, _vp]),
+    "spmvb200_col_range": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "spmvb200_csr_download": (C.c_int, [_vp, _vp, _vp, _vp]),
 }
 EXPORTS = tuple(sorted(_SIGS))

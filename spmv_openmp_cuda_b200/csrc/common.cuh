@@ -122,6 +122,22 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
 // x gather: read-only path, normal L1/L2 allocation (we WANT x to stay cached)
 __device__ __forceinline__ double ld_x(const double* x, uint32_t c) { return __ldg(x + c); }
 
+// Fused output delivery (multi-GPU x <- y iterations): besides y[row], the kernel that computes a row stores it to every
+// destination that wants global row (row + row_offset) -- peer-mapped vectors of the other GPUs of the box, written over
+// NVLink as posted stores while the SpMV is still running (the all-gather is the kernel's epilogue, not a collective after it).
+struct PushArgs {
+    int n;
+    double* dst[8];
+    uint32_t lo[8], hi[8];
+    uint32_t row_offset;
+};
+__device__ __forceinline__ void push_out(const PushArgs& p, uint32_t row, double v) {
+    const uint32_t g = row + p.row_offset;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < p.n && g >= p.lo[i] && g < p.hi[i]) p.dst[i][g] = v;
+}
+
 template <int LANES>
 __device__ __forceinline__ double subwarp_sum(double v) {
 #pragma unroll

@@ -20,6 +20,9 @@
 namespace spmvb200 {
 thread_local char g_err[512] = "";
 thread_local int g_quiet = 0;
+// output delivery of the launch in progress (spmvb200_spmv_device_push); n == 0: none
+static thread_local PushArgs g_push = {};
+static thread_local bool g_push_fused = false;  // set by a launcher whose kernel delivered the rows itself
 static unsigned long long g_launches = 0;
 }  // namespace spmvb200
 using namespace spmvb200;
@@ -851,10 +854,11 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
     static const bool no_exit = getenv("SPMVB200_ELL_NO_EARLY_EXIT") != nullptr;  // developer knob: walk all K slots like the reference
     if (m->ja16 && !no_exit)
         ell_colmajor_kernel<4, BLOCK, true><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1,
-                                                                                                           (uint32_t) m->K, m->ja16_base, x, y);
+                                                                                                           (uint32_t) m->K, m->ja16_base, x, y, g_push);
     else
         ell_colmajor_kernel<4, BLOCK, false><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0,
-                                                                                                            (uint32_t) r1, (uint32_t) m->K, 0, x, y);
+                                                                                                            (uint32_t) r1, (uint32_t) m->K, 0, x, y, g_push);
+    g_push_fused = true;
     ++g_launches;
 }
 
@@ -870,7 +874,8 @@ static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, c
     }
     const bool persist = m->xw_mode == 1;
     xwin_kernel<NW, ACC, UMAX><<<persist ? m->xw_ncta : m->xw_nrb, 32 * NW, smem, st>>>(persist ? m->xw_cta_rb : nullptr, m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
-                                                                 (uint32_t) m->M, (uint32_t) m->N, m->xw_W, m->xw_nbuf, ((uintptr_t) x & 15) == 0);
+                                                                 (uint32_t) m->M, (uint32_t) m->N, m->xw_W, m->xw_nbuf, ((uintptr_t) x & 15) == 0, g_push);
+    g_push_fused = true;
     ++g_launches;
     return 0;
 }
@@ -1097,17 +1102,138 @@ static int prefer_smem_once() {
     return 0;
 }
 
+static int ensure_events(spmvb200_matrix* m) {
+    if (!m->ev0) CU_TRY(cudaEventCreate(&m->ev0));
+    if (!m->ev1) CU_TRY(cudaEventCreate(&m->ev1));
+    return 0;
+}
+
 extern "C" int spmvb200_spmv_device(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, void* stream) {
     if (!m || !d_x || !d_y) return fail("spmv_device: null argument");
     if (prefer_smem_once()) return 1;
     return launch(m, kind, d_x, d_y, (cudaStream_t) stream);
 }
 
-static int ensure_events(spmvb200_matrix* m) {
-    if (!m->ev0) CU_TRY(cudaEventCreate(&m->ev0));
-    if (!m->ev1) CU_TRY(cudaEventCreate(&m->ev1));
+extern "C" int spmvb200_spmv_device_push(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, const spmvb200_push* push,
+                                         void* stream) {
+    if (!m || !d_x || !d_y || !push) return fail("spmv_device_push: null argument");
+    if (push->n < 0 || push->n > 8) return fail("spmv_device_push: %d destinations (at most 8)", push->n);
+    if (prefer_smem_once()) return 1;
+    // first use of a self-tuning kind: tune without deliveries (the tuning run launches every candidate)
+    if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0))
+        if (launch(m, kind, d_x, d_y, (cudaStream_t) stream)) return 1;
+    PushArgs a = {};
+    a.n = push->n;
+    for (int i = 0; i < push->n; ++i) {
+        if (!push->dst[i] || push->hi[i] > 0xffffffffull || push->lo[i] > push->hi[i]) return fail("spmv_device_push: bad destination %d", i);
+        a.dst[i] = push->dst[i];
+        a.lo[i] = (uint32_t) push->lo[i];
+        a.hi[i] = (uint32_t) push->hi[i];
+    }
+    if (push->row_offset + m->M > 0xffffffffull) return fail("spmv_device_push: row offset too large");
+    a.row_offset = (uint32_t) push->row_offset;
+    g_push = a;
+    g_push_fused = false;
+    const int rc = launch(m, kind, d_x, d_y, (cudaStream_t) stream);
+    const bool fused = g_push_fused;
+    g_push = PushArgs{};
+    if (rc) return 1;
+    if (!fused && a.n && m->M) {  // kernels without the fused epilogue: one more pass over y
+        push_rows_kernel<<<592, 256, 0, (cudaStream_t) stream>>>(d_y, (uint32_t) m->M, a);
+        ++g_launches;
+        CU_TRY(cudaPeekAtLastError());
+    }
     return 0;
 }
+
+// ---- peer memory plumbing for one-process-per-GPU jobs (CUDA IPC) and the cross-GPU barrier
+extern "C" int spmvb200_ipc_export(void* d_ptr, unsigned char handle[64]) {
+    if (!d_ptr || !handle) return fail("ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+extern "C" int spmvb200_ipc_open(const unsigned char handle[64], void** d_ptr) {
+    if (!d_ptr || !handle) return fail("ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int spmvb200_ipc_close(void* d_ptr) {
+    CU_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+extern "C" int spmvb200_peer_barrier(uint32_t* const* d_flags, int n, int rank, uint32_t epoch, void* stream) {
+    if (!d_flags || n < 1 || n > 8 || rank < 0 || rank >= n) return fail("peer_barrier: bad arguments");
+    BarrierArgs b = {};
+    for (int i = 0; i < n; ++i) {
+        if (!d_flags[i]) return fail("peer_barrier: null flag array %d", i);
+        b.flags[i] = d_flags[i];
+    }
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t) stream>>>(b, n, rank, epoch);
+    CU_TRY(cudaPeekAtLastError());
+    return 0;
+}
+
+// ---- iterated SpMV on one GPU: x <- A x, `iters` times, ping-pong between two vectors; the launch pair is captured in a CUDA
+// graph so that back-to-back SpMVs are not separated by launch latency
+extern "C" int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a, double* d_b, int iters, int use_graph, void* stream,
+                                       float* total_ms) {
+    if (!m || !d_a || !d_b || iters < 0) return fail("iterate_device: bad arguments");
+    if (m->M != m->N) return fail("iterate_device: matrix is %llu x %llu, iteration needs a square matrix", (unsigned long long) m->M, (unsigned long long) m->N);
+    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
+    if (prefer_smem_once() || ensure_events(m)) return 1;
+    cudaStream_t st = (cudaStream_t) stream;
+    cudaStream_t own = nullptr;
+    if (use_graph && (st == nullptr || st == cudaStreamLegacy)) {  // the legacy default stream cannot be captured
+        CU_TRY(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+        CU_TRY(cudaDeviceSynchronize());
+        st = own;
+    }
+    int rc = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    do {
+        // self-tuning kinds tune here (cannot happen inside a capture); d_b is scratch at this point
+        if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0))
+            if ((rc = launch(m, kind, d_a, d_b, st))) break;
+        const int pairs = iters / 2;
+        unsigned long long per_replay = 0;
+        if (use_graph && pairs > 0) {
+            const unsigned long long l0 = g_launches;
+            if ((rc = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess)) break;
+            int r1 = launch(m, kind, d_a, d_b, st);
+            int r2 = r1 ? 1 : launch(m, kind, d_b, d_a, st);
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (r1 || r2 || ce != cudaSuccess) { rc = 1; if (ce != cudaSuccess) fail("iterate_device: capture failed: %s", cudaGetErrorString(ce)); break; }
+            if ((rc = cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess)) break;
+            per_replay = g_launches - l0;  // kernels inside the graph: counted per replay below
+            g_launches = l0;
+        }
+        if ((rc = cudaEventRecord(m->ev0, st) != cudaSuccess)) break;
+        for (int i = 0; i < pairs && !rc; ++i) {
+            if (exec) { rc = cudaGraphLaunch(exec, st) != cudaSuccess; g_launches += per_replay; }
+            else rc = launch(m, kind, d_a, d_b, st) || launch(m, kind, d_b, d_a, st);
+        }
+        if (!rc && (iters & 1)) rc = launch(m, kind, d_a, d_b, st);
+        if (rc) break;
+        if ((rc = cudaEventRecord(m->ev1, st) != cudaSuccess)) break;
+        if ((rc = cudaEventSynchronize(m->ev1) != cudaSuccess)) break;
+        if (total_ms && (rc = cudaEventElapsedTime(total_ms, m->ev0, m->ev1) != cudaSuccess)) break;
+    } while (0);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (own) cudaStreamDestroy(own);
+    if (rc) {
+        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("iterate_device: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    return 0;
+}
+
 
 // ---- pipelined host path --------------------------------------------------------------------------
 // which kernel a (kind, handle) pair runs chunk-wise: 0/1 stream variants (+10 exact), 2.. vector lanes, 100 ELL column-major
@@ -1318,6 +1444,38 @@ extern "C" int spmvb200_time_device(spmvb200_matrix* m, int kind, const double* 
 extern "C" int spmvb200_adaptive_choice(const spmvb200_matrix* m, char* name, size_t len) {
     if (!m || !name || !len) return fail("adaptive_choice: bad arguments");
     snprintf(name, len, "%s", m->tuned >= 0 ? CAND_NAME[m->tuned] : "");
+    return 0;
+}
+
+// smallest and largest column id a CSR handle references (which part of x its rows read: halo planning of the multi-GPU iteration)
+__global__ void colminmax_kernel(const uint32_t* __restrict__ ja, uint64_t n, uint32_t* __restrict__ out) {
+    uint32_t mn = 0xffffffffu, mx = 0;
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t c = ja[i];
+        mn = min(mn, c);
+        mx = max(mx, c);
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, mn);
+        atomicMax(out + 1, mx);
+    }
+}
+extern "C" int spmvb200_col_range(const spmvb200_matrix* m, uint64_t* col_min, uint64_t* col_max) {
+    if (!m || m->format != SPMVB200_FMT_CSR || !col_min || !col_max) return fail("col_range: needs a CSR handle");
+    uint32_t* d = nullptr;
+    CU_TRY(cudaMalloc(&d, 8));
+    const uint32_t init[2] = {0xffffffffu, 0u};
+    CU_TRY(cudaMemcpy(d, init, 8, cudaMemcpyHostToDevice));
+    if (m->NZ) colminmax_kernel<<<1184, 256>>>(m->ja, m->NZ, d);
+    uint32_t h[2];
+    cudaError_t e = cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail("col_range: %s", cudaGetErrorString(e));
+    *col_min = m->NZ ? h[0] : 0;
+    *col_max = m->NZ ? h[1] : 0;
     return 0;
 }
 

@@ -327,7 +327,8 @@ __device__ __forceinline__ uint32_t ld_stream(const uint16_t* p) { return (uint3
 template <int UNROLL, int BLOCK, bool IDX16>
 __global__ void __launch_bounds__(BLOCK)
 ell_colmajor_kernel(const double* __restrict__ as, const void* __restrict__ ja_any, const uint32_t* __restrict__ rl,
-                    uint64_t pitch, uint32_t row_begin, uint32_t M, uint32_t K, int32_t base, const double* __restrict__ x, double* __restrict__ y) {
+                    uint64_t pitch, uint32_t row_begin, uint32_t M, uint32_t K, int32_t base, const double* __restrict__ x, double* __restrict__ y,
+                    const PushArgs push) {
     using idx_t = typename std::conditional<IDX16, uint16_t, uint32_t>::type;
     const uint32_t row = row_begin + blockIdx.x * BLOCK + threadIdx.x;  // rows [row_begin, M)
     const bool live = row < M;
@@ -361,7 +362,30 @@ ell_colmajor_kernel(const double* __restrict__ as, const void* __restrict__ ja_a
             acc = __dadd_rn(acc, __dmul_rn(v, ld_x(x, c)));
         }
     }
-    if (live) y[row] = acc;
+    if (live) {
+        y[row] = acc;
+        if (push.n) push_out(push, row, acc);
+    }
+}
+// kinds whose kernels have no fused delivery: copy the finished y to the destinations that want it
+__global__ void push_rows_kernel(const double* __restrict__ y, uint32_t M, const PushArgs push) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < M; r += stride) push_out(push, r, y[r]);
+}
+// barrier across the GPUs of a box: flags[q] is GPU q's flag array (peer-mapped on the others), epoch grows by one per use.
+// Thread p tells GPU p "rank has arrived at epoch", then waits for GPU p's arrival.  System-scope release / acquire.
+struct BarrierArgs {
+    uint32_t* flags[8];
+};
+__global__ void peer_barrier_kernel(const BarrierArgs b, int n, int rank, uint32_t epoch) {
+    const int p = threadIdx.x;
+    if (p >= n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(b.flags[p] + rank), "r"(epoch) : "memory");
+    uint32_t seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(b.flags[rank] + p) : "memory");
+    } while ((int32_t) (seen - epoch) < 0);
 }
 // range of (col - row) over the valid slots of a column-major ELL, then the 16-bit offsets themselves
 __global__ void ell_delta_range_kernel(const uint32_t* __restrict__ ja, const uint32_t* __restrict__ rl, uint64_t pitch, uint32_t M,

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(32 * NW, 1)
 xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb_tile0, const uint32_t* __restrict__ tile_win,
             const uint32_t* __restrict__ grp_off, const uint16_t* __restrict__ cp, const uint16_t* __restrict__ col,
             const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y, uint32_t M, uint32_t N, uint32_t W,
-            uint32_t nbuf, int x_aligned) {
+            uint32_t nbuf, int x_aligned, const PushArgs push) {
     constexpr uint32_t R = 32u * NW * ACC, G = NW * ACC;
     extern __shared__ __align__(128) unsigned char xw_smem[];
     double* xs = reinterpret_cast<double*>(xw_smem);                              // nbuf windows of W (+2) doubles
@@ -186,7 +186,10 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
 #pragma unroll
         for (int a = 0; a < ACC; ++a) {
             const uint32_t row = rb * R + a * NW * 32u + myrow;
-            if (row < M) y[row] = 0.0;
+            if (row < M) {
+                y[row] = 0.0;
+                if (push.n) push_out(push, row, 0.0);
+            }
         }
         if (++rb < rb1) t_end = __ldg(rb_tile0 + rb + 1);
     }
@@ -249,7 +252,10 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
 #pragma unroll
             for (int a = 0; a < ACC; ++a) {
                 const uint32_t row = rb * R + a * NW * 32u + myrow;
-                if (row < M) y[row] = acc[a];
+                if (row < M) {
+                    y[row] = acc[a];
+                    if (push.n) push_out(push, row, acc[a]);
+                }
                 acc[a] = 0.0;
             }
             if (++rb < rb1) t_end = __ldg(rb_tile0 + rb + 1);

@@ -108,3 +108,121 @@ class RowBlockSpmv:
 
 
 Config_none = engine.Config()
+
+
+def needed_rows(splits, col_ranges, rank):
+    """Which of `rank`'s rows [r0, r1) each other rank reads as columns of x: the intersection of [r0, r1) with that
+    rank's referenced column range [cmin, cmax] (None = the rank has no non-zeros).  Returns {peer: (lo, hi)} with lo < hi:
+    for a banded matrix this is the halo next to the block boundary, for an unstructured one the whole block."""
+    r0, r1 = splits[rank], splits[rank + 1]
+    out = {}
+    for p, cr in enumerate(col_ranges):
+        if p == rank or cr is None:
+            continue
+        lo, hi = max(r0, int(cr[0])), min(r1, int(cr[1]) + 1)
+        if lo < hi:
+            out[p] = (lo, hi)
+    return out
+
+
+class RowBlockIterate:
+    """x <- A x, repeated, over the GPUs of one box: A is row-block partitioned (one process per GPU,
+    `dmat` = this rank's rows [r0, r1) with global column ids), x is replicated.
+
+    mode="push": the exchange is FUSED into the SpMV -- every rank maps the other ranks' x buffers (CUDA IPC) and its kernel
+    stores each finished row straight into the next x of the ranks that read it (posted NVLink stores, only the rows a
+    peer's columns reference), followed by a one-block flag barrier across the GPUs; no collective library call per iteration.
+    mode="nccl": the plain way -- SpMV into the local y slice, then an NCCL all-gather of the slices (equal slices only).
+    torch.distributed is used for the one-time rendezvous (handles, column ranges) in both modes."""
+
+    def __init__(self, dmat, splits, kind, group=None, mode="push", halo=True):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.mode, self.kind, self.dmat = torch, dist, group, mode, kind, dmat
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.splits = [int(v) for v in splits]
+        self.r0, self.r1 = self.splits[self.rank], self.splits[self.rank + 1]
+        self.N = dmat.N
+        assert dmat.M == self.r1 - self.r0 and self.splits[-1] == self.N, "square matrix, row-block partitioned"
+        self.epoch = 0
+        self.peer = {}
+        lib, C = engine.lib(), engine.C
+        if mode == "nccl":
+            assert len({b - a for a, b in zip(self.splits[:-1], self.splits[1:])}) == 1, "all-gather needs equal slices"
+            self.x = [torch.zeros(self.N, dtype=torch.float64, device="cuda") for _ in range(2)]
+            self.y = torch.zeros(self.r1 - self.r0, dtype=torch.float64, device="cuda")
+            return
+        assert self.world <= 8
+        self.bufs = [engine.DeviceVector(self.N), engine.DeviceVector(self.N)]
+        self.flags = engine.DeviceVector(8)  # 64 bytes, used as uint32 flags
+        for v in self.bufs + [self.flags]:
+            v.fill_bytes(0)
+        mine = []
+        for v in self.bufs + [self.flags]:
+            h = (C.c_ubyte * 64)()
+            engine.check(lib.spmvb200_ipc_export(v.data_ptr(), h), "ipc_export")
+            mine.append(bytes(h))
+        cr = dmat.col_range if dmat.NZ else None
+        allh = [None] * self.world
+        dist.all_gather_object(allh, (mine, cr), group=group)
+        self.col_ranges = [a[1] for a in allh]
+        for p in range(self.world):
+            if p == self.rank:
+                self.peer[p] = [v.data_ptr() for v in self.bufs + [self.flags]]
+                continue
+            ptrs = []
+            for hb in allh[p][0]:
+                out = C.c_void_p()
+                engine.check(lib.spmvb200_ipc_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(out)), "ipc_open")
+                ptrs.append(out.value)
+            self.peer[p] = ptrs
+        # halo=False: deliver the whole block to everybody (a fused all-gather) even where only a halo is read
+        self.need = needed_rows(self.splits, self.col_ranges if halo else [(0, self.N - 1)] * self.world, self.rank)
+        self.flag_ptrs = (C.c_void_p * self.world)(*[self.peer[p][2] for p in range(self.world)])
+        dist.barrier(group=group)
+
+    # ---- x on entry (replicated: every rank fills the whole vector)
+    def set_x(self, x_host):
+        if self.mode == "nccl":
+            self.x[0].copy_(self.torch.from_numpy(np.ascontiguousarray(x_host)))
+        else:
+            engine.check(engine.lib().spmvb200_h2d(self.bufs[0].data_ptr(), engine.ptr(np.ascontiguousarray(x_host, dtype=np.float64)),
+                                                   self.N * 8), "h2d")
+        self.cur = 0
+
+    def step(self, stream=None):
+        lib = engine.lib()
+        cur, nxt = self.cur, 1 - self.cur
+        if self.mode == "nccl":
+            engine._launch(self.kind, self.dmat, self.x[cur], Config_none, self.y, stream)
+            self.dist.all_gather_into_tensor(self.x[nxt], self.y, group=self.group)
+        else:
+            peers = sorted(self.need)
+            engine.spmv_push(self.kind, self.dmat, self.bufs[cur].data_ptr(), self.bufs[nxt].data_ptr() + self.r0 * 8,
+                             [self.peer[p][nxt] for p in peers], [self.need[p][0] for p in peers], [self.need[p][1] for p in peers],
+                             self.r0, stream)
+            self.epoch += 1
+            engine.check(lib.spmvb200_peer_barrier(self.flag_ptrs, self.world, self.rank, self.epoch, stream), "peer_barrier")
+        self.cur = nxt
+
+    def my_slice(self):
+        """this rank's rows of the current x, as a host array"""
+        if self.mode == "nccl":
+            return self.x[self.cur][self.r0:self.r1].cpu().numpy()
+        out = np.empty(self.r1 - self.r0, dtype=np.float64)
+        engine.check(engine.lib().spmvb200_sync(), "sync")
+        engine.check(engine.lib().spmvb200_d2h(engine.ptr(out), self.bufs[self.cur].data_ptr() + self.r0 * 8, out.nbytes), "d2h")
+        return out
+
+    def close(self):
+        if self.mode == "push":
+            engine.check(engine.lib().spmvb200_sync(), "sync")
+            self.dist.barrier(group=self.group)
+            for p, ptrs in self.peer.items():
+                if p != self.rank:
+                    for q in ptrs:
+                        engine.lib().spmvb200_ipc_close(q)
+            self.peer = {}
+            self.dist.barrier(group=self.group)
+            for v in self.bufs + [self.flags]:
+                v.free()

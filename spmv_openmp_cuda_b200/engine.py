@@ -130,6 +130,13 @@ class DeviceSpmat:
         check(lib().spmvb200_xwin_info(self.handle, C.byref(R), C.byref(W), C.byref(nt), C.byref(ring), C.byref(moved)), "xwin_info")
         return dict(rows_per_block=R.value, window_cols=W.value, ntiles=nt.value, ring=ring.value, moved_bytes=moved.value)
 
+    @property
+    def col_range(self):
+        """(smallest, largest) column id referenced -- which part of x these rows read."""
+        lo, hi = C.c_uint64(), C.c_uint64()
+        check(lib().spmvb200_col_range(self.handle, C.byref(lo), C.byref(hi)), "col_range")
+        return lo.value, hi.value
+
     def download_csr(self):
         irp = np.empty(self.M + 1, dtype=np.uint64)
         ja = np.empty(self.NZ, dtype=np.uint64)
@@ -298,6 +305,26 @@ def time_kernel(kind, m, v, outV, reps=25, flush_l2=False):
     t = np.zeros(reps, dtype=np.float32)
     check(lib().spmvb200_time_device(m.handle, kind, ptr(v), ptr(outV), reps, int(flush_l2), ptr(t)), "time_device")
     return t
+
+
+def iterate(kind, m, a, b, iters, use_graph=True, stream=None):
+    """x <- A x, `iters` times on one GPU, ping-pong between device vectors a (x on entry) and b; the result is in b if iters
+    is odd, else in a.  Returns the CUDA-event time of all iterations in ms."""
+    ms = C.c_float(0)
+    check(lib().spmvb200_iterate_device(m.handle, kind, ptr(a), ptr(b), int(iters), int(bool(use_graph)), stream, C.byref(ms)), "iterate_device")
+    return ms.value
+
+
+def spmv_push(kind, m, v, outV, dst, lo, hi, row_offset, stream=None):
+    """SpMV with fused output delivery: row r also goes to dst[p][r + row_offset] when lo[p] <= r + row_offset < hi[p]
+    (dst: device pointers, e.g. the next x of the other GPUs mapped over CUDA IPC)."""
+    p = capi.Push()
+    p.n = len(dst)
+    for i, (d, a_, b_) in enumerate(zip(dst, lo, hi)):
+        p.dst[i], p.lo[i], p.hi[i] = ptr(d), int(a_), int(b_)
+    p.row_offset = int(row_offset)
+    check(lib().spmvb200_spmv_device_push(m.handle, kind, ptr(v), ptr(outV), C.byref(p), stream), "spmv_device_push")
+    return EXIT_SUCCESS
 
 
 def spmv_host(kind, m, x, y):

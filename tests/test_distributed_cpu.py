@@ -78,3 +78,17 @@ def test_partition_functions():
     pts = row_partition_by_nnz(np.arange(0, 33 * 32, 32, dtype=np.uint64), 8)
     assert pts == [0, 4, 8, 12, 16, 20, 24, 28, 32]
     assert row_partition_by_nnz(np.zeros(5, dtype=np.uint64), 3) == [0, 0, 0, 4]
+
+
+def test_needed_rows_halo_planning():
+    """Which of a rank's rows the other ranks read (fused delivery of the multi-GPU iteration): halos for a banded matrix,
+    whole blocks for an unstructured one, nothing for a rank without non-zeros."""
+    from spmv_openmp_cuda_b200.distributed import needed_rows
+    splits = [0, 100, 200, 300]
+    banded = [(0, 120), (80, 230), (170, 299)]
+    assert needed_rows(splits, banded, 0) == {1: (80, 100)}
+    assert needed_rows(splits, banded, 1) == {0: (100, 121), 2: (170, 200)}
+    assert needed_rows(splits, banded, 2) == {1: (200, 231)}
+    dense = [(0, 299)] * 3
+    assert needed_rows(splits, dense, 1) == {0: (100, 200), 2: (100, 200)}
+    assert needed_rows(splits, [(0, 50), None, (250, 299)], 1) == {}

@@ -201,6 +201,59 @@ def test_adaptive_child_formats(sp, orc, cand, name, monkeypatch):
     np.testing.assert_array_equal(dy.to_host(), y_ref)
 
 
+def test_iterated_spmv_graph_and_plain(sp, orc):
+    """x <- A x repeated: CUDA-graph replay and plain launches give the oracle's iterates bit for bit."""
+    mat = sp.synth.host_csr(sp.synth.lap2d(96))
+    x0 = sp.synth.host_vector(mat.N) * 1e4
+    refs = [x0]
+    for _ in range(7):
+        refs.append(orc.sgemv_serial(mat.IRP, mat.JA, mat.AS, refs[-1]))
+    d_csr = sp.spMatCpyCSR(mat)
+    handles = [(d_csr, sp.CSR_ROWS), (d_csr.to_ell(sp.FMT_ELL_COLMAJOR), sp.ELL_ROWS), (d_csr.to_xwin(512, 512), sp.XWIN_ROWS),
+               (d_csr.to_sell(64), sp.SELL_ROWS)]
+    for dm, kind in handles:
+        for iters in (0, 1, 6, 7):
+            for graph in (True, False):
+                a, b = sp.DeviceVector.from_host(x0), sp.DeviceVector(mat.N)
+                b.fill_bytes(0xFF)
+                ms = sp.iterate(kind, dm, a, b, iters, use_graph=graph)
+                got = (b if iters % 2 else a).to_host()
+                np.testing.assert_array_equal(got, refs[iters], err_msg="kind %d iters %d graph %s" % (kind, iters, graph))
+                assert ms >= 0
+    rect = sp.spMatCpyCSR(sp.Spmat.csr(7, np.array([0, 1, 2], dtype=np.uint64), np.array([0, 6], dtype=np.uint64), np.ones(2)))
+    with pytest.raises(sp.SpmvB200Error, match="square"):
+        sp.iterate(sp.CSR_ROWS, rect, sp.DeviceVector(7), sp.DeviceVector(7), 2)
+
+
+def test_fused_output_delivery(sp, orc):
+    """spmvb200_spmv_device_push: rows inside a destination's range land there (at their global index), nothing else is
+    touched; fused epilogue (ELL, x-window) and the extra pass (other kinds) agree."""
+    mat = sp.synth.host_csr(sp.synth.banded(9000, 32, 700))
+    x = sp.synth.host_vector(mat.N)
+    y_ref = _oracle_y(orc, mat, x)
+    a, b = 2000, 7000  # this "rank" owns rows [a, b) of a larger job
+    d_csr = sp.spMatCpyCSR(mat, a, b)
+    handles = [(d_csr, sp.CSR_ROWS), (d_csr, sp.CSR_ROWS_WARP), (d_csr, sp.CSR_ADAPTIVE), (d_csr.to_ell(sp.FMT_ELL_COLMAJOR), sp.ELL_ROWS),
+               (d_csr.to_xwin(512, 1024), sp.XWIN_ROWS), (d_csr.to_xwin(1024, 8192), sp.XWIN_ROWS)]
+    dx = sp.DeviceVector.from_host(x)
+    ranges = [(1500, 2600), (6990, 9000), (3000, 3001)]
+    for dm, kind in handles:
+        dy = sp.DeviceVector(b - a)
+        dsts = [sp.DeviceVector(mat.M) for _ in ranges]
+        for d in dsts + [dy]:
+            d.fill_bytes(0xFF)
+        sp.spmv_push(kind, dm, dx, dy, dsts, [r[0] for r in ranges], [r[1] for r in ranges], a)
+        sp.capi.check(sp.capi.lib().spmvb200_sync(), "sync")
+        exact = kind in (sp.CSR_ROWS, sp.ELL_ROWS, sp.XWIN_ROWS)
+        y = dy.to_host()
+        (np.testing.assert_array_equal if exact else np.testing.assert_allclose)(y, y_ref[a:b])
+        for d, (lo, hi) in zip(dsts, ranges):
+            got = d.to_host()
+            lo2, hi2 = max(lo, a), min(hi, b)
+            np.testing.assert_array_equal(got[lo2:hi2], y[lo2 - a:hi2 - a])
+            assert np.all(np.isnan(got[:lo2])) and np.all(np.isnan(got[hi2:])), "rows outside the range must stay untouched"
+
+
 def test_long_row_split_is_deterministic(sp):
     """Rows split across CTAs are combined in segment order by the last arriver: run-to-run identical."""
     mat = sp.synth.rmat_host_csr(14, 16)
