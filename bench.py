@@ -32,7 +32,11 @@ sys.path.insert(0, ROOT)
 # libgomp reads OMP_SCHEDULE when it is loaded: set it before anything pulls libgomp in.  The reference's
 # kernels use schedule(runtime); plain "static" crashes its ompGetRuntimeSchedule (ompGetICV.c:43)
 os.environ.setdefault("OMP_SCHEDULE", "nonmonotonic:static")
-os.environ.setdefault("OMP_PROC_BIND", "close")
+if "LOCAL_RANK" not in os.environ or "reference" in sys.argv:
+    # CPU baseline / reference arm only.  NEVER under torchrun for our own arm: with OMP_NUM_THREADS=1 (torchrun's default) a bound
+    # libgomp pins every rank's main thread to the same core, and the ranks then time-slice on it -- measured: a 6.5 ms stall
+    # at every cross-GPU synchronisation point of the end-to-end loop (4.1 ms per step instead of 0.8 at 2 GPUs)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
 if "reference" in sys.argv and "LOCAL_RANK" in os.environ:
     # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU reference arm (rank 0 only) uses all host cores
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
@@ -56,6 +60,8 @@ class ClockSampler:
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz, self._stop, self._t = [], set(), None, False, None
         try:
+            if os.environ.get("BENCH_NO_NVML"):
+                raise RuntimeError("sampling switched off")
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
@@ -181,8 +187,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--half-width", type=int, default=1 << 15, help="cfg4: band half width w")
-    ap.add_argument("--x-dist", default="allgather", choices=["allgather", "bcast"],
-                    help="N>1 e2e: every rank uploads its slice of x then NCCL all-gather (default), or rank 0 uploads all of x then NCCL broadcast")
+    ap.add_argument("--x-dist", default="push", choices=["push", "allgather", "bcast"],
+                    help="N>1 e2e: every rank uploads its slice of x, then either delivers the rows the other ranks read by peer stores + "
+                         "flag barrier (push, default), or NCCL all-gather; or rank 0 uploads all of x then NCCL broadcast")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -245,6 +252,7 @@ def main():
         r0, r1 = rank * rows_per, (rank + 1) * rows_per
         d_csr = synth.device_csr(spec, r0, r1)
         dm = d_csr.to_ell(sp.FMT_ELL_COLMAJOR)
+        col_range = d_csr.col_range
         d_csr.free()
         kind, kname = sp.ELL_ROWS, "ell_colmajor_kernel" + ("<idx16>" if dm.index_bits == 16 else "")
     else:
@@ -252,11 +260,14 @@ def main():
         Mtot = 1 << 25
         r0, r1 = rank * Mtot // nr, (rank + 1) * Mtot // nr
         dm = synth.device_csr(spec, r0, r1)
+        col_range = dm.col_range
         kind, kname = sp.CSR_ADAPTIVE, "csr_adaptive"
     Ncols = dm.N
     tot = torch.tensor([dm.NZ, dm.M], dtype=torch.int64, device="cuda")
-    if world > 1:
+    if world > 1 and "allreduce" not in os.environ.get("BENCH_SKIP", ""):
         dist.all_reduce(tot)
+    elif world > 1:
+        tot *= world
     nnz_total, rows_total = int(tot[0].item()), int(tot[1].item())
     # algorithmic bytes of the GLOBAL SpMV, split evenly: x is counted once for the whole job
     rowmeta = 4 * rows_total if args.workload == "cfg2" else 4 * (rows_total + 1)
@@ -276,7 +287,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    skip = os.environ.get("BENCH_SKIP", "").split(",")
+    for _ in range(0 if "warmup" in skip else args.warmup):
         step()
     sync_all()
     if kind == sp.CSR_ADAPTIVE:
@@ -287,7 +299,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(1 if "kloop" in skip else args.steps):
         step()
     ev1.record()
     sync_all()
@@ -310,21 +322,62 @@ def main():
     xs0, xs1 = rank * Ncols // nr, (rank + 1) * Ncols // nr  # this rank's slice of x (square matrix: its own rows)
     even = Ncols % nr == 0
 
+    dbg = os.environ.get("BENCH_E2E_DEBUG")
+    dbg_t = []
+
+    def mark():
+        if dbg:
+            torch.cuda.synchronize()
+            dbg_t.append(time.perf_counter())
+
+    pusher = None
+    if world > 1 and args.x_dist == "push":
+        from spmv_openmp_cuda_b200.distributed import RowBlockIterate
+
+        class _Rows:  # the handle + the column range of its CSR source
+            M, N, NZ, handle = dm.M, dm.N, dm.NZ, dm.handle
+        _Rows.col_range = col_range
+        allr = [None] * world
+        dist.all_gather_object(allr, (r0, r1))
+        pusher = RowBlockIterate(_Rows, [a_[0] for a_ in allr] + [allr[-1][1]], kind, mode="push")
+        pusher.set_x(hx.numpy())
+
     def e2e_step():
+        mark()
         if world == 1:
             capi.check(lib.spmvb200_spmv_host(dm.handle, kind, hx.data_ptr(), hy.data_ptr(), None), "spmv_host")
+        elif pusher is not None:
+            pusher.load_x_slice(hx.data_ptr() + r0 * 8, stream, after_h2d=mark)  # own slice over own PCIe link, halo rows to the peers, barrier
+            mark()
+            capi.check(lib.spmvb200_spmv_device(dm.handle, kind, pusher.x_ptr(), y.data_ptr(), stream), "spmv_device")
+            mark()
+            capi.check(lib.spmvb200_d2h_async(hy.data_ptr(), y.data_ptr(), dm.M * 8, stream), "d2h_async")
+            capi.check(lib.spmvb200_stream_sync(stream), "stream_sync")
+            mark()
         else:
             if args.x_dist == "allgather" and even:
                 x[xs0:xs1].copy_(hx[xs0:xs1], non_blocking=True)      # every rank: its slice over its own PCIe link
+                mark()
                 dist.all_gather_into_tensor(x, x[xs0:xs1])             # replicate over NVLink / NVSwitch
+                mark()
             else:
                 if rank == 0:
                     x.copy_(hx, non_blocking=True)
                 dist.broadcast(x, src=0)
             step()
+            mark()
             hy.copy_(y, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            mark()
 
+    e2e_stream = None
+    if world > 1 and not os.environ.get("BENCH_E2E_LEGACY_STREAM"):
+        # the end-to-end loop runs on a stream of its own (not the legacy default stream, which synchronises implicitly with
+        # every other blocking stream of the process)
+        e2e_stream = torch.cuda.Stream()
+        e2e_stream.wait_stream(torch.cuda.current_stream())
+        torch.cuda.set_stream(e2e_stream)
+        stream = e2e_stream.cuda_stream
     for _ in range(3):
         e2e_step()
     sync_all()
@@ -340,6 +393,10 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t.item()) / e2e_steps
     e2e_launch = int(lib.spmvb200_launch_count() - launches0) - launches
+    if dbg and world > 1 and len(dbg_t) >= 10:
+        last = dbg_t[-16:]
+        sys.stderr.write("rank %d e2e marks per step [start | h2d | allgather | spmv | d2h+sync], deltas in ms: %s\n" % (
+            rank, " ".join("%.3f" % ((b - a) * 1e3) for a, b in zip(last[:-1], last[1:]))))
     y_check = hy.numpy().copy()
 
     # ---- parity spot check of what was just measured (rank 0, sampled rows, against the oracle)
@@ -364,6 +421,8 @@ def main():
         "e2e": {"value": 2.0 * nnz_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "wall_ms_per_step": wall / e2e_steps,
                 "steps": e2e_steps, "h2d_bytes_per_step": int(Ncols * 8), "d2h_bytes_per_step": int(dm.M * 8 * nr),
                 "path": "spmvb200_spmv_host (pinned host x -> device in pieces, row chunks, y chunks -> pinned host)" if world == 1 else
+                        "per-rank H2D of its x slice, rows the other ranks read delivered by peer stores (CUDA IPC) + flag barrier, "
+                        "spmvb200_spmv_device, per-rank D2H of its y slice" if pusher is not None else
                         ("per-rank H2D of its x slice, NCCL all-gather, spmvb200_spmv_device, per-rank D2H of its y slice"
                          if args.x_dist == "allgather" and even else
                          "rank0 H2D x, NCCL broadcast, spmvb200_spmv_device, per-rank D2H of its y slice")},
@@ -390,6 +449,8 @@ def main():
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "unavailable", "sample": repr(e)}
     if rank == 0:
         emit(out)
+    if pusher is not None:
+        pusher.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

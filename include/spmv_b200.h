@@ -157,6 +157,9 @@ typedef struct {
 } spmvb200_push;
 int spmvb200_spmv_device_push(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, const spmvb200_push* push, void* stream);
 
+/* Deliver rows that already sit in device memory (e.g. this GPU's freshly uploaded slice of x) the same way. */
+int spmvb200_push_rows(const double* d_rows, uint64_t nrows, const spmvb200_push* push, void* stream);
+
 /* Peer-memory plumbing for one-process-per-GPU jobs: export a cudaMalloc'ed buffer as a 64-byte CUDA IPC handle, map
  * another process's handle (peer access is enabled on first use), unmap. */
 int spmvb200_ipc_export(void* d_ptr, unsigned char handle[64]);
@@ -203,6 +206,9 @@ int spmvb200_dfree(void* d_ptr);
 int spmvb200_h2d(void* d_dst, const void* h_src, size_t bytes);
 int spmvb200_d2h(void* h_dst, const void* d_src, size_t bytes);
 int spmvb200_sync(void);
+int spmvb200_h2d_async(void* d_dst, const void* h_src, size_t bytes, void* stream); /* h_src pinned for a true async copy */
+int spmvb200_d2h_async(void* h_dst, const void* d_src, size_t bytes, void* stream);
+int spmvb200_stream_sync(void* stream);
 
 /* ------------------------------------------------------------------ synthetic workloads
  * Seeded, counter-based generators of the BASELINE.json matrices; every row (R-MAT: every edge) is a

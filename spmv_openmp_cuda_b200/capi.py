@@ -67,6 +67,10 @@ _SIGS = {
     "spmvb200_h2d": (C.c_int, [_vp, _vp, C.c_size_t]),
     "spmvb200_d2h": (C.c_int, [_vp, _vp, C.c_size_t]),
     "spmvb200_sync": (C.c_int, []),
+    "spmvb200_h2d_async": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
+    "spmvb200_d2h_async": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
+    "spmvb200_stream_sync": (C.c_int, [_vp]),
+    "spmvb200_push_rows": (C.c_int, [_vp, _u64, C.POINTER(Push), _vp]),
     "spmvb200_synth_dims": (C.c_int, [C.POINTER(Synth), C.POINTER(_u64), C.POINTER(_u64)]),
     "spmvb200_synth_rowlen_host": (C.c_int, [C.POINTER(Synth), _u64, _u64, _vp]),
     "spmvb200_synth_fill_host": (C.c_int, [C.POINTER(Synth), _u64, _u64, _vp, _vp, _vp]),

@@ -1146,6 +1146,38 @@ extern "C" int spmvb200_spmv_device_push(spmvb200_matrix* m, int kind, const dou
     return 0;
 }
 
+extern "C" int spmvb200_h2d_async(void* d, const void* h, size_t bytes, void* stream) {
+    CU_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+    return 0;
+}
+extern "C" int spmvb200_d2h_async(void* h, const void* d, size_t bytes, void* stream) {
+    CU_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+    return 0;
+}
+extern "C" int spmvb200_stream_sync(void* stream) {
+    CU_TRY(cudaStreamSynchronize((cudaStream_t) stream));
+    return 0;
+}
+// deliver rows that already sit in device memory (e.g. this GPU's freshly uploaded slice of x) to the destinations that want them
+extern "C" int spmvb200_push_rows(const double* d_rows, uint64_t nrows, const spmvb200_push* push, void* stream) {
+    if (!d_rows || !push || push->n < 0 || push->n > 8 || nrows > 0xffffffffull) return fail("push_rows: bad arguments");
+    PushArgs a = {};
+    a.n = push->n;
+    for (int i = 0; i < push->n; ++i) {
+        if (!push->dst[i] || push->hi[i] > 0xffffffffull || push->lo[i] > push->hi[i]) return fail("push_rows: bad destination %d", i);
+        a.dst[i] = push->dst[i];
+        a.lo[i] = (uint32_t) push->lo[i];
+        a.hi[i] = (uint32_t) push->hi[i];
+    }
+    a.row_offset = (uint32_t) push->row_offset;
+    if (a.n && nrows) {
+        push_rows_kernel<<<592, 256, 0, (cudaStream_t) stream>>>(d_rows, (uint32_t) nrows, a);
+        ++g_launches;
+        CU_TRY(cudaPeekAtLastError());
+    }
+    return 0;
+}
+
 // ---- peer memory plumbing for one-process-per-GPU jobs (CUDA IPC) and the cross-GPU barrier
 extern "C" int spmvb200_ipc_export(void* d_ptr, unsigned char handle[64]) {
     if (!d_ptr || !handle) return fail("ipc_export: null argument");

@@ -182,6 +182,8 @@ class RowBlockIterate:
         dist.barrier(group=group)
 
     # ---- x on entry (replicated: every rank fills the whole vector)
+    cur = 0
+
     def set_x(self, x_host):
         if self.mode == "nccl":
             self.x[0].copy_(self.torch.from_numpy(np.ascontiguousarray(x_host)))
@@ -204,6 +206,32 @@ class RowBlockIterate:
             self.epoch += 1
             engine.check(lib.spmvb200_peer_barrier(self.flag_ptrs, self.world, self.rank, self.epoch, stream), "peer_barrier")
         self.cur = nxt
+
+    # ---- end-to-end step from host buffers (bench.py's N>1 e2e): no collective library in the data path
+    def load_x_slice(self, host_ptr, stream=None, after_h2d=None):
+        """This rank's slice x[r0:r1) comes up from (pinned) host memory over its own PCIe link into the current x buffer and
+        is delivered -- only the rows they read -- to the other ranks by peer stores; the flag barrier makes every rank's
+        x complete where it is read.  host_ptr: address of element r0.  The two x buffers alternate from call to call: a
+        peer may still be reading the previous one (its SpMV of the last step) while this step's rows arrive."""
+        assert self.mode == "push"
+        lib = engine.lib()
+        self.cur = 1 - self.cur
+        mine = self.bufs[self.cur].data_ptr() + self.r0 * 8
+        engine.check(lib.spmvb200_h2d_async(mine, host_ptr, (self.r1 - self.r0) * 8, stream), "h2d_async")
+        if after_h2d:
+            after_h2d()
+        peers = sorted(self.need)
+        p = engine.capi.Push()
+        p.n = len(peers)
+        for i, q in enumerate(peers):
+            p.dst[i], p.lo[i], p.hi[i] = self.peer[q][self.cur], self.need[q][0], self.need[q][1]
+        p.row_offset = self.r0
+        engine.check(lib.spmvb200_push_rows(mine, self.r1 - self.r0, engine.C.byref(p), stream), "push_rows")
+        self.epoch += 1
+        engine.check(lib.spmvb200_peer_barrier(self.flag_ptrs, self.world, self.rank, self.epoch, stream), "peer_barrier")
+
+    def x_ptr(self):
+        return self.bufs[self.cur].data_ptr()
 
     def my_slice(self):
         """this rank's rows of the current x, as a host array"""
