@@ -497,7 +497,12 @@ extern "C" int spmvb200_ell_from_csr(const spmvb200_matrix* csr, int format, spm
 }
 
 // ------------------------------------------------------------------------------------------------- SELL-32-sigma
+static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, spmvb200_matrix** out);
 extern "C" int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma, spmvb200_matrix** out) {
+    return sell_build(csr, sigma, 0xffffffffu, out);
+}
+// cap < 2^32-1: rows longer than cap are left empty (hybrid of the adaptive mode: they go to the per-row / per-segment CTAs)
+static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, spmvb200_matrix** out) {
     if (!out) return fail("sell_from_csr: null output");
     *out = nullptr;
     if (!csr || csr->format != SPMVB200_FMT_CSR) return fail("sell_from_csr: source is not a CSR handle");
@@ -525,7 +530,7 @@ extern "C" int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma
         if ((rc = cudaMalloc(&m->irp, ((size_t) nsl + 1) * 4) != cudaSuccess)) break;
         if ((rc = cudaMalloc(&slots, ((size_t) nsl + 1) * 8) != cudaSuccess)) break;
         if ((rc = cudaMalloc(&slots_scan, ((size_t) nsl + 1) * 8) != cudaSuccess)) break;
-        sell_keys_kernel<<<(Mpad + 255) / 256, 256>>>(csr->irp, (uint32_t) csr->M, Mpad, sigma, k0, v0);
+        sell_keys_kernel<<<(Mpad + 255) / 256, 256>>>(csr->irp, (uint32_t) csr->M, Mpad, sigma, cap, k0, v0);
         size_t b1 = 0, b2 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, v0, m->perm, (int) Mpad);
         cub::DeviceScan::ExclusiveSum(nullptr, b2, slots, slots_scan, (int) nsl + 1);
@@ -543,7 +548,7 @@ extern "C" int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma
         if ((rc = cudaMalloc(&m->as, (total + PAD) * 8) != cudaSuccess)) break;
         cudaMemset(m->ja + total, 0, PAD * 4);
         cudaMemset(m->as + total, 0, PAD * 8);
-        sell_fill_kernel<<<(Mpad + 255) / 256, 256>>>(csr->irp, csr->ja, csr->as, m->perm, m->irp, Mpad, m->ja, m->as);
+        sell_fill_kernel<<<(Mpad + 255) / 256, 256>>>(csr->irp, csr->ja, csr->as, m->perm, m->irp, Mpad, cap, m->ja, m->as);
         if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
         m->K = sigma;  // reported through spmvb200_dims as K
     } while (0);
@@ -852,12 +857,27 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
     constexpr int BLOCK = 256;
     if (r1 <= r0) return;
     static const bool no_exit = getenv("SPMVB200_ELL_NO_EARLY_EXIT") != nullptr;  // developer knob: walk all K slots like the reference
-    if (m->ja16 && !no_exit)
-        ell_colmajor_kernel<4, BLOCK, true><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1,
-                                                                                                           (uint32_t) m->K, m->ja16_base, x, y, g_push);
+    // slots in flight per thread: 4, or 3 when that leaves a shorter tail of one-at-a-time slots (K = 27: 3 x 9 exactly; measured
+    // 103.3 vs 105.2 us on cfg2; 5..9 lose more to occupancy than they gain)
+    static const int unroll_env = getenv("SPMVB200_ELL_UNROLL") ? atoi(getenv("SPMVB200_ELL_UNROLL")) : 0;  // developer knob
+    const int unroll16 = unroll_env ? unroll_env : ((m->K % 3) < (m->K % 4) ? 3 : 4);
+    const unsigned grid = (unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK);
+#define ELL16(U) ell_colmajor_kernel<U, BLOCK, true><<<grid, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, m->ja16_base, x, y, g_push)
+    if (m->ja16 && !no_exit) {
+        switch (unroll16) {
+            case 3: ELL16(3); break;
+            case 5: ELL16(5); break;
+            case 6: ELL16(6); break;
+            case 8: ELL16(8); break;
+            case 9: ELL16(9); break;
+            default: ELL16(4); break;
+        }
+    }
+#undef ELL16
+    else if (unroll16 == 3)
+        ell_colmajor_kernel<3, BLOCK, false><<<grid, BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, 0, x, y, g_push);
     else
-        ell_colmajor_kernel<4, BLOCK, false><<<(unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0,
-                                                                                                            (uint32_t) r1, (uint32_t) m->K, 0, x, y, g_push);
+        ell_colmajor_kernel<4, BLOCK, false><<<grid, BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, 0, x, y, g_push);
     g_push_fused = true;
     ++g_launches;
 }
@@ -948,7 +968,10 @@ static void launch_candidate(const spmvb200_matrix* m, int c, const double* x, d
     else if (c < 7) launch_csr_vector(m, cand_lanes(c), x, y, st, 0, m->M);
     else if (c < CAND_XWIN) launch_csr_vspan(m, cand_lanes(c), x, y, st);
     else if (c == CAND_XWIN) launch_xwin(m->xw_child, x, y, st);
-    else launch_sell(m->xw_child, x, y, st);
+    else {
+        launch_sell(m->xw_child, x, y, st);
+        if (m->lmax > (uint32_t) VEC_MID) launch_vector_tail(m, x, y, st);  // hybrid: rows the capped SELL copy left empty
+    }
 }
 static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
     // d_x / d_y are the caller's vectors: y is overwritten by every candidate with the same result
@@ -998,11 +1021,14 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
         }
         g_err[0] = 0;
     }
-    // SELL-32-sigma copy: only without long rows (a thread walks its whole row) and when the slices stay nearly padding-free
-    if (!getenv("SPMVB200_NO_SELL") && m->NZ >= (1u << 20) && m->lmax <= 512 && (!force || atoi(force) == CAND_SELL)) {
+    // SELL-32-sigma copy (a thread walks its whole row, coalesced, no shuffles).  Rows longer than VEC_MID are left out of it and go
+    // to the per-row / per-segment CTAs of the vector path (hybrid for skewed matrices); kept only while the slices stay nearly
+    // padding-free
+    if (!getenv("SPMVB200_NO_SELL") && m->NZ >= (1u << 20) && (!force || atoi(force) == CAND_SELL)) {
         g_quiet = 1;
         spmvb200_matrix* sell = nullptr;
-        const int rc = spmvb200_sell_from_csr(m, 0, &sell);
+        const bool hybrid = m->lmax > (uint32_t) VEC_MID;
+        const int rc = sell_build(m, 0, hybrid ? (uint32_t) VEC_MID : 0xffffffffu, &sell);
         g_quiet = 0;
         if (!rc) {
             float ms_min = 1e30f;
@@ -1014,6 +1040,7 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
                 for (int rep = 0; rep < 2; ++rep) {
                     CU_TRY(cudaEventRecord(s0, st));
                     launch_sell(sell, d_x, d_y, st);
+                    if (hybrid) launch_vector_tail(m, d_x, d_y, st);
                     CU_TRY(cudaEventRecord(s1, st));
                     CU_TRY(cudaEventSynchronize(s1));
                     float ms = 0;

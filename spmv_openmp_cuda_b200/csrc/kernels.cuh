@@ -462,11 +462,14 @@ sell_kernel(const uint32_t* __restrict__ slice_ptr, const uint32_t* __restrict__
 }
 
 // SELL construction (device): sort keys, slice lengths, fill
-__global__ void sell_keys_kernel(const uint32_t* __restrict__ irp, uint32_t M, uint32_t Mpad, uint32_t sigma, uint64_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals) {
+// cap: rows longer than this are left EMPTY here (their y entry is written by other kernels right after: the adaptive mode's
+// SELL + per-row-CTA hybrid for skewed matrices)
+__global__ void sell_keys_kernel(const uint32_t* __restrict__ irp, uint32_t M, uint32_t Mpad, uint32_t sigma, uint32_t cap,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= Mpad) return;
-    const uint32_t len = r < M ? irp[r + 1] - irp[r] : 0u;
+    uint32_t len = r < M ? irp[r + 1] - irp[r] : 0u;
+    if (len > cap) len = 0u;
     keys[r] = ((uint64_t) (r / sigma) << 32) | (uint64_t) (0xffffffffu - len);  // ascending sort = descending length per window
     vals[r] = r < M ? r : 0xffffffffu;
 }
@@ -479,13 +482,15 @@ __global__ void sell_slices_kernel(const uint64_t* __restrict__ keys_sorted, uin
     if ((i & 31) == 0) slice_slots[i >> 5] = (uint64_t) len * 32;  // first row of a slice is its longest
 }
 __global__ void sell_fill_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
-                                 const uint32_t* __restrict__ perm, const uint32_t* __restrict__ slice_ptr, uint32_t Mpad,
+                                 const uint32_t* __restrict__ perm, const uint32_t* __restrict__ slice_ptr, uint32_t Mpad, uint32_t cap,
                                  uint32_t* __restrict__ sja, double* __restrict__ sas) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Mpad) return;
     const uint32_t row = perm[i];
     const uint32_t sp0 = slice_ptr[i >> 5], wmax = (slice_ptr[(i >> 5) + 1] - sp0) >> 5;
-    const uint32_t s = row != 0xffffffffu ? irp[row] : 0u, len = row != 0xffffffffu ? irp[row + 1] - s : 0u;
+    const uint32_t s = row != 0xffffffffu ? irp[row] : 0u;
+    uint32_t len = row != 0xffffffffu ? irp[row + 1] - s : 0u;
+    if (len > cap) len = 0u;
     for (uint32_t k = 0; k < wmax; ++k) {
         const uint32_t o = sp0 + k * 32 + (i & 31);
         sas[o] = k < len ? as[s + k] : 0.0;

@@ -147,6 +147,21 @@ def test_edge_cases(sp, orc):
                 assert bad == 0, (name, f.__name__, worst)
 
 
+def test_unsorted_columns_all_kinds(sp, orc):
+    """The reference's parser keeps the file order inside a row (src/lib/parser.c:157-215): rows need not be column-sorted.
+    Every kind must still be right (the x-window build walks such rows instead of bisecting them; its windows are visited in
+    column order, so it meets the tolerance rather than bit-exactness there)."""
+    rng = np.random.default_rng(11)
+    M, N = 5000, 40000
+    lens = rng.integers(0, 40, M)
+    irp = np.zeros(M + 1, dtype=np.uint64)
+    irp[1:] = np.cumsum(lens)
+    ja = np.concatenate([rng.permutation(rng.choice(N, k, replace=False)) for k in lens]).astype(np.uint64)
+    mat = sp.Spmat.csr(N, irp, ja, rng.uniform(-1, 1, int(irp[-1])))
+    x = rng.uniform(-1, 1, N)
+    run_all_kinds(sp, orc, mat, x, _oracle_y(orc, mat, x))
+
+
 def test_xwin_limits_fail_loudly(sp):
     """More than 255 non-zeros of one row inside one window, or a bad geometry: an error, never a wrong answer."""
     irp = np.array([0, 300, 301], dtype=np.uint64)
@@ -252,6 +267,25 @@ def test_fused_output_delivery(sp, orc):
             lo2, hi2 = max(lo, a), min(hi, b)
             np.testing.assert_array_equal(got[lo2:hi2], y[lo2 - a:hi2 - a])
             assert np.all(np.isnan(got[:lo2])) and np.all(np.isnan(got[hi2:])), "rows outside the range must stay untouched"
+
+
+def test_adaptive_sell_hybrid_on_skewed_rows(sp, orc, monkeypatch):
+    """Forced SELL candidate on an R-MAT matrix: rows longer than 256 are left out of the SELL copy and computed by the per-row /
+    per-segment CTAs right after it."""
+    monkeypatch.setenv("SPMVB200_FORCE_CAND", "13")
+    mat = sp.synth.rmat_host_csr(17, 16)
+    assert mat.MAX_ROW_NZ > 2048 and mat.NZ >= 1 << 20
+    x = sp.synth.host_vector(mat.N)
+    y_ref = _oracle_y(orc, mat, x)
+    dm, dx, dy = sp.spMatCpyCSR(mat), sp.DeviceVector.from_host(x), sp.DeviceVector(mat.M)
+    for _ in range(2):
+        dy.fill_bytes(0xFF)
+        sp.cudaSpMVAdaptiveCSR(dm, dx, sp.Config(), dy)
+        y = dy.to_host()
+        assert orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=TAU)[0] == 0
+        short = np.diff(mat.IRP) <= 256
+        np.testing.assert_array_equal(y[short], y_ref[short])  # the SELL part sums in the serial order
+    assert dm.adaptive_choice == "sell"
 
 
 def test_long_row_split_is_deterministic(sp):
