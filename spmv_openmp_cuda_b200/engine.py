@@ -62,6 +62,38 @@ class Spmat:
         return cls(M, N, NZ, JA, AS, IRP=None, RL=RL, MAX_ROW_NZ=K)
 
 
+    # ---- binary cache next to the Matrix Market text: parsing a 1e8-entry .mtx takes minutes, this takes a read()
+    _MAGIC = b"SPMVB2\x00\x01"
+
+    def save(self, path):
+        """Raw little-endian dump: magic, (M, N, NZ, MAX_ROW_NZ, has_irp, has_rl) as uint64, then IRP / JA / AS / RL."""
+        with open(path, "wb") as f:
+            f.write(self._MAGIC)
+            np.array([self.M, self.N, self.NZ, self.MAX_ROW_NZ, self.IRP is not None, self.RL is not None], dtype="<u8").tofile(f)
+            for a in (self.IRP, self.JA, self.AS, self.RL):
+                if a is not None:
+                    np.array([a.size], dtype="<u8").tofile(f)
+                    a.tofile(f)
+
+    @classmethod
+    def load(cls, path):
+        with open(path, "rb") as f:
+            if f.read(8) != cls._MAGIC:
+                raise ValueError("%s is not a spmv_b200 binary matrix" % path)
+            M, N, NZ, K, has_irp, has_rl = (int(v) for v in np.fromfile(f, dtype="<u8", count=6))
+
+            def arr(dtype):
+                n = int(np.fromfile(f, dtype="<u8", count=1)[0])
+                a = np.fromfile(f, dtype=dtype, count=n)
+                if a.size != n:
+                    raise ValueError("%s is truncated" % path)
+                return a
+            IRP = arr("<u8") if has_irp else None
+            JA, AS = arr("<u8"), arr("<f8")
+            RL = arr("<u8") if has_rl else None
+        return cls(M, N, NZ, JA, AS, IRP=IRP, RL=RL, MAX_ROW_NZ=K)
+
+
 class Config:
     """CONFIG, src/include/config.h:21-32.  gridSize/blockSize are accepted and ignored by the engine
     (it chooses its own launch geometry)."""

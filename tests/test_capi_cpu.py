@@ -110,3 +110,28 @@ def test_generators_row_ranges_and_shapes(sp):
     x1, x2 = s.host_vector(100), s.host_vector(40, begin=60)
     np.testing.assert_array_equal(x1[60:], x2)
     assert np.all(np.abs(x1) < 3e-5) and np.all(np.isfinite(x1))
+
+
+def test_binary_matrix_cache_roundtrip(tmp_path):
+    """Spmat.save / Spmat.load: CSR and ELL round-trip bit for bit; garbage is refused."""
+    import spmv_openmp_cuda_b200 as sp
+    rng = np.random.default_rng(3)
+    lens = rng.integers(0, 9, 50)
+    irp = np.zeros(51, dtype=np.uint64)
+    irp[1:] = np.cumsum(lens)
+    ja = rng.integers(0, 70, int(irp[-1])).astype(np.uint64)
+    csr = sp.Spmat.csr(70, irp, ja, rng.uniform(-1, 1, int(irp[-1])))
+    ell = sp.Spmat.ell(4, 6, 3, np.arange(12, dtype=np.uint64) % 6, rng.uniform(-1, 1, 12), RL=np.array([3, 1, 0, 2], dtype=np.uint64))
+    for i, m in enumerate((csr, ell)):
+        path = str(tmp_path / ("m%d.bin" % i))
+        m.save(path)
+        r = sp.Spmat.load(path)
+        assert (r.M, r.N, r.NZ, r.MAX_ROW_NZ) == (m.M, m.N, m.NZ, m.MAX_ROW_NZ)
+        for a, b in ((r.IRP, m.IRP), (r.JA, m.JA), (r.AS, m.AS), (r.RL, m.RL)):
+            assert (a is None) == (b is None)
+            if a is not None:
+                np.testing.assert_array_equal(a, b)
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"%%MatrixMarket matrix coordinate real general\n")
+    with pytest.raises(ValueError):
+        sp.Spmat.load(str(bad))
