@@ -887,10 +887,12 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
 template <int NW, int ACC, int UMAX>
 static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
     const size_t smem = (size_t) m->xw_nbuf * (m->xw_W + 2) * 8 + XW_MAX_NBUF * 12;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[64] = {0};  // per device: function attributes belong to the device's context
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if (smem > configured[dev & 63]) {
         CU_TRY(cudaFuncSetAttribute(xwin_kernel<NW, ACC, UMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        configured = smem;
+        configured[dev & 63] = smem;
     }
     const bool persist = m->xw_mode == 1;
     xwin_kernel<NW, ACC, UMAX><<<persist ? m->xw_ncta : m->xw_nrb, 32 * NW, smem, st>>>(persist ? m->xw_cta_rb : nullptr, m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
@@ -1113,7 +1115,10 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
 }
 
 static int prefer_smem_once() {
-    static bool done = false;
+    static bool done_dev[64] = {false};  // per device: function attributes belong to the device's context
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    bool& done = done_dev[dev & 63];
     if (done) return 0;
     // streaming variant: 8 CTAs x 27 KB of shared memory per SM => largest carve-out.
     // gather variant (VARIANT=1): half the shared memory, the rest stays L1 for the x gathers.
