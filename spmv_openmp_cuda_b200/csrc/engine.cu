@@ -68,6 +68,11 @@ static void free_arrays(spmvb200_matrix* m) {
     cudaFree(m->d_x);
     cudaFree(m->d_y);
     cudaFree(m->flush);
+    for (int i = 0; i < 2; ++i) {
+        if (m->s_tail[i]) cudaStreamDestroy(m->s_tail[i]);
+        if (m->e_tail[i]) cudaEventDestroy(m->e_tail[i]);
+    }
+    if (m->e_fork) cudaEventDestroy(m->e_fork);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     destroy_pipe(m->pipe);
@@ -797,20 +802,52 @@ extern "C" const char* spmvb200_kind_name(int kind) {
 }
 
 // ------------------------------------------------------------------------------------------------- launch
-// rows the vector kernels skip: medium rows (one CTA each) and rows longer than a tile (one CTA per segment)
-static void launch_vector_tail(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+// Rows the vector kernels skip: medium rows (one CTA each) and rows longer than a tile (one CTA per segment).  They touch other rows
+// of y than the main kernel, so they run NEXT to it on two side streams -- forked before the main launch, joined after it (events:
+// legal inside a graph capture too).  On R-MAT (cfg3) the three kernels are 189 + 97 + 52 us back to back.
+static void tail_fork(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    if (!m->nmid && !m->nseg) return;
+    static const bool serial = getenv("SPMVB200_SERIAL_TAIL") != nullptr;  // developer knob: the old back-to-back order
+    if (!serial && !m->e_fork) {
+        bool ok = cudaEventCreateWithFlags(&m->e_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = cudaStreamCreateWithFlags(&m->s_tail[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&m->e_tail[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); m->e_fork = nullptr; }
+    }
+    const bool fork = !serial && m->e_fork && m->s_tail[0] && m->s_tail[1] && m->e_tail[0] && m->e_tail[1];
+    if (fork) cudaEventRecord(m->e_fork, st);
     if (m->nmid) {
-        csr_midrow_kernel<128><<<m->nmid, 128, 0, st>>>(m->mid_rows, m->irp, m->ja, m->as, x, y);
-        ++g_launches;
+        cudaStream_t s = fork ? m->s_tail[0] : st;
+        if (fork) cudaStreamWaitEvent(s, m->e_fork, 0);
+        static const bool warp_mid = getenv("SPMVB200_NO_WARP_MID") == nullptr;  // developer knob
+        const uint32_t lo = warp_mid ? (uint32_t) MIDW_MAX : 0u;  // rows up to MIDW_MAX: a warp each; longer: a CTA each
+        if (warp_mid) {
+            csr_midrow_warp_kernel<256><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y, 0u, (uint32_t) MIDW_MAX);
+            ++g_launches;
+        }
+        if (!warp_mid || m->lmax > (uint32_t) MIDW_MAX) {
+            csr_midrow_kernel<128><<<m->nmid, 128, 0, s>>>(m->mid_rows, m->irp, m->ja, m->as, x, y, lo);
+            ++g_launches;
+        }
+        if (fork) cudaEventRecord(m->e_tail[0], s);
     }
     if (m->nseg) {
-        csr_longrow_kernel<128><<<m->nseg, 128, 0, st>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+        cudaStream_t s = fork ? m->s_tail[1] : st;
+        if (fork) cudaStreamWaitEvent(s, m->e_fork, 0);
+        csr_longrow_kernel<128><<<m->nseg, 128, 0, s>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+        if (fork) cudaEventRecord(m->e_tail[1], s);
         ++g_launches;
     }
 }
+static void tail_join(spmvb200_matrix* m, cudaStream_t st) {
+    if (!m->e_fork || getenv("SPMVB200_SERIAL_TAIL")) return;
+    if (m->nmid) cudaStreamWaitEvent(st, m->e_tail[0], 0);
+    if (m->nseg) cudaStreamWaitEvent(st, m->e_tail[1], 0);
+}
 // rows [r0, r1) (whole matrix: 0, M); y is always indexed by the handle's row number
 template <int LANES>
-static void launch_csr_vector_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
+static void launch_csr_vector_t(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
     constexpr int BLOCK = 256;
     const uint64_t threads = (r1 - r0) * LANES;
     if (!threads) return;
@@ -820,7 +857,9 @@ static void launch_csr_vector_t(const spmvb200_matrix* m, const double* x, doubl
     ++g_launches;
 }
 // vector kernel for rows up to one tile + the long-row kernel for the rest (same stream, back to back)
-static void launch_csr_vector(const spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
+static void launch_csr_vector(spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
+    const bool whole = r0 == 0 && r1 == m->M;
+    if (whole) tail_fork(m, x, y, st);
     switch (lanes) {
         case 2: launch_csr_vector_t<2>(m, x, y, st, r0, r1); break;
         case 4: launch_csr_vector_t<4>(m, x, y, st, r0, r1); break;
@@ -828,14 +867,15 @@ static void launch_csr_vector(const spmvb200_matrix* m, int lanes, const double*
         case 16: launch_csr_vector_t<16>(m, x, y, st, r0, r1); break;
         default: launch_csr_vector_t<32>(m, x, y, st, r0, r1); break;
     }
-    if (r0 == 0 && r1 == m->M) launch_vector_tail(m, x, y, st);
+    if (whole) tail_join(m, st);
 }
 template <int LANES>
-static void launch_csr_vspan_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+static void launch_csr_vspan_t(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
     csr_vector_span_kernel<LANES, 1024><<<m->nspans, 1024, 0, st>>>(m->span_b, m->irp, m->ja, m->as, x, y, (uint32_t) VEC_MID);
     ++g_launches;
 }
-static void launch_csr_vspan(const spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st) {
+static void launch_csr_vspan(spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st) {
+    tail_fork(m, x, y, st);
     switch (lanes) {
         case 2: launch_csr_vspan_t<2>(m, x, y, st); break;
         case 4: launch_csr_vspan_t<4>(m, x, y, st); break;
@@ -843,7 +883,7 @@ static void launch_csr_vspan(const spmvb200_matrix* m, int lanes, const double* 
         case 16: launch_csr_vspan_t<16>(m, x, y, st); break;
         default: launch_csr_vspan_t<32>(m, x, y, st); break;
     }
-    launch_vector_tail(m, x, y, st);
+    tail_join(m, st);
 }
 // tiles [t0, t1) (whole matrix: 0, ntiles)
 template <bool ADAPT, int VARIANT>
@@ -964,15 +1004,17 @@ static const int CAND_SELL = 13;  // SELL-32-sigma copy (matrices without long r
 static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32",
                                         "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32", "xwindow", "sell"};
 static int cand_lanes(int c) { return c < 2 ? 0 : 2 << ((c - 2) % 5); }
-static void launch_candidate(const spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st) {
+static void launch_candidate(spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st) {
     if (c == 0) launch_csr_stream<true, 0>(m, x, y, st, 0, m->ntiles);
     else if (c == 1) launch_csr_stream<true, 1>(m, x, y, st, 0, m->ntiles);
     else if (c < 7) launch_csr_vector(m, cand_lanes(c), x, y, st, 0, m->M);
     else if (c < CAND_XWIN) launch_csr_vspan(m, cand_lanes(c), x, y, st);
     else if (c == CAND_XWIN) launch_xwin(m->xw_child, x, y, st);
     else {
+        const bool hybrid = m->lmax > (uint32_t) VEC_MID;  // rows the capped SELL copy left out (it does not write their y)
+        if (hybrid) tail_fork(m, x, y, st);
         launch_sell(m->xw_child, x, y, st);
-        if (m->lmax > (uint32_t) VEC_MID) launch_vector_tail(m, x, y, st);  // hybrid: rows the capped SELL copy left empty
+        if (hybrid) tail_join(m, st);
     }
 }
 static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
@@ -1041,8 +1083,9 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
                 launch_sell(sell, d_x, d_y, st);
                 for (int rep = 0; rep < 2; ++rep) {
                     CU_TRY(cudaEventRecord(s0, st));
+                    if (hybrid) tail_fork(m, d_x, d_y, st);
                     launch_sell(sell, d_x, d_y, st);
-                    if (hybrid) launch_vector_tail(m, d_x, d_y, st);
+                    if (hybrid) tail_join(m, st);
                     CU_TRY(cudaEventRecord(s1, st));
                     CU_TRY(cudaEventSynchronize(s1));
                     float ms = 0;
@@ -1310,7 +1353,7 @@ static int pipe_candidate(const spmvb200_matrix* m, int kind) {
         default: return -1;
     }
 }
-static void launch_chunk(const spmvb200_matrix* m, const HostPipe* p, int k, const double* x, double* y) {
+static void launch_chunk(spmvb200_matrix* m, const HostPipe* p, int k, const double* x, double* y) {
     const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
     const int c = p->cand;
     if (c == 100) launch_ell_colmajor(m, x, y, p->s_comp, r0, r1);

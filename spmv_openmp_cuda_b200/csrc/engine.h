@@ -72,6 +72,9 @@ struct spmvb200_matrix {
     double* d_y = nullptr;
     void* flush = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // side streams of the vector path: medium-row and long-row CTAs run next to the main kernel (fork / join by events)
+    cudaStream_t s_tail[2] = {nullptr, nullptr};
+    cudaEvent_t e_fork = nullptr, e_tail[2] = {nullptr, nullptr};
 };
 
 namespace spmvb200 {

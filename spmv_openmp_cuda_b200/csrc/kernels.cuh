@@ -469,9 +469,10 @@ __global__ void sell_keys_kernel(const uint32_t* __restrict__ irp, uint32_t M, u
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= Mpad) return;
     uint32_t len = r < M ? irp[r + 1] - irp[r] : 0u;
-    if (len > cap) len = 0u;
+    const bool capped = len > cap;  // not this copy's row: no entries here and NO write of y (other kernels own it, concurrently)
+    if (capped) len = 0u;
     keys[r] = ((uint64_t) (r / sigma) << 32) | (uint64_t) (0xffffffffu - len);  // ascending sort = descending length per window
-    vals[r] = r < M ? r : 0xffffffffu;
+    vals[r] = (r < M && !capped) ? r : 0xffffffffu;
 }
 __global__ void sell_slices_kernel(const uint64_t* __restrict__ keys_sorted, uint32_t Mpad, uint32_t* __restrict__ rl_sorted,
                                    uint64_t* __restrict__ slice_slots) {
@@ -630,10 +631,11 @@ __global__ void csr_to_ell_kernel(const uint32_t* __restrict__ irp, const uint32
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 csr_midrow_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja,
-                  const double* __restrict__ as, const double* __restrict__ x, double* __restrict__ y) {
+                  const double* __restrict__ as, const double* __restrict__ x, double* __restrict__ y, uint32_t len_lo) {
     __shared__ double s_red[BLOCK / 32];
     const uint32_t tid = threadIdx.x, row = rows[blockIdx.x];
     const uint32_t s = __ldg(irp + row), e = __ldg(irp + row + 1);
+    if (e - s <= len_lo) return;  // block-uniform: the warp-per-row kernel owns this row
     double t = 0;
     for (uint32_t i = (s & ~1u) + 2 * tid; i < e; i += 2 * BLOCK) {
         const double2 v = ld_stream(reinterpret_cast<const double2*>(as + i));
@@ -650,6 +652,30 @@ csr_midrow_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict_
         for (int w = 0; w < BLOCK / 32; ++w) tot += s_red[w];
         y[row] = tot;
     }
+}
+
+// Same rows, one WARP per row (8 rows per CTA): most medium rows of a power-law matrix sit just above VEC_MID, where a 128-thread
+// CTA spends its time in the block reduction; a warp keeps 64 rows in flight per SM instead of 16.  Rows above MIDW_MAX stay with
+// the CTA-per-row kernel.
+constexpr int MIDW_MAX = 1024;  // measured on R-MAT: 1024 + CTA-per-row above it beats a warp for every medium row (290 vs 308 us)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+csr_midrow_warp_kernel(const uint32_t* __restrict__ rows, uint32_t nrows, const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja,
+                       const double* __restrict__ as, const double* __restrict__ x, double* __restrict__ y, uint32_t len_lo, uint32_t len_hi) {
+    const uint32_t w = (blockIdx.x * BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nrows) return;
+    const uint32_t row = __ldg(rows + w);
+    const uint32_t s = __ldg(irp + row), e = __ldg(irp + row + 1);
+    if (e - s <= len_lo || e - s > len_hi) return;  // the other medium-row kernel owns this row
+    double t = 0;
+    for (uint32_t i = (s & ~1u) + 2 * lane; i < e; i += 64) {
+        const double2 v = ld_stream(reinterpret_cast<const double2*>(as + i));
+        const uint2 c = ld_stream(reinterpret_cast<const uint2*>(ja + i));
+        if (i >= s) t = fma(v.x, ld_x(x, c.x), t);
+        if (i + 1 < e) t = fma(v.y, ld_x(x, c.y), t);
+    }
+    t = subwarp_sum<32>(t);
+    if (lane == 0) y[row] = t;
 }
 
 // largest column id in a range of a column-id array / in the valid slots of a row range of a column-major ELL
