@@ -44,6 +44,10 @@ static void free_arrays(spmvb200_matrix* m) {
         spmvb200_free(m->xw_child);
         m->xw_child = nullptr;
     }
+    if (m->x_child) {
+        spmvb200_free(m->x_child);
+        m->x_child = nullptr;
+    }
     if (m->own) {
         cudaFree(m->irp);
         cudaFree(m->ja);
@@ -1116,6 +1120,64 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
     return 0;
 }
 
+// ---- SPMVB200_CSR_ROWS, the kind that must reproduce sgemvSerial bit for bit: the stream kernel, or -- timed at first use, for
+// matrices of at least 2^20 non-zeros -- an x-window copy (column-sorted rows only) or a SELL copy (no row longer than VEC_MID);
+// all three add a row's products left to right with separate mul / add roundings.
+template <typename F>
+static int time_best_of_2(F&& run, cudaStream_t st, float* ms_out) {
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    run();
+    float best = 1e30f;
+    for (int rep = 0; rep < 2; ++rep) {
+        CU_TRY(cudaEventRecord(e0, st));
+        run();
+        CU_TRY(cudaEventRecord(e1, st));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_out = best;
+    return 0;
+}
+static int tune_exact(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
+    float best_ms = 0;
+    if (time_best_of_2([&] { launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles); }, st, &best_ms)) return 1;
+    int best = 0;
+    m->tuned_x_ms[0] = best_ms;
+    m->tuned_x_ms[1] = m->tuned_x_ms[2] = -1.f;
+    const char* only = getenv("SPMVB200_EXACT_ONLY_STREAM");  // developer knob
+    if (!only && m->NZ >= (1u << 20)) {
+        g_quiet = 1;
+        spmvb200_matrix* xw = nullptr;
+        if (!xwin_build(m, 0, 0, 15.0, &xw)) {
+            float ms = 1e30f;
+            if (xw->xw_sorted && !tune_xwin(xw, d_x, d_y, st, &ms)) m->tuned_x_ms[1] = ms;
+            if (ms < 0.95f * best_ms) { best_ms = ms; best = CAND_XWIN; m->x_child = xw; } else spmvb200_free(xw);
+        }
+        spmvb200_matrix* sell = nullptr;
+        if (m->lmax <= (uint32_t) VEC_MID && !sell_build(m, 0, 0xffffffffu, &sell)) {
+            float ms = 1e30f;
+            if (sell->slots <= m->NZ + m->NZ / 4 && !time_best_of_2([&] { launch_sell(sell, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
+            if (ms < 0.95f * best_ms) {
+                if (m->x_child) spmvb200_free(m->x_child);
+                best_ms = ms; best = CAND_SELL; m->x_child = sell;
+            } else spmvb200_free(sell);
+        }
+        g_quiet = 0;
+        g_err[0] = 0;
+    }
+    m->tuned_x = best;
+    if (getenv("SPMVB200_VERBOSE"))
+        fprintf(stderr, "spmv_b200: exact-kind tuning M=%llu NZ=%llu -> stream=%.3fms xwindow=%.3fms sell=%.3fms, picked %s\n", (unsigned long long) m->M,
+                (unsigned long long) m->NZ, m->tuned_x_ms[0], m->tuned_x_ms[1], m->tuned_x_ms[2], best == 0 ? "stream" : best == CAND_XWIN ? "xwindow" : "sell");
+    return 0;
+}
+
 template <int LANES>
 static void launch_ell_rowmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
     constexpr int BLOCK = 256;
@@ -1129,7 +1191,12 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
     if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
     if (m->M == 0) return 0;
     switch (kind) {
-        case SPMVB200_CSR_ROWS: launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles); break;
+        case SPMVB200_CSR_ROWS:
+            if (m->tuned_x < 0 && tune_exact(m, d_x, d_y, st)) return 1;
+            if (m->tuned_x == CAND_XWIN) { if (launch_xwin(m->x_child, d_x, d_y, st)) return 1; }
+            else if (m->tuned_x == CAND_SELL) launch_sell(m->x_child, d_x, d_y, st);
+            else launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles);
+            break;
         case SPMVB200_CSR_ADAPTIVE:
             if (m->tuned < 0 && tune_adaptive(m, d_x, d_y, st)) return 1;
             launch_candidate(m, m->tuned, d_x, d_y, st);
@@ -1195,7 +1262,7 @@ extern "C" int spmvb200_spmv_device_push(spmvb200_matrix* m, int kind, const dou
     if (push->n < 0 || push->n > 8) return fail("spmv_device_push: %d destinations (at most 8)", push->n);
     if (prefer_smem_once()) return 1;
     // first use of a self-tuning kind: tune without deliveries (the tuning run launches every candidate)
-    if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0))
+    if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0))
         if (launch(m, kind, d_x, d_y, (cudaStream_t) stream)) return 1;
     PushArgs a = {};
     a.n = push->n;
@@ -1305,7 +1372,7 @@ extern "C" int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a
     cudaGraphExec_t exec = nullptr;
     do {
         // self-tuning kinds tune here (cannot happen inside a capture); d_b is scratch at this point
-        if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0))
+        if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0))
             if ((rc = launch(m, kind, d_a, d_b, st))) break;
         const int pairs = iters / 2;
         unsigned long long per_replay = 0;
@@ -1346,7 +1413,7 @@ extern "C" int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a
 // which kernel a (kind, handle) pair runs chunk-wise: 0/1 stream variants (+10 exact), 2.. vector lanes, 100 ELL column-major
 static int pipe_candidate(const spmvb200_matrix* m, int kind) {
     switch (kind) {
-        case SPMVB200_CSR_ROWS: return 10;
+        case SPMVB200_CSR_ROWS: return m->tuned_x == 0 ? 10 : -1;  // a re-tiled copy runs as one launch
         case SPMVB200_CSR_ADAPTIVE: return ((m->tuned >= 2 && m->nseg) || m->tuned >= 7) ? -1 : m->tuned;  // long rows / spans: one launch
         case SPMVB200_CSR_ROWS_WARP: return m->nseg ? -1 : 20 + m->vec_lanes;
         case SPMVB200_ELL_ROWS: return 100;
@@ -1446,7 +1513,7 @@ extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x,
     if (prefer_smem_once() || ensure_events(m)) return 1;
     if (!m->d_x) CU_TRY(cudaMalloc(&m->d_x, std::max<uint64_t>(m->N, 1) * 8));
     if (!m->d_y) CU_TRY(cudaMalloc(&m->d_y, std::max<uint64_t>(m->M, 1) * 8));
-    const bool untuned = kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0;
+    const bool untuned = (kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0);
     int cand = untuned ? -1 : pipe_candidate(m, kind);
     if (!untuned && (!m->pipe || m->pipe->kind != kind || m->pipe->cand != cand))
         if (build_pipe(m, kind, cand)) return 1;

@@ -44,6 +44,10 @@ struct spmvb200_matrix {
     int xw_mode = -1;                 // -1 not tuned yet, 0 one CTA per row block, 1 persistent CTAs (xw_cta_rb); first-use timing
     spmvb200_matrix* xw_child = nullptr;  // CSR handle: x-window or SELL copy built (and kept, if it won) by the adaptive mode's tuning run
     uint32_t lmax = 0;                    // CSR: longest row
+    // SPMVB200_CSR_ROWS (the bit-exact kind): -1 not tuned yet, 0 stream kernel, 12 x-window copy, 13 SELL copy (all three sum in the serial order)
+    int tuned_x = -1;
+    spmvb200_matrix* x_child = nullptr;
+    float tuned_x_ms[3] = {0, 0, 0};
     uint32_t* xw_rb_tile0 = nullptr;  // [nrb+1] first tile of a row block
     uint32_t* xw_tile_win = nullptr;  // [ntiles] window id
     uint32_t* xw_grp_off = nullptr;   // [ntiles*R/32+1] first entry of a (tile, 32-row group)
