@@ -330,7 +330,7 @@ def main():
             torch.cuda.synchronize()
             dbg_t.append(time.perf_counter())
 
-    pusher = None
+    pusher, push_err = None, ""
     if world > 1 and args.x_dist == "push":
         from spmv_openmp_cuda_b200.distributed import RowBlockIterate
 
@@ -339,8 +339,18 @@ def main():
         _Rows.col_range = col_range
         allr = [None] * world
         dist.all_gather_object(allr, (r0, r1))
-        pusher = RowBlockIterate(_Rows, [a_[0] for a_ in allr] + [allr[-1][1]], kind, mode="push")
-        pusher.set_x(hx.numpy())
+        try:
+            pusher = RowBlockIterate(_Rows, [a_[0] for a_ in allr] + [allr[-1][1]], kind, mode="push")
+            pusher.set_x(hx.numpy())
+        except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC not permitted in this container)
+            pusher, push_err = None, repr(e)
+        ok_all = torch.tensor([1 if pusher is not None else 0], device="cuda")
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        if not ok_all.item():  # every rank takes the same path: fall back to the NCCL all-gather of x
+            pusher = None
+            args.x_dist = "allgather"
+            if rank == 0:
+                sys.stderr.write("bench.py: peer-store exchange unavailable (%s); using --x-dist allgather\n" % (push_err or "another rank failed"))
 
     def e2e_step():
         mark()
