@@ -166,6 +166,7 @@ class RowBlockIterate:
         allh = [None] * self.world
         dist.all_gather_object(allh, (mine, cr), group=group)
         self.col_ranges = [a[1] for a in allh]
+        err = None
         for p in range(self.world):
             if p == self.rank:
                 self.peer[p] = [v.data_ptr() for v in self.bufs + [self.flags]]
@@ -173,9 +174,17 @@ class RowBlockIterate:
             ptrs = []
             for hb in allh[p][0]:
                 out = C.c_void_p()
-                engine.check(lib.spmvb200_ipc_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(out)), "ipc_open")
-                ptrs.append(out.value)
+                try:
+                    engine.check(lib.spmvb200_ipc_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(out)), "ipc_open")
+                    ptrs.append(out.value)
+                except engine.SpmvB200Error as e:  # keep going: every rank must reach the agreement below
+                    err = err or e
             self.peer[p] = ptrs
+        # all ranks agree on success before anyone uses (or gives up on) the peer mappings
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            raise engine.SpmvB200Error("peer mapping failed on rank(s) %s: %s" % ([i for i, o in enumerate(oks) if not o], err))
         # halo=False: deliver the whole block to everybody (a fused all-gather) even where only a halo is read
         self.need = needed_rows(self.splits, self.col_ranges if halo else [(0, self.N - 1)] * self.world, self.rank)
         self.flag_ptrs = (C.c_void_p * self.world)(*[self.peer[p][2] for p in range(self.world)])
