@@ -907,7 +907,18 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
     const int unroll16 = unroll_env ? unroll_env : ((m->K % 3) < (m->K % 4) ? 3 : 4);
     const unsigned grid = (unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK);
 #define ELL16(U) ell_colmajor_kernel<U, BLOCK, true><<<grid, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, m->ja16_base, x, y, g_push)
-    if (m->ja16 && !no_exit) {
+    // 16-bit ids: two rows per thread, 3 slots in flight (measured on cfg2: 96.9 us; one row per thread 103.0; pair x2 100.7, pair x4 107.1)
+    static const int pair_env = getenv("SPMVB200_ELL_PAIR") ? atoi(getenv("SPMVB200_ELL_PAIR")) : 3;  // developer knob: 0 = one row per thread
+    if (m->ja16 && !no_exit && pair_env && (r0 % 2) == 0) {
+        const unsigned g2 = (unsigned) (((r1 - r0 + 1) / 2 + BLOCK - 1) / BLOCK);
+#define ELLP(U) ell_colmajor_pair_kernel<U, BLOCK><<<g2, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, m->ja16_base, x, y, g_push)
+        switch (pair_env) {
+            case 2: ELLP(2); break;
+            case 3: ELLP(3); break;
+            default: ELLP(4); break;
+        }
+#undef ELLP
+    } else if (m->ja16 && !no_exit) {
         switch (unroll16) {
             case 3: ELL16(3); break;
             case 5: ELL16(5); break;

@@ -367,6 +367,69 @@ ell_colmajor_kernel(const double* __restrict__ as, const void* __restrict__ ja_a
         if (push.n) push_out(push, row, acc);
     }
 }
+// Two adjacent rows per thread (IDX16 only): slot k of rows 2t, 2t+1 is one 16-byte value load and one 4-byte id load, so a thread
+// has twice the bytes in flight per load instruction -- the 16-bit kernel is bound by bytes in flight (94 % occupancy, 82 KB per SM
+// outstanding at most), not by anything else.  Same left-to-right sums, same early exit (per warp: the longest of its 64 rows).
+template <int UNROLL, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+ell_colmajor_pair_kernel(const double* __restrict__ as, const uint16_t* __restrict__ ja16, const uint32_t* __restrict__ rl, uint64_t pitch,
+                         uint32_t row_begin, uint32_t M, int32_t base, const double* __restrict__ x, double* __restrict__ y, const PushArgs push) {
+    const uint32_t row = row_begin + 2u * (blockIdx.x * BLOCK + threadIdx.x);  // row_begin even, pitch a multiple of 64
+    const bool live0 = row < M, live1 = row + 1 < M;
+    uint32_t len0 = 0, len1 = 0;
+    if (live1) {
+        const uint2 l = __ldg(reinterpret_cast<const uint2*>(rl + row));
+        len0 = l.x;
+        len1 = l.y;
+    } else if (live0) {
+        len0 = __ldg(rl + row);
+    }
+    const uint32_t lmax = max(len0, len1);
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, lmax);
+    const double2* a = reinterpret_cast<const double2*>(as + row);
+    const uint32_t* j = reinterpret_cast<const uint32_t*>(ja16 + row);
+    const uint64_t p2 = pitch >> 1;
+    const uint32_t cb0 = (uint32_t) ((int32_t) row + base), cb1 = cb0 + 1u;
+    double acc0 = 0, acc1 = 0;
+    uint32_t k = 0;
+    for (; k + UNROLL <= wmax; k += UNROLL) {
+        double2 v[UNROLL];
+        uint32_t c[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const bool ok = k + u < lmax;
+            v[u] = ok ? ld_stream(a + (uint64_t) (k + u) * p2) : make_double2(0.0, 0.0);
+            c[u] = ok ? ld_stream(j + (uint64_t) (k + u) * p2) : 0u;
+        }
+        double x0[UNROLL], x1[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            x0[u] = (k + u < len0) ? ld_x(x, (c[u] & 0xffffu) + cb0) : 0.0;
+            x1[u] = (k + u < len1) ? ld_x(x, (c[u] >> 16) + cb1) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (k + u < len0) acc0 = __dadd_rn(acc0, __dmul_rn(v[u].x, x0[u]));
+            if (k + u < len1) acc1 = __dadd_rn(acc1, __dmul_rn(v[u].y, x1[u]));
+        }
+    }
+    for (; k < wmax; ++k) {
+        if (k < lmax) {
+            const double2 v = ld_stream(a + (uint64_t) k * p2);
+            const uint32_t c = ld_stream(j + (uint64_t) k * p2);
+            if (k < len0) acc0 = __dadd_rn(acc0, __dmul_rn(v.x, ld_x(x, (c & 0xffffu) + cb0)));
+            if (k < len1) acc1 = __dadd_rn(acc1, __dmul_rn(v.y, ld_x(x, (c >> 16) + cb1)));
+        }
+    }
+    if (live0) {
+        y[row] = acc0;
+        if (push.n) push_out(push, row, acc0);
+    }
+    if (live1) {
+        y[row + 1] = acc1;
+        if (push.n) push_out(push, row + 1, acc1);
+    }
+}
 // kinds whose kernels have no fused delivery: copy the finished y to the destinations that want it
 __global__ void push_rows_kernel(const double* __restrict__ y, uint32_t M, const PushArgs push) {
     const uint32_t stride = gridDim.x * blockDim.x;
