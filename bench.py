@@ -254,7 +254,8 @@ def main():
         dm = d_csr.to_ell(sp.FMT_ELL_COLMAJOR)
         col_range = d_csr.col_range
         d_csr.free()
-        kind, kname = sp.ELL_ROWS, "ell_colmajor_kernel" + ("<idx16>" if dm.index_bits == 16 else "")
+        # 16-bit column offsets: the two-rows-per-thread kernel; otherwise the one-row-per-thread kernel with 32-bit ids
+        kind, kname = sp.ELL_ROWS, ("ell_colmajor_pair_kernel<idx16>" if dm.index_bits == 16 else "ell_colmajor_kernel")
     else:
         spec = synth.banded(1 << 25, 32, args.half_width)
         Mtot = 1 << 25
