@@ -1595,7 +1595,7 @@ extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x,
 
 // L2 flush by READING a buffer larger than L2: leaves the cache full of CLEAN lines.  (A memset leaves it full of dirty
 // lines, whose write-back the next kernel's fills then pay for -- up to one extra byte written per byte read.)
-__global__ void flush_read_kernel(const uint4* __restrict__ p, size_t n, uint4* __restrict__ sink) {
+__global__ void flush_read_kernel(const uint4* p, size_t n, uint4* sink) {
     uint4 a = make_uint4(0, 0, 0, 0);
     const size_t stride = (size_t) gridDim.x * blockDim.x;
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
