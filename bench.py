@@ -441,9 +441,10 @@ def main():
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_local),
                      "index_bits": idx_bits, "moved_bytes_per_launch": int(bytes_local - (2 * nnz_total // nr if idx_bits == 16 else 0)),
+                     "frac_moved": (bytes_local - (2 * nnz_total // nr if idx_bits == 16 else 0)) / (ms_step * 1e-3) / 1e9 / peak,
                      "note": "per GPU = global algorithmic bytes / n_gpus; global = 12*nnz + 4*M(+1 for CSR) + 8*N + 8*M (DESIGN.md). "
                              "With index_bits 16 the kernel reads 2-byte column offsets (10 B per non-zero): it moves fewer bytes than the "
-                             "algorithmic figure it is scored against, so frac may exceed 1"},
+                             "algorithmic figure it is scored against, so frac may exceed 1; frac_moved = the bytes it really moves / (t * peak)"},
         "parity": parity,
     }
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
