@@ -1212,7 +1212,25 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
             if (m->tuned < 0 && tune_adaptive(m, d_x, d_y, st)) return 1;
             launch_candidate(m, m->tuned, d_x, d_y, st);
             break;
-        case SPMVB200_CSR_ROWS_WARP: launch_csr_vector(m, m->vec_lanes, d_x, d_y, st, 0, m->M); break;
+        case SPMVB200_CSR_ROWS_WARP:
+            if (!m->vec_tuned && m->format == SPMVB200_FMT_CSR) {
+                // first use: the sub-warp width guessed from the mean row length against its two neighbours (the x gather pattern
+                // decides, not the mean: 27-point stencil, mean 26.6 -> guess 16 lanes, 0.203 ms; 4 lanes: 0.141 ms)
+                m->vec_tuned = 1;
+                if (!getenv("SPMVB200_VEC_LANES") && m->NZ >= (1u << 18)) {
+                    int best = m->vec_lanes;
+                    float best_ms = 1e30f;
+                    for (int lanes = 2; lanes <= 32; lanes *= 2) {
+                        if (lanes > 4 * m->vec_lanes || 4 * lanes < m->vec_lanes) continue;
+                        float ms = 0;
+                        if (time_best_of_2([&] { launch_csr_vector(m, lanes, d_x, d_y, st, 0, m->M); }, st, &ms)) return 1;
+                        if (ms < best_ms) { best_ms = ms; best = lanes; }
+                    }
+                    m->vec_lanes = best;
+                }
+            }
+            launch_csr_vector(m, m->vec_lanes, d_x, d_y, st, 0, m->M);
+            break;
         case SPMVB200_ELL_ROWS: launch_ell_colmajor(m, d_x, d_y, st, 0, m->M); break;
         case SPMVB200_SELL_ROWS: launch_sell(m, d_x, d_y, st); break;
         case SPMVB200_XWIN_ROWS:
@@ -1273,7 +1291,8 @@ extern "C" int spmvb200_spmv_device_push(spmvb200_matrix* m, int kind, const dou
     if (push->n < 0 || push->n > 8) return fail("spmv_device_push: %d destinations (at most 8)", push->n);
     if (prefer_smem_once()) return 1;
     // first use of a self-tuning kind: tune without deliveries (the tuning run launches every candidate)
-    if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0))
+    if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0) ||
+        (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned))
         if (launch(m, kind, d_x, d_y, (cudaStream_t) stream)) return 1;
     PushArgs a = {};
     a.n = push->n;
@@ -1383,7 +1402,8 @@ extern "C" int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a
     cudaGraphExec_t exec = nullptr;
     do {
         // self-tuning kinds tune here (cannot happen inside a capture); d_b is scratch at this point
-        if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0))
+        if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0) ||
+            (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned))
             if ((rc = launch(m, kind, d_a, d_b, st))) break;
         const int pairs = iters / 2;
         unsigned long long per_replay = 0;
@@ -1524,7 +1544,8 @@ extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x,
     if (prefer_smem_once() || ensure_events(m)) return 1;
     if (!m->d_x) CU_TRY(cudaMalloc(&m->d_x, std::max<uint64_t>(m->N, 1) * 8));
     if (!m->d_y) CU_TRY(cudaMalloc(&m->d_y, std::max<uint64_t>(m->M, 1) * 8));
-    const bool untuned = (kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0);
+    const bool untuned = (kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0) ||
+                         (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned);
     int cand = untuned ? -1 : pipe_candidate(m, kind);
     if (!untuned && (!m->pipe || m->pipe->kind != kind || m->pipe->cand != cand))
         if (build_pipe(m, kind, cand)) return 1;

@@ -66,6 +66,7 @@ struct spmvb200_matrix {
     uint32_t* seg_tiles = nullptr;  // indices of the segment tiles (rows longer than one tile)
     uint32_t ntiles = 0, nlong = 0, nseg = 0;
     int vec_lanes = 32;
+    int vec_tuned = 0;  // CSR: the sub-warp width of SPMVB200_CSR_ROWS_WARP has been timed on this matrix (first use)
     // SPMVB200_CSR_ADAPTIVE: candidate chosen by the first-use tuning run (-1 = not tuned yet)
     int tuned = -1;
     float tuned_ms[16] = {0};
