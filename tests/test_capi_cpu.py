@@ -135,3 +135,27 @@ def test_binary_matrix_cache_roundtrip(tmp_path):
     bad.write_bytes(b"%%MatrixMarket matrix coordinate real general\n")
     with pytest.raises(ValueError):
         sp.Spmat.load(str(bad))
+
+
+def test_bench_reference_arm_contract_line():
+    """`bench.py --impl reference` (the reference's own OpenMP kernels on the host cores) prints exactly one JSON line with the
+    contract's keys; `bench.py` without a GPU refuses to run (no CPU fallback on the product arm)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["dtype"] == "f64" and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    import torch
+    if not torch.cuda.is_available():
+        ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600)
+        assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)
