@@ -18,3 +18,15 @@ def test_two_gpu_row_block_parity():
            "--master-port", "29517", os.path.join(ROOT, "tools", "multi_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MULTI_GPU_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_two_gpu_fused_iteration_parity():
+    """x <- A x over 2 GPUs with the exchange fused into the SpMV epilogue (peer stores over CUDA IPC + flag barrier) and with an
+    NCCL all-gather: every rank's slice equals the oracle's iterates (bit for bit where the kind sums in the serial order)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29518", os.path.join(ROOT, "tools", "multi_gpu_iterate.py"), "--parity-only"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTI_GPU_ITERATE OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

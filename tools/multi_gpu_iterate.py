@@ -68,6 +68,15 @@ def main():
                 ok = ok and bool(flag.item())
                 it.close()
 
+    if "--parity-only" in sys.argv:
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("MULTI_GPU_ITERATE", "OK" if flag.item() else "FAILED", flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if flag.item() == 1 else 1)
+
     # ---- timing: banded 2^22 rows per GPU, w = 2^15 (cfg4 row density), x-window kernel
     rows_per = 1 << 22
     M = rows_per * world
