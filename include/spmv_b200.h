@@ -133,6 +133,11 @@ const char* spmvb200_kind_name(int kind); /* the reference's mode string, e.g. "
  * vector with 2..32 lanes per row) on the handle's first adaptive launch and keeps the fastest;
  * this returns the winner's name ("" before that first launch). */
 int spmvb200_adaptive_choice(const spmvb200_matrix* m, char* name, size_t len);
+/* The bit-exact kinds pick at first use too: SPMVB200_CSR_ROWS between the stream kernel and an x-window or SELL copy,
+ * SPMVB200_ELL_ROWS (when the ELL rectangle is >= 1.25 x the non-zeros) between the column-major kernel and a SELL copy built
+ * from the ELL arrays; every candidate reproduces sgemvSerial (src/SpMV_CSR_OMP.c:229-250) bit for bit.  Returns
+ * "stream" | "ell" | "xwindow" | "sell" ("" before the first launch of that kind). */
+int spmvb200_exact_choice(const spmvb200_matrix* m, char* name, size_t len);
 
 /* ------------------------------------------------------------------ compute
  * Device-resident SpMV: y[0..rows) = A[row_begin..row_end) * x, d_x has N doubles, d_y has

@@ -51,6 +51,7 @@ _SIGS = {
     "spmvb200_kind_supported": (C.c_int, [_vp, C.c_int]),
     "spmvb200_kind_name": (C.c_char_p, [C.c_int]),
     "spmvb200_adaptive_choice": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
+    "spmvb200_exact_choice": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "spmvb200_spmv_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "spmvb200_spmv_device_push": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(Push), _vp]),
     "spmvb200_ipc_export": (C.c_int, [_vp, _vp]),

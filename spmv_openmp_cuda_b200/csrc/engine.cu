@@ -514,7 +514,9 @@ extern "C" int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma
 static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, spmvb200_matrix** out) {
     if (!out) return fail("sell_from_csr: null output");
     *out = nullptr;
-    if (!csr || csr->format != SPMVB200_FMT_CSR) return fail("sell_from_csr: source is not a CSR handle");
+    if (!csr || (csr->format != SPMVB200_FMT_CSR && csr->format != SPMVB200_FMT_ELL_COLMAJOR))
+        return fail("sell_from_csr: source is neither a CSR nor a column-major ELL handle");
+    const RowSrc src = {csr->irp, csr->rl, csr->ja, csr->as, csr->format == SPMVB200_FMT_CSR ? 0ull : csr->pitch};
     if (sigma == 0) sigma = 16384;
     if (sigma % 32) return fail("sell_from_csr: sigma must be a multiple of 32");
     spmvb200_matrix* m = new spmvb200_matrix();
@@ -539,7 +541,7 @@ static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, 
         if ((rc = cudaMalloc(&m->irp, ((size_t) nsl + 1) * 4) != cudaSuccess)) break;
         if ((rc = cudaMalloc(&slots, ((size_t) nsl + 1) * 8) != cudaSuccess)) break;
         if ((rc = cudaMalloc(&slots_scan, ((size_t) nsl + 1) * 8) != cudaSuccess)) break;
-        sell_keys_kernel<<<(Mpad + 255) / 256, 256>>>(csr->irp, (uint32_t) csr->M, Mpad, sigma, cap, k0, v0);
+        sell_keys_kernel<<<(Mpad + 255) / 256, 256>>>(src, (uint32_t) csr->M, Mpad, sigma, cap, k0, v0);
         size_t b1 = 0, b2 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, v0, m->perm, (int) Mpad);
         cub::DeviceScan::ExclusiveSum(nullptr, b2, slots, slots_scan, (int) nsl + 1);
@@ -557,7 +559,7 @@ static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, 
         if ((rc = cudaMalloc(&m->as, (total + PAD) * 8) != cudaSuccess)) break;
         cudaMemset(m->ja + total, 0, PAD * 4);
         cudaMemset(m->as + total, 0, PAD * 8);
-        sell_fill_kernel<<<(Mpad + 255) / 256, 256>>>(csr->irp, csr->ja, csr->as, m->perm, m->irp, Mpad, cap, m->ja, m->as);
+        sell_fill_kernel<<<(Mpad + 255) / 256, 256>>>(src, m->perm, m->irp, Mpad, cap, m->ja, m->as);
         if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
         m->K = sigma;  // reported through spmvb200_dims as K
     } while (0);
@@ -1189,6 +1191,34 @@ static int tune_exact(spmvb200_matrix* m, const double* d_x, double* d_y, cudaSt
     return 0;
 }
 
+// ---- SPMVB200_ELL_ROWS on a padded matrix: the column-major kernel exits early per WARP (a warp runs to the longest of its rows), so one
+// long row among 64 short ones keeps the warp's slot busy for K dependent round trips.  When the ELL rectangle is at least 1.25 x the
+// non-zeros, a SELL-32-sigma copy (rows sorted by length inside windows: warps see equal lengths) is built from the ELL arrays on the
+// device and timed against the column-major kernel at first use; it is kept only if it wins by 5 %.  Both add a row's products left
+// to right with separate mul / add roundings: bit-identical results either way.  tuned_x: 0 = column-major ELL, CAND_SELL = the copy.
+static int tune_ell(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
+    m->tuned_x = 0;
+    if (getenv("SPMVB200_NO_SELL") || getenv("SPMVB200_ELL_NO_SELL") || getenv("SPMVB200_ELL_NO_EARLY_EXIT") || m->NZ < (1u << 20) || !m->rl) return 0;
+    if ((double) m->K * (double) m->M < 1.25 * (double) m->NZ) return 0;
+    float ell_ms = 0;
+    if (time_best_of_2([&] { launch_ell_colmajor(m, d_x, d_y, st, 0, m->M); }, st, &ell_ms)) return 1;
+    m->tuned_x_ms[0] = ell_ms;
+    m->tuned_x_ms[1] = m->tuned_x_ms[2] = -1.f;
+    g_quiet = 1;
+    spmvb200_matrix* sell = nullptr;
+    if (!sell_build(m, 0, 0xffffffffu, &sell)) {
+        float ms = 1e30f;
+        if (!time_best_of_2([&] { launch_sell(sell, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
+        if (ms < 0.95f * ell_ms) { m->tuned_x = CAND_SELL; m->x_child = sell; } else spmvb200_free(sell);
+    }
+    g_quiet = 0;
+    g_err[0] = 0;
+    if (getenv("SPMVB200_VERBOSE"))
+        fprintf(stderr, "spmv_b200: ELL tuning M=%llu K=%llu NZ=%llu -> ell=%.3fms sell=%.3fms, picked %s\n", (unsigned long long) m->M,
+                (unsigned long long) m->K, (unsigned long long) m->NZ, m->tuned_x_ms[0], m->tuned_x_ms[2], m->tuned_x ? "sell" : "ell");
+    return 0;
+}
+
 template <int LANES>
 static void launch_ell_rowmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
     constexpr int BLOCK = 256;
@@ -1231,7 +1261,11 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
             }
             launch_csr_vector(m, m->vec_lanes, d_x, d_y, st, 0, m->M);
             break;
-        case SPMVB200_ELL_ROWS: launch_ell_colmajor(m, d_x, d_y, st, 0, m->M); break;
+        case SPMVB200_ELL_ROWS:
+            if (m->tuned_x < 0 && tune_ell(m, d_x, d_y, st)) return 1;
+            if (m->tuned_x == CAND_SELL) launch_sell(m->x_child, d_x, d_y, st);
+            else launch_ell_colmajor(m, d_x, d_y, st, 0, m->M);
+            break;
         case SPMVB200_SELL_ROWS: launch_sell(m, d_x, d_y, st); break;
         case SPMVB200_XWIN_ROWS:
             if (m->xw_mode < 0 && tune_xwin(m, d_x, d_y, st, nullptr)) return 1;
@@ -1291,7 +1325,7 @@ extern "C" int spmvb200_spmv_device_push(spmvb200_matrix* m, int kind, const dou
     if (push->n < 0 || push->n > 8) return fail("spmv_device_push: %d destinations (at most 8)", push->n);
     if (prefer_smem_once()) return 1;
     // first use of a self-tuning kind: tune without deliveries (the tuning run launches every candidate)
-    if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0) ||
+    if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || ((kind == SPMVB200_CSR_ROWS || kind == SPMVB200_ELL_ROWS) && m->tuned_x < 0) ||
         (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned))
         if (launch(m, kind, d_x, d_y, (cudaStream_t) stream)) return 1;
     PushArgs a = {};
@@ -1402,7 +1436,7 @@ extern "C" int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a
     cudaGraphExec_t exec = nullptr;
     do {
         // self-tuning kinds tune here (cannot happen inside a capture); d_b is scratch at this point
-        if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0) ||
+        if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || ((kind == SPMVB200_CSR_ROWS || kind == SPMVB200_ELL_ROWS) && m->tuned_x < 0) ||
             (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned))
             if ((rc = launch(m, kind, d_a, d_b, st))) break;
         const int pairs = iters / 2;
@@ -1447,7 +1481,7 @@ static int pipe_candidate(const spmvb200_matrix* m, int kind) {
         case SPMVB200_CSR_ROWS: return m->tuned_x == 0 ? 10 : -1;  // a re-tiled copy runs as one launch
         case SPMVB200_CSR_ADAPTIVE: return ((m->tuned >= 2 && m->nseg) || m->tuned >= 7) ? -1 : m->tuned;  // long rows / spans: one launch
         case SPMVB200_CSR_ROWS_WARP: return m->nseg ? -1 : 20 + m->vec_lanes;
-        case SPMVB200_ELL_ROWS: return 100;
+        case SPMVB200_ELL_ROWS: return m->tuned_x == 0 ? 100 : -1;  // the SELL copy runs as one launch
         default: return -1;
     }
 }
@@ -1461,6 +1495,11 @@ static void launch_chunk(spmvb200_matrix* m, const HostPipe* p, int k, const dou
     else if (c >= 20) launch_csr_vector(m, c - 20, x, y, p->s_comp, r0, r1);
     else launch_csr_vector(m, 2 << (c - 2), x, y, p->s_comp, r0, r1);
 }
+static int host_chunks_wanted() {
+    int nch = 4;  // measured on B200/PCIe5: 1 chunk 0.74 ms, 2: 0.63, 4: 0.54, 8: 0.59, 16: 0.70 per call (cfg2)
+    if (const char* e = getenv("SPMVB200_HOST_CHUNKS")) nch = std::max(1, atoi(e));  // developer knob
+    return nch;
+}
 static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
     destroy_pipe(m->pipe);  // rebuilt only when another kind is used through the host path
     m->pipe = nullptr;
@@ -1468,8 +1507,8 @@ static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
     m->pipe = p;
     p->kind = kind;
     p->cand = cand;
-    int nch = 4;  // measured on B200/PCIe5: 1 chunk 0.74 ms, 2: 0.63, 4: 0.54, 8: 0.59, 16: 0.70 per call (cfg2)
-    if (const char* e = getenv("SPMVB200_HOST_CHUNKS")) nch = std::max(1, atoi(e));
+    int nch = host_chunks_wanted();
+    p->nch_req = nch;
     if (m->M < 65536 || cand < 0) nch = 1;
     const bool stream = (cand == 0 || cand == 1 || cand == 10);
     if (stream) nch = (int) std::max<uint32_t>(1, std::min<uint32_t>(nch, m->ntiles));
@@ -1538,28 +1577,50 @@ static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
     return 0;
 }
 
+// If the caller's y is page-locked (cudaHostAlloc / cudaHostRegister) a kernel can store its rows straight into it: the
+// device->host transfer then rides along with the kernel as posted PCIe writes instead of following it as a copy-engine job.
+// Measured on cfg2 (16.8 MB of y, tools/e2e_probe.py, profiles/r01d_e2e_probe.log): a single x-window launch 0.737 -> 0.671 ms per
+// call; the sub-warp kernels (one 8-byte store per row and sub-warp) 0.769 -> 0.890 ms; inside the chunked pipeline 0.539 -> 0.628 ms
+// (the stores compete with the x pieces still coming up and run at 32-40 GB/s).  So by default only single x-window launches do it.
+// SPMVB200_HOST_DIRECT_Y (developer knob): 0 never, 1 default, 2 every single launch, 3 the chunked pipeline as well.
+// Returns the device-side alias of y, or nullptr (then y goes through d_y + cudaMemcpyAsync; always so for pageable memory).
+static double* mapped_alias(double* y, bool chunked, bool xwin_launch) {
+    const char* e = getenv("SPMVB200_HOST_DIRECT_Y");
+    const int mode = e ? atoi(e) : 1;
+    if (mode < (chunked ? 3 : (xwin_launch ? 1 : 2))) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, y) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
+}
+
 extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms) {
     if (!m || !x || !y) return fail("spmv_host: null argument");
     if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
     if (prefer_smem_once() || ensure_events(m)) return 1;
     if (!m->d_x) CU_TRY(cudaMalloc(&m->d_x, std::max<uint64_t>(m->N, 1) * 8));
     if (!m->d_y) CU_TRY(cudaMalloc(&m->d_y, std::max<uint64_t>(m->M, 1) * 8));
-    const bool untuned = (kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x < 0) ||
+    const bool untuned = (kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || ((kind == SPMVB200_CSR_ROWS || kind == SPMVB200_ELL_ROWS) && m->tuned_x < 0) ||
                          (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned);
     int cand = untuned ? -1 : pipe_candidate(m, kind);
-    if (!untuned && (!m->pipe || m->pipe->kind != kind || m->pipe->cand != cand))
+    if (!untuned && (!m->pipe || m->pipe->kind != kind || m->pipe->cand != cand || m->pipe->nch_req != host_chunks_wanted()))
         if (build_pipe(m, kind, cand)) return 1;
     if (untuned || m->pipe->nch <= 1) {  // plain path: x up, one launch, y down (also the adaptive mode's tuning call)
+        const bool xw = (kind == SPMVB200_XWIN_ROWS && m->xw_mode >= 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x == CAND_XWIN) ||
+                        (kind == SPMVB200_CSR_ADAPTIVE && m->tuned == CAND_XWIN);
+        const bool tuning = untuned || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0);  // tuning launches time candidates: those stay on device memory
+        double* const y_one = tuning ? nullptr : mapped_alias(y, false, xw);
+        double* const out = y_one ? y_one : m->d_y;
         CU_TRY(cudaMemcpyAsync(m->d_x, x, m->N * 8, cudaMemcpyHostToDevice, 0));
         CU_TRY(cudaEventRecord(m->ev0, 0));
-        if (launch(m, kind, m->d_x, m->d_y, 0)) return 1;
+        if (launch(m, kind, m->d_x, out, 0)) return 1;
         CU_TRY(cudaEventRecord(m->ev1, 0));
-        CU_TRY(cudaMemcpyAsync(y, m->d_y, m->M * 8, cudaMemcpyDeviceToHost, 0));
+        if (out == m->d_y) CU_TRY(cudaMemcpyAsync(y, m->d_y, m->M * 8, cudaMemcpyDeviceToHost, 0));
         CU_TRY(cudaStreamSynchronize(0));
         if (kernel_ms) CU_TRY(cudaEventElapsedTime(kernel_ms, m->ev0, m->ev1));
         return 0;
     }
     HostPipe* p = m->pipe;
+    double* const y_map = mapped_alias(y, true, false);
     const bool dbg = getenv("SPMVB200_PIPE_DEBUG") != nullptr;
     std::vector<cudaEvent_t> dbg_up, dbg_down;
     cudaEvent_t dbg0 = nullptr;
@@ -1576,10 +1637,10 @@ extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x,
     for (int k = 0; k < p->nch; ++k) {
         CU_TRY(cudaStreamWaitEvent(p->s_comp, p->x_ready[k], 0));
         CU_TRY(cudaEventRecord(p->k_start[k], p->s_comp));
-        launch_chunk(m, p, k, m->d_x, m->d_y);
+        launch_chunk(m, p, k, m->d_x, y_map ? y_map : m->d_y);
         CU_TRY(cudaEventRecord(p->k_end[k], p->s_comp));
         const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
-        if (r1 > r0) {
+        if (r1 > r0 && !y_map) {
             CU_TRY(cudaStreamWaitEvent(p->s_down, p->k_end[k], 0));
             CU_TRY(cudaMemcpyAsync(y + r0, m->d_y + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, p->s_down));
             if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, p->s_down); dbg_down.push_back(e); }
@@ -1650,6 +1711,13 @@ extern "C" int spmvb200_time_device(spmvb200_matrix* m, int kind, const double* 
 extern "C" int spmvb200_adaptive_choice(const spmvb200_matrix* m, char* name, size_t len) {
     if (!m || !name || !len) return fail("adaptive_choice: bad arguments");
     snprintf(name, len, "%s", m->tuned >= 0 ? CAND_NAME[m->tuned] : "");
+    return 0;
+}
+
+extern "C" int spmvb200_exact_choice(const spmvb200_matrix* m, char* name, size_t len) {
+    if (!m || !name || !len) return fail("exact_choice: bad arguments");
+    const bool ell = m->format == SPMVB200_FMT_ELL_COLMAJOR;
+    snprintf(name, len, "%s", m->tuned_x < 0 ? "" : m->tuned_x == CAND_XWIN ? "xwindow" : m->tuned_x == CAND_SELL ? "sell" : ell ? "ell" : "stream");
     return 0;
 }
 

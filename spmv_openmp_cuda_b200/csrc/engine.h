@@ -11,7 +11,7 @@ struct LongRec;
 // Plan of the pipelined host path (spmvb200_spmv_host): x goes up in pieces, row chunks start as soon as the
 // pieces they read have landed, y chunks go down while later chunks compute (three streams, full-duplex PCIe).
 struct HostPipe {
-    int kind = -1, cand = -1, nch = 0, npieces = 0;
+    int kind = -1, cand = -1, nch = 0, nch_req = 0, npieces = 0;
     std::vector<uint64_t> row_b;   // nch+1 row bounds
     std::vector<uint32_t> tile_b;  // nch+1 tile bounds (CSR stream kernel)
     std::vector<uint64_t> x_b;     // nch+1 bounds of the x pieces: chunk k reads only x[0, x_b[k+1])

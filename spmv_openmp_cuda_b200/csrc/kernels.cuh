@@ -35,6 +35,7 @@ constexpr int STREAM_TILE = 2048;        // non-zeros per tile (24 KB of values 
 constexpr int STREAM_BLOCK = 128;        // threads per CTA
 constexpr int STREAM_TILE_ROWS = 512;    // rows per tile (row-pointer slice in shared memory); 8 CTAs/SM fit
 constexpr int STREAM_LONG_T = 64;
+constexpr int STREAM_PRE_T = 48;         // exact kind: a tile whose longest row exceeds this multiplies element-parallel first
 constexpr int VEC_MID = 256;             // vector kernels: longer rows get a CTA of their own (csr_midrow_kernel)        // ADAPTIVE: rows longer than this are reduced by a whole warp
 
 // ---------------------------------------------------------------------------------------------
@@ -131,6 +132,28 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
 
     constexpr int RI = TILE_ROWS / BLOCK;
     static_assert(TILE_ROWS % BLOCK == 0, "tile rows must be a multiple of the block");
+    if (!ADAPTIVE) {
+        // ---- exact kind, tile with a long row: a thread walking e.g. 1500 non-zeros alone exposes one L2 gather after the other
+        // while its 127 neighbours idle.  All threads first turn the staged values into PRODUCTS (element-parallel: 16 independent
+        // gathers per thread), then the row's owner adds them left to right from shared memory: mul and add keep their separate
+        // roundings and their order, so the result is still bit-identical to sgemvSerial.
+        uint32_t mx = 0;
+        for (uint32_t r = tid; r < nrows; r += BLOCK) mx = max(mx, s_rp[r + 1] - s_rp[r]);
+        if (__syncthreads_or(mx > (uint32_t) STREAM_PRE_T)) {
+            const uint32_t lo = n0 - a0, hi = n1 - a0;
+#pragma unroll 4
+            for (uint32_t j = lo + tid; j < hi; j += BLOCK) s_val[j] = __dmul_rn(s_val[j], ld_x(x, s_col[j]));
+            __syncthreads();
+            for (uint32_t r = tid; r < nrows; r += BLOCK) {
+                const uint32_t e = s_rp[r + 1];
+                double acc = 0;
+#pragma unroll 8
+                for (uint32_t j = s_rp[r]; j < e; ++j) acc = __dadd_rn(acc, s_val[j]);
+                y[r0 + r] = acc;
+            }
+            return;
+        }
+    }
     if (nrows <= (uint32_t) BLOCK) {
         // ---- at most one row per thread: walk it with 4 independent gathers in flight
         if (tid < nrows) {
@@ -421,6 +444,7 @@ ell_colmajor_pair_kernel(const double* __restrict__ as, const uint16_t* __restri
             if (k < len1) acc1 = __dadd_rn(acc1, __dmul_rn(v.y, ld_x(x, (c >> 16) + cb1)));
         }
     }
+    // (storing the pair as one 16-byte word was measured 7 % SLOWER on cfg2: 101.0 vs 94.3 us, three runs each on one box)
     if (live0) {
         y[row] = acc0;
         if (push.n) push_out(push, row, acc0);
@@ -527,11 +551,21 @@ sell_kernel(const uint32_t* __restrict__ slice_ptr, const uint32_t* __restrict__
 // SELL construction (device): sort keys, slice lengths, fill
 // cap: rows longer than this are left EMPTY here (their y entry is written by other kernels right after: the adaptive mode's
 // SELL + per-row-CTA hybrid for skewed matrices)
-__global__ void sell_keys_kernel(const uint32_t* __restrict__ irp, uint32_t M, uint32_t Mpad, uint32_t sigma, uint32_t cap,
+// source of a SELL build: a CSR handle (pitch = 0) or a column-major ELL handle (slot k of row r at k * pitch + r, lengths in rl)
+struct RowSrc {
+    const uint32_t* irp;
+    const uint32_t* rl;
+    const uint32_t* ja;
+    const double* as;
+    uint64_t pitch;
+    __device__ __forceinline__ uint32_t len(uint32_t r) const { return pitch ? rl[r] : irp[r + 1] - irp[r]; }
+    __device__ __forceinline__ uint64_t at(uint32_t r, uint32_t k) const { return pitch ? (uint64_t) k * pitch + r : (uint64_t) irp[r] + k; }
+};
+__global__ void sell_keys_kernel(const RowSrc src, uint32_t M, uint32_t Mpad, uint32_t sigma, uint32_t cap,
                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= Mpad) return;
-    uint32_t len = r < M ? irp[r + 1] - irp[r] : 0u;
+    uint32_t len = r < M ? src.len(r) : 0u;
     const bool capped = len > cap;  // not this copy's row: no entries here and NO write of y (other kernels own it, concurrently)
     if (capped) len = 0u;
     keys[r] = ((uint64_t) (r / sigma) << 32) | (uint64_t) (0xffffffffu - len);  // ascending sort = descending length per window
@@ -545,20 +579,19 @@ __global__ void sell_slices_kernel(const uint64_t* __restrict__ keys_sorted, uin
     rl_sorted[i] = len;
     if ((i & 31) == 0) slice_slots[i >> 5] = (uint64_t) len * 32;  // first row of a slice is its longest
 }
-__global__ void sell_fill_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
-                                 const uint32_t* __restrict__ perm, const uint32_t* __restrict__ slice_ptr, uint32_t Mpad, uint32_t cap,
-                                 uint32_t* __restrict__ sja, double* __restrict__ sas) {
+__global__ void sell_fill_kernel(const RowSrc src, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ slice_ptr, uint32_t Mpad,
+                                 uint32_t cap, uint32_t* __restrict__ sja, double* __restrict__ sas) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Mpad) return;
     const uint32_t row = perm[i];
     const uint32_t sp0 = slice_ptr[i >> 5], wmax = (slice_ptr[(i >> 5) + 1] - sp0) >> 5;
-    const uint32_t s = row != 0xffffffffu ? irp[row] : 0u;
-    uint32_t len = row != 0xffffffffu ? irp[row + 1] - s : 0u;
+    uint32_t len = row != 0xffffffffu ? src.len(row) : 0u;
     if (len > cap) len = 0u;
     for (uint32_t k = 0; k < wmax; ++k) {
         const uint32_t o = sp0 + k * 32 + (i & 31);
-        sas[o] = k < len ? as[s + k] : 0.0;
-        sja[o] = k < len ? ja[s + k] : 0u;
+        const uint64_t e = k < len ? src.at(row, k) : 0ull;
+        sas[o] = k < len ? src.as[e] : 0.0;
+        sja[o] = k < len ? src.ja[e] : 0u;
     }
 }
 

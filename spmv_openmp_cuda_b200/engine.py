@@ -133,6 +133,13 @@ class DeviceSpmat:
         return buf.value.decode()
 
     @property
+    def exact_choice(self):
+        """what SPMVB200_CSR_ROWS / SPMVB200_ELL_ROWS picked at first use: stream | ell | xwindow | sell ("" before)"""
+        buf = C.create_string_buffer(64)
+        check(lib().spmvb200_exact_choice(self.handle, buf, 64), "exact_choice")
+        return buf.value.decode()
+
+    @property
     def index_bits(self):
         return int(lib().spmvb200_index_bits(self.handle))
 

@@ -288,6 +288,32 @@ def test_adaptive_sell_hybrid_on_skewed_rows(sp, orc, monkeypatch):
     assert dm.adaptive_choice == "sell"
 
 
+def test_ell_rows_picks_sell_copy_on_padded_matrix(sp, orc, monkeypatch):
+    """ELL_ROWS on mixed short/long rows (ELL rectangle >= 1.25 x nnz, >= 2^20 nnz): the handle times the column-major kernel against a
+    SELL copy built from the ELL arrays; whichever runs, y is bit-identical to sgemvSerial.  With the knob set the copy is never built."""
+    mat = sp.synth.host_csr(sp.synth.mixed(300000, 32, 0.05))
+    assert mat.NZ >= 1 << 20 and mat.MAX_ROW_NZ * mat.M > 1.25 * mat.NZ
+    ell = sp.synth.csr_to_ell_host(mat)
+    x = sp.synth.host_vector(mat.N)
+    y_ref = _oracle_y(orc, mat, x)
+    dx, dy = sp.DeviceVector.from_host(x), sp.DeviceVector(mat.M)
+    for forced_off in (False, True):
+        if forced_off:
+            monkeypatch.setenv("SPMVB200_ELL_NO_SELL", "1")
+        dm = sp.spMatCpyELL(ell)
+        assert dm.exact_choice == ""
+        for _ in range(2):
+            dy.fill_bytes(0xFF)
+            sp.cudaSpMVRowsELL(dm, dx, sp.Config(), dy)
+            np.testing.assert_array_equal(dy.to_host(), y_ref)
+        assert dm.exact_choice == ("ell" if forced_off else dm.exact_choice) and dm.exact_choice in ("ell", "sell")
+        # the copy also serves the other entry points of the kind: host buffers, CUDA-graph iteration is covered by test_iterate_*
+        y = np.full(mat.M, np.nan)
+        sp.spmv_host(sp.ELL_ROWS, dm, x, y)
+        np.testing.assert_array_equal(y, y_ref)
+        dm.free()
+
+
 def test_long_row_split_is_deterministic(sp):
     """Rows split across CTAs are combined in segment order by the last arriver: run-to-run identical."""
     mat = sp.synth.rmat_host_csr(14, 16)
@@ -326,8 +352,13 @@ def test_host_adapters_spmv_interf(sp, orc):
     lambda s: s.rmat_host_csr(17, 16),                  # rows longer than a tile inside the chunked CSR path
     lambda s: s.host_csr(s.mixed(150000, 48, 0.02)),    # uniform columns: every chunk needs all of x
 ])
-def test_pipelined_host_path(sp, orc, builder):
-    """spmvb200_spmv_host on matrices large enough for the chunked path: x pieces up, row chunks, y chunks down."""
+@pytest.mark.parametrize("pinned", [False, True])
+def test_pipelined_host_path(sp, orc, builder, pinned, monkeypatch):
+    """spmvb200_spmv_host on matrices large enough for the chunked path: x pieces up, row chunks, y chunks down.
+    pinned: y is page-locked, so the kernels store their rows straight into the caller's buffer (no device->host copy)."""
+    import torch
+    if pinned:
+        monkeypatch.setenv("SPMVB200_HOST_DIRECT_Y", "3")  # every kind, single launches and the chunked pipeline
     mat = builder(sp.synth)
     ell = sp.synth.csr_to_ell_host(mat) if mat.MAX_ROW_NZ * mat.M < 2e7 else None
     x = sp.synth.host_vector(mat.N)
@@ -337,7 +368,8 @@ def test_pipelined_host_path(sp, orc, builder):
            ([(sp.b200SpMVRowsELL, ell)] if ell is not None else [])
     for f, m in runs:
         for rep in range(3):
-            y = np.full(mat.M, np.nan)
+            y = torch.empty(mat.M, dtype=torch.float64).pin_memory().numpy() if pinned else np.empty(mat.M)
+            y.fill(np.nan)
             assert f(m, x, sp.Config(), y) == 0
             assert orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=TAU)[0] == 0, (f, rep)
             if f in (sp.b200SpMVRowsCSR, sp.b200SpMVRowsELL, sp.b200SpMVRowsSELL, sp.b200SpMVRowsXWIN):

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4]: ELL vs CSR on mixed short/long rows (M = 2^23, short rows 4 nnz, a fraction p of rows
 K_max long, uniform random columns), padding-ratio sweep, with and without the rowLens early exit.
-Run twice (the early exit is a process-wide developer knob):  python tools/cfg5_sweep.py ; SPMVB200_ELL_NO_EARLY_EXIT=1 python tools/cfg5_sweep.py ell"""
+Run three times (process-wide developer knobs):  python tools/cfg5_sweep.py ; SPMVB200_ELL_NO_SELL=1 python tools/cfg5_sweep.py ell
+(the column-major kernel alone, without the SELL copy ELL_ROWS may build at first use) ; SPMVB200_ELL_NO_EARLY_EXIT=1 python tools/cfg5_sweep.py ell"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -27,7 +28,7 @@ for kmax in (8, 16, 32, 48):
         e = d.to_ell(sp.FMT_ELL_COLMAJOR)
         sp.time_kernel(sp.ELL_ROWS, e, dx, dy, reps=2)
         t = float(sp.time_kernel(sp.ELL_ROWS, e, dx, dy, reps=10).mean())
-        rows.append(("ell_colmajor" + ("(no exit)" if noexit else ""), t, e.algorithmic_bytes))
+        rows.append(("ell_rows[%s]" % e.exact_choice + ("(no exit)" if noexit else ""), t, e.algorithmic_bytes))
         if not only_ell:
             sl = d.to_sell()
             sp.time_kernel(sp.SELL_ROWS, sl, dx, dy, reps=2)

@@ -35,6 +35,8 @@ def bench(label, dm, kinds, reps, flush):
         tmin, tmean = float(t.min()), float(t.mean())
         if kind == sp.CSR_ADAPTIVE:
             name = name + "[" + dm.adaptive_choice + "]"
+        elif kind in (sp.CSR_ROWS, sp.ELL_ROWS):
+            name = name + "[" + dm.exact_choice + "]"
         print("%-28s %-24s flush=%d  min %8.3f us  mean %8.3f us  %8.1f GB/s (mean)  frac %.3f  %7.1f GFLOP/s   [M=%d NZ=%d bytes=%.1f MB]" % (
             label, name, flush, tmin * 1e3, tmean * 1e3, B / tmean / 1e6, B / tmean / 1e6 / PEAK, 2 * dm.NZ / tmean / 1e6, dm.M, dm.NZ, B / 1e6), flush=True)
 
