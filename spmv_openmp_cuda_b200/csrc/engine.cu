@@ -811,7 +811,8 @@ extern "C" const char* spmvb200_kind_name(int kind) {
 // Rows the vector kernels skip: medium rows (one CTA each) and rows longer than a tile (one CTA per segment).  They touch other rows
 // of y than the main kernel, so they run NEXT to it on two side streams -- forked before the main launch, joined after it (events:
 // legal inside a graph capture too).  On R-MAT (cfg3) the three kernels are 189 + 97 + 52 us back to back.
-static void tail_fork(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+// exact: the medium rows go through the warp-per-row kernel that adds in the serial order (the bit-exact kind's SELL hybrid).
+static void tail_fork(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, bool exact = false) {
     if (!m->nmid && !m->nseg) return;
     static const bool serial = getenv("SPMVB200_SERIAL_TAIL") != nullptr;  // developer knob: the old back-to-back order
     if (!serial && !m->e_fork) {
@@ -828,11 +829,14 @@ static void tail_fork(spmvb200_matrix* m, const double* x, double* y, cudaStream
         if (fork) cudaStreamWaitEvent(s, m->e_fork, 0);
         static const bool warp_mid = getenv("SPMVB200_NO_WARP_MID") == nullptr;  // developer knob
         const uint32_t lo = warp_mid ? (uint32_t) MIDW_MAX : 0u;  // rows up to MIDW_MAX: a warp each; longer: a CTA each
-        if (warp_mid) {
+        if (exact) {
+            csr_midrow_exact_kernel<256><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y);
+            ++g_launches;
+        } else if (warp_mid) {
             csr_midrow_warp_kernel<256><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y, 0u, (uint32_t) MIDW_MAX);
             ++g_launches;
         }
-        if (!warp_mid || m->lmax > (uint32_t) MIDW_MAX) {
+        if (!exact && (!warp_mid || m->lmax > (uint32_t) MIDW_MAX)) {
             csr_midrow_kernel<128><<<m->nmid, 128, 0, s>>>(m->mid_rows, m->irp, m->ja, m->as, x, y, lo);
             ++g_launches;
         }
@@ -895,8 +899,9 @@ static void launch_csr_vspan(spmvb200_matrix* m, int lanes, const double* x, dou
 template <bool ADAPT, int VARIANT>
 static void launch_csr_stream(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint32_t t0, uint32_t t1) {
     if (t1 <= t0) return;
+    static const uint32_t pre_t = getenv("SPMVB200_PRE_T") ? (uint32_t) atoi(getenv("SPMVB200_PRE_T")) : (uint32_t) STREAM_PRE_T;  // developer knob
     csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, ADAPT, VARIANT>
-        <<<t1 - t0, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, x, y, m->partial, m->ticket, t0);
+        <<<t1 - t0, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, x, y, m->partial, m->ticket, t0, pre_t);
     ++g_launches;
 }
 static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
@@ -1157,6 +1162,12 @@ static int time_best_of_2(F&& run, cudaStream_t st, float* ms_out) {
     *ms_out = best;
     return 0;
 }
+static void launch_exact_sell(spmvb200_matrix* m, const spmvb200_matrix* sell, const double* x, double* y, cudaStream_t st) {
+    const bool hybrid = m->lmax > (uint32_t) VEC_MID;  // rows the capped SELL copy left out (it does not write their y)
+    if (hybrid) tail_fork(m, x, y, st, true);
+    launch_sell(sell, x, y, st);
+    if (hybrid) tail_join(m, st);
+}
 static int tune_exact(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
     float best_ms = 0;
     if (time_best_of_2([&] { launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles); }, st, &best_ms)) return 1;
@@ -1172,11 +1183,14 @@ static int tune_exact(spmvb200_matrix* m, const double* d_x, double* d_y, cudaSt
             if (xw->xw_sorted && !tune_xwin(xw, d_x, d_y, st, &ms)) m->tuned_x_ms[1] = ms;
             if (ms < 0.95f * best_ms) { best_ms = ms; best = CAND_XWIN; m->x_child = xw; } else spmvb200_free(xw);
         }
+        // rows longer than VEC_MID are left out of the SELL copy: a warp each adds them in the serial order next to it (exact hybrid);
+        // rows longer than a tile are split into segments as in the stream kernel (deterministic, within tolerance)
         spmvb200_matrix* sell = nullptr;
-        if (m->lmax <= (uint32_t) VEC_MID && !sell_build(m, 0, 0xffffffffu, &sell)) {
+        if (!getenv("SPMVB200_NO_SELL") && !sell_build(m, 0, m->lmax <= (uint32_t) VEC_MID ? 0xffffffffu : (uint32_t) VEC_MID, &sell)) {
             float ms = 1e30f;
-            if (sell->slots <= m->NZ + m->NZ / 4 && !time_best_of_2([&] { launch_sell(sell, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
-            if (ms < 0.95f * best_ms) {
+            if (sell->slots <= m->NZ + m->NZ / 4 && !time_best_of_2([&] { launch_exact_sell(m, sell, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
+            const char* f = getenv("SPMVB200_FORCE_EXACT");  // developer knob (tests): 13 = keep the SELL copy whatever the timing says
+            if (ms < 0.95f * best_ms || (f && atoi(f) == CAND_SELL && ms < 1e30f)) {
                 if (m->x_child) spmvb200_free(m->x_child);
                 best_ms = ms; best = CAND_SELL; m->x_child = sell;
             } else spmvb200_free(sell);
@@ -1235,7 +1249,7 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
         case SPMVB200_CSR_ROWS:
             if (m->tuned_x < 0 && tune_exact(m, d_x, d_y, st)) return 1;
             if (m->tuned_x == CAND_XWIN) { if (launch_xwin(m->x_child, d_x, d_y, st)) return 1; }
-            else if (m->tuned_x == CAND_SELL) launch_sell(m->x_child, d_x, d_y, st);
+            else if (m->tuned_x == CAND_SELL) launch_exact_sell(m, m->x_child, d_x, d_y, st);
             else launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles);
             break;
         case SPMVB200_CSR_ADAPTIVE:

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(BLOCK, 8)
 csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__ longrec,
                   const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
                   const double* __restrict__ x, double* __restrict__ y, double* __restrict__ partial,
-                  uint32_t* __restrict__ ticket, uint32_t tile_base) {
+                  uint32_t* __restrict__ ticket, uint32_t tile_base, uint32_t pre_t) {
     constexpr int CAP = TILE + 8;
     constexpr int NWARPS = BLOCK / 32;
     constexpr int MAXLONG = TILE / STREAM_LONG_T;
@@ -139,7 +139,7 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
         // roundings and their order, so the result is still bit-identical to sgemvSerial.
         uint32_t mx = 0;
         for (uint32_t r = tid; r < nrows; r += BLOCK) mx = max(mx, s_rp[r + 1] - s_rp[r]);
-        if (__syncthreads_or(mx > (uint32_t) STREAM_PRE_T)) {
+        if (__syncthreads_or(mx > pre_t)) {
             const uint32_t lo = n0 - a0, hi = n1 - a0;
 #pragma unroll 4
             for (uint32_t j = lo + tid; j < hi; j += BLOCK) s_val[j] = __dmul_rn(s_val[j], ld_x(x, s_col[j]));
@@ -772,6 +772,60 @@ csr_midrow_warp_kernel(const uint32_t* __restrict__ rows, uint32_t nrows, const 
     }
     t = subwarp_sum<32>(t);
     if (lane == 0) y[row] = t;
+}
+
+// Same rows for the BIT-EXACT kind: one warp per row.  A lane owns C = 8 CONSECUTIVE non-zeros of every 256-entry chunk (two 16-byte
+// column loads, four 16-byte value loads, 8 independent gathers), multiplies them, and the row's running sum then travels through the
+// lanes in order: at step l every lane adds its own 8 products to the sum so far, lane l's result is the one broadcast (one 64-bit shuffle
+// per 8 non-zeros).  mul and add keep their separate roundings and the serial order: bit-identical to sgemvSerial
+// (src/SpMV_CSR_OMP.c:229-250), with all loads 32 lanes wide.  What remains serial is the chain of dependent DADDs, one per non-zero.
+// Two earlier versions, both measured on the R-MAT medium rows (25 M non-zeros; the tolerance kernel above needs 97 us): every product
+// fetched by shuffle (2 SHFL per non-zero) 250 us; products parked in shared memory and read back as broadcasts 193-204 us (ncu: l1tex
+// 85 %, one shared-memory wavefront per non-zero on top of the gathers; its partial-chunk loop also had the LDS latency in the chain).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+csr_midrow_exact_kernel(const uint32_t* __restrict__ rows, uint32_t nrows, const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja,
+                        const double* __restrict__ as, const double* __restrict__ x, double* __restrict__ y) {
+    constexpr int C = 8, CH = 32 * C;
+    const uint32_t w = (blockIdx.x * BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nrows) return;  // warp-uniform
+    const uint32_t row = __ldg(rows + w);
+    const uint32_t s = __ldg(irp + row), e = __ldg(irp + row + 1);
+    double acc = 0;
+    for (uint32_t base = s & ~3u; base < e; base += CH) {  // 16-byte aligned chunk start; entries before s / from e on are masked
+        const uint32_t i0 = base + C * lane;
+        double p[C];
+        uint32_t c[C];
+#pragma unroll
+        for (int g = 0; g < C / 4; ++g) {
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (i0 + 4 * g < e) q = ld_stream(reinterpret_cast<const uint4*>(ja + i0 + 4 * g));  // overruns e by < 4: inside the arrays' slack
+            c[4 * g] = q.x; c[4 * g + 1] = q.y; c[4 * g + 2] = q.z; c[4 * g + 3] = q.w;
+        }
+#pragma unroll
+        for (int g = 0; g < C / 2; ++g) {
+            double2 v = make_double2(0.0, 0.0);
+            if (i0 + 2 * g < e) v = ld_stream(reinterpret_cast<const double2*>(as + i0 + 2 * g));
+            p[2 * g] = v.x; p[2 * g + 1] = v.y;
+        }
+        // Masked entries (before s in the first chunk, from e on in the last) become +0.0 and are added like the rest: the running sum
+        // starts at +0.0 and a round-to-nearest sum is -0.0 only if both operands are, so it is never -0.0 and "+ 0.0" is an exact no-op.
+        // One unpredicated chain for every chunk (a predicated tail loop put compare + select latency into the chain: 225 us).
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const bool ok = i0 + j >= s && i0 + j < e;
+            p[j] = ok ? __dmul_rn(p[j], ld_x(x, c[j])) : 0.0;
+        }
+        const uint32_t nl = (min(e, base + CH) - base + C - 1) / C;  // lanes that hold anything (warp-uniform)
+#pragma unroll 4
+        for (uint32_t l = 0; l < nl; ++l) {
+            double t = acc;
+#pragma unroll
+            for (int j = 0; j < C; ++j) t = __dadd_rn(t, p[j]);
+            acc = __shfl_sync(0xffffffffu, t, l);
+        }
+    }
+    if (lane == 0) y[row] = acc;
 }
 
 // largest column id in a range of a column-id array / in the valid slots of a row range of a column-major ELL

@@ -314,6 +314,30 @@ def test_ell_rows_picks_sell_copy_on_padded_matrix(sp, orc, monkeypatch):
         dm.free()
 
 
+def test_exact_kind_sell_hybrid_on_skewed_rows(sp, orc, monkeypatch):
+    """CSR_ROWS on an R-MAT matrix with the SELL copy forced: rows up to 256 come from the SELL copy, rows up to one tile from the
+    warp-per-row kernel that adds in the serial order (csr_midrow_exact_kernel) -- both bit-identical to sgemvSerial; rows longer than
+    a tile are split into segments (deterministic, within tolerance)."""
+    monkeypatch.setenv("SPMVB200_FORCE_EXACT", "13")
+    mat = sp.synth.rmat_host_csr(17, 16)
+    lens = np.diff(mat.IRP)
+    assert mat.NZ >= 1 << 20 and (lens > STREAM_TILE).any() and ((lens > 256) & (lens <= STREAM_TILE)).sum() > 10
+    x = sp.synth.host_vector(mat.N)
+    y_ref = _oracle_y(orc, mat, x)
+    dm, dx, dy = sp.spMatCpyCSR(mat), sp.DeviceVector.from_host(x), sp.DeviceVector(mat.M)
+    outs = []
+    for _ in range(3):
+        dy.fill_bytes(0xFF)
+        sp.cudaSpMVRowsCSR(dm, dx, sp.Config(), dy)
+        outs.append(dy.to_host())
+    assert dm.exact_choice == "sell"
+    y = outs[0]
+    np.testing.assert_array_equal(y[lens <= STREAM_TILE], y_ref[lens <= STREAM_TILE])
+    assert orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=TAU)[0] == 0
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o, y)
+
+
 def test_long_row_split_is_deterministic(sp):
     """Rows split across CTAs are combined in segment order by the last arriver: run-to-run identical."""
     mat = sp.synth.rmat_host_csr(14, 16)
