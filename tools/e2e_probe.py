@@ -18,7 +18,8 @@ hx.copy_(torch.from_numpy(synth.host_vector(dm.N)))
 dx = sp.DeviceVector.from_host(hx.numpy()); dy = sp.DeviceVector(dm.M)
 sp.cudaSpMVRowsELL(dm, dx, sp.Config(), dy)
 y_ref = dy.to_host()
-for name, kind, m in (("ELL_ROWS", sp.ELL_ROWS, dm), ("CSR_ROWS", sp.CSR_ROWS, d), ("CSR_ROWS_WARP", sp.CSR_ROWS_WARP, d)):
+KINDS = (("ELL_ROWS", sp.ELL_ROWS, dm), ("CSR_ROWS", sp.CSR_ROWS, d), ("CSR_ROWS_WARP", sp.CSR_ROWS_WARP, d))
+for name, kind, m in (KINDS[:1] if "--ell-only" in sys.argv else KINDS):
     for direct in (0, 1, 2, 3):
         for chunks in (1, 2, 4, 8, 16):
             os.environ["SPMVB200_HOST_DIRECT_Y"] = str(direct)
