@@ -2,6 +2,9 @@
 // on-device 64->32-bit narrowing / ELL transposition, plan building, kernel launch, D2H.
 // Replaces src/commons/cudaUtils.cu (spMatCpyCSR/ELL*, cudaFreeSpmat) and the launch+sync+download
 // code of src/main.cu:192-248 / test/SpMV_test.cu:103-145.  No CPU compute path exists here.
+// One translation unit in five files: this one (globals, plumbing, queries, timing loop, adapter cache) textually includes
+// engine_formats.inl (plan + uploads + SELL / x-window construction), engine_launch.inl (launchers, first-use tuning, kind switch),
+// engine_multigpu.inl (fused delivery, IPC, barrier, CUDA-graph iteration) and engine_hostpath.inl (spmvb200_spmv_host).
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -136,606 +139,7 @@ extern "C" int spmvb200_sync(void) {
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------- CSR plan
-static int scan_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, size_t n) {
-    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int) n);
-    if (e != cudaSuccess) return fail("plan scan: %s", cudaGetErrorString(e));
-    return 0;
-}
-
-// Builds, entirely on the device (plan.cuh), the row-block tiles of the stream kernel, the long-row records and
-// segment list, the medium-row list and the contiguous spans of the vector kernels.
-int spmvb200::finish_csr(spmvb200_matrix* m) {
-    const uint32_t M = (uint32_t) m->M;
-    const size_t n1 = (size_t) M + 1;
-    uint32_t last = 0;
-    CU_TRY(cudaMemcpy(&last, m->irp + M, 4, cudaMemcpyDeviceToHost));
-    if (last != m->NZ) return fail("CSR row pointer inconsistent: IRP[M]=%u, NZ=%llu", last, (unsigned long long) m->NZ);
-    uint32_t *cnt = nullptr, *idx = nullptr, *d_num = nullptr;  // cnt: tiles_at | long_at | segs_at ; idx: their scans
-    void* tmp = nullptr;
-    uint32_t *h_r0 = nullptr, *h_n0 = nullptr;
-    int rc = 0;
-    do {
-        if ((rc = cudaMalloc(&cnt, 3 * n1 * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&idx, 3 * n1 * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&d_num, 16) != cudaSuccess)) break;
-        size_t b_scan = 0, b_sel = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, b_scan, cnt, idx, (int) n1);
-        thrust::counting_iterator<uint32_t> rows_it(0);
-        MidRowPred pred{m->irp};
-        cub::DeviceSelect::If(nullptr, b_sel, rows_it, cnt, d_num, (int) M, pred);
-        const size_t tmp_bytes = std::max(b_scan, b_sel) + 16;
-        if ((rc = cudaMalloc(&tmp, tmp_bytes) != cudaSuccess)) break;
-        uint32_t lmax = 0;
-        if (M) {
-            cudaMemset(d_num, 0, 4);
-            row_len_from_irp_kernel<<<(M + 255) / 256, 256>>>(m->irp, M, nullptr, d_num);
-            if ((rc = cudaMemcpy(&lmax, d_num, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
-        }
-        m->lmax = lmax;
-        const uint32_t special = std::max<uint32_t>(1, std::min<uint32_t>(PLAN_SPECIAL_MAX, lmax));
-        plan_count_kernel<<<(unsigned) ((n1 + 255) / 256), 256>>>(m->irp, M, special, cnt, cnt + n1, cnt + 2 * n1);
-        for (int a = 0; a < 3 && !rc; ++a) rc = scan_u32(tmp, tmp_bytes, cnt + a * n1, idx + a * n1, n1);
-        if (rc) break;
-        uint32_t tot[3];
-        for (int a = 0; a < 3; ++a)
-            if ((rc = cudaMemcpy(&tot[a], idx + a * n1 + M, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
-        if (rc) break;
-        m->ntiles = tot[0];
-        m->nlong = tot[1];
-        m->nseg = tot[2];
-        if ((rc = cudaMalloc(&m->desc, ((size_t) m->ntiles + 1) * sizeof(TileDesc)) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->longrec, std::max<size_t>(1, m->nlong) * sizeof(LongRec)) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->seg_tiles, std::max<size_t>(1, m->nseg) * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->partial, std::max<size_t>(1, m->ntiles) * sizeof(double)) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->ticket, std::max<size_t>(1, m->nlong) * 4) != cudaSuccess)) break;
-        cudaMemset(m->ticket, 0, std::max<size_t>(1, m->nlong) * 4);
-        plan_scatter_kernel<<<(unsigned) ((n1 + 255) / 256), 256>>>(m->irp, M, (uint32_t) m->NZ, cnt, idx, idx + n1, idx + 2 * n1, m->ntiles, m->desc,
-                                                                   m->longrec, m->seg_tiles);
-        // rows the vector kernels hand to csr_midrow_kernel (cnt is free again: reuse it as the output list)
-        if (M) {
-            if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
-            if ((rc = cub::DeviceSelect::If(tmp, b_sel, rows_it, cnt, d_num, (int) M, pred) != cudaSuccess)) break;
-            if ((rc = cudaMemcpy(&m->nmid, d_num, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
-        }
-        if ((rc = cudaMalloc(&m->mid_rows, std::max<size_t>(1, m->nmid) * 4) != cudaSuccess)) break;
-        if (m->nmid && (rc = cudaMemcpy(m->mid_rows, cnt, (size_t) m->nmid * 4, cudaMemcpyDeviceToDevice) != cudaSuccess)) break;
-        // contiguous nnz-balanced row spans for the persistent vector kernel: SPANS_PER_SM big CTAs per SM
-        int dev = 0, sms = 148, per_sm = 2;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (const char* e = getenv("SPMVB200_SPANS_PER_SM")) per_sm = std::max(1, atoi(e));
-        m->nspans = (uint32_t) std::min<uint64_t>((uint64_t) sms * per_sm, std::max<uint64_t>(1, m->M));
-        if ((rc = cudaMalloc(&m->span_b, ((size_t) m->nspans + 1) * 4) != cudaSuccess)) break;
-        plan_spans_kernel<<<(m->nspans + 1 + 255) / 256, 256>>>(m->irp, M, m->NZ, m->nspans, m->span_b);
-        // host copy of the tile bounds (chunking of the pipelined host path): two flat arrays
-        const uint32_t nt1 = m->ntiles + 1;
-        if ((rc = cudaMalloc(&h_r0, (size_t) nt1 * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&h_n0, (size_t) nt1 * 4) != cudaSuccess)) break;
-        plan_split_desc_kernel<<<(nt1 + 255) / 256, 256>>>(m->desc, nt1, h_r0, h_n0);
-        m->h_tile_row0.resize(nt1);
-        m->h_tile_nnz0.resize(nt1);
-        if ((rc = cudaMemcpy(m->h_tile_row0.data(), h_r0, (size_t) nt1 * 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
-        if ((rc = cudaMemcpy(m->h_tile_nnz0.data(), h_n0, (size_t) nt1 * 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
-    } while (0);
-    cudaFree(cnt);
-    cudaFree(idx);
-    cudaFree(d_num);
-    cudaFree(tmp);
-    cudaFree(h_r0);
-    cudaFree(h_n0);
-    if (rc) {
-        if (cudaPeekAtLastError() != cudaSuccess || !g_err[0]) fail("CSR plan: %s", cudaGetErrorString(cudaGetLastError()));
-        return 1;
-    }
-    // sub-warp width of the vector kernel from the mean row length (2 non-zeros per lane and step)
-    const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
-    int lanes = 2;
-    while (lanes < 32 && lanes * 2 < mean) lanes *= 2;
-    if (const char* e = getenv("SPMVB200_VEC_LANES")) lanes = atoi(e);  // developer knob
-    m->vec_lanes = lanes;
-    return 0;
-}
-
-static int check_dims(uint64_t M, uint64_t N, uint64_t NZ) {
-    if (M >= 0x7fffffffull || N > 0xffffffffull || NZ >= 0xfffffff0ull)
-        return fail("matrix too large for 32-bit device indices: M=%llu N=%llu NZ=%llu", (unsigned long long) M,
-                    (unsigned long long) N, (unsigned long long) NZ);
-    return 0;
-}
-
-// chunked H2D + narrowing of a 64-bit index array (bounded staging buffer)
-static int upload_narrow(const uint64_t* h_src, uint64_t n, uint64_t sub, uint32_t* d_dst, int* d_overflow) {
-    const uint64_t CH = 1ull << 25;  // 32 Mi elements = 256 MB staging
-    uint64_t* stage = nullptr;
-    if (!n) return 0;
-    CU_TRY(cudaMalloc(&stage, std::min(n, CH) * 8));
-    for (uint64_t o = 0; o < n; o += CH) {
-        const uint64_t c = std::min(CH, n - o);
-        cudaError_t e = cudaMemcpy(stage, h_src + o, c * 8, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) {
-            cudaFree(stage);
-            return fail("H2D of index chunk failed: %s", cudaGetErrorString(e));
-        }
-        narrow_u64_kernel<<<1184, 256>>>(stage, d_dst + o, c, sub, d_overflow);
-    }
-    cudaError_t e = cudaDeviceSynchronize();
-    cudaFree(stage);
-    if (e != cudaSuccess) return fail("index narrowing failed: %s", cudaGetErrorString(e));
-    return 0;
-}
-
-static int read_overflow(int* d_overflow, const char* what) {
-    int h = 0;
-    CU_TRY(cudaMemcpy(&h, d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
-    if (h) return fail("%s: an index does not fit 32 bits", what);
-    return 0;
-}
-
-extern "C" int spmvb200_csr_upload(uint64_t M, uint64_t N, const uint64_t* irp, const uint64_t* ja, const double* as,
-                                   uint64_t row_begin, uint64_t row_end, spmvb200_matrix** out) {
-    if (!out) return fail("csr_upload: null output");
-    *out = nullptr;
-    if (!irp || (M && !ja && irp[M]) || row_begin > row_end || row_end > M) return fail("csr_upload: bad arguments");
-    int ndev = 0;
-    if (spmvb200_device_count(&ndev) || ndev == 0) return fail("csr_upload: no CUDA device (no CPU fallback)");
-    const uint64_t rows = row_end - row_begin, n0 = irp[row_begin], nz = irp[row_end] - n0;
-    if (check_dims(rows, N, nz)) return 1;
-    spmvb200_matrix* m = new spmvb200_matrix();
-    m->format = SPMVB200_FMT_CSR;
-    m->M = rows;
-    m->N = N;
-    m->NZ = nz;
-    m->own = 1;
-    int* d_of = nullptr;
-    int rc = 0;
-    do {
-        if ((rc = (cudaMalloc(&d_of, sizeof(int)) != cudaSuccess))) break;
-        cudaMemset(d_of, 0, sizeof(int));
-        if ((rc = (cudaMalloc(&m->irp, (rows + 1) * 4) != cudaSuccess))) break;
-        if ((rc = (cudaMalloc(&m->ja, (nz + PAD) * 4) != cudaSuccess))) break;
-        if ((rc = (cudaMalloc(&m->as, (nz + PAD) * 8) != cudaSuccess))) break;
-        cudaMemset(m->ja + nz, 0, PAD * 4);
-        cudaMemset(m->as + nz, 0, PAD * 8);
-        if ((rc = upload_narrow(irp + row_begin, rows + 1, n0, m->irp, d_of))) break;
-        if ((rc = upload_narrow(ja + n0, nz, 0, m->ja, d_of))) break;
-        if (nz && (rc = (cudaMemcpy(m->as, as + n0, nz * 8, cudaMemcpyHostToDevice) != cudaSuccess))) break;
-        if ((rc = read_overflow(d_of, "csr_upload"))) break;
-        rc = finish_csr(m);
-    } while (0);
-    cudaFree(d_of);
-    if (rc) {
-        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("csr_upload: %s", cudaGetErrorString(cudaGetLastError()));
-        free_arrays(m);
-        delete m;
-        return 1;
-    }
-    *out = m;
-    return 0;
-}
-
-extern "C" int spmvb200_csr_adopt_device(uint64_t M, uint64_t N, uint64_t NZ, uint32_t* d_irp32, uint32_t* d_ja32,
-                                         double* d_as, int own, spmvb200_matrix** out) {
-    if (!out) return fail("csr_adopt_device: null output");
-    *out = nullptr;
-    if (check_dims(M, N, NZ)) return 1;
-    spmvb200_matrix* m = new spmvb200_matrix();
-    m->format = SPMVB200_FMT_CSR;
-    m->M = M;
-    m->N = N;
-    m->NZ = NZ;
-    m->irp = d_irp32;
-    m->ja = d_ja32;
-    m->as = d_as;
-    m->own = own;
-    if (finish_csr(m)) {
-        m->own = 0;  // the caller keeps ownership on failure
-        free_arrays(m);
-        delete m;
-        return 1;
-    }
-    *out = m;
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------- ELL
-static uint64_t ell_pitch(int format, uint64_t rows, uint64_t K) {
-    return format == SPMVB200_FMT_ELL_COLMAJOR ? ((rows + 63) / 64) * 64 : ((std::max<uint64_t>(K, 1) + 3) / 4) * 4;
-}
-static int ell_alloc(spmvb200_matrix* m) {
-    const uint64_t slots = m->format == SPMVB200_FMT_ELL_COLMAJOR ? m->pitch * std::max<uint64_t>(m->K, 1) : m->pitch * std::max<uint64_t>(m->M, 1);
-    m->slots = slots;
-    CU_TRY(cudaMalloc(&m->ja, (slots + PAD) * 4));
-    CU_TRY(cudaMalloc(&m->as, (slots + PAD) * 8));
-    CU_TRY(cudaMemset(m->ja, 0, (slots + PAD) * 4));
-    CU_TRY(cudaMemset(m->as, 0, (slots + PAD) * 8));
-    CU_TRY(cudaMalloc(&m->rl, std::max<uint64_t>(m->M, 1) * 4));
-    return 0;
-}
-// column-major ELL: if every valid column id is within a 2^16 range of its row index, keep 16-bit offsets as well
-static int ell_try_idx16(spmvb200_matrix* m) {
-    if (m->format != SPMVB200_FMT_ELL_COLMAJOR || !m->M || !m->K || getenv("SPMVB200_ELL_NO_IDX16")) return 0;
-    long long* d_rng = nullptr;
-    CU_TRY(cudaMalloc(&d_rng, 16));
-    const long long init[2] = {(1ll << 62), -(1ll << 62)};
-    CU_TRY(cudaMemcpy(d_rng, init, 16, cudaMemcpyHostToDevice));
-    ell_delta_range_kernel<<<(unsigned) ((m->M + 255) / 256), 256>>>(m->ja, m->rl, m->pitch, (uint32_t) m->M, d_rng, d_rng + 1);
-    long long h[2];
-    cudaError_t e = cudaMemcpy(h, d_rng, 16, cudaMemcpyDeviceToHost);
-    cudaFree(d_rng);
-    if (e != cudaSuccess) return fail("ELL index range: %s", cudaGetErrorString(e));
-    if (h[0] > h[1] || h[1] - h[0] > 65535 || h[0] < -(1ll << 30) || h[0] > (1ll << 30)) return 0;  // empty, or too wide
-    m->ja16_base = (int32_t) h[0];
-    CU_TRY(cudaMalloc(&m->ja16, (m->slots + PAD) * 2));
-    CU_TRY(cudaMemset(m->ja16 + m->slots, 0, PAD * 2));
-    ell_make_idx16_kernel<<<(unsigned) ((m->M + 255) / 256), 256>>>(m->ja, m->rl, m->pitch, (uint32_t) m->M, (uint32_t) m->K, m->ja16_base, m->ja16);
-    CU_TRY(cudaDeviceSynchronize());
-    return 0;
-}
-
-static void ell_pick_lanes(spmvb200_matrix* m) {
-    int lanes = 1;
-    while (lanes < 32 && (uint64_t) lanes * 4 <= m->K) lanes *= 2;  // ~2-4 slots per lane
-    m->vec_lanes = lanes;
-}
-
-extern "C" int spmvb200_ell_upload(uint64_t M, uint64_t N, uint64_t K, const uint64_t* ja, const double* as,
-                                   const uint64_t* rl, uint64_t row_begin, uint64_t row_end, int format,
-                                   spmvb200_matrix** out) {
-    if (!out) return fail("ell_upload: null output");
-    *out = nullptr;
-    if (format != SPMVB200_FMT_ELL_COLMAJOR && format != SPMVB200_FMT_ELL_ROWMAJOR) return fail("ell_upload: bad format %d", format);
-    if (row_begin > row_end || row_end > M || (M && K && (!ja || !as))) return fail("ell_upload: bad arguments");
-    int ndev = 0;
-    if (spmvb200_device_count(&ndev) || ndev == 0) return fail("ell_upload: no CUDA device (no CPU fallback)");
-    const uint64_t rows = row_end - row_begin;
-    if (check_dims(rows, N, rows * K) || K > 0xffffffffull) return 1;
-    spmvb200_matrix* m = new spmvb200_matrix();
-    m->format = format;
-    m->M = rows;
-    m->N = N;
-    m->K = K;
-    m->own = 1;
-    m->pitch = ell_pitch(format, rows, K);
-    int* d_of = nullptr;
-    uint64_t *st_ja = nullptr, *st_rl = nullptr;
-    double* st_as = nullptr;
-    int rc = 0;
-    do {
-        if ((rc = ell_alloc(m))) break;
-        if ((rc = (cudaMalloc(&d_of, sizeof(int)) != cudaSuccess))) break;
-        cudaMemset(d_of, 0, sizeof(int));
-        if (rl) {
-            if ((rc = upload_narrow(rl + row_begin, rows, 0, m->rl, d_of))) break;
-        }
-        // row chunks of the row-major host arrays -> staging -> layout kernel
-        const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(rows, (1ull << 25) / std::max<uint64_t>(K, 1)));
-        if (rows && K) {
-            if ((rc = (cudaMalloc(&st_ja, chunk_rows * K * 8) != cudaSuccess))) break;
-            if ((rc = (cudaMalloc(&st_as, chunk_rows * K * 8) != cudaSuccess))) break;
-            for (uint64_t r = 0; r < rows && !rc; r += chunk_rows) {
-                const uint64_t cr = std::min(chunk_rows, rows - r);
-                const uint64_t ho = (row_begin + r) * K;
-                if ((rc = (cudaMemcpy(st_ja, ja + ho, cr * K * 8, cudaMemcpyHostToDevice) != cudaSuccess))) break;
-                if ((rc = (cudaMemcpy(st_as, as + ho, cr * K * 8, cudaMemcpyHostToDevice) != cudaSuccess))) break;
-                if (format == SPMVB200_FMT_ELL_COLMAJOR) {
-                    dim3 grid((unsigned) ((cr + 31) / 32), (unsigned) ((K + 31) / 32));
-                    ell_transpose_kernel<<<grid, dim3(32, 8)>>>(st_ja, st_as, (uint32_t) cr, (uint32_t) K, (uint32_t) r, m->pitch, m->ja, m->as, d_of);
-                } else {
-                    ell_repitch_kernel<<<1184, 256>>>(st_ja, st_as, (uint32_t) cr, (uint32_t) K, (uint32_t) r, m->pitch, m->ja, m->as, d_of);
-                }
-                if (!rl) ell_derive_rl_kernel<<<(unsigned) ((cr + 255) / 256), 256>>>(st_as, (uint32_t) cr, (uint32_t) K, (uint32_t) r, m->rl);
-                rc = cudaDeviceSynchronize() != cudaSuccess;
-            }
-            if (rc) break;
-        } else if (rows) {
-            cudaMemset(m->rl, 0, rows * 4);
-        }
-        if ((rc = read_overflow(d_of, "ell_upload"))) break;
-        // NZ = sum of row lengths (host side sum of the narrowed vector; upload time only)
-        std::vector<uint32_t> h_rl(rows);
-        if (rows && (rc = (cudaMemcpy(h_rl.data(), m->rl, rows * 4, cudaMemcpyDeviceToHost) != cudaSuccess))) break;
-        uint64_t nz = 0;
-        for (uint64_t r = 0; r < rows; ++r) {
-            if (h_rl[r] > K) { rc = fail("ell_upload: row length %u > K=%llu at row %llu", h_rl[r], (unsigned long long) K, (unsigned long long) r); break; }
-            nz += h_rl[r];
-        }
-        if (rc) break;
-        m->NZ = nz;
-        ell_pick_lanes(m);
-        if ((rc = ell_try_idx16(m))) break;
-    } while (0);
-    cudaFree(d_of);
-    cudaFree(st_ja);
-    cudaFree(st_as);
-    cudaFree(st_rl);
-    if (rc) {
-        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("ell_upload: %s", cudaGetErrorString(cudaGetLastError()));
-        free_arrays(m);
-        delete m;
-        return 1;
-    }
-    *out = m;
-    return 0;
-}
-
-extern "C" int spmvb200_ell_from_csr(const spmvb200_matrix* csr, int format, spmvb200_matrix** out) {
-    if (!out) return fail("ell_from_csr: null output");
-    *out = nullptr;
-    if (!csr || csr->format != SPMVB200_FMT_CSR) return fail("ell_from_csr: source is not a CSR handle");
-    if (format != SPMVB200_FMT_ELL_COLMAJOR && format != SPMVB200_FMT_ELL_ROWMAJOR) return fail("ell_from_csr: bad format %d", format);
-    spmvb200_matrix* m = new spmvb200_matrix();
-    m->format = format;
-    m->M = csr->M;
-    m->N = csr->N;
-    m->NZ = csr->NZ;
-    m->own = 1;
-    uint32_t* d_kmax = nullptr;
-    int rc = 0;
-    do {
-        if ((rc = (cudaMalloc(&d_kmax, 4) != cudaSuccess))) break;
-        cudaMemset(d_kmax, 0, 4);
-        if ((rc = (cudaMalloc(&m->rl, std::max<uint64_t>(m->M, 1) * 4) != cudaSuccess))) break;
-        if (m->M) row_len_from_irp_kernel<<<(unsigned) ((m->M + 255) / 256), 256>>>(csr->irp, (uint32_t) m->M, m->rl, d_kmax);
-        uint32_t kmax = 0;
-        if ((rc = (cudaMemcpy(&kmax, d_kmax, 4, cudaMemcpyDeviceToHost) != cudaSuccess))) break;
-        m->K = kmax;
-        m->pitch = ell_pitch(format, m->M, m->K);
-        uint32_t* keep_rl = m->rl;
-        m->rl = nullptr;
-        rc = ell_alloc(m);  // allocates a fresh rl too
-        if (rc) { cudaFree(keep_rl); break; }
-        cudaFree(m->rl);
-        m->rl = keep_rl;
-        if (m->M && m->K)
-            csr_to_ell_kernel<<<(unsigned) ((m->M + 255) / 256), 256>>>(csr->irp, csr->ja, csr->as, (uint32_t) m->M, (uint32_t) m->K, m->pitch,
-                                                                         format == SPMVB200_FMT_ELL_COLMAJOR, m->ja, m->as);
-        if ((rc = (cudaDeviceSynchronize() != cudaSuccess))) break;
-        ell_pick_lanes(m);
-        if ((rc = ell_try_idx16(m))) break;
-    } while (0);
-    cudaFree(d_kmax);
-    if (rc) {
-        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("ell_from_csr: %s", cudaGetErrorString(cudaGetLastError()));
-        free_arrays(m);
-        delete m;
-        return 1;
-    }
-    *out = m;
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------- SELL-32-sigma
-static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, spmvb200_matrix** out);
-extern "C" int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma, spmvb200_matrix** out) {
-    return sell_build(csr, sigma, 0xffffffffu, out);
-}
-// cap < 2^32-1: rows longer than cap are left empty (hybrid of the adaptive mode: they go to the per-row / per-segment CTAs)
-static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, spmvb200_matrix** out) {
-    if (!out) return fail("sell_from_csr: null output");
-    *out = nullptr;
-    if (!csr || (csr->format != SPMVB200_FMT_CSR && csr->format != SPMVB200_FMT_ELL_COLMAJOR))
-        return fail("sell_from_csr: source is neither a CSR nor a column-major ELL handle");
-    const RowSrc src = {csr->irp, csr->rl, csr->ja, csr->as, csr->format == SPMVB200_FMT_CSR ? 0ull : csr->pitch};
-    if (sigma == 0) sigma = 16384;
-    if (sigma % 32) return fail("sell_from_csr: sigma must be a multiple of 32");
-    spmvb200_matrix* m = new spmvb200_matrix();
-    m->format = SPMVB200_FMT_SELL;
-    m->M = csr->M;
-    m->N = csr->N;
-    m->NZ = csr->NZ;
-    m->own = 1;
-    m->Mpad = ((csr->M + 31) / 32) * 32;
-    const uint32_t Mpad = (uint32_t) m->Mpad, nsl = Mpad / 32;
-    uint64_t *k0 = nullptr, *k1 = nullptr, *slots = nullptr, *slots_scan = nullptr;
-    uint32_t* v0 = nullptr;
-    void* tmp = nullptr;
-    int rc = 0;
-    do {
-        if (Mpad == 0) { rc = fail("sell_from_csr: empty matrix"); break; }
-        if ((rc = cudaMalloc(&k0, (size_t) Mpad * 8) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&k1, (size_t) Mpad * 8) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&v0, (size_t) Mpad * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->perm, (size_t) Mpad * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->rl, (size_t) Mpad * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->irp, ((size_t) nsl + 1) * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&slots, ((size_t) nsl + 1) * 8) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&slots_scan, ((size_t) nsl + 1) * 8) != cudaSuccess)) break;
-        sell_keys_kernel<<<(Mpad + 255) / 256, 256>>>(src, (uint32_t) csr->M, Mpad, sigma, cap, k0, v0);
-        size_t b1 = 0, b2 = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, v0, m->perm, (int) Mpad);
-        cub::DeviceScan::ExclusiveSum(nullptr, b2, slots, slots_scan, (int) nsl + 1);
-        if ((rc = cudaMalloc(&tmp, std::max(b1, b2) + 16) != cudaSuccess)) break;
-        if ((rc = cub::DeviceRadixSort::SortPairs(tmp, b1, k0, k1, v0, m->perm, (int) Mpad) != cudaSuccess)) break;
-        cudaMemset(slots, 0, ((size_t) nsl + 1) * 8);
-        sell_slices_kernel<<<(Mpad + 255) / 256, 256>>>(k1, Mpad, m->rl, slots);
-        if ((rc = cub::DeviceScan::ExclusiveSum(tmp, b2, slots, slots_scan, (int) nsl + 1) != cudaSuccess)) break;
-        uint64_t total = 0;
-        if ((rc = cudaMemcpy(&total, slots_scan + nsl, 8, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
-        if (total >= 0xfffffff0ull) { rc = fail("sell_from_csr: %llu slots do not fit 32-bit offsets", (unsigned long long) total); break; }
-        m->slots = total;
-        narrow_u64_kernel<<<592, 256>>>(slots_scan, m->irp, (uint64_t) nsl + 1, 0, (int*) slots);  // slots[] reused as overflow flag sink
-        if ((rc = cudaMalloc(&m->ja, (total + PAD) * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->as, (total + PAD) * 8) != cudaSuccess)) break;
-        cudaMemset(m->ja + total, 0, PAD * 4);
-        cudaMemset(m->as + total, 0, PAD * 8);
-        sell_fill_kernel<<<(Mpad + 255) / 256, 256>>>(src, m->perm, m->irp, Mpad, cap, m->ja, m->as);
-        if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
-        m->K = sigma;  // reported through spmvb200_dims as K
-    } while (0);
-    cudaFree(k0);
-    cudaFree(k1);
-    cudaFree(v0);
-    cudaFree(slots);
-    cudaFree(slots_scan);
-    cudaFree(tmp);
-    if (rc) {
-        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("sell_from_csr: %s", cudaGetErrorString(cudaGetLastError()));
-        free_arrays(m);
-        delete m;
-        return 1;
-    }
-    *out = m;
-    return 0;
-}
-
-
-// ------------------------------------------------------------------------------------------------- x-window CSR
-// (xwin.cuh) built on the device from a CSR handle: mark (row block, window) pairs -> scan -> tile list ->
-// per-row counts -> scan -> jagged slot-major fill.
-// max_window_ratio > 0: give up right after the tile census (before anything big is allocated) when the x windows one SpMV
-// would stage exceed that many bytes per non-zero -- the adaptive mode's way of asking "is this matrix local enough?"
-static int xwin_build(const spmvb200_matrix* csr, uint32_t rows_per_block, uint32_t window_cols, double max_window_ratio,
-                      spmvb200_matrix** out) {
-    if (!out) return fail("xwin_from_csr: null output");
-    *out = nullptr;
-    if (!csr || csr->format != SPMVB200_FMT_CSR) return fail("xwin_from_csr: source is not a CSR handle");
-    uint32_t R = rows_per_block ? rows_per_block : 2048, W = window_cols ? window_cols : 8192;
-    if (const char* e = getenv("SPMVB200_XW_R")) R = (uint32_t) atoi(e);  // developer knobs
-    if (const char* e = getenv("SPMVB200_XW_W")) W = (uint32_t) atoi(e);
-    if (R < 512 || R > 4096 || (R & (R - 1))) return fail("xwin_from_csr: rows_per_block must be a power of two in [512, 4096] (got %u)", R);
-    if (W < 64 || W > 65536 || (W & 1)) return fail("xwin_from_csr: window_cols must be even and in [64, 65536] (got %u)", W);
-    if (csr->M == 0) return fail("xwin_from_csr: empty matrix");
-    const uint32_t M = (uint32_t) csr->M, G = R / 32;
-    const uint32_t nrb = (M + R - 1) / R;
-    const uint64_t nwin = (std::max<uint64_t>(csr->N, 1) + W - 1) / W;
-    const uint32_t nwords = (uint32_t) ((nwin + 31) / 32);
-    const uint64_t nbits_words = (uint64_t) nrb * nwords;
-    if (nbits_words > (1ull << 28)) return fail("xwin_from_csr: %u row blocks x %llu windows is too sparse a tiling for this format", nrb, (unsigned long long) nwin);
-    spmvb200_matrix* m = new spmvb200_matrix();
-    m->format = SPMVB200_FMT_XWIN;
-    m->M = csr->M;
-    m->N = csr->N;
-    m->NZ = csr->NZ;
-    m->own = 1;
-    m->xw_R = R;
-    m->xw_W = W;
-    m->xw_nrb = nrb;
-    m->K = W;
-    uint32_t *bitmap = nullptr, *pc = nullptr, *scan = nullptr, *tile_rb = nullptr, *grp_cnt = nullptr;
-    int* d_flags = nullptr;  // [0] unsorted rows seen, [1] more than 255 entries of one row in one window
-    void* tmp = nullptr;
-    int rc = 0;
-    do {
-        if ((rc = cudaMalloc(&bitmap, nbits_words * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&pc, (nbits_words + 1) * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&scan, (nbits_words + 1) * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&d_flags, 8) != cudaSuccess)) break;
-        cudaMemset(bitmap, 0, nbits_words * 4);
-        cudaMemset(d_flags, 0, 8);
-        xw_mark_kernel<<<(M + 255) / 256, 256>>>(csr->irp, csr->ja, M, R, W, nwords, bitmap, d_flags);
-        xw_popc_kernel<<<(unsigned) ((nbits_words + 1 + 255) / 256), 256>>>(bitmap, nbits_words, pc);
-        size_t b1 = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, b1, pc, scan, (int) (nbits_words + 1));
-        if ((rc = cudaMalloc(&tmp, b1 + 16) != cudaSuccess)) break;
-        if ((rc = cub::DeviceScan::ExclusiveSum(tmp, b1, pc, scan, (int) (nbits_words + 1)) != cudaSuccess)) break;
-        uint32_t ntiles = 0;
-        int h_flags[2] = {0, 0};
-        if ((rc = cudaMemcpy(&ntiles, scan + nbits_words, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
-        if ((rc = cudaMemcpy(h_flags, d_flags, 8, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
-        m->xw_ntiles = ntiles;
-        m->xw_sorted = !h_flags[0];
-        if (max_window_ratio > 0 && (double) ntiles * W * 8 > max_window_ratio * (double) std::max<uint64_t>(csr->NZ, 1)) {
-            rc = fail("xwin_from_csr: %u tiles of %u columns: %.1f bytes of x windows per non-zero, not local enough", ntiles, W,
-                      (double) ntiles * W * 8 / (double) std::max<uint64_t>(csr->NZ, 1));
-            break;
-        }
-        const uint64_t ngroups = (uint64_t) ntiles * G;
-        if (ngroups >= 0x7fffffffull) { rc = fail("xwin_from_csr: %llu (tile, group) pairs: tiling too fine", (unsigned long long) ngroups); break; }
-        if ((rc = cudaMalloc(&m->xw_rb_tile0, ((size_t) nrb + 1) * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->xw_tile_win, std::max<size_t>(1, ntiles) * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&tile_rb, std::max<size_t>(1, ntiles) * 4) != cudaSuccess)) break;
-        xw_tiles_kernel<<<(unsigned) ((nbits_words + 1 + 255) / 256), 256>>>(bitmap, scan, nrb, nwords, m->xw_rb_tile0, m->xw_tile_win, tile_rb);
-        if ((rc = cudaMalloc(&m->xw_cnt, std::max<size_t>(1, (size_t) ntiles * R) * 2) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&grp_cnt, (ngroups + 1) * 4) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->xw_grp_off, (ngroups + 1) * 4) != cudaSuccess)) break;
-        const unsigned cblocks = (unsigned) (((ngroups + 1) * 32 + 255) / 256);
-        if (m->xw_sorted)
-            xw_count_kernel<true><<<cblocks, 256>>>(csr->irp, csr->ja, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, grp_cnt, d_flags + 1);
-        else
-            xw_count_kernel<false><<<cblocks, 256>>>(csr->irp, csr->ja, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, grp_cnt, d_flags + 1);
-        size_t b2 = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, b2, grp_cnt, m->xw_grp_off, (int) (ngroups + 1));
-        if (b2 > b1) {
-            cudaFree(tmp);
-            tmp = nullptr;
-            if ((rc = cudaMalloc(&tmp, b2 + 16) != cudaSuccess)) break;
-        }
-        if ((rc = cub::DeviceScan::ExclusiveSum(tmp, b2, grp_cnt, m->xw_grp_off, (int) (ngroups + 1)) != cudaSuccess)) break;
-        uint32_t total = 0;
-        if ((rc = cudaMemcpy(&total, m->xw_grp_off + ngroups, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
-        if ((rc = cudaMemcpy(h_flags, d_flags, 8, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
-        if (h_flags[1]) { rc = fail("xwin_from_csr: a row has more than 255 non-zeros inside one %u-column window (format limit)", W); break; }
-        if (total != csr->NZ) { rc = fail("xwin_from_csr: internal count mismatch (%u entries placed, NZ=%llu)", total, (unsigned long long) csr->NZ); break; }
-        if ((rc = cudaMalloc(&m->xw_col, (m->NZ + PAD) * 2) != cudaSuccess)) break;
-        if ((rc = cudaMalloc(&m->as, (m->NZ + PAD) * 8) != cudaSuccess)) break;
-        cudaMemset(m->xw_col + m->NZ, 0, PAD * 2);
-        cudaMemset(m->as + m->NZ, 0, PAD * 8);
-        if (ngroups) {
-            const unsigned fblocks = (unsigned) ((ngroups * 32 + 255) / 256);
-            if (m->xw_sorted)
-                xw_fill_kernel<true><<<fblocks, 256>>>(csr->irp, csr->ja, csr->as, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, m->xw_grp_off, m->xw_col, m->as);
-            else
-                xw_fill_kernel<false><<<fblocks, 256>>>(csr->irp, csr->ja, csr->as, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, m->xw_grp_off, m->xw_col, m->as);
-        }
-        {   // persistent CTAs: one per SM (or per row block if there are fewer), contiguous row blocks balanced by non-zeros
-            int dev = 0, sms = 148;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            m->xw_ncta = std::min<uint32_t>(nrb, (uint32_t) sms);
-            if (const char* e = getenv("SPMVB200_XW_NCTA")) {  // developer knob: force persistent CTAs of this count
-                m->xw_ncta = std::min<uint32_t>(nrb, (uint32_t) std::max(1, atoi(e)));
-                m->xw_mode = 1;
-            }
-            if (const char* e = getenv("SPMVB200_XW_MODE")) m->xw_mode = atoi(e);
-            if ((rc = cudaMalloc(&m->xw_cta_rb, ((size_t) m->xw_ncta + 1) * 4) != cudaSuccess)) break;
-            xw_cta_split_kernel<<<(m->xw_ncta + 1 + 255) / 256, 256>>>(m->xw_rb_tile0, m->xw_grp_off, G, nrb, m->NZ, m->xw_ncta, m->xw_cta_rb);
-        }
-        if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
-        // ring depth: as many windows as fit next to the barriers in the 227 KB a CTA may use
-        uint32_t nbuf = (uint32_t) std::min<uint64_t>(XW_MAX_NBUF, (232448 - 256) / (((uint64_t) W + 2) * 8));
-        if (const char* e = getenv("SPMVB200_XW_NBUF")) nbuf = std::min<uint32_t>(nbuf, (uint32_t) std::max(1, atoi(e)));
-        if (nbuf < 2) { rc = fail("xwin_from_csr: window of %u columns leaves no room for double buffering", W); break; }
-        m->xw_nbuf = std::min<uint32_t>(nbuf, 4);
-        m->xw_nw = R >= 1024 ? 32 : 16;
-        if (const char* e = getenv("SPMVB200_XW_NW")) m->xw_nw = (uint32_t) atoi(e);
-        if ((m->xw_nw != 16 && m->xw_nw != 32) || R / (32 * m->xw_nw) < 1 || R / (32 * m->xw_nw) > (m->xw_nw == 32 ? 4u : 8u)) { rc = fail("xwin_from_csr: no kernel for R=%u with %u warps", R, m->xw_nw); break; }
-    } while (0);
-    cudaFree(bitmap);
-    cudaFree(pc);
-    cudaFree(scan);
-    cudaFree(tile_rb);
-    cudaFree(grp_cnt);
-    cudaFree(d_flags);
-    cudaFree(tmp);
-    if (rc) {
-        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("xwin_from_csr: %s", cudaGetErrorString(cudaGetLastError()));
-        free_arrays(m);
-        delete m;
-        return 1;
-    }
-    *out = m;
-    return 0;
-}
-
-extern "C" int spmvb200_xwin_from_csr(const spmvb200_matrix* csr, uint32_t rows_per_block, uint32_t window_cols,
-                                      spmvb200_matrix** out) {
-    return xwin_build(csr, rows_per_block, window_cols, 0.0, out);
-}
-
-extern "C" int spmvb200_xwin_info(const spmvb200_matrix* m, uint32_t* rows_per_block, uint32_t* window_cols, uint32_t* ntiles,
-                                  uint32_t* ring, uint64_t* moved_bytes) {
-    if (!m || m->format != SPMVB200_FMT_XWIN) return fail("xwin_info: not an x-window handle");
-    if (rows_per_block) *rows_per_block = m->xw_R;
-    if (window_cols) *window_cols = m->xw_W;
-    if (ntiles) *ntiles = m->xw_ntiles;
-    if (ring) *ring = m->xw_nbuf;
-    // what one SpMV reads and writes: entries, per-row counts, group offsets, tile list, y -- and the x windows (from L2)
-    if (moved_bytes)
-        *moved_bytes = 10 * m->NZ + (uint64_t) m->xw_ntiles * m->xw_R * 2 + (uint64_t) m->xw_ntiles * (m->xw_R / 32) * 4 + (uint64_t) m->xw_ntiles * 4 +
-                       8 * m->M + (uint64_t) m->xw_ntiles * m->xw_W * 8;
-    return 0;
-}
+#include "engine_formats.inl"
 
 extern "C" int spmvb200_free(spmvb200_matrix* m) {
     if (!m) return 0;
@@ -807,525 +211,7 @@ extern "C" const char* spmvb200_kind_name(int kind) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------- launch
-// Rows the vector kernels skip: medium rows (one CTA each) and rows longer than a tile (one CTA per segment).  They touch other rows
-// of y than the main kernel, so they run NEXT to it on two side streams -- forked before the main launch, joined after it (events:
-// legal inside a graph capture too).  On R-MAT (cfg3) the three kernels are 189 + 97 + 52 us back to back.
-// exact: the medium rows go through the warp-per-row kernel that adds in the serial order (the bit-exact kind's SELL hybrid).
-static void tail_fork(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, bool exact = false) {
-    if (!m->nmid && !m->nseg) return;
-    static const bool serial = getenv("SPMVB200_SERIAL_TAIL") != nullptr;  // developer knob: the old back-to-back order
-    if (!serial && !m->e_fork) {
-        bool ok = cudaEventCreateWithFlags(&m->e_fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int i = 0; i < 2 && ok; ++i)
-            ok = cudaStreamCreateWithFlags(&m->s_tail[i], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&m->e_tail[i], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) { cudaGetLastError(); m->e_fork = nullptr; }
-    }
-    const bool fork = !serial && m->e_fork && m->s_tail[0] && m->s_tail[1] && m->e_tail[0] && m->e_tail[1];
-    if (fork) cudaEventRecord(m->e_fork, st);
-    if (m->nmid) {
-        cudaStream_t s = fork ? m->s_tail[0] : st;
-        if (fork) cudaStreamWaitEvent(s, m->e_fork, 0);
-        static const bool warp_mid = getenv("SPMVB200_NO_WARP_MID") == nullptr;  // developer knob
-        const uint32_t lo = warp_mid ? (uint32_t) MIDW_MAX : 0u;  // rows up to MIDW_MAX: a warp each; longer: a CTA each
-        if (exact) {
-            csr_midrow_exact_kernel<256><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y);
-            ++g_launches;
-        } else if (warp_mid) {
-            csr_midrow_warp_kernel<256><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y, 0u, (uint32_t) MIDW_MAX);
-            ++g_launches;
-        }
-        if (!exact && (!warp_mid || m->lmax > (uint32_t) MIDW_MAX)) {
-            csr_midrow_kernel<128><<<m->nmid, 128, 0, s>>>(m->mid_rows, m->irp, m->ja, m->as, x, y, lo);
-            ++g_launches;
-        }
-        if (fork) cudaEventRecord(m->e_tail[0], s);
-    }
-    if (m->nseg) {
-        cudaStream_t s = fork ? m->s_tail[1] : st;
-        if (fork) cudaStreamWaitEvent(s, m->e_fork, 0);
-        csr_longrow_kernel<128><<<m->nseg, 128, 0, s>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
-        if (fork) cudaEventRecord(m->e_tail[1], s);
-        ++g_launches;
-    }
-}
-static void tail_join(spmvb200_matrix* m, cudaStream_t st) {
-    if (!m->e_fork || getenv("SPMVB200_SERIAL_TAIL")) return;
-    if (m->nmid) cudaStreamWaitEvent(st, m->e_tail[0], 0);
-    if (m->nseg) cudaStreamWaitEvent(st, m->e_tail[1], 0);
-}
-// rows [r0, r1) (whole matrix: 0, M); y is always indexed by the handle's row number
-template <int LANES>
-static void launch_csr_vector_t(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
-    constexpr int BLOCK = 256;
-    const uint64_t threads = (r1 - r0) * LANES;
-    if (!threads) return;
-    // whole-matrix launches leave rows longer than VEC_MID to the per-row CTAs below; row-chunk launches keep them
-    csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(
-        m->irp, m->ja, m->as, x, y, (uint32_t) r0, (uint32_t) r1, (uint32_t) ((r0 == 0 && r1 == m->M) ? VEC_MID : STREAM_TILE));
-    ++g_launches;
-}
-// vector kernel for rows up to one tile + the long-row kernel for the rest (same stream, back to back)
-static void launch_csr_vector(spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
-    const bool whole = r0 == 0 && r1 == m->M;
-    if (whole) tail_fork(m, x, y, st);
-    switch (lanes) {
-        case 2: launch_csr_vector_t<2>(m, x, y, st, r0, r1); break;
-        case 4: launch_csr_vector_t<4>(m, x, y, st, r0, r1); break;
-        case 8: launch_csr_vector_t<8>(m, x, y, st, r0, r1); break;
-        case 16: launch_csr_vector_t<16>(m, x, y, st, r0, r1); break;
-        default: launch_csr_vector_t<32>(m, x, y, st, r0, r1); break;
-    }
-    if (whole) tail_join(m, st);
-}
-template <int LANES>
-static void launch_csr_vspan_t(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
-    csr_vector_span_kernel<LANES, 1024><<<m->nspans, 1024, 0, st>>>(m->span_b, m->irp, m->ja, m->as, x, y, (uint32_t) VEC_MID);
-    ++g_launches;
-}
-static void launch_csr_vspan(spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st) {
-    tail_fork(m, x, y, st);
-    switch (lanes) {
-        case 2: launch_csr_vspan_t<2>(m, x, y, st); break;
-        case 4: launch_csr_vspan_t<4>(m, x, y, st); break;
-        case 8: launch_csr_vspan_t<8>(m, x, y, st); break;
-        case 16: launch_csr_vspan_t<16>(m, x, y, st); break;
-        default: launch_csr_vspan_t<32>(m, x, y, st); break;
-    }
-    tail_join(m, st);
-}
-// tiles [t0, t1) (whole matrix: 0, ntiles)
-template <bool ADAPT, int VARIANT>
-static void launch_csr_stream(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint32_t t0, uint32_t t1) {
-    if (t1 <= t0) return;
-    static const uint32_t pre_t = getenv("SPMVB200_PRE_T") ? (uint32_t) atoi(getenv("SPMVB200_PRE_T")) : (uint32_t) STREAM_PRE_T;  // developer knob
-    csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, ADAPT, VARIANT>
-        <<<t1 - t0, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, x, y, m->partial, m->ticket, t0, pre_t);
-    ++g_launches;
-}
-static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
-    constexpr int BLOCK = 256;
-    if (r1 <= r0) return;
-    static const bool no_exit = getenv("SPMVB200_ELL_NO_EARLY_EXIT") != nullptr;  // developer knob: walk all K slots like the reference
-    // slots in flight per thread: 4, or 3 when that leaves a shorter tail of one-at-a-time slots (K = 27: 3 x 9 exactly; measured
-    // 103.3 vs 105.2 us on cfg2; 5..9 lose more to occupancy than they gain)
-    static const int unroll_env = getenv("SPMVB200_ELL_UNROLL") ? atoi(getenv("SPMVB200_ELL_UNROLL")) : 0;  // developer knob
-    const int unroll16 = unroll_env ? unroll_env : ((m->K % 3) < (m->K % 4) ? 3 : 4);
-    const unsigned grid = (unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK);
-#define ELL16(U) ell_colmajor_kernel<U, BLOCK, true><<<grid, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, m->ja16_base, x, y, g_push)
-    // 16-bit ids: two rows per thread, 3 slots in flight (measured on cfg2: 96.9 us; one row per thread 103.0; pair x2 100.7, pair x4 107.1)
-    static const int pair_env = getenv("SPMVB200_ELL_PAIR") ? atoi(getenv("SPMVB200_ELL_PAIR")) : 3;  // developer knob: 0 = one row per thread
-    if (m->ja16 && !no_exit && pair_env && (r0 % 2) == 0) {
-        const unsigned g2 = (unsigned) (((r1 - r0 + 1) / 2 + BLOCK - 1) / BLOCK);
-#define ELLP(U) ell_colmajor_pair_kernel<U, BLOCK><<<g2, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, m->ja16_base, x, y, g_push)
-        switch (pair_env) {
-            case 2: ELLP(2); break;
-            case 3: ELLP(3); break;
-            default: ELLP(4); break;
-        }
-#undef ELLP
-    } else if (m->ja16 && !no_exit) {
-        switch (unroll16) {
-            case 3: ELL16(3); break;
-            case 5: ELL16(5); break;
-            case 6: ELL16(6); break;
-            case 8: ELL16(8); break;
-            case 9: ELL16(9); break;
-            default: ELL16(4); break;
-        }
-    }
-#undef ELL16
-    else if (unroll16 == 3)
-        ell_colmajor_kernel<3, BLOCK, false><<<grid, BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, 0, x, y, g_push);
-    else
-        ell_colmajor_kernel<4, BLOCK, false><<<grid, BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, 0, x, y, g_push);
-    g_push_fused = true;
-    ++g_launches;
-}
-
-
-// ---- x-window CSR: one CTA per row block, NW warps, ring of x windows in shared memory
-template <int NW, int ACC, int UMAX>
-static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
-    const size_t smem = (size_t) m->xw_nbuf * (m->xw_W + 2) * 8 + XW_MAX_NBUF * 12;
-    static size_t configured[64] = {0};  // per device: function attributes belong to the device's context
-    int dev = 0;
-    CU_TRY(cudaGetDevice(&dev));
-    if (smem > configured[dev & 63]) {
-        CU_TRY(cudaFuncSetAttribute(xwin_kernel<NW, ACC, UMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        configured[dev & 63] = smem;
-    }
-    const bool persist = m->xw_mode == 1;
-    xwin_kernel<NW, ACC, UMAX><<<persist ? m->xw_ncta : m->xw_nrb, 32 * NW, smem, st>>>(persist ? m->xw_cta_rb : nullptr, m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
-                                                                 (uint32_t) m->M, (uint32_t) m->N, m->xw_W, m->xw_nbuf, ((uintptr_t) x & 15) == 0, g_push);
-    g_push_fused = true;
-    ++g_launches;
-    return 0;
-}
-// (warps, row groups per warp, largest batch in slots): up to 2*UMAX*ACC loads in flight per lane
-static int launch_xwin(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
-    const uint32_t acc = m->xw_R / (32 * m->xw_nw);
-    static const int u_env = getenv("SPMVB200_XW_U") ? atoi(getenv("SPMVB200_XW_U")) : 0;  // developer knob
-#define XW_CASE(NW, ACC, UDEF, UALT, UALT2)                                                  \
-    if (m->xw_nw == NW && acc == ACC) {                                                      \
-        if (u_env == UALT) return launch_xwin_t<NW, ACC, UALT>(m, x, y, st);                 \
-        if (u_env == UALT2) return launch_xwin_t<NW, ACC, UALT2>(m, x, y, st);               \
-        return launch_xwin_t<NW, ACC, UDEF>(m, x, y, st);                                    \
-    }
-    XW_CASE(32, 1, 8, 6, 4)
-    XW_CASE(32, 2, 5, 4, 6)
-    XW_CASE(32, 4, 3, 2, 4)
-    XW_CASE(16, 1, 8, 6, 4)
-    XW_CASE(16, 2, 8, 6, 4)
-    XW_CASE(16, 4, 6, 4, 8)
-    XW_CASE(16, 8, 3, 4, 2)
-#undef XW_CASE
-    return fail("x-window kernel: no instantiation for R=%u, %u warps", m->xw_R, m->xw_nw);
-}
-
-// first use of an x-window handle: one CTA per row block, or persistent CTAs?  (Persistent wins when a row block has few
-// tiles -- no pipeline refill per row block; per-row-block wins on wide bands, where concurrent CTAs then share windows.)
-static int tune_xwin(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, float* best_ms_out) {
-    cudaEvent_t e0, e1;
-    CU_TRY(cudaEventCreate(&e0));
-    CU_TRY(cudaEventCreate(&e1));
-    float best_ms = 1e30f;
-    int best = 0;
-    for (int mode = 0; mode < 2; ++mode) {
-        m->xw_mode = mode;
-        if (launch_xwin(m, x, y, st)) return 1;
-        float ms_min = 1e30f;
-        for (int rep = 0; rep < 2; ++rep) {
-            CU_TRY(cudaEventRecord(e0, st));
-            if (launch_xwin(m, x, y, st)) return 1;
-            CU_TRY(cudaEventRecord(e1, st));
-            CU_TRY(cudaEventSynchronize(e1));
-            float ms = 0;
-            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
-            ms_min = std::min(ms_min, ms);
-        }
-        if (ms_min < best_ms) { best_ms = ms_min; best = mode; }
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    m->xw_mode = best;
-    if (best_ms_out) *best_ms_out = best_ms;
-    return 0;
-}
-
-static void launch_sell(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
-    sell_kernel<4, 256><<<(unsigned) ((m->Mpad + 255) / 256), 256, 0, st>>>(m->irp, m->perm, m->rl, m->as, m->ja, (uint32_t) m->Mpad, x, y);
-    ++g_launches;
-}
-
-// ---- SPMVB200_CSR_ADAPTIVE: candidates; the fastest on this matrix is picked at first use
-static const int N_CAND = 14;
-static const int CAND_XWIN = 12;  // x-window copy (built during tuning when the tile census says it can pay off)
-static const int CAND_SELL = 13;  // SELL-32-sigma copy (matrices without long rows: thread per row, coalesced, no shuffles)
-static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32",
-                                        "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32", "xwindow", "sell"};
-static int cand_lanes(int c) { return c < 2 ? 0 : 2 << ((c - 2) % 5); }
-static void launch_candidate(spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st) {
-    if (c == 0) launch_csr_stream<true, 0>(m, x, y, st, 0, m->ntiles);
-    else if (c == 1) launch_csr_stream<true, 1>(m, x, y, st, 0, m->ntiles);
-    else if (c < 7) launch_csr_vector(m, cand_lanes(c), x, y, st, 0, m->M);
-    else if (c < CAND_XWIN) launch_csr_vspan(m, cand_lanes(c), x, y, st);
-    else if (c == CAND_XWIN) launch_xwin(m->xw_child, x, y, st);
-    else {
-        const bool hybrid = m->lmax > (uint32_t) VEC_MID;  // rows the capped SELL copy left out (it does not write their y)
-        if (hybrid) tail_fork(m, x, y, st);
-        launch_sell(m->xw_child, x, y, st);
-        if (hybrid) tail_join(m, st);
-    }
-}
-static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
-    // d_x / d_y are the caller's vectors: y is overwritten by every candidate with the same result
-    cudaEvent_t e0, e1;
-    CU_TRY(cudaEventCreate(&e0));
-    CU_TRY(cudaEventCreate(&e1));
-    int best = 0;
-    float best_ms = 1e30f;
-    const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
-    m->tuned_ms[CAND_XWIN] = m->tuned_ms[CAND_SELL] = -1.f;
-    for (int c = 0; c < CAND_XWIN; ++c) {
-        m->tuned_ms[c] = -1.f;
-        if (c >= 2 && (cand_lanes(c) > 4 * mean + 2 || (double) cand_lanes(c) * 64 < mean)) continue;  // hopeless widths
-        if (const char* e = getenv("SPMVB200_FORCE_CAND")) if (atoi(e) != c) continue;  // developer knob
-        launch_candidate(m, c, d_x, d_y, st);
-        float ms_min = 1e30f;
-        for (int rep = 0; rep < 2; ++rep) {
-            CU_TRY(cudaEventRecord(e0, st));
-            launch_candidate(m, c, d_x, d_y, st);
-            CU_TRY(cudaEventRecord(e1, st));
-            CU_TRY(cudaEventSynchronize(e1));
-            float ms = 0;
-            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
-            ms_min = std::min(ms_min, ms);
-        }
-        m->tuned_ms[c] = ms_min;
-        if (ms_min < best_ms) { best_ms = ms_min; best = c; }
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    // x-window copy: costs a second copy of the matrix (10.x B per non-zero), so it is only built when the matrix is big
-    // enough to matter, and kept only if it beats everything else by 5 %
-    const char* force = getenv("SPMVB200_FORCE_CAND");
-    if (!getenv("SPMVB200_NO_XWINDOW") && m->NZ >= (1u << 20) && (!force || atoi(force) == CAND_XWIN)) {
-        g_quiet = 1;  // "does not fit this format" is an expected answer here, not an error to print
-        spmvb200_matrix* xw = nullptr;
-        // window traffic (L2 -> shared memory) above ~1.5x the matrix stream cannot win: stop at the tile census
-        const int rc = xwin_build(m, 0, 0, 15.0, &xw);
-        g_quiet = 0;
-        if (!rc) {
-            float ms = -1.f;
-            if (!tune_xwin(xw, d_x, d_y, st, &ms)) {
-                m->tuned_ms[CAND_XWIN] = ms;
-                if (ms < 0.95f * best_ms || force) { best_ms = ms; best = CAND_XWIN; }
-            }
-            if (best == CAND_XWIN) m->xw_child = xw; else spmvb200_free(xw);
-        }
-        g_err[0] = 0;
-    }
-    // SELL-32-sigma copy (a thread walks its whole row, coalesced, no shuffles).  Rows longer than VEC_MID are left out of it and go
-    // to the per-row / per-segment CTAs of the vector path (hybrid for skewed matrices); kept only while the slices stay nearly
-    // padding-free
-    if (!getenv("SPMVB200_NO_SELL") && m->NZ >= (1u << 20) && (!force || atoi(force) == CAND_SELL)) {
-        g_quiet = 1;
-        spmvb200_matrix* sell = nullptr;
-        const bool hybrid = m->lmax > (uint32_t) VEC_MID;
-        const int rc = sell_build(m, 0, hybrid ? (uint32_t) VEC_MID : 0xffffffffu, &sell);
-        g_quiet = 0;
-        if (!rc) {
-            float ms_min = 1e30f;
-            if (sell->slots <= m->NZ + m->NZ / 4) {
-                cudaEvent_t s0, s1;
-                CU_TRY(cudaEventCreate(&s0));
-                CU_TRY(cudaEventCreate(&s1));
-                launch_sell(sell, d_x, d_y, st);
-                for (int rep = 0; rep < 2; ++rep) {
-                    CU_TRY(cudaEventRecord(s0, st));
-                    if (hybrid) tail_fork(m, d_x, d_y, st);
-                    launch_sell(sell, d_x, d_y, st);
-                    if (hybrid) tail_join(m, st);
-                    CU_TRY(cudaEventRecord(s1, st));
-                    CU_TRY(cudaEventSynchronize(s1));
-                    float ms = 0;
-                    CU_TRY(cudaEventElapsedTime(&ms, s0, s1));
-                    ms_min = std::min(ms_min, ms);
-                }
-                cudaEventDestroy(s0);
-                cudaEventDestroy(s1);
-                m->tuned_ms[CAND_SELL] = ms_min;
-            }
-            if (ms_min < 0.95f * best_ms || (force && ms_min < 1e30f)) {
-                if (m->xw_child) spmvb200_free(m->xw_child);
-                m->xw_child = sell;
-                best_ms = ms_min;
-                best = CAND_SELL;
-            } else {
-                spmvb200_free(sell);
-            }
-        }
-        g_err[0] = 0;
-    }
-    m->tuned = best;
-    if (getenv("SPMVB200_VERBOSE")) {
-        fprintf(stderr, "spmv_b200: adaptive tuning M=%llu NZ=%llu ->", (unsigned long long) m->M, (unsigned long long) m->NZ);
-        for (int c = 0; c < N_CAND; ++c) fprintf(stderr, " %s=%.3fms%s", CAND_NAME[c], m->tuned_ms[c], c == best ? "*" : "");
-        fprintf(stderr, "\n");
-    }
-    return 0;
-}
-
-// ---- SPMVB200_CSR_ROWS, the kind that must reproduce sgemvSerial bit for bit: the stream kernel, or -- timed at first use, for
-// matrices of at least 2^20 non-zeros -- an x-window copy (column-sorted rows only) or a SELL copy (no row longer than VEC_MID);
-// all three add a row's products left to right with separate mul / add roundings.
-template <typename F>
-static int time_best_of_2(F&& run, cudaStream_t st, float* ms_out) {
-    cudaEvent_t e0, e1;
-    CU_TRY(cudaEventCreate(&e0));
-    CU_TRY(cudaEventCreate(&e1));
-    run();
-    float best = 1e30f;
-    for (int rep = 0; rep < 2; ++rep) {
-        CU_TRY(cudaEventRecord(e0, st));
-        run();
-        CU_TRY(cudaEventRecord(e1, st));
-        CU_TRY(cudaEventSynchronize(e1));
-        float ms = 0;
-        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
-        best = std::min(best, ms);
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    *ms_out = best;
-    return 0;
-}
-static void launch_exact_sell(spmvb200_matrix* m, const spmvb200_matrix* sell, const double* x, double* y, cudaStream_t st) {
-    const bool hybrid = m->lmax > (uint32_t) VEC_MID;  // rows the capped SELL copy left out (it does not write their y)
-    if (hybrid) tail_fork(m, x, y, st, true);
-    launch_sell(sell, x, y, st);
-    if (hybrid) tail_join(m, st);
-}
-static int tune_exact(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
-    float best_ms = 0;
-    if (time_best_of_2([&] { launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles); }, st, &best_ms)) return 1;
-    int best = 0;
-    m->tuned_x_ms[0] = best_ms;
-    m->tuned_x_ms[1] = m->tuned_x_ms[2] = -1.f;
-    const char* only = getenv("SPMVB200_EXACT_ONLY_STREAM");  // developer knob
-    if (!only && m->NZ >= (1u << 20)) {
-        g_quiet = 1;
-        spmvb200_matrix* xw = nullptr;
-        if (!xwin_build(m, 0, 0, 15.0, &xw)) {
-            float ms = 1e30f;
-            if (xw->xw_sorted && !tune_xwin(xw, d_x, d_y, st, &ms)) m->tuned_x_ms[1] = ms;
-            if (ms < 0.95f * best_ms) { best_ms = ms; best = CAND_XWIN; m->x_child = xw; } else spmvb200_free(xw);
-        }
-        // rows longer than VEC_MID are left out of the SELL copy: a warp each adds them in the serial order next to it (exact hybrid);
-        // rows longer than a tile are split into segments as in the stream kernel (deterministic, within tolerance)
-        spmvb200_matrix* sell = nullptr;
-        if (!getenv("SPMVB200_NO_SELL") && !sell_build(m, 0, m->lmax <= (uint32_t) VEC_MID ? 0xffffffffu : (uint32_t) VEC_MID, &sell)) {
-            float ms = 1e30f;
-            if (sell->slots <= m->NZ + m->NZ / 4 && !time_best_of_2([&] { launch_exact_sell(m, sell, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
-            const char* f = getenv("SPMVB200_FORCE_EXACT");  // developer knob (tests): 13 = keep the SELL copy whatever the timing says
-            if (ms < 0.95f * best_ms || (f && atoi(f) == CAND_SELL && ms < 1e30f)) {
-                if (m->x_child) spmvb200_free(m->x_child);
-                best_ms = ms; best = CAND_SELL; m->x_child = sell;
-            } else spmvb200_free(sell);
-        }
-        g_quiet = 0;
-        g_err[0] = 0;
-    }
-    m->tuned_x = best;
-    if (getenv("SPMVB200_VERBOSE"))
-        fprintf(stderr, "spmv_b200: exact-kind tuning M=%llu NZ=%llu -> stream=%.3fms xwindow=%.3fms sell=%.3fms, picked %s\n", (unsigned long long) m->M,
-                (unsigned long long) m->NZ, m->tuned_x_ms[0], m->tuned_x_ms[1], m->tuned_x_ms[2], best == 0 ? "stream" : best == CAND_XWIN ? "xwindow" : "sell");
-    return 0;
-}
-
-// ---- SPMVB200_ELL_ROWS on a padded matrix: the column-major kernel exits early per WARP (a warp runs to the longest of its rows), so one
-// long row among 64 short ones keeps the warp's slot busy for K dependent round trips.  When the ELL rectangle is at least 1.25 x the
-// non-zeros, a SELL-32-sigma copy (rows sorted by length inside windows: warps see equal lengths) is built from the ELL arrays on the
-// device and timed against the column-major kernel at first use; it is kept only if it wins by 5 %.  Both add a row's products left
-// to right with separate mul / add roundings: bit-identical results either way.  tuned_x: 0 = column-major ELL, CAND_SELL = the copy.
-static int tune_ell(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
-    m->tuned_x = 0;
-    if (getenv("SPMVB200_NO_SELL") || getenv("SPMVB200_ELL_NO_SELL") || getenv("SPMVB200_ELL_NO_EARLY_EXIT") || m->NZ < (1u << 20) || !m->rl) return 0;
-    if ((double) m->K * (double) m->M < 1.25 * (double) m->NZ) return 0;
-    float ell_ms = 0;
-    if (time_best_of_2([&] { launch_ell_colmajor(m, d_x, d_y, st, 0, m->M); }, st, &ell_ms)) return 1;
-    m->tuned_x_ms[0] = ell_ms;
-    m->tuned_x_ms[1] = m->tuned_x_ms[2] = -1.f;
-    g_quiet = 1;
-    spmvb200_matrix* sell = nullptr;
-    if (!sell_build(m, 0, 0xffffffffu, &sell)) {
-        float ms = 1e30f;
-        if (!time_best_of_2([&] { launch_sell(sell, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
-        if (ms < 0.95f * ell_ms) { m->tuned_x = CAND_SELL; m->x_child = sell; } else spmvb200_free(sell);
-    }
-    g_quiet = 0;
-    g_err[0] = 0;
-    if (getenv("SPMVB200_VERBOSE"))
-        fprintf(stderr, "spmv_b200: ELL tuning M=%llu K=%llu NZ=%llu -> ell=%.3fms sell=%.3fms, picked %s\n", (unsigned long long) m->M,
-                (unsigned long long) m->K, (unsigned long long) m->NZ, m->tuned_x_ms[0], m->tuned_x_ms[2], m->tuned_x ? "sell" : "ell");
-    return 0;
-}
-
-template <int LANES>
-static void launch_ell_rowmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
-    constexpr int BLOCK = 256;
-    const uint64_t threads = m->M * LANES;
-    ell_rowmajor_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) m->M,
-                                                                                                       (uint32_t) m->K, x, y);
-    ++g_launches;
-}
-
-static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, cudaStream_t st) {
-    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
-    if (m->M == 0) return 0;
-    switch (kind) {
-        case SPMVB200_CSR_ROWS:
-            if (m->tuned_x < 0 && tune_exact(m, d_x, d_y, st)) return 1;
-            if (m->tuned_x == CAND_XWIN) { if (launch_xwin(m->x_child, d_x, d_y, st)) return 1; }
-            else if (m->tuned_x == CAND_SELL) launch_exact_sell(m, m->x_child, d_x, d_y, st);
-            else launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles);
-            break;
-        case SPMVB200_CSR_ADAPTIVE:
-            if (m->tuned < 0 && tune_adaptive(m, d_x, d_y, st)) return 1;
-            launch_candidate(m, m->tuned, d_x, d_y, st);
-            break;
-        case SPMVB200_CSR_ROWS_WARP:
-            if (!m->vec_tuned && m->format == SPMVB200_FMT_CSR) {
-                // first use: the sub-warp width guessed from the mean row length against its two neighbours (the x gather pattern
-                // decides, not the mean: 27-point stencil, mean 26.6 -> guess 16 lanes, 0.203 ms; 4 lanes: 0.141 ms)
-                m->vec_tuned = 1;
-                if (!getenv("SPMVB200_VEC_LANES") && m->NZ >= (1u << 18)) {
-                    int best = m->vec_lanes;
-                    float best_ms = 1e30f;
-                    for (int lanes = 2; lanes <= 32; lanes *= 2) {
-                        if (lanes > 4 * m->vec_lanes || 4 * lanes < m->vec_lanes) continue;
-                        float ms = 0;
-                        if (time_best_of_2([&] { launch_csr_vector(m, lanes, d_x, d_y, st, 0, m->M); }, st, &ms)) return 1;
-                        if (ms < best_ms) { best_ms = ms; best = lanes; }
-                    }
-                    m->vec_lanes = best;
-                }
-            }
-            launch_csr_vector(m, m->vec_lanes, d_x, d_y, st, 0, m->M);
-            break;
-        case SPMVB200_ELL_ROWS:
-            if (m->tuned_x < 0 && tune_ell(m, d_x, d_y, st)) return 1;
-            if (m->tuned_x == CAND_SELL) launch_sell(m->x_child, d_x, d_y, st);
-            else launch_ell_colmajor(m, d_x, d_y, st, 0, m->M);
-            break;
-        case SPMVB200_SELL_ROWS: launch_sell(m, d_x, d_y, st); break;
-        case SPMVB200_XWIN_ROWS:
-            if (m->xw_mode < 0 && tune_xwin(m, d_x, d_y, st, nullptr)) return 1;
-            if (launch_xwin(m, d_x, d_y, st)) return 1;
-            break;
-        case SPMVB200_ELL_ROWS_NT:
-            switch (m->vec_lanes) {
-                case 1: launch_ell_rowmajor<1>(m, d_x, d_y, st); break;
-                case 2: launch_ell_rowmajor<2>(m, d_x, d_y, st); break;
-                case 4: launch_ell_rowmajor<4>(m, d_x, d_y, st); break;
-                case 8: launch_ell_rowmajor<8>(m, d_x, d_y, st); break;
-                case 16: launch_ell_rowmajor<16>(m, d_x, d_y, st); break;
-                default: launch_ell_rowmajor<32>(m, d_x, d_y, st); break;
-            }
-            break;
-        case SPMVB200_ELL_ROWS_WARP_NT: launch_ell_rowmajor<32>(m, d_x, d_y, st); break;
-    }
-    CU_TRY(cudaPeekAtLastError());
-    return 0;
-}
-
-static int prefer_smem_once() {
-    static bool done_dev[64] = {false};  // per device: function attributes belong to the device's context
-    int dev = 0;
-    CU_TRY(cudaGetDevice(&dev));
-    bool& done = done_dev[dev & 63];
-    if (done) return 0;
-    // streaming variant: 8 CTAs x 27 KB of shared memory per SM => largest carve-out.
-    // gather variant (VARIANT=1): half the shared memory, the rest stays L1 for the x gathers.
-    int carve1 = 50;
-    if (const char* e = getenv("SPMVB200_CARVEOUT")) carve1 = atoi(e);  // developer knob
-    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, false, 0>,
-                                cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, true, 0>,
-                                cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, true, 1>,
-                                cudaFuncAttributePreferredSharedMemoryCarveout, carve1));
-    done = true;
-    return 0;
-}
-
-static int ensure_events(spmvb200_matrix* m) {
-    if (!m->ev0) CU_TRY(cudaEventCreate(&m->ev0));
-    if (!m->ev1) CU_TRY(cudaEventCreate(&m->ev1));
-    return 0;
-}
+#include "engine_launch.inl"
 
 extern "C" int spmvb200_spmv_device(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, void* stream) {
     if (!m || !d_x || !d_y) return fail("spmv_device: null argument");
@@ -1333,361 +219,9 @@ extern "C" int spmvb200_spmv_device(spmvb200_matrix* m, int kind, const double* 
     return launch(m, kind, d_x, d_y, (cudaStream_t) stream);
 }
 
-extern "C" int spmvb200_spmv_device_push(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, const spmvb200_push* push,
-                                         void* stream) {
-    if (!m || !d_x || !d_y || !push) return fail("spmv_device_push: null argument");
-    if (push->n < 0 || push->n > 8) return fail("spmv_device_push: %d destinations (at most 8)", push->n);
-    if (prefer_smem_once()) return 1;
-    // first use of a self-tuning kind: tune without deliveries (the tuning run launches every candidate)
-    if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || ((kind == SPMVB200_CSR_ROWS || kind == SPMVB200_ELL_ROWS) && m->tuned_x < 0) ||
-        (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned))
-        if (launch(m, kind, d_x, d_y, (cudaStream_t) stream)) return 1;
-    PushArgs a = {};
-    a.n = push->n;
-    for (int i = 0; i < push->n; ++i) {
-        if (!push->dst[i] || push->hi[i] > 0xffffffffull || push->lo[i] > push->hi[i]) return fail("spmv_device_push: bad destination %d", i);
-        a.dst[i] = push->dst[i];
-        a.lo[i] = (uint32_t) push->lo[i];
-        a.hi[i] = (uint32_t) push->hi[i];
-    }
-    if (push->row_offset + m->M > 0xffffffffull) return fail("spmv_device_push: row offset too large");
-    a.row_offset = (uint32_t) push->row_offset;
-    g_push = a;
-    g_push_fused = false;
-    const int rc = launch(m, kind, d_x, d_y, (cudaStream_t) stream);
-    const bool fused = g_push_fused;
-    g_push = PushArgs{};
-    if (rc) return 1;
-    if (!fused && a.n && m->M) {  // kernels without the fused epilogue: one more pass over y
-        push_rows_kernel<<<592, 256, 0, (cudaStream_t) stream>>>(d_y, (uint32_t) m->M, a);
-        ++g_launches;
-        CU_TRY(cudaPeekAtLastError());
-    }
-    return 0;
-}
+#include "engine_multigpu.inl"
 
-extern "C" int spmvb200_h2d_async(void* d, const void* h, size_t bytes, void* stream) {
-    CU_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t) stream));
-    return 0;
-}
-extern "C" int spmvb200_d2h_async(void* h, const void* d, size_t bytes, void* stream) {
-    CU_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
-    return 0;
-}
-extern "C" int spmvb200_stream_sync(void* stream) {
-    CU_TRY(cudaStreamSynchronize((cudaStream_t) stream));
-    return 0;
-}
-// deliver rows that already sit in device memory (e.g. this GPU's freshly uploaded slice of x) to the destinations that want them
-extern "C" int spmvb200_push_rows(const double* d_rows, uint64_t nrows, const spmvb200_push* push, void* stream) {
-    if (!d_rows || !push || push->n < 0 || push->n > 8 || nrows > 0xffffffffull) return fail("push_rows: bad arguments");
-    PushArgs a = {};
-    a.n = push->n;
-    for (int i = 0; i < push->n; ++i) {
-        if (!push->dst[i] || push->hi[i] > 0xffffffffull || push->lo[i] > push->hi[i]) return fail("push_rows: bad destination %d", i);
-        a.dst[i] = push->dst[i];
-        a.lo[i] = (uint32_t) push->lo[i];
-        a.hi[i] = (uint32_t) push->hi[i];
-    }
-    a.row_offset = (uint32_t) push->row_offset;
-    if (a.n && nrows) {
-        push_rows_kernel<<<592, 256, 0, (cudaStream_t) stream>>>(d_rows, (uint32_t) nrows, a);
-        ++g_launches;
-        CU_TRY(cudaPeekAtLastError());
-    }
-    return 0;
-}
-
-// ---- peer memory plumbing for one-process-per-GPU jobs (CUDA IPC) and the cross-GPU barrier
-extern "C" int spmvb200_ipc_export(void* d_ptr, unsigned char handle[64]) {
-    if (!d_ptr || !handle) return fail("ipc_export: null argument");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    cudaIpcMemHandle_t h;
-    CU_TRY(cudaIpcGetMemHandle(&h, d_ptr));
-    memcpy(handle, &h, 64);
-    return 0;
-}
-extern "C" int spmvb200_ipc_open(const unsigned char handle[64], void** d_ptr) {
-    if (!d_ptr || !handle) return fail("ipc_open: null argument");
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle, 64);
-    CU_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    return 0;
-}
-extern "C" int spmvb200_ipc_close(void* d_ptr) {
-    CU_TRY(cudaIpcCloseMemHandle(d_ptr));
-    return 0;
-}
-extern "C" int spmvb200_peer_barrier(uint32_t* const* d_flags, int n, int rank, uint32_t epoch, void* stream) {
-    if (!d_flags || n < 1 || n > 8 || rank < 0 || rank >= n) return fail("peer_barrier: bad arguments");
-    BarrierArgs b = {};
-    for (int i = 0; i < n; ++i) {
-        if (!d_flags[i]) return fail("peer_barrier: null flag array %d", i);
-        b.flags[i] = d_flags[i];
-    }
-    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t) stream>>>(b, n, rank, epoch);
-    CU_TRY(cudaPeekAtLastError());
-    return 0;
-}
-
-// ---- iterated SpMV on one GPU: x <- A x, `iters` times, ping-pong between two vectors; the launch pair is captured in a CUDA
-// graph so that back-to-back SpMVs are not separated by launch latency
-extern "C" int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a, double* d_b, int iters, int use_graph, void* stream,
-                                       float* total_ms) {
-    if (!m || !d_a || !d_b || iters < 0) return fail("iterate_device: bad arguments");
-    if (m->M != m->N) return fail("iterate_device: matrix is %llu x %llu, iteration needs a square matrix", (unsigned long long) m->M, (unsigned long long) m->N);
-    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
-    if (prefer_smem_once() || ensure_events(m)) return 1;
-    cudaStream_t st = (cudaStream_t) stream;
-    cudaStream_t own = nullptr;
-    if (use_graph && (st == nullptr || st == cudaStreamLegacy)) {  // the legacy default stream cannot be captured
-        CU_TRY(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
-        CU_TRY(cudaDeviceSynchronize());
-        st = own;
-    }
-    int rc = 0;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    do {
-        // self-tuning kinds tune here (cannot happen inside a capture); d_b is scratch at this point
-        if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || ((kind == SPMVB200_CSR_ROWS || kind == SPMVB200_ELL_ROWS) && m->tuned_x < 0) ||
-            (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned))
-            if ((rc = launch(m, kind, d_a, d_b, st))) break;
-        const int pairs = iters / 2;
-        unsigned long long per_replay = 0;
-        if (use_graph && pairs > 0) {
-            const unsigned long long l0 = g_launches;
-            if ((rc = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess)) break;
-            int r1 = launch(m, kind, d_a, d_b, st);
-            int r2 = r1 ? 1 : launch(m, kind, d_b, d_a, st);
-            cudaError_t ce = cudaStreamEndCapture(st, &graph);
-            if (r1 || r2 || ce != cudaSuccess) { rc = 1; if (ce != cudaSuccess) fail("iterate_device: capture failed: %s", cudaGetErrorString(ce)); break; }
-            if ((rc = cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess)) break;
-            per_replay = g_launches - l0;  // kernels inside the graph: counted per replay below
-            g_launches = l0;
-        }
-        if ((rc = cudaEventRecord(m->ev0, st) != cudaSuccess)) break;
-        for (int i = 0; i < pairs && !rc; ++i) {
-            if (exec) { rc = cudaGraphLaunch(exec, st) != cudaSuccess; g_launches += per_replay; }
-            else rc = launch(m, kind, d_a, d_b, st) || launch(m, kind, d_b, d_a, st);
-        }
-        if (!rc && (iters & 1)) rc = launch(m, kind, d_a, d_b, st);
-        if (rc) break;
-        if ((rc = cudaEventRecord(m->ev1, st) != cudaSuccess)) break;
-        if ((rc = cudaEventSynchronize(m->ev1) != cudaSuccess)) break;
-        if (total_ms && (rc = cudaEventElapsedTime(total_ms, m->ev0, m->ev1) != cudaSuccess)) break;
-    } while (0);
-    if (exec) cudaGraphExecDestroy(exec);
-    if (graph) cudaGraphDestroy(graph);
-    if (own) cudaStreamDestroy(own);
-    if (rc) {
-        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("iterate_device: %s", cudaGetErrorString(cudaGetLastError()));
-        return 1;
-    }
-    return 0;
-}
-
-
-// ---- pipelined host path --------------------------------------------------------------------------
-// which kernel a (kind, handle) pair runs chunk-wise: 0/1 stream variants (+10 exact), 2.. vector lanes, 100 ELL column-major
-static int pipe_candidate(const spmvb200_matrix* m, int kind) {
-    switch (kind) {
-        case SPMVB200_CSR_ROWS: return m->tuned_x == 0 ? 10 : -1;  // a re-tiled copy runs as one launch
-        case SPMVB200_CSR_ADAPTIVE: return ((m->tuned >= 2 && m->nseg) || m->tuned >= 7) ? -1 : m->tuned;  // long rows / spans: one launch
-        case SPMVB200_CSR_ROWS_WARP: return m->nseg ? -1 : 20 + m->vec_lanes;
-        case SPMVB200_ELL_ROWS: return m->tuned_x == 0 ? 100 : -1;  // the SELL copy runs as one launch
-        default: return -1;
-    }
-}
-static void launch_chunk(spmvb200_matrix* m, const HostPipe* p, int k, const double* x, double* y) {
-    const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
-    const int c = p->cand;
-    if (c == 100) launch_ell_colmajor(m, x, y, p->s_comp, r0, r1);
-    else if (c == 10) launch_csr_stream<false, 0>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
-    else if (c == 0) launch_csr_stream<true, 0>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
-    else if (c == 1) launch_csr_stream<true, 1>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
-    else if (c >= 20) launch_csr_vector(m, c - 20, x, y, p->s_comp, r0, r1);
-    else launch_csr_vector(m, 2 << (c - 2), x, y, p->s_comp, r0, r1);
-}
-static int host_chunks_wanted() {
-    int nch = 4;  // measured on B200/PCIe5: 1 chunk 0.74 ms, 2: 0.63, 4: 0.54, 8: 0.59, 16: 0.70 per call (cfg2)
-    if (const char* e = getenv("SPMVB200_HOST_CHUNKS")) nch = std::max(1, atoi(e));  // developer knob
-    return nch;
-}
-static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
-    destroy_pipe(m->pipe);  // rebuilt only when another kind is used through the host path
-    m->pipe = nullptr;
-    HostPipe* p = new HostPipe();
-    m->pipe = p;
-    p->kind = kind;
-    p->cand = cand;
-    int nch = host_chunks_wanted();
-    p->nch_req = nch;
-    if (m->M < 65536 || cand < 0) nch = 1;
-    const bool stream = (cand == 0 || cand == 1 || cand == 10);
-    if (stream) nch = (int) std::max<uint32_t>(1, std::min<uint32_t>(nch, m->ntiles));
-    p->nch = nch;
-    p->row_b.assign(nch + 1, m->M);
-    p->tile_b.assign(nch + 1, m->ntiles);
-    p->row_b[0] = 0;
-    p->tile_b[0] = 0;
-    for (int k = 1; k < nch; ++k) {
-        if (stream) {
-            uint32_t t = (uint32_t) ((uint64_t) m->ntiles * k / nch);
-            // never cut inside the segment run of a long row: its y entry is written by whichever segment finishes last
-            while (t < m->ntiles && t > 0 && (m->h_tile_row0[t] & SEG_FLAG) && (m->h_tile_row0[t - 1] & SEG_FLAG) &&
-                   (m->h_tile_row0[t] == m->h_tile_row0[t - 1]))
-                ++t;
-            t = std::max(t, p->tile_b[k - 1]);
-            p->tile_b[k] = t;
-            p->row_b[k] = m->h_tile_row0[t] & ~SEG_FLAG;
-        } else {
-            p->row_b[k] = std::max<uint64_t>(p->row_b[k - 1], (m->M * k / nch) & ~255ull);
-        }
-    }
-    // x pieces: piece k ends right after the largest column id row chunks 0..k read, so that chunk k can start
-    // the moment "its" piece has landed (banded / stencil matrices: pieces ~ equal; unstructured: piece 0 = all of x)
-    p->x_b.assign(nch + 1, m->N);
-    p->x_b[0] = 0;
-    if (nch > 1) {
-        uint32_t* d_cm = nullptr;
-        CU_TRY(cudaMalloc(&d_cm, nch * 4));
-        CU_TRY(cudaMemset(d_cm, 0, nch * 4));
-        for (int k = 0; k < nch; ++k) {
-            if (m->format == SPMVB200_FMT_CSR) {
-                uint64_t n0, n1;
-                if (stream) { n0 = m->h_tile_nnz0[p->tile_b[k]]; n1 = m->h_tile_nnz0[p->tile_b[k + 1]]; }
-                else {
-                    uint32_t h[2] = {0, 0};
-                    CU_TRY(cudaMemcpy(&h[0], m->irp + p->row_b[k], 4, cudaMemcpyDeviceToHost));
-                    CU_TRY(cudaMemcpy(&h[1], m->irp + p->row_b[k + 1], 4, cudaMemcpyDeviceToHost));
-                    n0 = h[0]; n1 = h[1];
-                }
-                if (n1 > n0) colmax_flat_kernel<<<592, 256>>>(m->ja, n0, n1, d_cm + k);
-            } else if (p->row_b[k + 1] > p->row_b[k]) {
-                const uint32_t r0 = (uint32_t) p->row_b[k], r1 = (uint32_t) p->row_b[k + 1];
-                colmax_ell_cm_kernel<<<(r1 - r0 + 255) / 256, 256>>>(m->ja, m->rl, m->pitch, r0, r1, d_cm + k);
-            }
-        }
-        std::vector<uint32_t> h_cm(nch);
-        cudaError_t e = cudaMemcpy(h_cm.data(), d_cm, nch * 4, cudaMemcpyDeviceToHost);
-        cudaFree(d_cm);
-        if (e != cudaSuccess) return fail("host-path plan: %s", cudaGetErrorString(e));
-        for (int k = 0; k < nch; ++k) {
-            const uint64_t need = std::min<uint64_t>(m->N, ((uint64_t) h_cm[k] + 1 + 511) & ~511ull);  // 4 KB granules
-            p->x_b[k + 1] = std::max(p->x_b[k], k + 1 == nch ? m->N : need);
-        }
-    }
-    p->npieces = nch;
-    CU_TRY(cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking));
-    CU_TRY(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
-    CU_TRY(cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking));
-    p->x_ready.resize(nch);
-    p->k_start.resize(nch);
-    p->k_end.resize(nch);
-    for (auto& ev : p->x_ready) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    for (auto& ev : p->k_start) CU_TRY(cudaEventCreate(&ev));
-    for (auto& ev : p->k_end) CU_TRY(cudaEventCreate(&ev));
-    return 0;
-}
-
-// If the caller's y is page-locked (cudaHostAlloc / cudaHostRegister) a kernel can store its rows straight into it: the
-// device->host transfer then rides along with the kernel as posted PCIe writes instead of following it as a copy-engine job.
-// Measured on cfg2 (16.8 MB of y, tools/e2e_probe.py, profiles/r01d_e2e_probe.log): a single x-window launch 0.737 -> 0.671 ms per
-// call; the sub-warp kernels (one 8-byte store per row and sub-warp) 0.769 -> 0.890 ms; inside the chunked pipeline 0.539 -> 0.628 ms
-// (the stores compete with the x pieces still coming up and run at 32-40 GB/s).  So by default only single x-window launches do it.
-// SPMVB200_HOST_DIRECT_Y (developer knob): 0 never, 1 default, 2 every single launch, 3 the chunked pipeline as well.
-// Returns the device-side alias of y, or nullptr (then y goes through d_y + cudaMemcpyAsync; always so for pageable memory).
-static double* mapped_alias(double* y, bool chunked, bool xwin_launch) {
-    const char* e = getenv("SPMVB200_HOST_DIRECT_Y");
-    const int mode = e ? atoi(e) : 1;
-    if (mode < (chunked ? 3 : (xwin_launch ? 1 : 2))) return nullptr;
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, y) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
-}
-
-extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms) {
-    if (!m || !x || !y) return fail("spmv_host: null argument");
-    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
-    if (prefer_smem_once() || ensure_events(m)) return 1;
-    if (!m->d_x) CU_TRY(cudaMalloc(&m->d_x, std::max<uint64_t>(m->N, 1) * 8));
-    if (!m->d_y) CU_TRY(cudaMalloc(&m->d_y, std::max<uint64_t>(m->M, 1) * 8));
-    const bool untuned = (kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || ((kind == SPMVB200_CSR_ROWS || kind == SPMVB200_ELL_ROWS) && m->tuned_x < 0) ||
-                         (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned);
-    int cand = untuned ? -1 : pipe_candidate(m, kind);
-    if (!untuned && (!m->pipe || m->pipe->kind != kind || m->pipe->cand != cand || m->pipe->nch_req != host_chunks_wanted()))
-        if (build_pipe(m, kind, cand)) return 1;
-    if (untuned || m->pipe->nch <= 1) {  // plain path: x up, one launch, y down (also the adaptive mode's tuning call)
-        const bool xw = (kind == SPMVB200_XWIN_ROWS && m->xw_mode >= 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x == CAND_XWIN) ||
-                        (kind == SPMVB200_CSR_ADAPTIVE && m->tuned == CAND_XWIN);
-        const bool tuning = untuned || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0);  // tuning launches time candidates: those stay on device memory
-        double* const y_one = tuning ? nullptr : mapped_alias(y, false, xw);
-        double* const out = y_one ? y_one : m->d_y;
-        CU_TRY(cudaMemcpyAsync(m->d_x, x, m->N * 8, cudaMemcpyHostToDevice, 0));
-        CU_TRY(cudaEventRecord(m->ev0, 0));
-        if (launch(m, kind, m->d_x, out, 0)) return 1;
-        CU_TRY(cudaEventRecord(m->ev1, 0));
-        if (out == m->d_y) CU_TRY(cudaMemcpyAsync(y, m->d_y, m->M * 8, cudaMemcpyDeviceToHost, 0));
-        CU_TRY(cudaStreamSynchronize(0));
-        if (kernel_ms) CU_TRY(cudaEventElapsedTime(kernel_ms, m->ev0, m->ev1));
-        return 0;
-    }
-    HostPipe* p = m->pipe;
-    double* const y_map = mapped_alias(y, true, false);
-    const bool dbg = getenv("SPMVB200_PIPE_DEBUG") != nullptr;
-    std::vector<cudaEvent_t> dbg_up, dbg_down;
-    cudaEvent_t dbg0 = nullptr;
-    if (dbg) {
-        cudaEventCreate(&dbg0);
-        cudaEventRecord(dbg0, p->s_up);
-    }
-    for (int j = 0; j < p->nch; ++j) {
-        const uint64_t o = p->x_b[j], n = p->x_b[j + 1] - o;
-        if (n) CU_TRY(cudaMemcpyAsync(m->d_x + o, x + o, n * 8, cudaMemcpyHostToDevice, p->s_up));
-        CU_TRY(cudaEventRecord(p->x_ready[j], p->s_up));
-        if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, p->s_up); dbg_up.push_back(e); }
-    }
-    for (int k = 0; k < p->nch; ++k) {
-        CU_TRY(cudaStreamWaitEvent(p->s_comp, p->x_ready[k], 0));
-        CU_TRY(cudaEventRecord(p->k_start[k], p->s_comp));
-        launch_chunk(m, p, k, m->d_x, y_map ? y_map : m->d_y);
-        CU_TRY(cudaEventRecord(p->k_end[k], p->s_comp));
-        const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
-        if (r1 > r0 && !y_map) {
-            CU_TRY(cudaStreamWaitEvent(p->s_down, p->k_end[k], 0));
-            CU_TRY(cudaMemcpyAsync(y + r0, m->d_y + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, p->s_down));
-            if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, p->s_down); dbg_down.push_back(e); }
-        }
-    }
-    CU_TRY(cudaPeekAtLastError());
-    CU_TRY(cudaStreamSynchronize(p->s_comp));
-    CU_TRY(cudaStreamSynchronize(p->s_down));
-    CU_TRY(cudaStreamSynchronize(p->s_up));
-    if (dbg) {
-        float ms;
-        fprintf(stderr, "pipe: x piece bounds=");
-        for (int k = 0; k <= p->nch; ++k) fprintf(stderr, "%llu ", (unsigned long long) p->x_b[k]);
-        fprintf(stderr, "\n  up done at:");
-        for (auto e : dbg_up) { cudaEventElapsedTime(&ms, dbg0, e); fprintf(stderr, " %.3f", ms); cudaEventDestroy(e); }
-        fprintf(stderr, "\n  kernels [start,end]:");
-        for (int k = 0; k < p->nch; ++k) { float a, b; cudaEventElapsedTime(&a, dbg0, p->k_start[k]); cudaEventElapsedTime(&b, dbg0, p->k_end[k]); fprintf(stderr, " [%.3f,%.3f]", a, b); }
-        fprintf(stderr, "\n  down done at:");
-        for (auto e : dbg_down) { cudaEventElapsedTime(&ms, dbg0, e); fprintf(stderr, " %.3f", ms); cudaEventDestroy(e); }
-        fprintf(stderr, "\n");
-        cudaEventDestroy(dbg0);
-    }
-    if (kernel_ms) {
-        float tot = 0;
-        for (int k = 0; k < p->nch; ++k) {
-            float ms = 0;
-            CU_TRY(cudaEventElapsedTime(&ms, p->k_start[k], p->k_end[k]));
-            tot += ms;
-        }
-        *kernel_ms = tot;
-    }
-    return 0;
-}
+#include "engine_hostpath.inl"
 
 // L2 flush by READING a buffer larger than L2: leaves the cache full of CLEAN lines.  (A memset leaves it full of dirty
 // lines, whose write-back the next kernel's fills then pay for -- up to one extra byte written per byte read.)

@@ -1,0 +1,203 @@
+// engine_hostpath.inl -- part of engine.cu (textually included there: one translation unit, file-local helpers stay static).
+// host-buffer path: x pieces up, row chunks, y chunks down (spmvb200_spmv_host).
+
+// ---- pipelined host path --------------------------------------------------------------------------
+// which kernel a (kind, handle) pair runs chunk-wise: 0/1 stream variants (+10 exact), 2.. vector lanes, 100 ELL column-major
+static int pipe_candidate(const spmvb200_matrix* m, int kind) {
+    switch (kind) {
+        case SPMVB200_CSR_ROWS: return m->tuned_x == 0 ? 10 : -1;  // a re-tiled copy runs as one launch
+        case SPMVB200_CSR_ADAPTIVE: return ((m->tuned >= 2 && m->nseg) || m->tuned >= 7) ? -1 : m->tuned;  // long rows / spans: one launch
+        case SPMVB200_CSR_ROWS_WARP: return m->nseg ? -1 : 20 + m->vec_lanes;
+        case SPMVB200_ELL_ROWS: return m->tuned_x == 0 ? 100 : -1;  // the SELL copy runs as one launch
+        default: return -1;
+    }
+}
+static void launch_chunk(spmvb200_matrix* m, const HostPipe* p, int k, const double* x, double* y) {
+    const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
+    const int c = p->cand;
+    if (c == 100) launch_ell_colmajor(m, x, y, p->s_comp, r0, r1);
+    else if (c == 10) launch_csr_stream<false, 0>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
+    else if (c == 0) launch_csr_stream<true, 0>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
+    else if (c == 1) launch_csr_stream<true, 1>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
+    else if (c >= 20) launch_csr_vector(m, c - 20, x, y, p->s_comp, r0, r1);
+    else launch_csr_vector(m, 2 << (c - 2), x, y, p->s_comp, r0, r1);
+}
+static int host_chunks_wanted() {
+    int nch = 4;  // measured on B200/PCIe5: 1 chunk 0.74 ms, 2: 0.63, 4: 0.54, 8: 0.59, 16: 0.70 per call (cfg2)
+    if (const char* e = getenv("SPMVB200_HOST_CHUNKS")) nch = std::max(1, atoi(e));  // developer knob
+    return nch;
+}
+static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
+    destroy_pipe(m->pipe);  // rebuilt only when another kind is used through the host path
+    m->pipe = nullptr;
+    HostPipe* p = new HostPipe();
+    m->pipe = p;
+    p->kind = kind;
+    p->cand = cand;
+    int nch = host_chunks_wanted();
+    p->nch_req = nch;
+    if (m->M < 65536 || cand < 0) nch = 1;
+    const bool stream = (cand == 0 || cand == 1 || cand == 10);
+    if (stream) nch = (int) std::max<uint32_t>(1, std::min<uint32_t>(nch, m->ntiles));
+    p->nch = nch;
+    p->row_b.assign(nch + 1, m->M);
+    p->tile_b.assign(nch + 1, m->ntiles);
+    p->row_b[0] = 0;
+    p->tile_b[0] = 0;
+    for (int k = 1; k < nch; ++k) {
+        if (stream) {
+            uint32_t t = (uint32_t) ((uint64_t) m->ntiles * k / nch);
+            // never cut inside the segment run of a long row: its y entry is written by whichever segment finishes last
+            while (t < m->ntiles && t > 0 && (m->h_tile_row0[t] & SEG_FLAG) && (m->h_tile_row0[t - 1] & SEG_FLAG) &&
+                   (m->h_tile_row0[t] == m->h_tile_row0[t - 1]))
+                ++t;
+            t = std::max(t, p->tile_b[k - 1]);
+            p->tile_b[k] = t;
+            p->row_b[k] = m->h_tile_row0[t] & ~SEG_FLAG;
+        } else {
+            p->row_b[k] = std::max<uint64_t>(p->row_b[k - 1], (m->M * k / nch) & ~255ull);
+        }
+    }
+    // x pieces: piece k ends right after the largest column id row chunks 0..k read, so that chunk k can start
+    // the moment "its" piece has landed (banded / stencil matrices: pieces ~ equal; unstructured: piece 0 = all of x)
+    p->x_b.assign(nch + 1, m->N);
+    p->x_b[0] = 0;
+    if (nch > 1) {
+        uint32_t* d_cm = nullptr;
+        CU_TRY(cudaMalloc(&d_cm, nch * 4));
+        CU_TRY(cudaMemset(d_cm, 0, nch * 4));
+        for (int k = 0; k < nch; ++k) {
+            if (m->format == SPMVB200_FMT_CSR) {
+                uint64_t n0, n1;
+                if (stream) { n0 = m->h_tile_nnz0[p->tile_b[k]]; n1 = m->h_tile_nnz0[p->tile_b[k + 1]]; }
+                else {
+                    uint32_t h[2] = {0, 0};
+                    CU_TRY(cudaMemcpy(&h[0], m->irp + p->row_b[k], 4, cudaMemcpyDeviceToHost));
+                    CU_TRY(cudaMemcpy(&h[1], m->irp + p->row_b[k + 1], 4, cudaMemcpyDeviceToHost));
+                    n0 = h[0]; n1 = h[1];
+                }
+                if (n1 > n0) colmax_flat_kernel<<<592, 256>>>(m->ja, n0, n1, d_cm + k);
+            } else if (p->row_b[k + 1] > p->row_b[k]) {
+                const uint32_t r0 = (uint32_t) p->row_b[k], r1 = (uint32_t) p->row_b[k + 1];
+                colmax_ell_cm_kernel<<<(r1 - r0 + 255) / 256, 256>>>(m->ja, m->rl, m->pitch, r0, r1, d_cm + k);
+            }
+        }
+        std::vector<uint32_t> h_cm(nch);
+        cudaError_t e = cudaMemcpy(h_cm.data(), d_cm, nch * 4, cudaMemcpyDeviceToHost);
+        cudaFree(d_cm);
+        if (e != cudaSuccess) return fail("host-path plan: %s", cudaGetErrorString(e));
+        for (int k = 0; k < nch; ++k) {
+            const uint64_t need = std::min<uint64_t>(m->N, ((uint64_t) h_cm[k] + 1 + 511) & ~511ull);  // 4 KB granules
+            p->x_b[k + 1] = std::max(p->x_b[k], k + 1 == nch ? m->N : need);
+        }
+    }
+    p->npieces = nch;
+    CU_TRY(cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking));
+    p->x_ready.resize(nch);
+    p->k_start.resize(nch);
+    p->k_end.resize(nch);
+    for (auto& ev : p->x_ready) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : p->k_start) CU_TRY(cudaEventCreate(&ev));
+    for (auto& ev : p->k_end) CU_TRY(cudaEventCreate(&ev));
+    return 0;
+}
+
+// If the caller's y is page-locked (cudaHostAlloc / cudaHostRegister) a kernel can store its rows straight into it: the
+// device->host transfer then rides along with the kernel as posted PCIe writes instead of following it as a copy-engine job.
+// Measured on cfg2 (16.8 MB of y, tools/e2e_probe.py, profiles/r01d_e2e_probe.log): a single x-window launch 0.737 -> 0.671 ms per
+// call; the sub-warp kernels (one 8-byte store per row and sub-warp) 0.769 -> 0.890 ms; inside the chunked pipeline 0.539 -> 0.628 ms
+// (the stores compete with the x pieces still coming up and run at 32-40 GB/s).  So by default only single x-window launches do it.
+// SPMVB200_HOST_DIRECT_Y (developer knob): 0 never, 1 default, 2 every single launch, 3 the chunked pipeline as well.
+// Returns the device-side alias of y, or nullptr (then y goes through d_y + cudaMemcpyAsync; always so for pageable memory).
+static double* mapped_alias(double* y, bool chunked, bool xwin_launch) {
+    const char* e = getenv("SPMVB200_HOST_DIRECT_Y");
+    const int mode = e ? atoi(e) : 1;
+    if (mode < (chunked ? 3 : (xwin_launch ? 1 : 2))) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, y) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
+}
+
+extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms) {
+    if (!m || !x || !y) return fail("spmv_host: null argument");
+    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
+    if (prefer_smem_once() || ensure_events(m)) return 1;
+    if (!m->d_x) CU_TRY(cudaMalloc(&m->d_x, std::max<uint64_t>(m->N, 1) * 8));
+    if (!m->d_y) CU_TRY(cudaMalloc(&m->d_y, std::max<uint64_t>(m->M, 1) * 8));
+    const bool untuned = (kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || ((kind == SPMVB200_CSR_ROWS || kind == SPMVB200_ELL_ROWS) && m->tuned_x < 0) ||
+                         (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned);
+    int cand = untuned ? -1 : pipe_candidate(m, kind);
+    if (!untuned && (!m->pipe || m->pipe->kind != kind || m->pipe->cand != cand || m->pipe->nch_req != host_chunks_wanted()))
+        if (build_pipe(m, kind, cand)) return 1;
+    if (untuned || m->pipe->nch <= 1) {  // plain path: x up, one launch, y down (also the adaptive mode's tuning call)
+        const bool xw = (kind == SPMVB200_XWIN_ROWS && m->xw_mode >= 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x == CAND_XWIN) ||
+                        (kind == SPMVB200_CSR_ADAPTIVE && m->tuned == CAND_XWIN);
+        const bool tuning = untuned || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0);  // tuning launches time candidates: those stay on device memory
+        double* const y_one = tuning ? nullptr : mapped_alias(y, false, xw);
+        double* const out = y_one ? y_one : m->d_y;
+        CU_TRY(cudaMemcpyAsync(m->d_x, x, m->N * 8, cudaMemcpyHostToDevice, 0));
+        CU_TRY(cudaEventRecord(m->ev0, 0));
+        if (launch(m, kind, m->d_x, out, 0)) return 1;
+        CU_TRY(cudaEventRecord(m->ev1, 0));
+        if (out == m->d_y) CU_TRY(cudaMemcpyAsync(y, m->d_y, m->M * 8, cudaMemcpyDeviceToHost, 0));
+        CU_TRY(cudaStreamSynchronize(0));
+        if (kernel_ms) CU_TRY(cudaEventElapsedTime(kernel_ms, m->ev0, m->ev1));
+        return 0;
+    }
+    HostPipe* p = m->pipe;
+    double* const y_map = mapped_alias(y, true, false);
+    const bool dbg = getenv("SPMVB200_PIPE_DEBUG") != nullptr;
+    std::vector<cudaEvent_t> dbg_up, dbg_down;
+    cudaEvent_t dbg0 = nullptr;
+    if (dbg) {
+        cudaEventCreate(&dbg0);
+        cudaEventRecord(dbg0, p->s_up);
+    }
+    for (int j = 0; j < p->nch; ++j) {
+        const uint64_t o = p->x_b[j], n = p->x_b[j + 1] - o;
+        if (n) CU_TRY(cudaMemcpyAsync(m->d_x + o, x + o, n * 8, cudaMemcpyHostToDevice, p->s_up));
+        CU_TRY(cudaEventRecord(p->x_ready[j], p->s_up));
+        if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, p->s_up); dbg_up.push_back(e); }
+    }
+    for (int k = 0; k < p->nch; ++k) {
+        CU_TRY(cudaStreamWaitEvent(p->s_comp, p->x_ready[k], 0));
+        CU_TRY(cudaEventRecord(p->k_start[k], p->s_comp));
+        launch_chunk(m, p, k, m->d_x, y_map ? y_map : m->d_y);
+        CU_TRY(cudaEventRecord(p->k_end[k], p->s_comp));
+        const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
+        if (r1 > r0 && !y_map) {
+            CU_TRY(cudaStreamWaitEvent(p->s_down, p->k_end[k], 0));
+            CU_TRY(cudaMemcpyAsync(y + r0, m->d_y + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, p->s_down));
+            if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, p->s_down); dbg_down.push_back(e); }
+        }
+    }
+    CU_TRY(cudaPeekAtLastError());
+    CU_TRY(cudaStreamSynchronize(p->s_comp));
+    CU_TRY(cudaStreamSynchronize(p->s_down));
+    CU_TRY(cudaStreamSynchronize(p->s_up));
+    if (dbg) {
+        float ms;
+        fprintf(stderr, "pipe: x piece bounds=");
+        for (int k = 0; k <= p->nch; ++k) fprintf(stderr, "%llu ", (unsigned long long) p->x_b[k]);
+        fprintf(stderr, "\n  up done at:");
+        for (auto e : dbg_up) { cudaEventElapsedTime(&ms, dbg0, e); fprintf(stderr, " %.3f", ms); cudaEventDestroy(e); }
+        fprintf(stderr, "\n  kernels [start,end]:");
+        for (int k = 0; k < p->nch; ++k) { float a, b; cudaEventElapsedTime(&a, dbg0, p->k_start[k]); cudaEventElapsedTime(&b, dbg0, p->k_end[k]); fprintf(stderr, " [%.3f,%.3f]", a, b); }
+        fprintf(stderr, "\n  down done at:");
+        for (auto e : dbg_down) { cudaEventElapsedTime(&ms, dbg0, e); fprintf(stderr, " %.3f", ms); cudaEventDestroy(e); }
+        fprintf(stderr, "\n");
+        cudaEventDestroy(dbg0);
+    }
+    if (kernel_ms) {
+        float tot = 0;
+        for (int k = 0; k < p->nch; ++k) {
+            float ms = 0;
+            CU_TRY(cudaEventElapsedTime(&ms, p->k_start[k], p->k_end[k]));
+            tot += ms;
+        }
+        *kernel_ms = tot;
+    }
+    return 0;
+}

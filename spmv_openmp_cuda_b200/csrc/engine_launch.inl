@@ -1,0 +1,522 @@
+// engine_launch.inl -- part of engine.cu (textually included there: one translation unit, file-local helpers stay static).
+// launch: kernel launchers, first-use tuning of the self-tuning kinds, the kind -> kernel switch.
+
+// ------------------------------------------------------------------------------------------------- launch
+// Rows the vector kernels skip: medium rows (one CTA each) and rows longer than a tile (one CTA per segment).  They touch other rows
+// of y than the main kernel, so they run NEXT to it on two side streams -- forked before the main launch, joined after it (events:
+// legal inside a graph capture too).  On R-MAT (cfg3) the three kernels are 189 + 97 + 52 us back to back.
+// exact: the medium rows go through the warp-per-row kernel that adds in the serial order (the bit-exact kind's SELL hybrid).
+static void tail_fork(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, bool exact = false) {
+    if (!m->nmid && !m->nseg) return;
+    static const bool serial = getenv("SPMVB200_SERIAL_TAIL") != nullptr;  // developer knob: the old back-to-back order
+    if (!serial && !m->e_fork) {
+        bool ok = cudaEventCreateWithFlags(&m->e_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = cudaStreamCreateWithFlags(&m->s_tail[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&m->e_tail[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); m->e_fork = nullptr; }
+    }
+    const bool fork = !serial && m->e_fork && m->s_tail[0] && m->s_tail[1] && m->e_tail[0] && m->e_tail[1];
+    if (fork) cudaEventRecord(m->e_fork, st);
+    if (m->nmid) {
+        cudaStream_t s = fork ? m->s_tail[0] : st;
+        if (fork) cudaStreamWaitEvent(s, m->e_fork, 0);
+        static const bool warp_mid = getenv("SPMVB200_NO_WARP_MID") == nullptr;  // developer knob
+        const uint32_t lo = warp_mid ? (uint32_t) MIDW_MAX : 0u;  // rows up to MIDW_MAX: a warp each; longer: a CTA each
+        if (exact) {
+            csr_midrow_exact_kernel<256><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y);
+            ++g_launches;
+        } else if (warp_mid) {
+            csr_midrow_warp_kernel<256><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y, 0u, (uint32_t) MIDW_MAX);
+            ++g_launches;
+        }
+        if (!exact && (!warp_mid || m->lmax > (uint32_t) MIDW_MAX)) {
+            csr_midrow_kernel<128><<<m->nmid, 128, 0, s>>>(m->mid_rows, m->irp, m->ja, m->as, x, y, lo);
+            ++g_launches;
+        }
+        if (fork) cudaEventRecord(m->e_tail[0], s);
+    }
+    if (m->nseg) {
+        cudaStream_t s = fork ? m->s_tail[1] : st;
+        if (fork) cudaStreamWaitEvent(s, m->e_fork, 0);
+        csr_longrow_kernel<128><<<m->nseg, 128, 0, s>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+        if (fork) cudaEventRecord(m->e_tail[1], s);
+        ++g_launches;
+    }
+}
+static void tail_join(spmvb200_matrix* m, cudaStream_t st) {
+    if (!m->e_fork || getenv("SPMVB200_SERIAL_TAIL")) return;
+    if (m->nmid) cudaStreamWaitEvent(st, m->e_tail[0], 0);
+    if (m->nseg) cudaStreamWaitEvent(st, m->e_tail[1], 0);
+}
+// rows [r0, r1) (whole matrix: 0, M); y is always indexed by the handle's row number
+template <int LANES>
+static void launch_csr_vector_t(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
+    constexpr int BLOCK = 256;
+    const uint64_t threads = (r1 - r0) * LANES;
+    if (!threads) return;
+    // whole-matrix launches leave rows longer than VEC_MID to the per-row CTAs below; row-chunk launches keep them
+    csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(
+        m->irp, m->ja, m->as, x, y, (uint32_t) r0, (uint32_t) r1, (uint32_t) ((r0 == 0 && r1 == m->M) ? VEC_MID : STREAM_TILE));
+    ++g_launches;
+}
+// vector kernel for rows up to one tile + the long-row kernel for the rest (same stream, back to back)
+static void launch_csr_vector(spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
+    const bool whole = r0 == 0 && r1 == m->M;
+    if (whole) tail_fork(m, x, y, st);
+    switch (lanes) {
+        case 2: launch_csr_vector_t<2>(m, x, y, st, r0, r1); break;
+        case 4: launch_csr_vector_t<4>(m, x, y, st, r0, r1); break;
+        case 8: launch_csr_vector_t<8>(m, x, y, st, r0, r1); break;
+        case 16: launch_csr_vector_t<16>(m, x, y, st, r0, r1); break;
+        default: launch_csr_vector_t<32>(m, x, y, st, r0, r1); break;
+    }
+    if (whole) tail_join(m, st);
+}
+template <int LANES>
+static void launch_csr_vspan_t(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    csr_vector_span_kernel<LANES, 1024><<<m->nspans, 1024, 0, st>>>(m->span_b, m->irp, m->ja, m->as, x, y, (uint32_t) VEC_MID);
+    ++g_launches;
+}
+static void launch_csr_vspan(spmvb200_matrix* m, int lanes, const double* x, double* y, cudaStream_t st) {
+    tail_fork(m, x, y, st);
+    switch (lanes) {
+        case 2: launch_csr_vspan_t<2>(m, x, y, st); break;
+        case 4: launch_csr_vspan_t<4>(m, x, y, st); break;
+        case 8: launch_csr_vspan_t<8>(m, x, y, st); break;
+        case 16: launch_csr_vspan_t<16>(m, x, y, st); break;
+        default: launch_csr_vspan_t<32>(m, x, y, st); break;
+    }
+    tail_join(m, st);
+}
+// tiles [t0, t1) (whole matrix: 0, ntiles)
+template <bool ADAPT, int VARIANT>
+static void launch_csr_stream(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint32_t t0, uint32_t t1) {
+    if (t1 <= t0) return;
+    static const uint32_t pre_t = getenv("SPMVB200_PRE_T") ? (uint32_t) atoi(getenv("SPMVB200_PRE_T")) : (uint32_t) STREAM_PRE_T;  // developer knob
+    csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, ADAPT, VARIANT>
+        <<<t1 - t0, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, x, y, m->partial, m->ticket, t0, pre_t);
+    ++g_launches;
+}
+static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
+    constexpr int BLOCK = 256;
+    if (r1 <= r0) return;
+    static const bool no_exit = getenv("SPMVB200_ELL_NO_EARLY_EXIT") != nullptr;  // developer knob: walk all K slots like the reference
+    // slots in flight per thread: 4, or 3 when that leaves a shorter tail of one-at-a-time slots (K = 27: 3 x 9 exactly; measured
+    // 103.3 vs 105.2 us on cfg2; 5..9 lose more to occupancy than they gain)
+    static const int unroll_env = getenv("SPMVB200_ELL_UNROLL") ? atoi(getenv("SPMVB200_ELL_UNROLL")) : 0;  // developer knob
+    const int unroll16 = unroll_env ? unroll_env : ((m->K % 3) < (m->K % 4) ? 3 : 4);
+    const unsigned grid = (unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK);
+#define ELL16(U) ell_colmajor_kernel<U, BLOCK, true><<<grid, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, m->ja16_base, x, y, g_push)
+    // 16-bit ids: two rows per thread, 3 slots in flight (measured on cfg2: 96.9 us; one row per thread 103.0; pair x2 100.7, pair x4 107.1)
+    static const int pair_env = getenv("SPMVB200_ELL_PAIR") ? atoi(getenv("SPMVB200_ELL_PAIR")) : 3;  // developer knob: 0 = one row per thread
+    if (m->ja16 && !no_exit && pair_env && (r0 % 2) == 0) {
+        const unsigned g2 = (unsigned) (((r1 - r0 + 1) / 2 + BLOCK - 1) / BLOCK);
+#define ELLP(U) ell_colmajor_pair_kernel<U, BLOCK><<<g2, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, m->ja16_base, x, y, g_push)
+        switch (pair_env) {
+            case 2: ELLP(2); break;
+            case 3: ELLP(3); break;
+            default: ELLP(4); break;
+        }
+#undef ELLP
+    } else if (m->ja16 && !no_exit) {
+        switch (unroll16) {
+            case 3: ELL16(3); break;
+            case 5: ELL16(5); break;
+            case 6: ELL16(6); break;
+            case 8: ELL16(8); break;
+            case 9: ELL16(9); break;
+            default: ELL16(4); break;
+        }
+    }
+#undef ELL16
+    else if (unroll16 == 3)
+        ell_colmajor_kernel<3, BLOCK, false><<<grid, BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, 0, x, y, g_push);
+    else
+        ell_colmajor_kernel<4, BLOCK, false><<<grid, BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, 0, x, y, g_push);
+    g_push_fused = true;
+    ++g_launches;
+}
+
+
+// ---- x-window CSR: one CTA per row block, NW warps, ring of x windows in shared memory
+template <int NW, int ACC, int UMAX>
+static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    const size_t smem = (size_t) m->xw_nbuf * (m->xw_W + 2) * 8 + XW_MAX_NBUF * 12;
+    static size_t configured[64] = {0};  // per device: function attributes belong to the device's context
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if (smem > configured[dev & 63]) {
+        CU_TRY(cudaFuncSetAttribute(xwin_kernel<NW, ACC, UMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured[dev & 63] = smem;
+    }
+    const bool persist = m->xw_mode == 1;
+    xwin_kernel<NW, ACC, UMAX><<<persist ? m->xw_ncta : m->xw_nrb, 32 * NW, smem, st>>>(persist ? m->xw_cta_rb : nullptr, m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
+                                                                 (uint32_t) m->M, (uint32_t) m->N, m->xw_W, m->xw_nbuf, ((uintptr_t) x & 15) == 0, g_push);
+    g_push_fused = true;
+    ++g_launches;
+    return 0;
+}
+// (warps, row groups per warp, largest batch in slots): up to 2*UMAX*ACC loads in flight per lane
+static int launch_xwin(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    const uint32_t acc = m->xw_R / (32 * m->xw_nw);
+    static const int u_env = getenv("SPMVB200_XW_U") ? atoi(getenv("SPMVB200_XW_U")) : 0;  // developer knob
+#define XW_CASE(NW, ACC, UDEF, UALT, UALT2)                                                  \
+    if (m->xw_nw == NW && acc == ACC) {                                                      \
+        if (u_env == UALT) return launch_xwin_t<NW, ACC, UALT>(m, x, y, st);                 \
+        if (u_env == UALT2) return launch_xwin_t<NW, ACC, UALT2>(m, x, y, st);               \
+        return launch_xwin_t<NW, ACC, UDEF>(m, x, y, st);                                    \
+    }
+    XW_CASE(32, 1, 8, 6, 4)
+    XW_CASE(32, 2, 5, 4, 6)
+    XW_CASE(32, 4, 3, 2, 4)
+    XW_CASE(16, 1, 8, 6, 4)
+    XW_CASE(16, 2, 8, 6, 4)
+    XW_CASE(16, 4, 6, 4, 8)
+    XW_CASE(16, 8, 3, 4, 2)
+#undef XW_CASE
+    return fail("x-window kernel: no instantiation for R=%u, %u warps", m->xw_R, m->xw_nw);
+}
+
+// first use of an x-window handle: one CTA per row block, or persistent CTAs?  (Persistent wins when a row block has few
+// tiles -- no pipeline refill per row block; per-row-block wins on wide bands, where concurrent CTAs then share windows.)
+static int tune_xwin(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, float* best_ms_out) {
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    int best = 0;
+    for (int mode = 0; mode < 2; ++mode) {
+        m->xw_mode = mode;
+        if (launch_xwin(m, x, y, st)) return 1;
+        float ms_min = 1e30f;
+        for (int rep = 0; rep < 2; ++rep) {
+            CU_TRY(cudaEventRecord(e0, st));
+            if (launch_xwin(m, x, y, st)) return 1;
+            CU_TRY(cudaEventRecord(e1, st));
+            CU_TRY(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            ms_min = std::min(ms_min, ms);
+        }
+        if (ms_min < best_ms) { best_ms = ms_min; best = mode; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    m->xw_mode = best;
+    if (best_ms_out) *best_ms_out = best_ms;
+    return 0;
+}
+
+static void launch_sell(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    sell_kernel<4, 256><<<(unsigned) ((m->Mpad + 255) / 256), 256, 0, st>>>(m->irp, m->perm, m->rl, m->as, m->ja, (uint32_t) m->Mpad, x, y);
+    ++g_launches;
+}
+
+// ---- SPMVB200_CSR_ADAPTIVE: candidates; the fastest on this matrix is picked at first use
+static const int N_CAND = 14;
+static const int CAND_XWIN = 12;  // x-window copy (built during tuning when the tile census says it can pay off)
+static const int CAND_SELL = 13;  // SELL-32-sigma copy (matrices without long rows: thread per row, coalesced, no shuffles)
+static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32",
+                                        "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32", "xwindow", "sell"};
+static int cand_lanes(int c) { return c < 2 ? 0 : 2 << ((c - 2) % 5); }
+static void launch_candidate(spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st) {
+    if (c == 0) launch_csr_stream<true, 0>(m, x, y, st, 0, m->ntiles);
+    else if (c == 1) launch_csr_stream<true, 1>(m, x, y, st, 0, m->ntiles);
+    else if (c < 7) launch_csr_vector(m, cand_lanes(c), x, y, st, 0, m->M);
+    else if (c < CAND_XWIN) launch_csr_vspan(m, cand_lanes(c), x, y, st);
+    else if (c == CAND_XWIN) launch_xwin(m->xw_child, x, y, st);
+    else {
+        const bool hybrid = m->lmax > (uint32_t) VEC_MID;  // rows the capped SELL copy left out (it does not write their y)
+        if (hybrid) tail_fork(m, x, y, st);
+        launch_sell(m->xw_child, x, y, st);
+        if (hybrid) tail_join(m, st);
+    }
+}
+static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
+    // d_x / d_y are the caller's vectors: y is overwritten by every candidate with the same result
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    int best = 0;
+    float best_ms = 1e30f;
+    const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
+    m->tuned_ms[CAND_XWIN] = m->tuned_ms[CAND_SELL] = -1.f;
+    for (int c = 0; c < CAND_XWIN; ++c) {
+        m->tuned_ms[c] = -1.f;
+        if (c >= 2 && (cand_lanes(c) > 4 * mean + 2 || (double) cand_lanes(c) * 64 < mean)) continue;  // hopeless widths
+        if (const char* e = getenv("SPMVB200_FORCE_CAND")) if (atoi(e) != c) continue;  // developer knob
+        launch_candidate(m, c, d_x, d_y, st);
+        float ms_min = 1e30f;
+        for (int rep = 0; rep < 2; ++rep) {
+            CU_TRY(cudaEventRecord(e0, st));
+            launch_candidate(m, c, d_x, d_y, st);
+            CU_TRY(cudaEventRecord(e1, st));
+            CU_TRY(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            ms_min = std::min(ms_min, ms);
+        }
+        m->tuned_ms[c] = ms_min;
+        if (ms_min < best_ms) { best_ms = ms_min; best = c; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // x-window copy: costs a second copy of the matrix (10.x B per non-zero), so it is only built when the matrix is big
+    // enough to matter, and kept only if it beats everything else by 5 %
+    const char* force = getenv("SPMVB200_FORCE_CAND");
+    if (!getenv("SPMVB200_NO_XWINDOW") && m->NZ >= (1u << 20) && (!force || atoi(force) == CAND_XWIN)) {
+        g_quiet = 1;  // "does not fit this format" is an expected answer here, not an error to print
+        spmvb200_matrix* xw = nullptr;
+        // window traffic (L2 -> shared memory) above ~1.5x the matrix stream cannot win: stop at the tile census
+        const int rc = xwin_build(m, 0, 0, 15.0, &xw);
+        g_quiet = 0;
+        if (!rc) {
+            float ms = -1.f;
+            if (!tune_xwin(xw, d_x, d_y, st, &ms)) {
+                m->tuned_ms[CAND_XWIN] = ms;
+                if (ms < 0.95f * best_ms || force) { best_ms = ms; best = CAND_XWIN; }
+            }
+            if (best == CAND_XWIN) m->xw_child = xw; else spmvb200_free(xw);
+        }
+        g_err[0] = 0;
+    }
+    // SELL-32-sigma copy (a thread walks its whole row, coalesced, no shuffles).  Rows longer than VEC_MID are left out of it and go
+    // to the per-row / per-segment CTAs of the vector path (hybrid for skewed matrices); kept only while the slices stay nearly
+    // padding-free
+    if (!getenv("SPMVB200_NO_SELL") && m->NZ >= (1u << 20) && (!force || atoi(force) == CAND_SELL)) {
+        g_quiet = 1;
+        spmvb200_matrix* sell = nullptr;
+        const bool hybrid = m->lmax > (uint32_t) VEC_MID;
+        const int rc = sell_build(m, 0, hybrid ? (uint32_t) VEC_MID : 0xffffffffu, &sell);
+        g_quiet = 0;
+        if (!rc) {
+            float ms_min = 1e30f;
+            if (sell->slots <= m->NZ + m->NZ / 4) {
+                cudaEvent_t s0, s1;
+                CU_TRY(cudaEventCreate(&s0));
+                CU_TRY(cudaEventCreate(&s1));
+                launch_sell(sell, d_x, d_y, st);
+                for (int rep = 0; rep < 2; ++rep) {
+                    CU_TRY(cudaEventRecord(s0, st));
+                    if (hybrid) tail_fork(m, d_x, d_y, st);
+                    launch_sell(sell, d_x, d_y, st);
+                    if (hybrid) tail_join(m, st);
+                    CU_TRY(cudaEventRecord(s1, st));
+                    CU_TRY(cudaEventSynchronize(s1));
+                    float ms = 0;
+                    CU_TRY(cudaEventElapsedTime(&ms, s0, s1));
+                    ms_min = std::min(ms_min, ms);
+                }
+                cudaEventDestroy(s0);
+                cudaEventDestroy(s1);
+                m->tuned_ms[CAND_SELL] = ms_min;
+            }
+            if (ms_min < 0.95f * best_ms || (force && ms_min < 1e30f)) {
+                if (m->xw_child) spmvb200_free(m->xw_child);
+                m->xw_child = sell;
+                best_ms = ms_min;
+                best = CAND_SELL;
+            } else {
+                spmvb200_free(sell);
+            }
+        }
+        g_err[0] = 0;
+    }
+    m->tuned = best;
+    if (getenv("SPMVB200_VERBOSE")) {
+        fprintf(stderr, "spmv_b200: adaptive tuning M=%llu NZ=%llu ->", (unsigned long long) m->M, (unsigned long long) m->NZ);
+        for (int c = 0; c < N_CAND; ++c) fprintf(stderr, " %s=%.3fms%s", CAND_NAME[c], m->tuned_ms[c], c == best ? "*" : "");
+        fprintf(stderr, "\n");
+    }
+    return 0;
+}
+
+// ---- SPMVB200_CSR_ROWS, the kind that must reproduce sgemvSerial bit for bit: the stream kernel, or -- timed at first use, for
+// matrices of at least 2^20 non-zeros -- an x-window copy (column-sorted rows only) or a SELL copy (no row longer than VEC_MID);
+// all three add a row's products left to right with separate mul / add roundings.
+template <typename F>
+static int time_best_of_2(F&& run, cudaStream_t st, float* ms_out) {
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    run();
+    float best = 1e30f;
+    for (int rep = 0; rep < 2; ++rep) {
+        CU_TRY(cudaEventRecord(e0, st));
+        run();
+        CU_TRY(cudaEventRecord(e1, st));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_out = best;
+    return 0;
+}
+static void launch_exact_sell(spmvb200_matrix* m, const spmvb200_matrix* sell, const double* x, double* y, cudaStream_t st) {
+    const bool hybrid = m->lmax > (uint32_t) VEC_MID;  // rows the capped SELL copy left out (it does not write their y)
+    if (hybrid) tail_fork(m, x, y, st, true);
+    launch_sell(sell, x, y, st);
+    if (hybrid) tail_join(m, st);
+}
+static int tune_exact(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
+    float best_ms = 0;
+    if (time_best_of_2([&] { launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles); }, st, &best_ms)) return 1;
+    int best = 0;
+    m->tuned_x_ms[0] = best_ms;
+    m->tuned_x_ms[1] = m->tuned_x_ms[2] = -1.f;
+    const char* only = getenv("SPMVB200_EXACT_ONLY_STREAM");  // developer knob
+    if (!only && m->NZ >= (1u << 20)) {
+        g_quiet = 1;
+        spmvb200_matrix* xw = nullptr;
+        if (!xwin_build(m, 0, 0, 15.0, &xw)) {
+            float ms = 1e30f;
+            if (xw->xw_sorted && !tune_xwin(xw, d_x, d_y, st, &ms)) m->tuned_x_ms[1] = ms;
+            if (ms < 0.95f * best_ms) { best_ms = ms; best = CAND_XWIN; m->x_child = xw; } else spmvb200_free(xw);
+        }
+        // rows longer than VEC_MID are left out of the SELL copy: a warp each adds them in the serial order next to it (exact hybrid);
+        // rows longer than a tile are split into segments as in the stream kernel (deterministic, within tolerance)
+        spmvb200_matrix* sell = nullptr;
+        if (!getenv("SPMVB200_NO_SELL") && !sell_build(m, 0, m->lmax <= (uint32_t) VEC_MID ? 0xffffffffu : (uint32_t) VEC_MID, &sell)) {
+            float ms = 1e30f;
+            if (sell->slots <= m->NZ + m->NZ / 4 && !time_best_of_2([&] { launch_exact_sell(m, sell, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
+            const char* f = getenv("SPMVB200_FORCE_EXACT");  // developer knob (tests): 13 = keep the SELL copy whatever the timing says
+            if (ms < 0.95f * best_ms || (f && atoi(f) == CAND_SELL && ms < 1e30f)) {
+                if (m->x_child) spmvb200_free(m->x_child);
+                best_ms = ms; best = CAND_SELL; m->x_child = sell;
+            } else spmvb200_free(sell);
+        }
+        g_quiet = 0;
+        g_err[0] = 0;
+    }
+    m->tuned_x = best;
+    if (getenv("SPMVB200_VERBOSE"))
+        fprintf(stderr, "spmv_b200: exact-kind tuning M=%llu NZ=%llu -> stream=%.3fms xwindow=%.3fms sell=%.3fms, picked %s\n", (unsigned long long) m->M,
+                (unsigned long long) m->NZ, m->tuned_x_ms[0], m->tuned_x_ms[1], m->tuned_x_ms[2], best == 0 ? "stream" : best == CAND_XWIN ? "xwindow" : "sell");
+    return 0;
+}
+
+// ---- SPMVB200_ELL_ROWS on a padded matrix: the column-major kernel exits early per WARP (a warp runs to the longest of its rows), so one
+// long row among 64 short ones keeps the warp's slot busy for K dependent round trips.  When the ELL rectangle is at least 1.25 x the
+// non-zeros, a SELL-32-sigma copy (rows sorted by length inside windows: warps see equal lengths) is built from the ELL arrays on the
+// device and timed against the column-major kernel at first use; it is kept only if it wins by 5 %.  Both add a row's products left
+// to right with separate mul / add roundings: bit-identical results either way.  tuned_x: 0 = column-major ELL, CAND_SELL = the copy.
+static int tune_ell(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
+    m->tuned_x = 0;
+    if (getenv("SPMVB200_NO_SELL") || getenv("SPMVB200_ELL_NO_SELL") || getenv("SPMVB200_ELL_NO_EARLY_EXIT") || m->NZ < (1u << 20) || !m->rl) return 0;
+    if ((double) m->K * (double) m->M < 1.25 * (double) m->NZ) return 0;
+    float ell_ms = 0;
+    if (time_best_of_2([&] { launch_ell_colmajor(m, d_x, d_y, st, 0, m->M); }, st, &ell_ms)) return 1;
+    m->tuned_x_ms[0] = ell_ms;
+    m->tuned_x_ms[1] = m->tuned_x_ms[2] = -1.f;
+    g_quiet = 1;
+    spmvb200_matrix* sell = nullptr;
+    if (!sell_build(m, 0, 0xffffffffu, &sell)) {
+        float ms = 1e30f;
+        if (!time_best_of_2([&] { launch_sell(sell, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
+        if (ms < 0.95f * ell_ms) { m->tuned_x = CAND_SELL; m->x_child = sell; } else spmvb200_free(sell);
+    }
+    g_quiet = 0;
+    g_err[0] = 0;
+    if (getenv("SPMVB200_VERBOSE"))
+        fprintf(stderr, "spmv_b200: ELL tuning M=%llu K=%llu NZ=%llu -> ell=%.3fms sell=%.3fms, picked %s\n", (unsigned long long) m->M,
+                (unsigned long long) m->K, (unsigned long long) m->NZ, m->tuned_x_ms[0], m->tuned_x_ms[2], m->tuned_x ? "sell" : "ell");
+    return 0;
+}
+
+template <int LANES>
+static void launch_ell_rowmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    constexpr int BLOCK = 256;
+    const uint64_t threads = m->M * LANES;
+    ell_rowmajor_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) m->M,
+                                                                                                       (uint32_t) m->K, x, y);
+    ++g_launches;
+}
+
+static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, cudaStream_t st) {
+    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
+    if (m->M == 0) return 0;
+    switch (kind) {
+        case SPMVB200_CSR_ROWS:
+            if (m->tuned_x < 0 && tune_exact(m, d_x, d_y, st)) return 1;
+            if (m->tuned_x == CAND_XWIN) { if (launch_xwin(m->x_child, d_x, d_y, st)) return 1; }
+            else if (m->tuned_x == CAND_SELL) launch_exact_sell(m, m->x_child, d_x, d_y, st);
+            else launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles);
+            break;
+        case SPMVB200_CSR_ADAPTIVE:
+            if (m->tuned < 0 && tune_adaptive(m, d_x, d_y, st)) return 1;
+            launch_candidate(m, m->tuned, d_x, d_y, st);
+            break;
+        case SPMVB200_CSR_ROWS_WARP:
+            if (!m->vec_tuned && m->format == SPMVB200_FMT_CSR) {
+                // first use: the sub-warp width guessed from the mean row length against its two neighbours (the x gather pattern
+                // decides, not the mean: 27-point stencil, mean 26.6 -> guess 16 lanes, 0.203 ms; 4 lanes: 0.141 ms)
+                m->vec_tuned = 1;
+                if (!getenv("SPMVB200_VEC_LANES") && m->NZ >= (1u << 18)) {
+                    int best = m->vec_lanes;
+                    float best_ms = 1e30f;
+                    for (int lanes = 2; lanes <= 32; lanes *= 2) {
+                        if (lanes > 4 * m->vec_lanes || 4 * lanes < m->vec_lanes) continue;
+                        float ms = 0;
+                        if (time_best_of_2([&] { launch_csr_vector(m, lanes, d_x, d_y, st, 0, m->M); }, st, &ms)) return 1;
+                        if (ms < best_ms) { best_ms = ms; best = lanes; }
+                    }
+                    m->vec_lanes = best;
+                }
+            }
+            launch_csr_vector(m, m->vec_lanes, d_x, d_y, st, 0, m->M);
+            break;
+        case SPMVB200_ELL_ROWS:
+            if (m->tuned_x < 0 && tune_ell(m, d_x, d_y, st)) return 1;
+            if (m->tuned_x == CAND_SELL) launch_sell(m->x_child, d_x, d_y, st);
+            else launch_ell_colmajor(m, d_x, d_y, st, 0, m->M);
+            break;
+        case SPMVB200_SELL_ROWS: launch_sell(m, d_x, d_y, st); break;
+        case SPMVB200_XWIN_ROWS:
+            if (m->xw_mode < 0 && tune_xwin(m, d_x, d_y, st, nullptr)) return 1;
+            if (launch_xwin(m, d_x, d_y, st)) return 1;
+            break;
+        case SPMVB200_ELL_ROWS_NT:
+            switch (m->vec_lanes) {
+                case 1: launch_ell_rowmajor<1>(m, d_x, d_y, st); break;
+                case 2: launch_ell_rowmajor<2>(m, d_x, d_y, st); break;
+                case 4: launch_ell_rowmajor<4>(m, d_x, d_y, st); break;
+                case 8: launch_ell_rowmajor<8>(m, d_x, d_y, st); break;
+                case 16: launch_ell_rowmajor<16>(m, d_x, d_y, st); break;
+                default: launch_ell_rowmajor<32>(m, d_x, d_y, st); break;
+            }
+            break;
+        case SPMVB200_ELL_ROWS_WARP_NT: launch_ell_rowmajor<32>(m, d_x, d_y, st); break;
+    }
+    CU_TRY(cudaPeekAtLastError());
+    return 0;
+}
+
+static int prefer_smem_once() {
+    static bool done_dev[64] = {false};  // per device: function attributes belong to the device's context
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    bool& done = done_dev[dev & 63];
+    if (done) return 0;
+    // streaming variant: 8 CTAs x 27 KB of shared memory per SM => largest carve-out.
+    // gather variant (VARIANT=1): half the shared memory, the rest stays L1 for the x gathers.
+    int carve1 = 50;
+    if (const char* e = getenv("SPMVB200_CARVEOUT")) carve1 = atoi(e);  // developer knob
+    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, false, 0>,
+                                cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, true, 0>,
+                                cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU_TRY(cudaFuncSetAttribute(csr_stream_kernel<STREAM_TILE, STREAM_BLOCK, STREAM_TILE_ROWS, true, 1>,
+                                cudaFuncAttributePreferredSharedMemoryCarveout, carve1));
+    done = true;
+    return 0;
+}
+
+static int ensure_events(spmvb200_matrix* m) {
+    if (!m->ev0) CU_TRY(cudaEventCreate(&m->ev0));
+    if (!m->ev1) CU_TRY(cudaEventCreate(&m->ev1));
+    return 0;
+}
