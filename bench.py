@@ -121,15 +121,20 @@ def cpu_reference(spec_fn, steps, warmup, label):
     if oracle.ref_available():
         kind = "reference"
         grid = int(min(65535, 4 * cores))  # gridRows caps the parallelism of *Blocks* (SpMV_CSR_OMP.c:70-76)
-        cfg = oracle.ref_config(grid_rows=grid, grid_cols=8, threads=cores, chunks=0)
         rmat = oracle.ref_spmat(mat.M, mat.N, mat.NZ, mat.JA, mat.AS, irp=mat.IRP, rl=mat.RL)
-        cands = [("spmvRowsBlocksCSR", rmat), ("spmvRowsBasicCSR", rmat)]
         ell = synth.csr_to_ell_host(mat)
         emat = oracle.ref_spmat(ell.M, ell.N, ell.NZ, ell.JA, ell.AS, rl=ell.RL, max_row_nz=ell.MAX_ROW_NZ)
-        cands += [("spmvRowsBlocksELL", emat), ("spmvRowsBasicELL", emat)]
+        # both settings of SIMD_ROWS_REDUCTION (src/include/config.h:92-94; TRUE is the reference's default): same unmodified sources
+        variants = [v for v in ("default", "nosimd") if oracle.ref_available(v)]
+        cfgs = {v: oracle.ref_config(grid_rows=grid, grid_cols=8, threads=cores, chunks=0, variant=v) for v in variants}
+        cands = []
+        for v in variants:
+            tag = "" if v == "default" else "[SIMD_ROWS_REDUCTION=FALSE]"
+            cands += [("spmvRowsBlocksCSR" + tag, (rmat, v)), ("spmvRowsBasicCSR" + tag, (rmat, v)),
+                      ("spmvRowsBlocksELL" + tag, (emat, v)), ("spmvRowsBasicELL" + tag, (emat, v))]
 
         def run(name, m):
-            return oracle.ref_call(name, m, x, cfg, mat.M)
+            return oracle.ref_call(name.split("[")[0], m[0], x, cfgs[m[1]], mat.M, variant=m[1])
     else:
         kind = "port"
         cands = [("oracle_spmv_rows_blocks_csr", None), ("oracle_spmv_rows_basic_csr", None)]

@@ -173,20 +173,22 @@ class RefConfig(C.Structure):
                 ("chunkDistrbFunc", C.c_void_p)]
 
 
-_ref = None
+_ref = {}
+# build variants of the same unmodified sources: "default" = the reference's own configuration (SIMD_ROWS_REDUCTION TRUE,
+# src/include/config.h:92-94), "nosimd" = -DSIMD_ROWS_REDUCTION=FALSE (the other setting SURVEY.md §8d asks the CPU baseline to try)
+REF_VARIANTS = {"default": REF_SO, "nosimd": os.path.join(HERE, "_ref", "libspmv_ref_nosimd.so")}
 
 
-def ref_available():
-    return os.path.exists(REF_SO)
+def ref_available(variant="default"):
+    return os.path.exists(REF_VARIANTS[variant])
 
 
-def ref():
+def ref(variant="default"):
     """The unmodified reference, compiled by `make -C oracle ref`.  None-safe: raises if absent."""
-    global _ref
-    if _ref is None:
-        if not ref_available():
-            raise FileNotFoundError(REF_SO + " (build with `make -C oracle ref` where /root/reference exists)")
-        L = C.CDLL(REF_SO)
+    if variant not in _ref:
+        if not ref_available(variant):
+            raise FileNotFoundError(REF_VARIANTS[variant] + " (build with `make -C oracle ref` where /root/reference exists)")
+        L = C.CDLL(REF_VARIANTS[variant])  # RTLD_LOCAL: the variants define the same symbols and must not interpose each other
         assert L.refshim_sizeof_spmat() == C.sizeof(RefSpmat), "spmat ABI mismatch"
         assert L.refshim_sizeof_config() == C.sizeof(RefConfig), "CONFIG ABI mismatch"
         assert L.refshim_rowlens() == 1
@@ -206,8 +208,8 @@ def ref():
         L.refshim_free_spmat.argtypes = [C.POINTER(RefSpmat)]
         L.doubleVectorsDiff.argtypes = [_f64p, _f64p, C.c_ulong, C.POINTER(C.c_double)]
         L.doubleVectorsDiff.restype = C.c_int
-        _ref = L
-    return _ref
+        _ref[variant] = L
+    return _ref[variant]
 
 
 def ref_spmat(M, N, nz, ja, as_, irp=None, rl=None, max_row_nz=0):
@@ -221,18 +223,19 @@ def ref_spmat(M, N, nz, ja, as_, irp=None, rl=None, max_row_nz=0):
     return m
 
 
-def ref_config(grid_rows=8, grid_cols=8, threads=None, chunks=0):
-    """chunks: 0 = chunksNOOP, 1 = chunksFair, 2 = chunksFairFolded (ompChunksDivide.h:33-91)."""
+def ref_config(grid_rows=8, grid_cols=8, threads=None, chunks=0, variant="default"):
+    """chunks: 0 = chunksNOOP, 1 = chunksFair, 2 = chunksFairFolded (ompChunksDivide.h:33-91).  The chunk function pointer belongs
+    to one build variant: pass the variant the config will be used with."""
     c = RefConfig()
     c.gridRows, c.gridCols = grid_rows, grid_cols
     c.threadNum = threads or omp_max_threads()
-    c.chunkDistrbFunc = ref().refshim_chunks_fn(chunks)
+    c.chunkDistrbFunc = ref(variant).refshim_chunks_fn(chunks)
     return c
 
 
-def ref_call(name, mat, x, cfg, M):
+def ref_call(name, mat, x, cfg, M, variant="default"):
     y = np.empty(M, dtype=np.float64)
-    rc = getattr(ref(), name)(C.byref(mat), _c(x, np.float64), C.byref(cfg), y)
+    rc = getattr(ref(variant), name)(C.byref(mat), _c(x, np.float64), C.byref(cfg), y)
     if rc:
         raise RuntimeError("reference %s returned %d" % (name, rc))
     return y
