@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""compute-sanitizer target for the paths that need >= 2^20 non-zeros to be taken: the exact kind's SELL hybrid with the serial-order
-row kernel (R-MAT) and ELL_ROWS' SELL copy built from the ELL arrays (mixed short / long rows)."""
+"""Stand-alone check (plain, or under compute-sanitizer where the pool allows it -- this one does not) of the paths that need >= 2^20
+non-zeros to be taken: the exact kind's SELL hybrid with the serial-order row kernel (R-MAT) and ELL_ROWS' SELL copy built from the ELL
+arrays (mixed short / long rows).  The same cases are in tests/test_gpu_parity.py."""
 import os, sys
 os.environ["SPMVB200_FORCE_EXACT"] = "13"
 import numpy as np
