@@ -34,9 +34,9 @@ constexpr uint32_t SEG_FLAG = 0x80000000u;
 constexpr int STREAM_TILE = 2048;        // non-zeros per tile (24 KB of values + column ids)
 constexpr int STREAM_BLOCK = 128;        // threads per CTA
 constexpr int STREAM_TILE_ROWS = 512;    // rows per tile (row-pointer slice in shared memory); 8 CTAs/SM fit
-constexpr int STREAM_LONG_T = 64;
+constexpr int STREAM_LONG_T = 64;         // ADAPTIVE: rows longer than this are reduced by a whole warp
 constexpr int STREAM_PRE_T = 48;         // exact kind: a tile whose longest row exceeds this multiplies element-parallel first
-constexpr int VEC_MID = 256;             // vector kernels: longer rows get a CTA of their own (csr_midrow_kernel)        // ADAPTIVE: rows longer than this are reduced by a whole warp
+constexpr int VEC_MID = 256;             // vector kernels / SELL copies: longer rows go to the per-row kernels (csr_midrow_*)
 
 // ---------------------------------------------------------------------------------------------
 // CSR "stream" kernel.  One CTA per tile:
