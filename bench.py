@@ -395,11 +395,12 @@ def main():
         e2e_stream.wait_stream(torch.cuda.current_stream())
         torch.cuda.set_stream(e2e_stream)
         stream = e2e_stream.cuda_stream
-    for _ in range(3):
+    for _ in range(max(3, args.warmup)):
         e2e_step()
-    # The host<->device legs share the box's PCIe / host memory with whatever else runs there: the same binary measured 0.53-0.88 ms per
-    # step in four back-to-back runs on one box (profiles/README.md, r01k).  So the loop is timed in blocks of e2e_steps steps and the MEDIAN
-    # block is reported (all blocks are listed next to it).
+    # The same binary measured 0.53-0.88 ms per step in four back-to-back runs on one box (profiles/README.md, r01k).  It is a warm-up effect of
+    # the host<->device legs, not of the buffers: in one process the first 150 calls ran at 0.83 ms and every later one at 0.54 ms, with
+    # cudaHostAlloc'ed and with huge-page + cudaHostRegister'ed buffers alike (tools/hugepage_probe.py, profiles/r01m_e2e_warmup_probe.log).
+    # So the loop is timed in blocks of e2e_steps steps and the MEDIAN block is reported (all blocks are listed next to it).
     block_ms, block_wall = [], []
     for _ in range(max(1, args.e2e_blocks)):
         sync_all()
