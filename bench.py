@@ -402,6 +402,7 @@ def main():
     # cudaHostAlloc'ed and with huge-page + cudaHostRegister'ed buffers alike (tools/hugepage_probe.py, profiles/r01m_e2e_warmup_probe.log).
     # So the loop is timed in blocks of e2e_steps steps and the MEDIAN block is reported (all blocks are listed next to it).
     block_ms, block_wall = [], []
+    launches_e2e0 = int(lib.spmvb200_launch_count())
     for _ in range(max(1, args.e2e_blocks)):
         sync_all()
         t0 = time.perf_counter()
@@ -417,7 +418,7 @@ def main():
         block_ms.append(float(e2e_t.item()) / e2e_steps)
     mid = sorted(range(len(block_ms)), key=lambda i: block_ms[i])[len(block_ms) // 2]
     e2e_ms, wall = block_ms[mid], block_wall[mid]
-    e2e_launch = int(lib.spmvb200_launch_count() - launches0) - launches
+    e2e_launch = int(lib.spmvb200_launch_count()) - launches_e2e0  # kernels launched inside the timed blocks (all of them)
     if dbg and world > 1 and len(dbg_t) >= 10:
         last = dbg_t[-16:]
         sys.stderr.write("rank %d e2e marks per step [start | h2d | allgather | spmv | d2h+sync], deltas in ms: %s\n" % (
