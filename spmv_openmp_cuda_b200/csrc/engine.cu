@@ -180,6 +180,7 @@ extern "C" uint64_t spmvb200_device_bytes(const spmvb200_matrix* m) {
 extern "C" int spmvb200_index_bits(const spmvb200_matrix* m) {
     if (!m) return 0;
     if (m->format == SPMVB200_FMT_XWIN) return 16;
+    if (m->format == SPMVB200_FMT_ELL_COLMAJOR && m->x_child && m->tuned_x > 0) return 32;  // ELL_ROWS runs its SELL copy (32-bit ids)
     if (m->format == SPMVB200_FMT_ELL_COLMAJOR && m->ja16 && !getenv("SPMVB200_ELL_NO_EARLY_EXIT")) return 16;
     return 32;
 }
