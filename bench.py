@@ -1,22 +1,27 @@
 #!/usr/bin/env python
-"""Headline benchmark of the B200 SpMV engine (contract: see the task statement / DESIGN.md §Measurement).
+"""Headline benchmark of the B200 SpMV engine (contract: the task statement / DESIGN.md §5).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg2]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-A "step" is one SpMV (y = A*x, fp64) over the workload:
-  cfg2 (default): BASELINE.json configs[1] -- ELL, 27-point 3-D stencil on 128^3 PER GPU (2 097 152 rows,
-        55 742 968 nnz per GPU).  With N GPUs the global grid is 128 x 128 x (128*N), row-block
-        partitioned in z-slabs (weak scaling), x replicated on every GPU.
-  cfg4: BASELINE.json configs[3] -- CSR, random banded 2^25 rows x 32 nnz/row, row-block partitioned over
-        the N GPUs (strong scaling).
-`value`  : whole-job GFLOP/s (2*nnz/t), matrix and x resident in HBM, CUDA-event timed on the launch
-           stream, max over ranks.
-`e2e`    : the same metric through the host-buffer call spmvb200_spmv_host (the SPMV_INTERF-shaped entry
-           point of include/spmv_b200.h): per step x goes host(pinned)->device, [N>1: NCCL broadcast of x
-           from rank 0 over NVLink], kernel, y slice device->host(pinned).
---impl reference times the reference's own OpenMP CPU implementation (oracle/_ref, compiled from the
-unmodified sources; falls back to the oracle port) on the host cores, rank 0 only.
+A "step" is one SpMV (y = A*x, fp64) over the workload.
+
+  cfg4 (default, every N): BASELINE.json configs[3] -- CSR, random banded 2^25 rows x 32 nnz/row (2^30 nnz, half width 2^15), the
+        matrix the metric's "1/2/4/8 GPUs vs host OpenMP CSR" is quoted on; it fits one B200 (13.6 GB).  Row-block partitioned over
+        the N GPUs (the reference's own CPU decomposition, spmvRowsBlocksCSR, one block per GPU): STRONG scaling.
+  cfg2: BASELINE.json configs[1] -- ELL, 27-point 3-D stencil 128^3 per GPU (weak scaling); at N=1 its line (and a cfg1 line) is
+        also measured after the cfg4 run and reported under the extra keys "cfg2" / "cfg1".
+
+`value`  : whole-job GFLOP/s (2*nnz/t) of the iterated step x <- A x with x replicated on every GPU: the SpMV kernel itself
+           stores the rows the other GPUs read into THEIR next x (posted NVLink stores from its epilogue) and a flag barrier
+           separates iterations -- the exchange is INSIDE the timed region (at N=1 there is nobody to deliver to).  CUDA events on
+           the launch stream, barrier + synchronize on both sides, max over ranks.  `kernel_only` = the same kernel without the
+           exchange.
+`e2e`    : the same metric through the host-buffer entry point with caller-allocated (malloc / numpy, i.e. pageable) buffers, as
+           the reference's driver passes them (src/main.cu:155,181): N=1 spmvb200_spmv_host, N>1 spmvb200_shard_spmv_host (every
+           rank: its x slice up over its own PCIe link, halo rows to the peers, kernel chunks, its y slice down).
+--impl reference times the reference's own OpenMP CPU implementation (oracle/_ref, compiled from the unmodified sources; the
+oracle port if that is absent) on the host cores over the FULL matrix of the same workload, rank 0 only.
 """
 import argparse
 import json
@@ -43,6 +48,8 @@ if "reference" in sys.argv and "LOCAL_RANK" in os.environ:
 
 METRIC = "SpMV GFLOP/s (2*nnz/t), fp64"
 UNIT = "GFLOP/s"
+CFG4_ROWS = 1 << 25
+RESET_EVERY = 64  # x <- A x grows ~3.3x per step on cfg4 (32 U(-1,1) entries per row): restart from x0 before fp64 overflows
 
 
 def measured_peak():
@@ -53,12 +60,35 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-# ------------------------------------------------------------------------------------------ clocks
+def workload(name, nr, half_width):
+    """name -> (description, scaling, synth spec of the GLOBAL matrix for nr ranks, split points, format)"""
+    from spmv_openmp_cuda_b200 import synth
+    if name == "cfg2":
+        rows_per = 128 * 128 * 128
+        return ("cfg2: ELL fp64 SpMV, 27-point 3-D stencil 128^3 per GPU (2097152 rows, 55742968 nnz per GPU), "
+                "column-major pitched ELL + row-length early exit, kernel cudaSpMVRowsELL", "weak",
+                synth.stencil27(128, 128, 128 * nr), [g * rows_per for g in range(nr + 1)], "ell")
+    return ("cfg4: CSR fp64 SpMV, random banded 2^25 rows x 32 nnz/row (2^30 nnz, half width w=%d), row-block partitioned over the "
+            "GPUs, kernel cudaSpMVRowsCSR (bit-exact kind)" % half_width, "strong",
+            synth.banded(CFG4_ROWS, 32, half_width), [g * CFG4_ROWS // nr for g in range(nr + 1)], "csr")
+
+
+def make_config(wl_name, rows_total, nnz_total, nr, fmt):
+    """The `config` object of the JSON line -- built by ONE function for both arms so that they carry identical keys and values."""
+    rowmeta = 4 * rows_total if fmt == "ell" else 4 * (rows_total + 1)
+    bytes_local = (12 * nnz_total + rowmeta + 16 * rows_total) // nr
+    return {"workload": wl_name, "rows_total": int(rows_total), "nnz_total": int(nnz_total), "rows_per_gpu": int(rows_total // nr),
+            "parallelism": "row-block x%d" % nr,
+            "l2": "no flush: per-GPU inputs (%.0f MB) exceed the 126 MB L2" % (bytes_local / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------ clocks / link
 class ClockSampler:
-    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock, throttle reasons and the PCIe link state through NVML while a timed region runs."""
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz, self._stop, self._t = [], set(), None, False, None
+        self.link = []
         try:
             if os.environ.get("BENCH_NO_NVML"):
                 raise RuntimeError("sampling switched off")
@@ -86,6 +116,11 @@ class ClockSampler:
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
+                try:
+                    self.link.append((nv.nvmlDeviceGetCurrPcieLinkGeneration(self.h), nv.nvmlDeviceGetCurrPcieLinkWidth(self.h),
+                                      nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM)))
+                except Exception:  # noqa: BLE001
+                    pass
             except Exception:  # noqa: BLE001
                 pass
             time.sleep(0.005)
@@ -94,26 +129,31 @@ class ClockSampler:
         if self.nv:
             self._t = threading.Thread(target=self._loop, daemon=True)
             self._t.start()
+        return self
 
     def stop(self):
         self._stop = True
         if self._t:
             self._t.join()
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.link:
+            gens, widths, mem = zip(*self.link)
+            out["pcie_gen_min_max"] = [int(min(gens)), int(max(gens))]
+            out["pcie_width_min_max"] = [int(min(widths)), int(max(widths))]
+            out["mem_mhz_min_max"] = [int(min(mem)), int(max(mem))]
+        return out
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference(spec_fn, steps, warmup, label):
-    """Time the reference's OpenMP CPU SpMV (best of its CSR/ELL row kernels) on the host cores.
-    Returns (value GFLOP/s, ms_per_step, info dict)."""
+def cpu_reference(spec, row_begin, row_end, steps, warmup, label):
+    """Time the reference's OpenMP CPU SpMV (best of its CSR/ELL row kernels) on the host cores over rows [row_begin, row_end) of
+    the workload's matrix.  Returns (value GFLOP/s, ms_per_step, info dict)."""
     import oracle
     from spmv_openmp_cuda_b200 import synth
 
     t0 = time.time()
-    mat = synth.host_csr(spec_fn())
+    mat = synth.host_csr(spec, row_begin, row_end)
     x = synth.host_vector(mat.N)
     cores = oracle.omp_max_threads()
     flops = 2.0 * mat.NZ
@@ -122,7 +162,7 @@ def cpu_reference(spec_fn, steps, warmup, label):
         kind = "reference"
         grid = int(min(65535, 4 * cores))  # gridRows caps the parallelism of *Blocks* (SpMV_CSR_OMP.c:70-76)
         rmat = oracle.ref_spmat(mat.M, mat.N, mat.NZ, mat.JA, mat.AS, irp=mat.IRP, rl=mat.RL)
-        ell = synth.csr_to_ell_host(mat)
+        ell = synth.csr_to_ell_host(mat)  # rows of equal length (cfg4): the ELL arrays ARE the CSR arrays, no copy
         emat = oracle.ref_spmat(ell.M, ell.N, ell.NZ, ell.JA, ell.AS, rl=ell.RL, max_row_nz=ell.MAX_ROW_NZ)
         # both settings of SIMD_ROWS_REDUCTION (src/include/config.h:92-94; TRUE is the reference's default): same unmodified sources
         variants = [v for v in ("default", "nosimd") if oracle.ref_available(v)]
@@ -143,10 +183,11 @@ def cpu_reference(spec_fn, steps, warmup, label):
             if name == "oracle_spmv_rows_blocks_csr":
                 return oracle.spmv_rows_blocks_csr(mat.IRP, mat.JA, mat.AS, x, grid_rows=4 * cores)
             return oracle.spmv_rows_basic_csr(mat.IRP, mat.JA, mat.AS, x)
+    nprobe = 3 if mat.NZ < (1 << 29) else 2
     y_ref = None
-    for name, m in cands:  # pick the fastest variant on 3 probes each
+    for name, m in cands:  # pick the fastest variant on a few probes each
         ts = []
-        for _ in range(3):
+        for _ in range(nprobe):
             t = time.perf_counter()
             y = run(name, m)
             ts.append(time.perf_counter() - t)
@@ -163,8 +204,8 @@ def cpu_reference(spec_fn, steps, warmup, label):
         run(best, m)
     dt = (time.perf_counter() - t) / max(steps, 1)
     info = {"value": flops / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%s, full per-GPU matrix (M=%d, nnz=%d), %d timed calls of %s after %d warm-ups; probes (s): %s; setup %.1f s"
-                      % (label, mat.M, mat.NZ, steps, best, warmup,
+            "sample": "%s, rows [%d, %d) of the matrix (M=%d, nnz=%d), %d timed calls of %s after %d warm-ups; probes (s): %s; setup %.1f s"
+                      % (label, row_begin, row_end, mat.M, mat.NZ, steps, best, warmup,
                          {k: round(v, 5) for k, v in results.items()}, time.time() - t0)}
     return flops / dt / 1e9, dt * 1e3, info
 
@@ -181,21 +222,93 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+def log(msg):
+    if os.environ.get("BENCH_VERBOSE"):
+        sys.stderr.write("bench[%s] %s\n" % (os.environ.get("RANK", "0"), msg))
+
+
+def side_line(name, steps, peak):
+    """N=1 extra lines: cfg2 (the ELL headline of round 1) and cfg1 (L2-flushed isolated launches and CUDA-graph replay)."""
+    import spmv_openmp_cuda_b200 as sp
+    from spmv_openmp_cuda_b200 import synth
+    if name == "cfg2":
+        d_csr = synth.device_csr(synth.stencil27(128))
+        dm, kind = d_csr.to_ell(sp.FMT_ELL_COLMAJOR), sp.ELL_ROWS
+        d_csr.free()
+    else:
+        d_csr = synth.device_csr(synth.lap2d(1024))
+        dm, kind = d_csr.to_ell(sp.FMT_ELL_COLMAJOR), sp.ELL_ROWS
+        d_csr.free()
+    x, y = sp.DeviceVector(dm.N), sp.DeviceVector(dm.M)
+    synth.device_vector_fill(x.data_ptr(), dm.N)
+    sp.time_kernel(kind, dm, x, y, reps=5)
+    t = sp.time_kernel(kind, dm, x, y, reps=steps, flush_l2=(name == "cfg1"))
+    ms = float(np.mean(t))
+    B = dm.algorithmic_bytes
+    out = {"workload": name, "kernel": "ell_colmajor_pair_kernel<idx16>" if dm.index_bits == 16 else "ell_colmajor_kernel",
+           "rows": dm.M, "nnz": dm.NZ, "launches": steps, "ms_per_step": ms, "ms_min": float(np.min(t)),
+           "l2": "flushed between launches (read of a 512 MB buffer)" if name == "cfg1" else "inputs exceed L2",
+           "value": 2.0 * dm.NZ / (ms * 1e-3) / 1e9, "unit": UNIT, "algorithmic_bytes_per_launch": int(B),
+           "roofline_frac": B / (ms * 1e-3) / 1e9 / peak}
+    if name == "cfg1":  # back to back from a CUDA graph: what an iterative solver sees (L2-warm: 84 MB fit the 126 MB L2)
+        b = sp.DeviceVector(dm.N)
+        iters = 200
+        g_ms = sp.iterate(kind, dm, x, b, iters, use_graph=True) / iters
+        out["graph_replay_ms_per_step"] = g_ms
+        out["graph_replay_roofline_frac"] = B / (g_ms * 1e-3) / 1e9 / peak
+        b.free()
+    x.free()
+    y.free()
+    dm.free()
+    return out
+
+
+def link_ceiling(nbytes_up, nbytes_down, world, dist, torch, reps=10):
+    """Bare duplex copy of this rank's per-step host<->device bytes (pinned, two streams, nothing else): the floor any host-buffer
+    step has on this box.  All ranks copy at once (they share the host's memory / PCIe root); max over ranks."""
+    hu = torch.empty(max(nbytes_up, 8) // 8, dtype=torch.float64).pin_memory()
+    hd = torch.empty(max(nbytes_down, 8) // 8, dtype=torch.float64).pin_memory()
+    du, dd = torch.empty_like(hu, device="cuda"), torch.empty_like(hd, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    best = {"duplex": 1e30, "up": 1e30, "down": 1e30}
+    for mode in ("duplex", "up", "down"):
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record(s1)
+            s2.wait_event(e0)
+            if mode != "down":
+                with torch.cuda.stream(s1):
+                    du.copy_(hu, non_blocking=True)
+            if mode != "up":
+                with torch.cuda.stream(s2):
+                    hd.copy_(dd, non_blocking=True)
+            e1.record(s1)
+            e2.record(s2)
+            torch.cuda.synchronize()
+            best[mode] = min(best[mode], max(e0.elapsed_time(e1), e0.elapsed_time(e2)))
+    t = torch.tensor([best["duplex"], best["up"], best["down"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.tolist()]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
-    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of one block of the end-to-end loop (default: min(steps, 200))")
+    ap.add_argument("--workload", default="cfg4", choices=["cfg2", "cfg4"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of one block of the end-to-end loop (default: min(steps, 50))")
     ap.add_argument("--e2e-blocks", type=int, default=5, help="blocks of the end-to-end loop; the median block is reported")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-side", action="store_true", help="N=1: skip the cfg2 / cfg1 side lines")
     ap.add_argument("--half-width", type=int, default=1 << 15, help="cfg4: band half width w")
-    ap.add_argument("--x-dist", default="push", choices=["push", "allgather", "bcast"],
-                    help="N>1 e2e: every rank uploads its slice of x, then either delivers the rows the other ranks read by peer stores + "
-                         "flag barrier (push, default), or NCCL all-gather; or rank 0 uploads all of x then NCCL broadcast")
+    ap.add_argument("--ref-rows", type=int, default=0, help="reference arm: rows of the matrix to time (default: all)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -205,33 +318,22 @@ def main():
 
     from spmv_openmp_cuda_b200 import synth
 
-    if args.workload == "cfg2":
-        wl_name = ("cfg2: ELL fp64 SpMV, 27-point 3-D stencil 128^3 per GPU (2097152 rows, 55742968 nnz per GPU), "
-                   "column-major pitched ELL + row-length early exit, kernel cudaSpMVRowsELL")
-        scaling = "weak"
-
-        def slab_spec():
-            return synth.stencil27(128, 128, 128)
-    else:
-        wl_name = ("cfg4: CSR fp64 SpMV, random banded 2^25 rows x 32 nnz/row (half width w=%d), row-block partitioned, "
-                   "kernel: adaptive CSR mode" % args.half_width)
-        scaling = "strong"
-
-        def slab_spec():
-            return synth.banded(1 << 21, 32, args.half_width)  # bounded CPU sample: 2^21 rows of the same generator
-
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = min(args.steps, 50)
-        value, ms, info = cpu_reference(slab_spec, steps, min(args.warmup, 5), args.workload)
-        emit(({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": steps,
-                          "warmup": min(args.warmup, 5), "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": wl_name, "note": "reference OpenMP CPU implementation on the host cores"},
-                          "cpu_baseline": info,
-                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        wl_name, scaling, spec, splits, fmt = workload(args.workload, N, args.half_width)
+        steps, warm = min(args.steps, 30), min(args.warmup, 5)
+        Mtot = splits[-1]
+        rows = args.ref_rows or Mtot  # the FULL matrix the GPU arm runs (cfg4: 2^30 nnz, ~18 GB of host arrays)
+        value, ms, info = cpu_reference(spec, 0, rows, steps, warm, args.workload)
+        emit({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": steps, "warmup": warm,
+              "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+              "config": make_config(wl_name, Mtot, info_nnz(info) if rows == Mtot else -1, N, fmt),
+              "reference_note": "the reference's OpenMP CPU implementation on %d host threads, rows [0, %d) of the matrix per step%s"
+                                % (info["cores"], rows, "" if rows == Mtot else " (a SAMPLE: --ref-rows)"),
+              "cpu_baseline": info,
+              "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return 0
 
     # ---------------------------------------------------------------- our arm
@@ -240,251 +342,265 @@ def main():
 
     import spmv_openmp_cuda_b200 as sp
     from spmv_openmp_cuda_b200 import capi
+    from spmv_openmp_cuda_b200.distributed import RowBlockShard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    capi.check(capi.lib().spmvb200_set_device(local_rank), "set_device")
+    lib = capi.lib()
+    capi.check(lib.spmvb200_set_device(local_rank), "set_device")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == N or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
     nr = world  # ranks actually running
-
-    # ---- build this rank's row block on its GPU
-    if args.workload == "cfg2":
-        spec = synth.stencil27(128, 128, 128 * nr)
-        rows_per = 128 * 128 * 128
-        r0, r1 = rank * rows_per, (rank + 1) * rows_per
-        d_csr = synth.device_csr(spec, r0, r1)
-        dm = d_csr.to_ell(sp.FMT_ELL_COLMAJOR)
-        col_range = d_csr.col_range
-        d_csr.free()
-        # 16-bit column offsets: the two-rows-per-thread kernel; otherwise the one-row-per-thread kernel with 32-bit ids
-        kind, kname = sp.ELL_ROWS, ("ell_colmajor_pair_kernel<idx16>" if dm.index_bits == 16 else "ell_colmajor_kernel")
-    else:
-        spec = synth.banded(1 << 25, 32, args.half_width)
-        Mtot = 1 << 25
-        r0, r1 = rank * Mtot // nr, (rank + 1) * Mtot // nr
-        dm = synth.device_csr(spec, r0, r1)
-        col_range = dm.col_range
-        kind, kname = sp.CSR_ADAPTIVE, "csr_adaptive"
-    Ncols = dm.N
-    tot = torch.tensor([dm.NZ, dm.M], dtype=torch.int64, device="cuda")
-    if world > 1 and "allreduce" not in os.environ.get("BENCH_SKIP", ""):
-        dist.all_reduce(tot)
-    elif world > 1:
-        tot *= world
-    nnz_total, rows_total = int(tot[0].item()), int(tot[1].item())
-    # algorithmic bytes of the GLOBAL SpMV (SURVEY.md §8d), split evenly: x is counted once for the whole job
-    rowmeta = 4 * rows_total if args.workload == "cfg2" else 4 * (rows_total + 1)
-    bytes_local = (12 * nnz_total + rowmeta + 8 * Ncols + 8 * rows_total) // nr
-
-    x = torch.empty(Ncols, dtype=torch.float64, device="cuda")
-    y = torch.empty(dm.M, dtype=torch.float64, device="cuda")
-    synth.device_vector_fill(x, Ncols)
-    stream = torch.cuda.current_stream().cuda_stream
-    lib = capi.lib()
-
-    def step():
-        capi.check(lib.spmvb200_spmv_device(dm.handle, kind, x.data_ptr(), y.data_ptr(), stream), "spmv_device")
+    peak, peak_src = measured_peak()
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    skip = os.environ.get("BENCH_SKIP", "").split(",")
-    for _ in range(0 if "warmup" in skip else args.warmup):
-        step()
-    sync_all()
-    if kind == sp.CSR_ADAPTIVE:
-        kname = "csr_adaptive[%s]" % dm.adaptive_choice
-    idx_bits = dm.index_bits if kind == sp.ELL_ROWS else (16 if "xwindow" in kname else 32)
-    launches0 = lib.spmvb200_launch_count()
-    sampler = ClockSampler(local_rank)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
-    ev0.record()
-    for _ in range(1 if "kloop" in skip else args.steps):
-        step()
-    ev1.record()
-    sync_all()
-    clocks = sampler.stop()
-    ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_step = float(ms_total.item()) / args.steps
-    launches = int(lib.spmvb200_launch_count() - launches0)
-    gflops = 2.0 * nnz_total / (ms_step * 1e-3) / 1e9
-    peak, peak_src = measured_peak()
-    achieved = bytes_local / (ms_step * 1e-3) / 1e9  # per GPU: the dominant kernel's launch on one GPU
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- end to end through the host-buffer entry point
-    e2e_steps = args.e2e_steps or min(args.steps, 200)
-    hx = torch.empty(Ncols, dtype=torch.float64).pin_memory()
-    hy = torch.empty(dm.M, dtype=torch.float64).pin_memory()
-    hx.copy_(x.cpu())
-    e2e_ms = None
-    xs0, xs1 = rank * Ncols // nr, (rank + 1) * Ncols // nr  # this rank's slice of x (square matrix: its own rows)
-    even = Ncols % nr == 0
+    def allmin_flag(ok):
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
 
-    dbg = os.environ.get("BENCH_E2E_DEBUG")
-    dbg_t = []
+    # ---- this rank's row block, built on its GPU
+    wl_name, scaling, spec, splits, fmt = workload(args.workload, nr, args.half_width)
+    r0, r1 = splits[rank], splits[rank + 1]
+    t_setup = time.time()
+    d_csr = synth.device_csr(spec, r0, r1)
+    col_range = d_csr.col_range
+    if fmt == "ell":
+        dm = d_csr.to_ell(sp.FMT_ELL_COLMAJOR)
+        d_csr.free()
+        kind = sp.ELL_ROWS
+    else:
+        dm, kind = d_csr, sp.CSR_ROWS
+    Ncols, Mloc = dm.N, dm.M
+    nnz_total = int(allsum(torch, dist, world, dm.NZ))
+    rows_total = splits[-1]
+    # algorithmic bytes of the GLOBAL SpMV (SURVEY.md §8d), split evenly: x is counted once for the whole job
+    rowmeta = 4 * rows_total if fmt == "ell" else 4 * (rows_total + 1)
+    bytes_local = (12 * nnz_total + rowmeta + 8 * Ncols + 8 * rows_total) // nr
 
-    def mark():
-        if dbg:
-            torch.cuda.synchronize()
-            dbg_t.append(time.perf_counter())
+    shard = RowBlockShard(dm, splits, kind, nbuf=3, col_range=col_range)
+    stream = torch.cuda.current_stream().cuda_stream
+    if world > 1:  # a stream of our own: the legacy default stream synchronises implicitly with every other blocking stream
+        own = torch.cuda.Stream()
+        torch.cuda.set_stream(own)
+        stream = own.cuda_stream
+    X0 = shard.x_ptr(0)
+    synth.device_vector_fill(X0, Ncols)  # replicated x0: every rank generates the whole vector (pure function of the index)
+    capi.check(lib.spmvb200_tune(dm.handle, kind, X0, shard.x_ptr(1), stream), "tune")  # first-use pick, outside every timed region
+    choice = dm.exact_choice
+    kname = {"xwindow": "xwin_kernel", "sell": "sell_kernel", "stream": "csr_stream_kernel",
+             "ell": "ell_colmajor_pair_kernel<idx16>" if dm.index_bits == 16 else "ell_colmajor_kernel"}.get(choice, choice)
+    idx_bits = 16 if choice == "xwindow" else dm.index_bits
+    log("setup %.1f s, pick %s, halo rows %d" % (time.time() - t_setup, choice, shard.halo_rows))
 
-    pusher, push_err = None, ""
-    if world > 1 and args.x_dist == "push":
-        from spmv_openmp_cuda_b200.distributed import RowBlockIterate
+    seq = {"i": 0, "cur": 0}
 
-        class _Rows:  # the handle + the column range of its CSR source
-            M, N, NZ, handle = dm.M, dm.N, dm.NZ, dm.handle
-        _Rows.col_range = col_range
-        allr = [None] * world
-        dist.all_gather_object(allr, (r0, r1))
-        try:
-            pusher = RowBlockIterate(_Rows, [a_[0] for a_ in allr] + [allr[-1][1]], kind, mode="push")
-            pusher.set_x(hx.numpy())
-        except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC not permitted in this container)
-            pusher, push_err = None, repr(e)
-        ok_all = torch.tensor([1 if pusher is not None else 0], device="cuda")
-        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
-        if not ok_all.item():  # every rank takes the same path: fall back to the NCCL all-gather of x
-            pusher = None
-            args.x_dist = "allgather"
-            if rank == 0:
-                sys.stderr.write("bench.py: peer-store exchange unavailable (%s); using --x-dist allgather\n" % (push_err or "another rank failed"))
+    def step():
+        """x <- A x; every RESET_EVERY steps the source is the pristine x0 again (a pointer choice, no copy)"""
+        src = 0 if seq["i"] % RESET_EVERY == 0 else seq["cur"]
+        dst = 2 if src == 1 else 1
+        shard.step(src, dst, stream)
+        seq["cur"], seq["i"] = dst, seq["i"] + 1
 
-    def e2e_step():
-        mark()
-        if world == 1:
-            capi.check(lib.spmvb200_spmv_host(dm.handle, kind, hx.data_ptr(), hy.data_ptr(), None), "spmv_host")
-        elif pusher is not None:
-            pusher.load_x_slice(hx.data_ptr() + r0 * 8, stream, after_h2d=mark)  # own slice over own PCIe link, halo rows to the peers, barrier
-            mark()
-            capi.check(lib.spmvb200_spmv_device(dm.handle, kind, pusher.x_ptr(), y.data_ptr(), stream), "spmv_device")
-            mark()
-            capi.check(lib.spmvb200_d2h_async(hy.data_ptr(), y.data_ptr(), dm.M * 8, stream), "d2h_async")
-            capi.check(lib.spmvb200_stream_sync(stream), "stream_sync")
-            mark()
-        else:
-            if args.x_dist == "allgather" and even:
-                x[xs0:xs1].copy_(hx[xs0:xs1], non_blocking=True)      # every rank: its slice over its own PCIe link
-                mark()
-                dist.all_gather_into_tensor(x, x[xs0:xs1])             # replicate over NVLink / NVSwitch
-                mark()
-            else:
-                if rank == 0:
-                    x.copy_(hx, non_blocking=True)
-                dist.broadcast(x, src=0)
-            step()
-            mark()
-            hy.copy_(y, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            mark()
+    def kernel_step():
+        capi.check(lib.spmvb200_spmv_device(dm.handle, kind, X0, shard.x_ptr(2), stream), "spmv_device")
 
-    e2e_stream = None
-    if world > 1 and not os.environ.get("BENCH_E2E_LEGACY_STREAM"):
-        # the end-to-end loop runs on a stream of its own (not the legacy default stream, which synchronises implicitly with
-        # every other blocking stream of the process)
-        e2e_stream = torch.cuda.Stream()
-        e2e_stream.wait_stream(torch.cuda.current_stream())
-        torch.cuda.set_stream(e2e_stream)
-        stream = e2e_stream.cuda_stream
-    for _ in range(max(3, args.warmup)):
-        e2e_step()
-    # The same binary measured 0.53-0.88 ms per step in four back-to-back runs on one box (profiles/README.md, r01k).  It is a warm-up effect of
-    # the host<->device legs, not of the buffers: in one process the first 150 calls ran at 0.83 ms and every later one at 0.54 ms, with
-    # cudaHostAlloc'ed and with huge-page + cudaHostRegister'ed buffers alike (tools/hugepage_probe.py, profiles/r01m_e2e_warmup_probe.log).
-    # So the loop is timed in blocks of e2e_steps steps and the MEDIAN block is reported (all blocks are listed next to it).
-    block_ms, block_wall = [], []
-    launches_e2e0 = int(lib.spmvb200_launch_count())
-    for _ in range(max(1, args.e2e_blocks)):
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
         sync_all()
-        t0 = time.perf_counter()
+        l0 = lib.spmvb200_launch_count()
+        sampler = ClockSampler(local_rank).start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
+        for _ in range(steps):
+            fn()
         ev1.record()
         sync_all()
-        block_wall.append((time.perf_counter() - t0) * 1e3)
-        e2e_t = torch.tensor([max(ev0.elapsed_time(ev1), 0.0)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        block_ms.append(float(e2e_t.item()) / e2e_steps)
-    mid = sorted(range(len(block_ms)), key=lambda i: block_ms[i])[len(block_ms) // 2]
-    e2e_ms, wall = block_ms[mid], block_wall[mid]
-    e2e_launch = int(lib.spmvb200_launch_count()) - launches_e2e0  # kernels launched inside the timed blocks (all of them)
-    if dbg and world > 1 and len(dbg_t) >= 10:
-        last = dbg_t[-16:]
-        sys.stderr.write("rank %d e2e marks per step [start | h2d | allgather | spmv | d2h+sync], deltas in ms: %s\n" % (
-            rank, " ".join("%.3f" % ((b - a) * 1e3) for a, b in zip(last[:-1], last[1:]))))
-    y_check = hy.numpy().copy()
+        clocks = sampler.stop()
+        return allmax(ev0.elapsed_time(ev1)) / steps, int(lib.spmvb200_launch_count() - l0), clocks
 
-    # ---- parity spot check of what was just measured (rank 0, sampled rows, against the oracle)
-    parity = None
-    if rank == 0:
-        import oracle
-        a, b = 0, min(dm.M, 20000)
-        h = synth.host_csr(spec, r0 + a, r0 + b)
-        xs = hx.numpy()
-        yr = oracle.sgemv_serial(h.IRP, h.JA, h.AS, xs)
-        parity = {"rows_checked": int(b - a), "bit_identical": bool(np.array_equal(yr, y_check[a:b])),
-                  "ref_check_failed": bool(oracle.double_vectors_diff(yr, y_check[a:b])[0])}
+    ms_step, launches, clocks = timed(step, args.steps, args.warmup)
+    ms_kernel = ms_step
+    if world > 1:
+        ms_kernel, _, _ = timed(kernel_step, args.steps, 3)
+    gflops = 2.0 * nnz_total / (ms_step * 1e-3) / 1e9
+    achieved = bytes_local / (ms_step * 1e-3) / 1e9  # per GPU: the dominant kernel's launch on one GPU
+
+    # ---- parity of what was just timed: two iterations from x0, rows on BOTH sides of every slab boundary (the rows whose columns
+    # were delivered by a peer) and a block in the middle, against the oracle's serial SpMV -- every rank checks its own rows
+    import oracle
+    xh0 = synth.host_vector(Ncols)
+    shard.step(0, 1, stream)
+    shard.step(1, 2, stream)
+    sync_all()
+    CH = 256
+    blocks = sorted({(max(r0, a), min(r1, a + CH)) for a in (r0, r1 - CH, (r0 + r1) // 2) if r1 - r0 > 0})
+    par_ok, rows_checked, x1_full = True, 0, np.full(Ncols, np.nan)
+    for a, b in blocks:
+        hb = synth.host_csr(spec, a, b)
+        cols = hb.JA
+        ca, cb = int(cols.min()), int(cols.max()) + 1
+        h1 = synth.host_csr(spec, ca, cb)  # the rows of A that produce the x1 entries these rows read (square matrix)
+        x1_full[ca:cb] = oracle.sgemv_serial(h1.IRP, h1.JA, h1.AS, xh0)
+        want = oracle.sgemv_serial(hb.IRP, hb.JA, hb.AS, x1_full)
+        got = shard.rows_of(2, a, b)
+        par_ok &= bool(np.array_equal(want, got))
+        rows_checked += b - a
+    parity = {"bit_identical": allmin_flag(par_ok), "ranks_checked": nr, "rows_checked_per_rank": int(rows_checked),
+              "what": "x2 = A(A x0) through the timed path; per rank: first %d rows, last %d rows (both read x rows delivered by the "
+                      "neighbouring GPU's kernel) and %d rows in the middle, vs the oracle's sgemvSerial" % (CH, CH, CH)}
+
+    # ---- end to end through the host-buffer entry point: caller-allocated pageable buffers, as the reference driver passes them
+    e2e_steps = args.e2e_steps or min(args.steps, 50)
+    hx = xh0  # numpy (malloc'ed, pageable) -- the library page-locks a buffer in place when it comes back a second time
+    hy = np.empty(Mloc, dtype=np.float64)
+    hx_slice = hx[r0:r1]
+    hpx = torch.empty(r1 - r0 if world > 1 else Ncols, dtype=torch.float64).pin_memory()  # cudaHostAlloc'ed twins
+    hpy = torch.empty(Mloc, dtype=torch.float64).pin_memory()
+    hpx.numpy()[:] = hx_slice if world > 1 else hx
+
+    def e2e_step_of(xbuf, ybuf):
+        if world == 1:
+            return lambda: capi.check(lib.spmvb200_spmv_host(dm.handle, kind, capi.ptr(xbuf), capi.ptr(ybuf), None), "spmv_host")
+        return lambda: shard.spmv_host(xbuf, ybuf)
+
+    def e2e_timed(fn, blocks_n):
+        sync_all()
+        t_first = time.perf_counter()
+        fn()
+        first_ms = (time.perf_counter() - t_first) * 1e3
+        for _ in range(max(3, args.warmup)):
+            fn()
+        block_ms = []
+        l0 = int(lib.spmvb200_launch_count())
+        sampler = ClockSampler(local_rank).start()
+        for _ in range(max(1, blocks_n)):
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                fn()
+            torch.cuda.synchronize()
+            block_ms.append(allmax((time.perf_counter() - t0) * 1e3) / e2e_steps)
+        link = sampler.stop()
+        return block_ms, int(lib.spmvb200_launch_count()) - l0, first_ms, link
+
+    blocks_pg, e2e_launch, first_ms, link = e2e_timed(e2e_step_of(hx_slice if world > 1 else hx, hy), args.e2e_blocks)
+    y_check = hy.copy()
+    blocks_pin, _, _, _ = e2e_timed(e2e_step_of(hpx, hpy), max(1, args.e2e_blocks // 2))
+    e2e_ms = float(np.median(blocks_pg))
+    # e2e parity: y = A x0 rows at both ends of the slice (they read halo rows uploaded by the NEIGHBOUR and pushed here)
+    e2e_ok = True
+    for a, b in blocks:
+        hb = synth.host_csr(spec, a, b)
+        e2e_ok &= bool(np.array_equal(oracle.sgemv_serial(hb.IRP, hb.JA, hb.AS, xh0), y_check[a - r0:b - r0]))
+    e2e_ok &= bool(np.array_equal(y_check, hpy.numpy()))
+    parity["e2e_bit_identical"] = allmin_flag(e2e_ok)
+    up_b, down_b = (r1 - r0 if world > 1 else Ncols) * 8, Mloc * 8
+    ceil_ms = link_ceiling(up_b, down_b, world, dist, torch)
+    capi.check(lib.spmvb200_host_unregister(None), "host_unregister")  # before the numpy buffers are freed
 
     out = {
         "metric": METRIC, "value": gflops, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": wl_name, "rows_per_gpu": int(dm.M), "nnz_total": nnz_total, "parallelism": "row-block x%d" % nr,
-                   "l2": "no flush: per-GPU inputs (%.0f MB) exceed the 126 MB L2" % (bytes_local / 1e6),
-                   "x": "replicated on every GPU, resident for `value`; host->device (+NCCL broadcast for N>1) inside `e2e`"},
+        "config": make_config(wl_name, rows_total, nnz_total, nr, fmt),
+        "step": "x <- A x, x replicated: the SpMV kernel stores the %d rows per GPU that other GPUs read into their next x "
+                "(peer stores over NVLink) + flag barrier, inside the timed region; source reset to x0 every %d steps"
+                % (shard.halo_rows, RESET_EVERY) if world > 1 else
+                "x <- A x on one GPU (ping-pong vectors; source reset to x0 every %d steps)" % RESET_EVERY,
+        "kernel_only": {"ms_per_step": ms_kernel, "value": 2.0 * nnz_total / (ms_kernel * 1e-3) / 1e9, "unit": UNIT,
+                        "exchange_overhead_frac": ms_step / ms_kernel - 1.0},
+        "nvlink_bytes_per_step": int(allsum(torch, dist, world, shard.halo_rows * 8)),
         "hbm_gbs": achieved * nr, "clocks": clocks,
-        "e2e": {"value": 2.0 * nnz_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "wall_ms_per_step": wall / e2e_steps,
-                "steps": e2e_steps, "blocks_ms_per_step": [round(b, 4) for b in block_ms], "statistic": "median block of %d steps" % e2e_steps,
-                "h2d_bytes_per_step": int(Ncols * 8), "d2h_bytes_per_step": int(dm.M * 8 * nr),
-                "path": "spmvb200_spmv_host (pinned host x -> device in pieces, row chunks, y chunks -> pinned host)" if world == 1 else
-                        "per-rank H2D of its x slice, rows the other ranks read delivered by peer stores (CUDA IPC) + flag barrier, "
-                        "spmvb200_spmv_device, per-rank D2H of its y slice" if pusher is not None else
-                        ("per-rank H2D of its x slice, NCCL all-gather, spmvb200_spmv_device, per-rank D2H of its y slice"
-                         if args.x_dist == "allgather" and even else
-                         "rank0 H2D x, NCCL broadcast, spmvb200_spmv_device, per-rank D2H of its y slice")},
+        "e2e": {"value": 2.0 * nnz_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "blocks_ms_per_step": [round(b, 4) for b in blocks_pg], "statistic": "median block of %d steps, host clock, max over ranks" % e2e_steps,
+                "h2d_bytes_per_step": int(Ncols * 8), "d2h_bytes_per_step": int(rows_total * 8),
+                "buffers": "caller-allocated pageable (numpy / malloc) x and y; the library page-locks them in place on their second use",
+                "first_call_ms": first_ms,
+                "pinned": {"ms_per_step": float(np.median(blocks_pin)), "blocks_ms_per_step": [round(b, 4) for b in blocks_pin],
+                           "buffers": "cudaHostAlloc'ed x and y"},
+                "link_ceiling": {"duplex_ms": ceil_ms[0], "up_only_ms": ceil_ms[1], "down_only_ms": ceil_ms[2],
+                                 "what": "bare pinned cudaMemcpyAsync of the same per-rank bytes, up and down at once on two streams, "
+                                         "all ranks together, best of 10, max over ranks",
+                                 "aggregate_gbs": (Ncols + rows_total) * 8 / (ceil_ms[0] * 1e-3) / 1e9,
+                                 "frac_achieved": ceil_ms[0] / e2e_ms},
+                "link_state": link,
+                "path": "spmvb200_spmv_host: x host -> device in pieces, row chunks of the x-window kernel as their pieces land, y chunks "
+                        "-> host while later chunks compute" if world == 1 else
+                        "spmvb200_shard_spmv_host on every rank: its x slice up over its own PCIe link (halo rows first, delivered to the "
+                        "peers by peer stores + flag barrier while the rest uploads), row chunks, its y slice down"},
         "gpu_launches": launches, "gpu_launches_e2e": e2e_launch,
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_local),
                      "index_bits": idx_bits, "moved_bytes_per_launch": int(bytes_local - (2 * nnz_total // nr if idx_bits == 16 else 0)),
                      "frac_moved": (bytes_local - (2 * nnz_total // nr if idx_bits == 16 else 0)) / (ms_step * 1e-3) / 1e9 / peak,
                      "note": "per GPU = global algorithmic bytes / n_gpus; global = 12*nnz + 4*M(+1 for CSR) + 8*N + 8*M (DESIGN.md). "
-                             "With index_bits 16 the kernel reads 2-byte column offsets (10 B per non-zero): it moves fewer bytes than the "
-                             "algorithmic figure it is scored against, so frac may exceed 1; frac_moved = the bytes it really moves / (t * peak)"},
+                             "With index_bits 16 the kernel reads 2-byte column ids (10 B per non-zero): it moves fewer bytes than the "
+                             "algorithmic figure it is scored against; frac_moved = the bytes it really moves / (t * peak)"},
         "parity": parity,
     }
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            tr = json.load(open(traffic_file)).get(kname)
-            # the captures are single-GPU launches of the named workloads: per-GPU traffic of a strong-scaled run is not in the file
-            out["roofline"]["traffic"] = tr if (args.workload == "cfg2" or nr == 1) else None
+            tr = json.load(open(traffic_file)).get(kname + "@" + args.workload)
+            # {"bytes": dram read+write per launch, "capture": file under profiles/, "git": commit of the captured build}: a single-GPU
+            # capture of the named workload -- per-GPU traffic of a partitioned run is not in the file
+            if tr and nr == 1:
+                out["roofline"]["traffic"] = tr["bytes"]
+                out["roofline"]["traffic_source"] = {k: tr[k] for k in tr if k != "bytes"}
         except Exception:  # noqa: BLE001
             pass
+    shard.close()
+    dm.free()
+    if rank == 0 and N == 1 and not args.no_side:
+        for name in ("cfg2", "cfg1"):
+            try:
+                out[name] = side_line(name, 50, peak)
+            except Exception as e:  # noqa: BLE001
+                out[name] = {"error": repr(e)}
     if rank == 0 and N == 1 and not args.no_cpu:
         try:
-            _, _, info = cpu_reference(slab_spec, args.cpu_steps, 2, args.workload)
+            # bounded sample: the first 2^23 rows of the same matrix (2^28 nnz, ~4.5 GB of host arrays); --impl reference times all of it
+            sample_rows = min(rows_total, 1 << 23)
+            _, _, info = cpu_reference(spec, 0, sample_rows, args.cpu_steps, 2, args.workload)
             out["cpu_baseline"] = info
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "unavailable", "sample": repr(e)}
     if rank == 0:
         emit(out)
-    if pusher is not None:
-        pusher.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def allsum(torch, dist, world, v):
+    t = torch.tensor([int(v)], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t)
+    return int(t.item())
+
+
+def info_nnz(info):
+    """nnz out of the cpu_reference sample string (kept there for the human reader)"""
+    import re
+    m = re.search(r"nnz=(\d+)", info["sample"])
+    return int(m.group(1)) if m else 0
 
 
 if __name__ == "__main__":

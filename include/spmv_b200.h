@@ -26,13 +26,16 @@
 extern "C" {
 #endif
 
-#define SPMVB200_VERSION 100
+#define SPMVB200_VERSION 200
 
 /* Kernel selectors.  Values 0..4 are the reference's CUDA compute modes in table order
  * (SpmvCUDA_CSRFuncs[0..1], SpmvCUDA_ELLFuncs[0..2], src/include/SpMV.h:130-142; mode strings
  * src/include/SpMV.h:37-41); later values are new modes appended after them. */
 typedef enum {
-    SPMVB200_CSR_ROWS          = 0, /* replaces cudaSpMVRowsCSR                 src/SpMV_CUDA.cu:33-49   */
+    SPMVB200_CSR_ROWS          = 0, /* replaces cudaSpMVRowsCSR                 src/SpMV_CUDA.cu:33-49.  Bit-identical to sgemvSerial
+                                       (src/SpMV_CSR_OMP.c:229-250) for every row of at most 2048 non-zeros; a longer row is split into
+                                       2048-entry segments whose partial sums are combined in segment order: deterministic, within
+                                       1e-12 * sum|a_ij x_j| of the serial sum, but not the same bits */
     SPMVB200_CSR_ROWS_WARP     = 1, /* replaces cudaSpMVWarpPerRowCSR           src/SpMV_CUDA.cu:52-73   */
     SPMVB200_ELL_ROWS          = 2, /* replaces cudaSpMVRowsELL (column-major)  src/SpMV_CUDA.cu:79-96   */
     SPMVB200_ELL_ROWS_NT       = 3, /* replaces cudaSpMVRowsELLNNTransposed     src/SpMV_CUDA.cu:99-115  */
@@ -147,6 +150,23 @@ int spmvb200_exact_choice(const spmvb200_matrix* m, char* name, size_t len);
  * -- the engine picks its own launch geometry. */
 int spmvb200_spmv_device(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, void* stream);
 
+/* First-use picks.  SPMVB200_CSR_ROWS / _ROWS_WARP / _ADAPTIVE, SPMVB200_ELL_ROWS and SPMVB200_XWIN_ROWS choose their kernel (and may
+ * build a re-tiled copy of the matrix) the first time they run on a handle.  That first call BLOCKS: it allocates, synchronises the
+ * device and -- in timed mode -- times candidates with CUDA events.  spmvb200_tune does it explicitly (d_y is scratch); afterwards
+ * spmvb200_spmv_device is a pure asynchronous launch.  If the first launch of an unpicked handle happens on a stream that is being
+ * CAPTURED, nothing is picked: the kind's plain kernel (stream / sub-warp / column-major ELL) is recorded into the graph instead. */
+int spmvb200_tune(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, void* stream);
+/* 0 (default) = timed: fastest candidate on this GPU, may differ from run to run, so the tolerance kinds (_ROWS_WARP, _ADAPTIVE) may
+ * return different bits in different processes.  1 = deterministic: the pick is a pure function of the matrix structure; nothing
+ * is timed.  Also settable with the environment variable SPMVB200_TUNE=deterministic.  Process-wide; the bit-exact kinds return
+ * the same bits in either mode. */
+int spmvb200_set_tuning_mode(int mode);
+int spmvb200_get_tuning_mode(void);
+/* Read / install a handle's picks (8 integers, see csrc/engine.cu): record them once, install them in every later process or on
+ * every rank of a multi-GPU job, and all of them run the same kernels. */
+int spmvb200_tuning_get(const spmvb200_matrix* m, int32_t picks[8]);
+int spmvb200_tuning_set(spmvb200_matrix* m, const int32_t picks[8]);
+
 /* Same launch, with FUSED OUTPUT DELIVERY for x <- y iterations over the GPUs of one box: besides
  * d_y, the kernel that computes row r stores it to dst[p][r + row_offset] for every destination p whose range
  * [lo[p], hi[p]) contains the global index r + row_offset.  Destinations are device-visible pointers -- typically the next
@@ -175,6 +195,31 @@ int spmvb200_ipc_close(void* d_ptr);
  * its stream (including stores to peer memory) is visible to the others' later work. */
 int spmvb200_peer_barrier(uint32_t* const* d_flags, int n, int rank, uint32_t epoch, void* stream);
 
+/* ------------------------------------------------------------------ row-block partition over the GPUs of one box
+ * One process per GPU: rank g holds rows [splits[g], splits[g+1]) of a square matrix as handle `m` (global column
+ * ids) and a replicated x.  This follows the reference's own CPU decomposition -- contiguous row blocks, spmvRowsBlocksCSR,
+ * src/SpMV_CSR_OMP.c:65-99 with the block arithmetic of src/include/macros.h:33-36 -- with one block per GPU.  The shard owns
+ * `nbuf` (2..4) x buffers of N doubles; peers map them through CUDA IPC.  Rendezvous: every rank calls _export, the caller
+ * all-gathers the blobs (spmvb200_shard_blob_bytes each, rank order) with whatever it has (MPI, torch.distributed, a file), every rank
+ * calls _connect.  col_range = {smallest, largest} column id the rank's rows reference (NULL: taken from a CSR handle; whole x for
+ * other formats) -- it decides which rows each peer needs (a halo for banded matrices).
+ *   _step      : x[dst][my rows] = A_local * x[src], and the rows the peers read are stored into THEIR x[dst] by the SpMV kernel's
+ *                epilogue (posted NVLink stores), then a flag barrier across the GPUs; asynchronous on `stream`.
+ *   _spmv_host : the whole host-buffer step in one call: x_slice (my rows of x, host) up over this GPU's PCIe link, halo rows first
+ *                and delivered to the peers + barrier while the rest uploads, row chunks as their x pieces land, y chunks down while
+ *                later chunks compute; returns when y_slice (my rows of y, host) is complete.  Every rank must make the call. */
+typedef struct spmvb200_shard spmvb200_shard;
+int spmvb200_shard_create(spmvb200_matrix* m, int kind, int rank, int world, const uint64_t* splits, int nbuf,
+                          const uint64_t* col_range, spmvb200_shard** out);
+size_t spmvb200_shard_blob_bytes(const spmvb200_shard* s);
+int spmvb200_shard_export(spmvb200_shard* s, unsigned char* blob);
+int spmvb200_shard_connect(spmvb200_shard* s, const unsigned char* blobs);
+double* spmvb200_shard_x(spmvb200_shard* s, int buf);
+int spmvb200_shard_halo_rows(const spmvb200_shard* s, uint64_t* rows); /* rows of mine delivered to peers per step (sum over peers) */
+int spmvb200_shard_step(spmvb200_shard* s, int src, int dst, void* stream);
+int spmvb200_shard_spmv_host(spmvb200_shard* s, const double* x_slice, double* y_slice, float* kernel_ms);
+int spmvb200_shard_free(spmvb200_shard* s);
+
 /* Iterated SpMV on one GPU (square matrices): x <- A x, `iters` times, ping-pong between d_a (holds x on entry) and d_b; the
  * result is in d_b if iters is odd, else in d_a.  use_graph != 0 captures the launch pair in a CUDA graph (no launch latency
  * between consecutive SpMVs).  *total_ms (may be NULL) = CUDA-event time of all iterations.  Synchronises before returning. */
@@ -187,6 +232,10 @@ int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a, double* d
  * returns after y is complete.  *kernel_ms (may be NULL) receives the CUDA-event time of the kernel
  * alone -- the value a driver stores in ElapsedInternal (src/include/config.h:112). */
 int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms);
+/* Pageable x / y (what the reference driver passes: malloc, src/main.cu:155,181) are page-locked in place with cudaHostRegister the
+ * second time the same address and size come back, and stay so until this call (p == NULL: all) or spmvb200_cache_drop(NULL).
+ * Call it before free()ing such a buffer.  SPMVB200_NO_HOST_REGISTER=1 disables the registration altogether. */
+int spmvb200_host_unregister(const void* p);
 
 /* Repeat the kernel `reps` times on device-resident vectors and return per-repetition CUDA-event
  * times in ms (times_ms[reps]); with flush_l2 != 0 a buffer larger than L2 is read (1: leaves clean lines) or
@@ -203,7 +252,19 @@ int spmvb200_time_device(spmvb200_matrix* m, int kind, const double* d_x, double
 int spmvb200_cached_spmv(const void* key, int kind, int is_ell, uint64_t M, uint64_t N, uint64_t K,
                          const uint64_t* irp, const uint64_t* ja, const double* as, const uint64_t* rl,
                          const double* x, double* y, double* elapsed_internal_s);
+/* The cached copy is re-uploaded when the pointers, the dimensions or a content fingerprint change (row pointer / row lengths plus
+ * 4096 evenly spaced (JA, AS) samples).  An in-place edit confined to values the fingerprint does not sample is NOT seen: call
+ * spmvb200_cache_drop(key) after editing a matrix in place. */
 int spmvb200_cache_drop(const void* key); /* key == NULL drops everything */
+
+/* ------------------------------------------------------------------ comparators (host arrays; no compute path)
+ * The strict check of SURVEY.md §8c: |y_i - yref_i| <= tau * sum_j |a_ij x_j| for every row, NaN / Inf anywhere in y fails
+ * (the reference's doubleVectorsDiff, src/commons/utils.c:362-393, is an absolute 7e-4 and lets never-written outputs pass).
+ * n_bad = rows that fail, worst_ratio = max |dy| / sum|a x|. */
+int spmvb200_compare_strict_csr(uint64_t M, const uint64_t* irp, const uint64_t* ja, const double* as, const double* x,
+                                const double* y_ref, const double* y, double tau, uint64_t* n_bad, double* worst_ratio);
+/* doubleVectorsDiff semantics (largest |a-b|, failed when it exceeds the threshold; reference: 7e-4), but NaN fails */
+int spmvb200_compare_abs(uint64_t n, const double* a, const double* b, double threshold, int* failed, double* max_diff);
 
 /* ------------------------------------------------------------------ device vectors (plumbing) */
 int spmvb200_dmalloc(void** d_ptr, size_t bytes);

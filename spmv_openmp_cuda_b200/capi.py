@@ -54,6 +54,23 @@ _SIGS = {
     "spmvb200_exact_choice": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "spmvb200_spmv_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "spmvb200_spmv_device_push": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(Push), _vp]),
+    "spmvb200_tune": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "spmvb200_set_tuning_mode": (C.c_int, [C.c_int]),
+    "spmvb200_get_tuning_mode": (C.c_int, []),
+    "spmvb200_tuning_get": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "spmvb200_tuning_set": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "spmvb200_shard_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(_u64), C.c_int, C.POINTER(_u64), C.POINTER(_vp)]),
+    "spmvb200_shard_blob_bytes": (C.c_size_t, [_vp]),
+    "spmvb200_shard_export": (C.c_int, [_vp, _vp]),
+    "spmvb200_shard_connect": (C.c_int, [_vp, _vp]),
+    "spmvb200_shard_x": (_vp, [_vp, C.c_int]),
+    "spmvb200_shard_halo_rows": (C.c_int, [_vp, C.POINTER(_u64)]),
+    "spmvb200_shard_step": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "spmvb200_shard_spmv_host": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_float)]),
+    "spmvb200_shard_free": (C.c_int, [_vp]),
+    "spmvb200_host_unregister": (C.c_int, [_vp]),
+    "spmvb200_compare_strict_csr": (C.c_int, [_u64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.POINTER(_u64), C.POINTER(C.c_double)]),
+    "spmvb200_compare_abs": (C.c_int, [_u64, _vp, _vp, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "spmvb200_ipc_export": (C.c_int, [_vp, _vp]),
     "spmvb200_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
     "spmvb200_ipc_close": (C.c_int, [_vp]),

@@ -9,6 +9,8 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -23,10 +25,7 @@
 namespace spmvb200 {
 thread_local char g_err[512] = "";
 thread_local int g_quiet = 0;
-// output delivery of the launch in progress (spmvb200_spmv_device_push); n == 0: none
-static thread_local PushArgs g_push = {};
-static thread_local bool g_push_fused = false;  // set by a launcher whose kernel delivered the rows itself
-static unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};
 }  // namespace spmvb200
 using namespace spmvb200;
 
@@ -51,6 +50,12 @@ static void free_arrays(spmvb200_matrix* m) {
         spmvb200_free(m->x_child);
         m->x_child = nullptr;
     }
+    if (m->tail) {
+        spmvb200_free(m->tail);
+        m->tail = nullptr;
+    }
+    cudaFree(m->tail_map);
+    cudaFree(m->tail_y);
     if (m->own) {
         cudaFree(m->irp);
         cudaFree(m->ja);
@@ -88,7 +93,7 @@ static void free_arrays(spmvb200_matrix* m) {
 
 extern "C" const char* spmvb200_last_error(void) { return g_err; }
 extern "C" int spmvb200_version(void) { return SPMVB200_VERSION; }
-extern "C" unsigned long long spmvb200_launch_count(void) { return g_launches; }
+extern "C" unsigned long long spmvb200_launch_count(void) { return g_launches.load(); }
 
 extern "C" int spmvb200_device_count(int* count) {
     if (!count) return fail("device_count: null argument");
@@ -220,9 +225,87 @@ extern "C" int spmvb200_spmv_device(spmvb200_matrix* m, int kind, const double* 
     return launch(m, kind, d_x, d_y, (cudaStream_t) stream);
 }
 
+// Make the first-use pick of a self-tuning kind NOW (blocking: allocates, synchronises, and -- in timed mode -- times candidates on
+// d_x / d_y, which are scratch here: d_y is overwritten).  After it, spmvb200_spmv_device is a pure asynchronous launch and may be
+// captured into a CUDA graph with the tuned kernel inside.
+extern "C" int spmvb200_tune(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, void* stream) {
+    if (!m || !d_x || !d_y) return fail("tune: null argument");
+    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
+    if (prefer_smem_once()) return 1;
+    if (!needs_tuning(m, kind)) return 0;
+    if (stream_capturing((cudaStream_t) stream)) return fail("tune: the stream is capturing; tune before cudaStreamBeginCapture");
+    if (launch(m, kind, d_x, d_y, (cudaStream_t) stream)) return 1;
+    CU_TRY(cudaStreamSynchronize((cudaStream_t) stream));
+    return 0;
+}
+extern "C" int spmvb200_set_tuning_mode(int mode) {
+    if (mode != 0 && mode != 1) return fail("set_tuning_mode: 0 = timed, 1 = deterministic");
+    g_tune_mode = mode;
+    return 0;
+}
+extern "C" int spmvb200_get_tuning_mode(void) { return tune_mode(); }
+// t[0] adaptive candidate (-1: not picked yet)   t[1] exact-kind / ELL pick (-1; 0 plain kernel; 12 x-window copy; 13 SELL copy)
+// t[2] lanes of the warp kind (0: not picked)     t[3] x-window launch shape of this handle or of the adaptive kind's copy (-1)
+// t[4] x-window launch shape of the exact kind's copy (-1)                                 t[5..7] reserved (0)
+extern "C" int spmvb200_tuning_get(const spmvb200_matrix* m, int32_t t[8]) {
+    if (!m || !t) return fail("tuning_get: null argument");
+    for (int i = 0; i < 8; ++i) t[i] = 0;
+    t[0] = m->tuned;
+    t[1] = m->tuned_x;
+    t[2] = m->vec_tuned ? m->vec_lanes : 0;
+    t[3] = m->format == SPMVB200_FMT_XWIN ? m->xw_mode : (m->tuned == CAND_XWIN && m->xw_child ? m->xw_child->xw_mode : -1);
+    t[4] = (m->tuned_x == CAND_XWIN && m->x_child) ? m->x_child->xw_mode : -1;
+    return 0;
+}
+// Install picks recorded earlier (same matrix, e.g. another process or another GPU of the job) instead of timing: every rank / run
+// then executes the same kernels and the tolerance kinds return the same bits.  Builds the re-tiled copies the picks name.
+extern "C" int spmvb200_tuning_set(spmvb200_matrix* m, const int32_t t[8]) {
+    if (!m || !t) return fail("tuning_set: null argument");
+    if (m->format == SPMVB200_FMT_XWIN) {
+        if (t[3] >= 0) m->xw_mode = t[3] ? 1 : 0;
+        return 0;
+    }
+    const bool csr = m->format == SPMVB200_FMT_CSR, ell = m->format == SPMVB200_FMT_ELL_COLMAJOR;
+    if (csr && t[0] >= 0) {
+        if (t[0] >= N_CAND) return fail("tuning_set: adaptive candidate %d out of range", t[0]);
+        if (m->xw_child) { spmvb200_free(m->xw_child); m->xw_child = nullptr; }
+        m->tuned = -1;
+        if (t[0] == CAND_XWIN || t[0] == CAND_SELL) {
+            if (build_child(m, t[0], false, &m->xw_child)) return fail("tuning_set: the matrix does not fit the %s copy", CAND_NAME[t[0]]);
+            if (t[0] == CAND_XWIN) m->xw_child->xw_mode = t[3] >= 0 ? (t[3] ? 1 : 0) : xwin_mode_rule(m->xw_child);
+        }
+        m->tuned = t[0];
+    }
+    if ((csr || ell) && t[1] >= 0) {
+        if (t[1] != 0 && t[1] != CAND_SELL && !(csr && t[1] == CAND_XWIN)) return fail("tuning_set: exact-kind pick %d not valid for this format", t[1]);
+        if (m->x_child) { spmvb200_free(m->x_child); m->x_child = nullptr; }
+        m->tuned_x = -1;
+        if (csr && t[1] != 0) {
+            if (build_child(m, t[1], true, &m->x_child)) return fail("tuning_set: the matrix does not fit the %s copy", CAND_NAME[t[1]]);
+            if (t[1] == CAND_XWIN) m->x_child->xw_mode = t[4] >= 0 ? (t[4] ? 1 : 0) : xwin_mode_rule(m->x_child);
+        } else if (ell && t[1] == CAND_SELL) {
+            const int q = g_quiet;
+            g_quiet = 1;
+            const int rc = sell_build(m, 0, 0xffffffffu, &m->x_child);
+            g_quiet = q;
+            if (rc) return fail("tuning_set: SELL copy of the ELL handle could not be built");
+        }
+        m->tuned_x = t[1];
+    }
+    if (csr && t[2] > 0) {
+        if (t[2] != 2 && t[2] != 4 && t[2] != 8 && t[2] != 16 && t[2] != 32) return fail("tuning_set: %d lanes", t[2]);
+        m->vec_lanes = t[2];
+        m->vec_tuned = 1;
+    }
+    if (m->pipe) { destroy_pipe(m->pipe); m->pipe = nullptr; }
+    return 0;
+}
+
 #include "engine_multigpu.inl"
 
 #include "engine_hostpath.inl"
+
+#include "engine_shard.inl"
 
 // L2 flush by READING a buffer larger than L2: leaves the cache full of CLEAN lines.  (A memset leaves it full of dirty
 // lines, whose write-back the next kernel's fills then pay for -- up to one extra byte written per byte read.)
@@ -322,6 +405,48 @@ extern "C" int spmvb200_csr_download(const spmvb200_matrix* m, uint64_t* irp, ui
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------- comparators (host arrays)
+// The reference's check (doubleVectorsDiff, src/commons/utils.c:362-393) is an absolute 7e-4 on |x| < 3e-5 inputs and its NaN
+// handling lets "never written" outputs pass (SURVEY.md §2.3-1,8).  The strict check a GPU kernel has to pass here:
+//   |y_i - yref_i| <= tau * sum_j |a_ij x_j|   for every row, any NaN / Inf in y fails.   (pure host loops over the caller's arrays:
+// a comparator, not a compute path -- the SpMV itself never runs on the CPU.)
+extern "C" int spmvb200_compare_strict_csr(uint64_t M, const uint64_t* irp, const uint64_t* ja, const double* as, const double* x,
+                                           const double* y_ref, const double* y, double tau, uint64_t* n_bad, double* worst_ratio) {
+    if (!irp || !y_ref || !y || (irp[M] && (!ja || !as || !x))) return fail("compare_strict_csr: null argument");
+    uint64_t bad = 0;
+    double worst = 0.0;
+#pragma omp parallel for reduction(+ : bad) reduction(max : worst) schedule(static)
+    for (int64_t r = 0; r < (int64_t) M; ++r) {
+        double scale = 0.0;
+        for (uint64_t j = irp[r]; j < irp[r + 1]; ++j) scale += fabs(as[j] * x[ja[j]]);
+        const double d = fabs(y[r] - y_ref[r]);
+        if (!(d <= tau * scale) || y[r] != y[r] || fabs(y[r]) > 1.7976931348623157e308) {
+            if (!(d == 0.0 && scale == 0.0)) ++bad;
+        }
+        const double ratio = scale > 0 ? d / scale : (d > 0 ? 1e300 : 0.0);
+        if (ratio == ratio && ratio > worst) worst = ratio;
+    }
+    if (n_bad) *n_bad = bad;
+    if (worst_ratio) *worst_ratio = worst;
+    return 0;
+}
+// doubleVectorsDiff with the reference's threshold semantics but NaN-aware: returns the largest |a-b|, *failed = 1 if any difference
+// exceeds `threshold` (the reference uses DOUBLE_DIFF_THREASH = 7e-4, src/include/config.h:101) or any entry is NaN.
+extern "C" int spmvb200_compare_abs(uint64_t n, const double* a, const double* b, double threshold, int* failed, double* max_diff) {
+    if ((n && (!a || !b)) || !failed) return fail("compare_abs: null argument");
+    double mx = 0.0;
+    int f = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const double d = fabs(a[i] - b[i]);
+        if (d != d) { f = 1; continue; }
+        if (d > mx) mx = d;
+    }
+    if (mx > threshold) f = 1;
+    *failed = f;
+    if (max_diff) *max_diff = mx;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------- adapter cache
 namespace {
 struct CacheKey {
@@ -331,9 +456,35 @@ struct CacheKey {
 };
 struct CacheVal {
     spmvb200_matrix* m;
-    const void *ja, *as;
-    uint64_t M, N, K;
+    const void *ja, *as, *irp, *rl;
+    uint64_t M, N, K, NZ, fp;
 };
+// Content fingerprint of the caller's host arrays: the row pointer (CSR) / row-length vector (every entry up to 2^20 rows) plus 4096 evenly spaced samples
+// of JA and AS.  A freed-and-reallocated matrix of the same shape at the same addresses, or an in-place edit that touches the
+// structure or any sampled entry, changes it; an edit confined to unsampled values does not -- such callers must call
+// spmvb200_cache_drop(key) (stated in the header and in INTEGRATION.md).  ~2 us per 10^5 rows: noise next to the PCIe copies.
+uint64_t host_fingerprint(uint64_t M, uint64_t slots, const uint64_t* irp, const uint64_t* ja, const double* as, const uint64_t* rl) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ M ^ (slots << 1);
+    const uint64_t rstep = std::max<uint64_t>(1, M >> 20);  // every row up to 2^20 rows, ~10^6 evenly spaced ones beyond
+    if (irp) {
+        for (uint64_t r = 0; r <= M; r += rstep) h = (h ^ irp[r]) * 0x100000001B3ull;
+        h = (h ^ irp[M]) * 0x100000001B3ull;
+    }
+    if (rl) for (uint64_t r = 0; r < M; r += rstep) h = (h ^ rl[r]) * 0x100000001B3ull;
+    const uint64_t step = std::max<uint64_t>(1, slots / 4096);
+    for (uint64_t j = 0; j < slots; j += step) {
+        uint64_t bits;
+        memcpy(&bits, as + j, 8);
+        h = (h ^ ja[j]) * 0x100000001B3ull;
+        h = (h ^ bits) * 0x100000001B3ull;
+    }
+    if (slots) {
+        uint64_t bits;
+        memcpy(&bits, as + slots - 1, 8);
+        h = (h ^ ja[slots - 1] ^ bits) * 0x100000001B3ull;
+    }
+    return h;
+}
 std::map<CacheKey, CacheVal> g_cache;
 std::mutex g_cache_mu;
 }  // namespace
@@ -347,11 +498,17 @@ extern "C" int spmvb200_cached_spmv(const void* key, int kind, int is_ell, uint6
     else if (kind == SPMVB200_SELL_ROWS) fmt = SPMVB200_FMT_SELL;  // built on the device from the CSR input
     else if (kind == SPMVB200_XWIN_ROWS) fmt = SPMVB200_FMT_XWIN;  // likewise
     if ((fmt == SPMVB200_FMT_CSR || fmt == SPMVB200_FMT_SELL || fmt == SPMVB200_FMT_XWIN) == (is_ell != 0)) return fail("cached_spmv: kind %d does not match the %s input", kind, is_ell ? "ELL" : "CSR");
+    if (!ja && M) return fail("cached_spmv: null JA");
+    if (!as && M && (is_ell ? K != 0 : (irp && irp[M] != 0))) return fail("cached_spmv: null AS");
+    if (!is_ell && !irp) return fail("cached_spmv: null IRP");
+    const uint64_t NZ = is_ell ? M * K : irp[M];
+    const uint64_t fp = host_fingerprint(M, NZ, irp, ja, as, is_ell ? rl : nullptr);
     spmvb200_matrix* m = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto it = g_cache.find({key, fmt});
-        if (it != g_cache.end() && (it->second.ja != ja || it->second.as != as || it->second.M != M || it->second.N != N || it->second.K != K)) {
+        if (it != g_cache.end() && (it->second.ja != ja || it->second.as != as || it->second.irp != irp || it->second.rl != rl || it->second.M != M ||
+                                    it->second.N != N || it->second.K != K || it->second.NZ != NZ || it->second.fp != fp)) {
             spmvb200_free(it->second.m);  // the host matrix behind this key changed
             g_cache.erase(it);
             it = g_cache.end();
@@ -366,7 +523,7 @@ extern "C" int spmvb200_cached_spmv(const void* key, int kind, int is_ell, uint6
                 if (rc) return 1;
                 m = conv;
             }
-            g_cache[{key, fmt}] = {m, ja, as, M, N, K};
+            g_cache[{key, fmt}] = {m, ja, as, irp, rl, M, N, K, NZ, fp};
         } else {
             m = it->second.m;
         }
@@ -378,6 +535,7 @@ extern "C" int spmvb200_cached_spmv(const void* key, int kind, int is_ell, uint6
 }
 
 extern "C" int spmvb200_cache_drop(const void* key) {
+    if (!key) spmvb200_host_unregister(nullptr);
     std::lock_guard<std::mutex> lk(g_cache_mu);
     for (auto it = g_cache.begin(); it != g_cache.end();) {
         if (!key || it->first.key == key) {

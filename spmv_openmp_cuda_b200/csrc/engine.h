@@ -54,6 +54,11 @@ struct spmvb200_matrix {
     uint16_t* xw_cnt = nullptr;       // [ntiles*R] entries of a row inside a tile | its place in the group's sorted order << 8
     uint16_t* xw_col = nullptr;       // [NZ+PAD] window-local column ids
     int own = 1;
+    // stand-alone SELL handle of a skewed matrix: rows longer than VEC_MID live in `tail` (a compact CSR handle of just those rows,
+    // run by the per-row / per-segment kernels next to the slices); tail_map[i] = original row of tail row i, tail_y = its scratch output
+    spmvb200_matrix* tail = nullptr;
+    uint32_t* tail_map = nullptr;
+    double* tail_y = nullptr;
     // CSR stream plan
     spmvb200::TileDesc* desc = nullptr;
     spmvb200::LongRec* longrec = nullptr;

@@ -102,6 +102,55 @@ int spmvb200::finish_csr(spmvb200_matrix* m) {
     return 0;
 }
 
+// Structure check at upload time: every kernel gathers x[col] unchecked and walks [irp[r], irp[r+1]) unchecked, so a malformed
+// input (column id >= N from a wrong header, a row pointer that decreases) must become an error return here, not an out-of-bounds
+// device read later.  flags[0]: row pointer not monotone, flags[1]: column id >= N.  One streaming pass over the ids.
+__global__ void csr_validate_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, uint64_t M, uint64_t NZ, uint64_t N,
+                                    int* __restrict__ flags) {
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x, t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad_r = false, bad_c = false;
+    for (uint64_t r = t; r < M; r += stride) bad_r |= irp[r] > irp[r + 1];
+    for (uint64_t j = t; j < NZ; j += stride) bad_c |= (uint64_t) ja[j] >= N;
+    if (bad_r) flags[0] = 1;
+    if (bad_c) flags[1] = 1;
+}
+__global__ void ell_validate_kernel(const uint32_t* __restrict__ ja, const uint32_t* __restrict__ rl, uint64_t pitch, uint32_t M, uint32_t K,
+                                    int colmajor, uint64_t N, int* __restrict__ flags) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const uint32_t len = min(rl[r], K);
+    bool bad = false;
+    for (uint32_t k = 0; k < len; ++k) bad |= (uint64_t) ja[colmajor ? (uint64_t) k * pitch + r : (uint64_t) r * pitch + k] >= N;
+    if (bad) flags[1] = 1;
+}
+static int validate_csr(const spmvb200_matrix* m, const char* who) {
+    int* d = nullptr;
+    CU_TRY(cudaMalloc(&d, 8));
+    CU_TRY(cudaMemset(d, 0, 8));
+    csr_validate_kernel<<<1184, 256>>>(m->irp, m->ja, m->M, m->NZ, m->N, d);
+    int h[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail("%s: structure check: %s", who, cudaGetErrorString(e));
+    if (h[0]) return fail("%s: the row pointer is not monotone (IRP[r] > IRP[r+1] for some row)", who);
+    if (h[1]) return fail("%s: a column id is >= N=%llu", who, (unsigned long long) m->N);
+    return 0;
+}
+static int validate_ell(const spmvb200_matrix* m, const char* who) {
+    if (!m->M || !m->K) return 0;
+    int* d = nullptr;
+    CU_TRY(cudaMalloc(&d, 8));
+    CU_TRY(cudaMemset(d, 0, 8));
+    ell_validate_kernel<<<(unsigned) ((m->M + 255) / 256), 256>>>(m->ja, m->rl, m->pitch, (uint32_t) m->M, (uint32_t) m->K,
+                                                                     m->format == SPMVB200_FMT_ELL_COLMAJOR, m->N, d);
+    int h[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail("%s: structure check: %s", who, cudaGetErrorString(e));
+    if (h[1]) return fail("%s: a column id is >= N=%llu", who, (unsigned long long) m->N);
+    return 0;
+}
+
 static int check_dims(uint64_t M, uint64_t N, uint64_t NZ) {
     if (M >= 0x7fffffffull || N > 0xffffffffull || NZ >= 0xfffffff0ull)
         return fail("matrix too large for 32-bit device indices: M=%llu N=%llu NZ=%llu", (unsigned long long) M,
@@ -141,7 +190,7 @@ extern "C" int spmvb200_csr_upload(uint64_t M, uint64_t N, const uint64_t* irp, 
                                    uint64_t row_begin, uint64_t row_end, spmvb200_matrix** out) {
     if (!out) return fail("csr_upload: null output");
     *out = nullptr;
-    if (!irp || (M && !ja && irp[M]) || row_begin > row_end || row_end > M) return fail("csr_upload: bad arguments");
+    if (!irp || (M && irp[M] && (!ja || !as)) || row_begin > row_end || row_end > M) return fail("csr_upload: bad arguments (null IRP, or null JA / AS with NZ > 0)");
     int ndev = 0;
     if (spmvb200_device_count(&ndev) || ndev == 0) return fail("csr_upload: no CUDA device (no CPU fallback)");
     const uint64_t rows = row_end - row_begin, n0 = irp[row_begin], nz = irp[row_end] - n0;
@@ -166,6 +215,7 @@ extern "C" int spmvb200_csr_upload(uint64_t M, uint64_t N, const uint64_t* irp, 
         if ((rc = upload_narrow(ja + n0, nz, 0, m->ja, d_of))) break;
         if (nz && (rc = (cudaMemcpy(m->as, as + n0, nz * 8, cudaMemcpyHostToDevice) != cudaSuccess))) break;
         if ((rc = read_overflow(d_of, "csr_upload"))) break;
+        if ((rc = validate_csr(m, "csr_upload"))) break;
         rc = finish_csr(m);
     } while (0);
     cudaFree(d_of);
@@ -184,6 +234,7 @@ extern "C" int spmvb200_csr_adopt_device(uint64_t M, uint64_t N, uint64_t NZ, ui
     if (!out) return fail("csr_adopt_device: null output");
     *out = nullptr;
     if (check_dims(M, N, NZ)) return 1;
+    if (!d_irp32 || (NZ && (!d_ja32 || !d_as))) return fail("csr_adopt_device: null array");
     spmvb200_matrix* m = new spmvb200_matrix();
     m->format = SPMVB200_FMT_CSR;
     m->M = M;
@@ -193,7 +244,7 @@ extern "C" int spmvb200_csr_adopt_device(uint64_t M, uint64_t N, uint64_t NZ, ui
     m->ja = d_ja32;
     m->as = d_as;
     m->own = own;
-    if (finish_csr(m)) {
+    if (validate_csr(m, "csr_adopt_device") || finish_csr(m)) {
         m->own = 0;  // the caller keeps ownership on failure
         free_arrays(m);
         delete m;
@@ -307,6 +358,7 @@ extern "C" int spmvb200_ell_upload(uint64_t M, uint64_t N, uint64_t K, const uin
         }
         if (rc) break;
         m->NZ = nz;
+        if ((rc = validate_ell(m, "ell_upload"))) break;
         ell_pick_lanes(m);
         if ((rc = ell_try_idx16(m))) break;
     } while (0);
@@ -372,8 +424,93 @@ extern "C" int spmvb200_ell_from_csr(const spmvb200_matrix* csr, int format, spm
 
 // ------------------------------------------------------------------------------------------------- SELL-32-sigma
 static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, spmvb200_matrix** out);
+// A thread-per-row format must not walk a 10^5-entry row with one thread (R-MAT: 37 ms for one SpMV).  A stand-alone SELL handle
+// therefore leaves rows longer than VEC_MID out of its slices and keeps them as a compact CSR handle of its own (`tail`): the
+// per-row / per-segment kernels run them next to the slices and a scatter writes their y entries.
+struct LongRowPred {
+    const uint32_t* irp;
+    uint32_t thr;
+    __device__ bool operator()(uint32_t r) const { return irp[r + 1] - irp[r] > thr; }
+};
+__global__ void tail_len_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ map, uint32_t n, uint32_t* __restrict__ len) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) len[i] = irp[map[i] + 1] - irp[map[i]];
+    if (i == n) len[i] = 0;
+}
+__global__ void tail_copy_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
+                                 const uint32_t* __restrict__ map, const uint32_t* __restrict__ irp_t, uint32_t n, uint32_t* __restrict__ ja_t,
+                                 double* __restrict__ as_t) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const uint32_t s = irp[map[w]], len = irp[map[w] + 1] - s, d = irp_t[w];
+    for (uint32_t k = lane; k < len; k += 32) {
+        ja_t[d + k] = ja[s + k];
+        as_t[d + k] = as[s + k];
+    }
+}
+__global__ void tail_scatter_kernel(const double* __restrict__ yt, const uint32_t* __restrict__ map, uint32_t n, double* __restrict__ y) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[map[i]] = yt[i];
+}
+static int sell_attach_tail(const spmvb200_matrix* csr, spmvb200_matrix* sell) {
+    const uint32_t M = (uint32_t) csr->M;
+    uint32_t *map = nullptr, *d_num = nullptr, *len = nullptr, *irp_t = nullptr, *ja_t = nullptr;
+    double* as_t = nullptr;
+    void* tmp = nullptr;
+    int rc = 0;
+    do {
+        if ((rc = cudaMalloc(&map, (size_t) M * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&d_num, 4) != cudaSuccess)) break;
+        thrust::counting_iterator<uint32_t> rows_it(0);
+        LongRowPred pred{csr->irp, (uint32_t) VEC_MID};
+        size_t b_sel = 0, b_scan = 0;
+        cub::DeviceSelect::If(nullptr, b_sel, rows_it, map, d_num, (int) M, pred);
+        cub::DeviceScan::ExclusiveSum(nullptr, b_scan, len, irp_t, (int) M + 1);
+        if ((rc = cudaMalloc(&tmp, std::max(b_sel, b_scan) + 16) != cudaSuccess)) break;
+        if ((rc = cub::DeviceSelect::If(tmp, b_sel, rows_it, map, d_num, (int) M, pred) != cudaSuccess)) break;
+        uint32_t n = 0;
+        if ((rc = cudaMemcpy(&n, d_num, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        if (!n) { rc = fail("sell tail: no long rows found"); break; }
+        if ((rc = cudaMalloc(&len, ((size_t) n + 1) * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&irp_t, ((size_t) n + 1) * 4) != cudaSuccess)) break;
+        tail_len_kernel<<<(n + 1 + 255) / 256, 256>>>(csr->irp, map, n, len);
+        if ((rc = cub::DeviceScan::ExclusiveSum(tmp, b_scan, len, irp_t, (int) n + 1) != cudaSuccess)) break;
+        uint32_t nz = 0;
+        if ((rc = cudaMemcpy(&nz, irp_t + n, 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&ja_t, ((size_t) nz + PAD) * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&as_t, ((size_t) nz + PAD) * 8) != cudaSuccess)) break;
+        cudaMemset(ja_t + nz, 0, PAD * 4);
+        cudaMemset(as_t + nz, 0, PAD * 8);
+        tail_copy_kernel<<<(unsigned) (((uint64_t) n * 32 + 255) / 256), 256>>>(csr->irp, csr->ja, csr->as, map, irp_t, n, ja_t, as_t);
+        if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
+        if ((rc = spmvb200_csr_adopt_device(n, csr->N, nz, irp_t, ja_t, as_t, 1, &sell->tail))) break;
+        irp_t = nullptr; ja_t = nullptr; as_t = nullptr;  // owned by the tail handle now
+        if ((rc = cudaMalloc(&sell->tail_y, (size_t) n * 8) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&sell->tail_map, (size_t) n * 4) != cudaSuccess)) break;
+        if ((rc = cudaMemcpy(sell->tail_map, map, (size_t) n * 4, cudaMemcpyDeviceToDevice) != cudaSuccess)) break;
+    } while (0);
+    cudaFree(map);
+    cudaFree(d_num);
+    cudaFree(len);
+    cudaFree(irp_t);
+    cudaFree(ja_t);
+    cudaFree(as_t);
+    cudaFree(tmp);
+    if (rc) {
+        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("sell tail: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    return 0;
+}
 extern "C" int spmvb200_sell_from_csr(const spmvb200_matrix* csr, uint32_t sigma, spmvb200_matrix** out) {
-    return sell_build(csr, sigma, 0xffffffffu, out);
+    const bool skewed = csr && csr->format == SPMVB200_FMT_CSR && csr->lmax > (uint32_t) VEC_MID;
+    if (sell_build(csr, sigma, skewed ? (uint32_t) VEC_MID : 0xffffffffu, out)) return 1;
+    if (skewed && sell_attach_tail(csr, *out)) {
+        spmvb200_free(*out);
+        *out = nullptr;
+        return 1;
+    }
+    return 0;
 }
 // cap < 2^32-1: rows longer than cap are left empty (hybrid of the adaptive mode: they go to the per-row / per-segment CTAs)
 static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, spmvb200_matrix** out) {

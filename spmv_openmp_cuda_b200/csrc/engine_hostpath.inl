@@ -2,10 +2,19 @@
 // host-buffer path: x pieces up, row chunks, y chunks down (spmvb200_spmv_host).
 
 // ---- pipelined host path --------------------------------------------------------------------------
-// which kernel a (kind, handle) pair runs chunk-wise: 0/1 stream variants (+10 exact), 2.. vector lanes, 100 ELL column-major
+// the x-window handle a (kind, handle) pair runs, if any: the handle itself or the copy its first-use pick kept
+static const spmvb200_matrix* xwin_of(const spmvb200_matrix* m, int kind) {
+    if (kind == SPMVB200_XWIN_ROWS && m->format == SPMVB200_FMT_XWIN) return m;
+    if (kind == SPMVB200_CSR_ROWS && m->tuned_x == CAND_XWIN) return m->x_child;
+    if (kind == SPMVB200_CSR_ADAPTIVE && m->tuned == CAND_XWIN) return m->xw_child;
+    return nullptr;
+}
+// which kernel a (kind, handle) pair runs chunk-wise: 0/1 stream variants (+10 exact), 2.. vector lanes, 100 ELL column-major,
+// 200 x-window (chunks of whole row blocks, one CTA per row block)
 static int pipe_candidate(const spmvb200_matrix* m, int kind) {
+    if (xwin_of(m, kind)) return 200;
     switch (kind) {
-        case SPMVB200_CSR_ROWS: return m->tuned_x == 0 ? 10 : -1;  // a re-tiled copy runs as one launch
+        case SPMVB200_CSR_ROWS: return m->tuned_x == 0 ? 10 : -1;  // the SELL copy runs as one launch
         case SPMVB200_CSR_ADAPTIVE: return ((m->tuned >= 2 && m->nseg) || m->tuned >= 7) ? -1 : m->tuned;  // long rows / spans: one launch
         case SPMVB200_CSR_ROWS_WARP: return m->nseg ? -1 : 20 + m->vec_lanes;
         case SPMVB200_ELL_ROWS: return m->tuned_x == 0 ? 100 : -1;  // the SELL copy runs as one launch
@@ -15,15 +24,21 @@ static int pipe_candidate(const spmvb200_matrix* m, int kind) {
 static void launch_chunk(spmvb200_matrix* m, const HostPipe* p, int k, const double* x, double* y) {
     const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
     const int c = p->cand;
-    if (c == 100) launch_ell_colmajor(m, x, y, p->s_comp, r0, r1);
+    if (c == 200) {
+        const spmvb200_matrix* xw = xwin_of(m, p->kind);
+        launch_xwin(xw, x, y, p->s_comp, nullptr, (uint32_t) (r0 / xw->xw_R), (uint32_t) ((r1 + xw->xw_R - 1) / xw->xw_R));
+    } else if (c == 100) launch_ell_colmajor(m, x, y, p->s_comp, r0, r1);
     else if (c == 10) launch_csr_stream<false, 0>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
     else if (c == 0) launch_csr_stream<true, 0>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
     else if (c == 1) launch_csr_stream<true, 1>(m, x, y, p->s_comp, p->tile_b[k], p->tile_b[k + 1]);
     else if (c >= 20) launch_csr_vector(m, c - 20, x, y, p->s_comp, r0, r1);
     else launch_csr_vector(m, 2 << (c - 2), x, y, p->s_comp, r0, r1);
 }
-static int host_chunks_wanted() {
-    int nch = 4;  // measured on B200/PCIe5: 1 chunk 0.74 ms, 2: 0.63, 4: 0.54, 8: 0.59, 16: 0.70 per call (cfg2)
+static int host_chunks_wanted(const spmvb200_matrix* m) {
+    // measured on B200/PCIe5, cfg2 (16.8 MB vectors): 1 chunk 0.74 ms, 2: 0.63, 4: 0.54, 8: 0.59, 16: 0.70 per call -- a chunk
+    // should stay above ~4 MB; longer vectors (cfg4: 268 MB) take more chunks so that the serial head (first x piece) and tail
+    // (last y chunk) of the pipeline stay short
+    int nch = (int) std::min<uint64_t>(16, std::max<uint64_t>(4, (std::max(m->M, m->N) * 8) >> 24));
     if (const char* e = getenv("SPMVB200_HOST_CHUNKS")) nch = std::max(1, atoi(e));  // developer knob
     return nch;
 }
@@ -34,11 +49,13 @@ static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
     m->pipe = p;
     p->kind = kind;
     p->cand = cand;
-    int nch = host_chunks_wanted();
+    int nch = host_chunks_wanted(m);
     p->nch_req = nch;
     if (m->M < 65536 || cand < 0) nch = 1;
     const bool stream = (cand == 0 || cand == 1 || cand == 10);
+    const spmvb200_matrix* xw = cand == 200 ? xwin_of(m, kind) : nullptr;
     if (stream) nch = (int) std::max<uint32_t>(1, std::min<uint32_t>(nch, m->ntiles));
+    if (xw) nch = (int) std::max<uint32_t>(1, std::min<uint32_t>(nch, xw->xw_nrb));
     p->nch = nch;
     p->row_b.assign(nch + 1, m->M);
     p->tile_b.assign(nch + 1, m->ntiles);
@@ -54,6 +71,8 @@ static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
             t = std::max(t, p->tile_b[k - 1]);
             p->tile_b[k] = t;
             p->row_b[k] = m->h_tile_row0[t] & ~SEG_FLAG;
+        } else if (xw) {
+            p->row_b[k] = std::min<uint64_t>(m->M, ((uint64_t) xw->xw_nrb * k / nch) * xw->xw_R);  // whole row blocks
         } else {
             p->row_b[k] = std::max<uint64_t>(p->row_b[k - 1], (m->M * k / nch) & ~255ull);
         }
@@ -62,7 +81,18 @@ static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
     // the moment "its" piece has landed (banded / stencil matrices: pieces ~ equal; unstructured: piece 0 = all of x)
     p->x_b.assign(nch + 1, m->N);
     p->x_b[0] = 0;
-    if (nch > 1) {
+    if (nch > 1 && xw) {
+        // x-window copy: the columns a chunk reads end with the last window of its row blocks' tile lists (ascending per row block)
+        std::vector<uint32_t> t0(xw->xw_nrb + 1), win(std::max<uint32_t>(xw->xw_ntiles, 1));
+        CU_TRY(cudaMemcpy(t0.data(), xw->xw_rb_tile0, t0.size() * 4, cudaMemcpyDeviceToHost));
+        if (xw->xw_ntiles) CU_TRY(cudaMemcpy(win.data(), xw->xw_tile_win, (size_t) xw->xw_ntiles * 4, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < nch; ++k) {
+            uint64_t need = 0;
+            for (uint64_t rb = p->row_b[k] / xw->xw_R; rb < (p->row_b[k + 1] + xw->xw_R - 1) / xw->xw_R; ++rb)
+                if (t0[rb + 1] > t0[rb]) need = std::max<uint64_t>(need, ((uint64_t) win[t0[rb + 1] - 1] + 1) * xw->xw_W);
+            p->x_b[k + 1] = std::max(p->x_b[k], k + 1 == nch ? m->N : std::min<uint64_t>(m->N, need));
+        }
+    } else if (nch > 1) {
         uint32_t* d_cm = nullptr;
         CU_TRY(cudaMalloc(&d_cm, nch * 4));
         CU_TRY(cudaMemset(d_cm, 0, nch * 4));
@@ -120,16 +150,58 @@ static double* mapped_alias(double* y, bool chunked, bool xwin_launch) {
     return a.type == cudaMemoryTypeHost ? static_cast<double*>(a.devicePointer) : nullptr;
 }
 
+// ---- pageable caller buffers --------------------------------------------------------------------
+// The reference driver hands malloc'ed x and y (src/main.cu:155,181): pageable memory goes through the driver's staging copies at
+// roughly half the pinned rate and cannot overlap with anything.  A buffer that comes back a SECOND time with the same address and
+// size (the harness reuses its vectors for every repetition) is page-locked in place with cudaHostRegister and stays so until
+// spmvb200_host_unregister (or spmvb200_cache_drop(NULL)); at most 16 buffers are tracked.  SPMVB200_NO_HOST_REGISTER switches it off.
+namespace {
+struct HostReg {
+    size_t bytes = 0;
+    int seen = 0;
+    bool registered = false;
+};
+std::map<const void*, HostReg> g_hostreg;
+std::mutex g_hostreg_mu;
+}  // namespace
+static void host_buffer_seen(const void* p, size_t bytes) {
+    static const bool off = getenv("SPMVB200_NO_HOST_REGISTER") != nullptr;
+    if (off || bytes < (1u << 20)) return;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return; }
+    if (a.type != cudaMemoryTypeUnregistered) return;  // already page-locked (or not host memory at all)
+    std::lock_guard<std::mutex> lk(g_hostreg_mu);
+    if (g_hostreg.size() >= 16 && !g_hostreg.count(p)) return;
+    HostReg& r = g_hostreg[p];
+    if (r.bytes != bytes) { r.bytes = bytes; r.seen = 0; r.registered = false; }
+    if (r.seen < 0 || ++r.seen < 2) return;
+    if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) r.registered = true;
+    else { cudaGetLastError(); r.seen = -1; }  // e.g. read-only mapping: stay on the pageable path for this buffer
+}
+extern "C" int spmvb200_host_unregister(const void* p) {
+    std::lock_guard<std::mutex> lk(g_hostreg_mu);
+    for (auto it = g_hostreg.begin(); it != g_hostreg.end();) {
+        if (!p || it->first == p) {
+            if (it->second.registered && cudaHostUnregister(const_cast<void*>(it->first)) != cudaSuccess) cudaGetLastError();
+            it = g_hostreg.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    return 0;
+}
+
 extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms) {
     if (!m || !x || !y) return fail("spmv_host: null argument");
+    host_buffer_seen(x, m->N * 8);
+    host_buffer_seen(y, m->M * 8);
     if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
     if (prefer_smem_once() || ensure_events(m)) return 1;
     if (!m->d_x) CU_TRY(cudaMalloc(&m->d_x, std::max<uint64_t>(m->N, 1) * 8));
     if (!m->d_y) CU_TRY(cudaMalloc(&m->d_y, std::max<uint64_t>(m->M, 1) * 8));
-    const bool untuned = (kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || ((kind == SPMVB200_CSR_ROWS || kind == SPMVB200_ELL_ROWS) && m->tuned_x < 0) ||
-                         (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned);
+    const bool untuned = kind != SPMVB200_XWIN_ROWS && needs_tuning(m, kind);
     int cand = untuned ? -1 : pipe_candidate(m, kind);
-    if (!untuned && (!m->pipe || m->pipe->kind != kind || m->pipe->cand != cand || m->pipe->nch_req != host_chunks_wanted()))
+    if (!untuned && (!m->pipe || m->pipe->kind != kind || m->pipe->cand != cand || m->pipe->nch_req != host_chunks_wanted(m)))
         if (build_pipe(m, kind, cand)) return 1;
     if (untuned || m->pipe->nch <= 1) {  // plain path: x up, one launch, y down (also the adaptive mode's tuning call)
         const bool xw = (kind == SPMVB200_XWIN_ROWS && m->xw_mode >= 0) || (kind == SPMVB200_CSR_ROWS && m->tuned_x == CAND_XWIN) ||

@@ -2,6 +2,48 @@
 // launch: kernel launchers, first-use tuning of the self-tuning kinds, the kind -> kernel switch.
 
 // ------------------------------------------------------------------------------------------------- launch
+// Per-launch state handed down to the launchers (no globals: two host threads may drive two handles at once).
+//   push  : fused output delivery of spmvb200_spmv_device_push (n == 0: none)
+//   fused : set by a launcher whose kernel delivered the rows from its own epilogue
+struct LaunchCtx {
+    PushArgs push = {};
+    bool fused = false;
+};
+static const PushArgs NO_PUSH = {};
+static inline const PushArgs& push_of(const LaunchCtx* lc) { return lc ? lc->push : NO_PUSH; }
+
+// two timing events that are destroyed on every exit path
+struct ScopedEvents {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int init() {
+        CU_TRY(cudaEventCreate(&e0));
+        CU_TRY(cudaEventCreate(&e1));
+        return 0;
+    }
+    ~ScopedEvents() {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
+// a child handle that is freed unless it is released to its new owner
+struct ScopedChild {
+    spmvb200_matrix* m = nullptr;
+    ~ScopedChild() { if (m) spmvb200_free(m); }
+    spmvb200_matrix* release() { spmvb200_matrix* r = m; m = nullptr; return r; }
+};
+
+// How the self-tuning kinds pick their kernel at first use (spmvb200_set_tuning_mode / SPMVB200_TUNE):
+//   0 timed         : candidates are timed on the caller's vectors (best of two); fastest pick, may differ between runs
+//   1 deterministic : the pick is a pure function of the matrix structure (rules below) -- tolerance kinds then return the same
+//                     bits in every process, and nothing is timed (no event synchronisation inside the first launch)
+static int g_tune_mode = -1;
+static int tune_mode() {
+    if (g_tune_mode < 0) {
+        const char* e = getenv("SPMVB200_TUNE");
+        g_tune_mode = (e && (e[0] == 'd' || e[0] == '1')) ? 1 : 0;
+    }
+    return g_tune_mode;
+}
 // Rows the vector kernels skip: medium rows (one CTA each) and rows longer than a tile (one CTA per segment).  They touch other rows
 // of y than the main kernel, so they run NEXT to it on two side streams -- forked before the main launch, joined after it (events:
 // legal inside a graph capture too).  On R-MAT (cfg3) the three kernels are 189 + 97 + 52 us back to back.
@@ -45,7 +87,8 @@ static void tail_fork(spmvb200_matrix* m, const double* x, double* y, cudaStream
     }
 }
 static void tail_join(spmvb200_matrix* m, cudaStream_t st) {
-    if (!m->e_fork || getenv("SPMVB200_SERIAL_TAIL")) return;
+    static const bool serial = getenv("SPMVB200_SERIAL_TAIL") != nullptr;
+    if (!m->e_fork || serial) return;
     if (m->nmid) cudaStreamWaitEvent(st, m->e_tail[0], 0);
     if (m->nseg) cudaStreamWaitEvent(st, m->e_tail[1], 0);
 }
@@ -98,9 +141,10 @@ static void launch_csr_stream(const spmvb200_matrix* m, const double* x, double*
         <<<t1 - t0, STREAM_BLOCK, 0, st>>>(m->desc, m->longrec, m->irp, m->ja, m->as, x, y, m->partial, m->ticket, t0, pre_t);
     ++g_launches;
 }
-static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1) {
+static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, uint64_t r0, uint64_t r1, LaunchCtx* lc = nullptr) {
     constexpr int BLOCK = 256;
     if (r1 <= r0) return;
+    const PushArgs& g_push = push_of(lc);
     static const bool no_exit = getenv("SPMVB200_ELL_NO_EARLY_EXIT") != nullptr;  // developer knob: walk all K slots like the reference
     // slots in flight per thread: 4, or 3 when that leaves a shorter tail of one-at-a-time slots (K = 27: 3 x 9 exactly; measured
     // 103.3 vs 105.2 us on cfg2; 5..9 lose more to occupancy than they gain)
@@ -134,14 +178,14 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
         ell_colmajor_kernel<3, BLOCK, false><<<grid, BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, 0, x, y, g_push);
     else
         ell_colmajor_kernel<4, BLOCK, false><<<grid, BLOCK, 0, st>>>(m->as, m->ja, no_exit ? nullptr : m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, 0, x, y, g_push);
-    g_push_fused = true;
+    if (lc) lc->fused = true;
     ++g_launches;
 }
 
 
 // ---- x-window CSR: one CTA per row block, NW warps, ring of x windows in shared memory
 template <int NW, int ACC, int UMAX>
-static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, LaunchCtx* lc, uint32_t rb0, uint32_t rb1) {
     const size_t smem = (size_t) m->xw_nbuf * (m->xw_W + 2) * 8 + XW_MAX_NBUF * 12;
     static size_t configured[64] = {0};  // per device: function attributes belong to the device's context
     int dev = 0;
@@ -150,22 +194,26 @@ static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, c
         CU_TRY(cudaFuncSetAttribute(xwin_kernel<NW, ACC, UMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         configured[dev & 63] = smem;
     }
-    const bool persist = m->xw_mode == 1;
-    xwin_kernel<NW, ACC, UMAX><<<persist ? m->xw_ncta : m->xw_nrb, 32 * NW, smem, st>>>(persist ? m->xw_cta_rb : nullptr, m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
-                                                                 (uint32_t) m->M, (uint32_t) m->N, m->xw_W, m->xw_nbuf, ((uintptr_t) x & 15) == 0, g_push);
-    g_push_fused = true;
+    // a row-block sub-range (chunked host path) always runs one CTA per row block
+    const bool whole = rb0 == 0 && rb1 >= m->xw_nrb;
+    const bool persist = m->xw_mode == 1 && whole;
+    if (rb1 > m->xw_nrb) rb1 = m->xw_nrb;
+    if (rb1 <= rb0) return 0;
+    xwin_kernel<NW, ACC, UMAX><<<persist ? m->xw_ncta : rb1 - rb0, 32 * NW, smem, st>>>(persist ? m->xw_cta_rb : nullptr, m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
+                                                                 (uint32_t) m->M, (uint32_t) m->N, m->xw_W, m->xw_nbuf, ((uintptr_t) x & 15) == 0, rb0, push_of(lc));
+    if (lc) lc->fused = true;
     ++g_launches;
     return 0;
 }
 // (warps, row groups per warp, largest batch in slots): up to 2*UMAX*ACC loads in flight per lane
-static int launch_xwin(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+static int launch_xwin(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, LaunchCtx* lc = nullptr, uint32_t rb0 = 0, uint32_t rb1 = 0xffffffffu) {
     const uint32_t acc = m->xw_R / (32 * m->xw_nw);
     static const int u_env = getenv("SPMVB200_XW_U") ? atoi(getenv("SPMVB200_XW_U")) : 0;  // developer knob
 #define XW_CASE(NW, ACC, UDEF, UALT, UALT2)                                                  \
     if (m->xw_nw == NW && acc == ACC) {                                                      \
-        if (u_env == UALT) return launch_xwin_t<NW, ACC, UALT>(m, x, y, st);                 \
-        if (u_env == UALT2) return launch_xwin_t<NW, ACC, UALT2>(m, x, y, st);               \
-        return launch_xwin_t<NW, ACC, UDEF>(m, x, y, st);                                    \
+        if (u_env == UALT) return launch_xwin_t<NW, ACC, UALT>(m, x, y, st, lc, rb0, rb1);   \
+        if (u_env == UALT2) return launch_xwin_t<NW, ACC, UALT2>(m, x, y, st, lc, rb0, rb1); \
+        return launch_xwin_t<NW, ACC, UDEF>(m, x, y, st, lc, rb0, rb1);                      \
     }
     XW_CASE(32, 1, 8, 6, 4)
     XW_CASE(32, 2, 5, 4, 6)
@@ -180,10 +228,17 @@ static int launch_xwin(const spmvb200_matrix* m, const double* x, double* y, cud
 
 // first use of an x-window handle: one CTA per row block, or persistent CTAs?  (Persistent wins when a row block has few
 // tiles -- no pipeline refill per row block; per-row-block wins on wide bands, where concurrent CTAs then share windows.)
+// Deterministic rule (measured: cfg2 as CSR, 5 tiles per row block, and cfg4 with w = 2^12, 3 tiles: persistent +8 %;
+// cfg4 with w = 2^15, 9 tiles: per-row-block).
+static int xwin_mode_rule(const spmvb200_matrix* m) { return (uint64_t) m->xw_ntiles <= 6ull * std::max<uint32_t>(m->xw_nrb, 1) ? 1 : 0; }
 static int tune_xwin(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, float* best_ms_out) {
-    cudaEvent_t e0, e1;
-    CU_TRY(cudaEventCreate(&e0));
-    CU_TRY(cudaEventCreate(&e1));
+    if (tune_mode() == 1) {
+        m->xw_mode = xwin_mode_rule(m);
+        if (best_ms_out) *best_ms_out = 0.f;
+        return 0;
+    }
+    ScopedEvents ev;
+    if (ev.init()) return 1;
     float best_ms = 1e30f;
     int best = 0;
     for (int mode = 0; mode < 2; ++mode) {
@@ -191,23 +246,23 @@ static int tune_xwin(spmvb200_matrix* m, const double* x, double* y, cudaStream_
         if (launch_xwin(m, x, y, st)) return 1;
         float ms_min = 1e30f;
         for (int rep = 0; rep < 2; ++rep) {
-            CU_TRY(cudaEventRecord(e0, st));
+            CU_TRY(cudaEventRecord(ev.e0, st));
             if (launch_xwin(m, x, y, st)) return 1;
-            CU_TRY(cudaEventRecord(e1, st));
-            CU_TRY(cudaEventSynchronize(e1));
+            CU_TRY(cudaEventRecord(ev.e1, st));
+            CU_TRY(cudaEventSynchronize(ev.e1));
             float ms = 0;
-            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            CU_TRY(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
             ms_min = std::min(ms_min, ms);
         }
         if (ms_min < best_ms) { best_ms = ms_min; best = mode; }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     m->xw_mode = best;
     if (best_ms_out) *best_ms_out = best_ms;
     return 0;
 }
 
+// SELL-32-sigma, thread per row.  A stand-alone SELL handle built from a CSR parent (spmvb200_sell_from_csr) leaves rows longer than
+// VEC_MID out of the slices and keeps the parent's arrays for them: those rows run on the per-row kernels next to the slices.
 static void launch_sell(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
     sell_kernel<4, 256><<<(unsigned) ((m->Mpad + 255) / 256), 256, 0, st>>>(m->irp, m->perm, m->rl, m->as, m->ja, (uint32_t) m->Mpad, x, y);
     ++g_launches;
@@ -220,12 +275,13 @@ static const int CAND_SELL = 13;  // SELL-32-sigma copy (matrices without long r
 static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32",
                                         "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32", "xwindow", "sell"};
 static int cand_lanes(int c) { return c < 2 ? 0 : 2 << ((c - 2) % 5); }
-static void launch_candidate(spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st) {
+static int cand_of_lanes(int lanes) { int c = 2; while (c < 6 && cand_lanes(c) < lanes) ++c; return c; }
+static void launch_candidate(spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st, LaunchCtx* lc = nullptr) {
     if (c == 0) launch_csr_stream<true, 0>(m, x, y, st, 0, m->ntiles);
     else if (c == 1) launch_csr_stream<true, 1>(m, x, y, st, 0, m->ntiles);
     else if (c < 7) launch_csr_vector(m, cand_lanes(c), x, y, st, 0, m->M);
     else if (c < CAND_XWIN) launch_csr_vspan(m, cand_lanes(c), x, y, st);
-    else if (c == CAND_XWIN) launch_xwin(m->xw_child, x, y, st);
+    else if (c == CAND_XWIN) launch_xwin(m->xw_child, x, y, st, lc);
     else {
         const bool hybrid = m->lmax > (uint32_t) VEC_MID;  // rows the capped SELL copy left out (it does not write their y)
         if (hybrid) tail_fork(m, x, y, st);
@@ -233,95 +289,113 @@ static void launch_candidate(spmvb200_matrix* m, int c, const double* x, double*
         if (hybrid) tail_join(m, st);
     }
 }
+
+// Re-tiled copies a CSR handle may keep next to its arrays.  exact: the copy must sum in the serial order (x-window: column-sorted
+// rows only).  Returns 0 and the child, or non-zero when the matrix does not fit the format ("not local enough", too much padding).
+static int build_child(spmvb200_matrix* m, int cand, bool exact, spmvb200_matrix** out) {
+    *out = nullptr;
+    ScopedChild c;
+    const int quiet0 = g_quiet;
+    g_quiet = 1;  // "does not fit this format" is an expected answer here, not an error to print
+    int rc = 1;
+    if (cand == CAND_XWIN && !getenv("SPMVB200_NO_XWINDOW")) {
+        // window traffic (L2 -> shared memory) above ~1.5x the matrix stream cannot win: stop at the tile census
+        rc = xwin_build(m, 0, 0, 15.0, &c.m);
+        if (!rc && exact && !c.m->xw_sorted) rc = 1;
+    } else if (cand == CAND_SELL && !getenv("SPMVB200_NO_SELL")) {
+        // rows longer than VEC_MID are left out of the copy: per-row / per-segment CTAs take them (hybrid for skewed matrices);
+        // kept only while the slices stay nearly padding-free
+        rc = sell_build(m, 0, m->lmax <= (uint32_t) VEC_MID ? 0xffffffffu : (uint32_t) VEC_MID, &c.m);
+        if (!rc && c.m->slots > m->NZ + m->NZ / 4) rc = 1;
+    }
+    g_quiet = quiet0;
+    g_err[0] = 0;
+    if (rc) return 1;
+    *out = c.release();
+    return 0;
+}
+
+template <typename F>
+static int time_best_of_2(F&& run, cudaStream_t st, float* ms_out) {
+    ScopedEvents ev;
+    if (ev.init()) return 1;
+    run();
+    float best = 1e30f;
+    for (int rep = 0; rep < 2; ++rep) {
+        CU_TRY(cudaEventRecord(ev.e0, st));
+        run();
+        CU_TRY(cudaEventRecord(ev.e1, st));
+        CU_TRY(cudaEventSynchronize(ev.e1));
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+        best = std::min(best, ms);
+    }
+    *ms_out = best;
+    return 0;
+}
+
 static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
+    for (int c = 0; c < N_CAND; ++c) m->tuned_ms[c] = -1.f;
+    const bool big = m->NZ >= (1u << 20);  // a second copy of the matrix (10.x B per non-zero) only when the matrix is big enough to matter
+    if (tune_mode() == 1) {
+        // deterministic: x-window copy if the matrix is local enough, else a nearly padding-free SELL copy, else the sub-warp kernel
+        // with the width the mean row length suggests
+        spmvb200_matrix* ch = nullptr;
+        if (big && !build_child(m, CAND_XWIN, false, &ch)) {
+            ch->xw_mode = xwin_mode_rule(ch);
+            m->xw_child = ch;
+            m->tuned = CAND_XWIN;
+        } else if (big && !build_child(m, CAND_SELL, false, &ch)) {
+            m->xw_child = ch;
+            m->tuned = CAND_SELL;
+        } else {
+            m->tuned = cand_of_lanes(m->vec_lanes);
+        }
+        return 0;
+    }
     // d_x / d_y are the caller's vectors: y is overwritten by every candidate with the same result
-    cudaEvent_t e0, e1;
-    CU_TRY(cudaEventCreate(&e0));
-    CU_TRY(cudaEventCreate(&e1));
     int best = 0;
     float best_ms = 1e30f;
     const double mean = m->M ? (double) m->NZ / (double) m->M : 0.0;
-    m->tuned_ms[CAND_XWIN] = m->tuned_ms[CAND_SELL] = -1.f;
+    const char* force = getenv("SPMVB200_FORCE_CAND");  // developer knob
     for (int c = 0; c < CAND_XWIN; ++c) {
-        m->tuned_ms[c] = -1.f;
         if (c >= 2 && (cand_lanes(c) > 4 * mean + 2 || (double) cand_lanes(c) * 64 < mean)) continue;  // hopeless widths
-        if (const char* e = getenv("SPMVB200_FORCE_CAND")) if (atoi(e) != c) continue;  // developer knob
-        launch_candidate(m, c, d_x, d_y, st);
-        float ms_min = 1e30f;
-        for (int rep = 0; rep < 2; ++rep) {
-            CU_TRY(cudaEventRecord(e0, st));
-            launch_candidate(m, c, d_x, d_y, st);
-            CU_TRY(cudaEventRecord(e1, st));
-            CU_TRY(cudaEventSynchronize(e1));
-            float ms = 0;
-            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
-            ms_min = std::min(ms_min, ms);
-        }
-        m->tuned_ms[c] = ms_min;
-        if (ms_min < best_ms) { best_ms = ms_min; best = c; }
+        if (force && atoi(force) != c) continue;
+        float ms = 0;
+        if (time_best_of_2([&] { launch_candidate(m, c, d_x, d_y, st); }, st, &ms)) return 1;
+        m->tuned_ms[c] = ms;
+        if (ms < best_ms) { best_ms = ms; best = c; }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    // x-window copy: costs a second copy of the matrix (10.x B per non-zero), so it is only built when the matrix is big
-    // enough to matter, and kept only if it beats everything else by 5 %
-    const char* force = getenv("SPMVB200_FORCE_CAND");
-    if (!getenv("SPMVB200_NO_XWINDOW") && m->NZ >= (1u << 20) && (!force || atoi(force) == CAND_XWIN)) {
-        g_quiet = 1;  // "does not fit this format" is an expected answer here, not an error to print
-        spmvb200_matrix* xw = nullptr;
-        // window traffic (L2 -> shared memory) above ~1.5x the matrix stream cannot win: stop at the tile census
-        const int rc = xwin_build(m, 0, 0, 15.0, &xw);
-        g_quiet = 0;
-        if (!rc) {
+    // x-window copy: kept only if it beats everything else by 5 %
+    if (big && (!force || atoi(force) == CAND_XWIN)) {
+        ScopedChild xw;
+        if (!build_child(m, CAND_XWIN, false, &xw.m)) {
             float ms = -1.f;
-            if (!tune_xwin(xw, d_x, d_y, st, &ms)) {
+            if (!tune_xwin(xw.m, d_x, d_y, st, &ms)) {
                 m->tuned_ms[CAND_XWIN] = ms;
-                if (ms < 0.95f * best_ms || force) { best_ms = ms; best = CAND_XWIN; }
+                if (ms < 0.95f * best_ms || force) { best_ms = ms; best = CAND_XWIN; m->xw_child = xw.release(); }
             }
-            if (best == CAND_XWIN) m->xw_child = xw; else spmvb200_free(xw);
         }
-        g_err[0] = 0;
     }
-    // SELL-32-sigma copy (a thread walks its whole row, coalesced, no shuffles).  Rows longer than VEC_MID are left out of it and go
-    // to the per-row / per-segment CTAs of the vector path (hybrid for skewed matrices); kept only while the slices stay nearly
-    // padding-free
-    if (!getenv("SPMVB200_NO_SELL") && m->NZ >= (1u << 20) && (!force || atoi(force) == CAND_SELL)) {
-        g_quiet = 1;
-        spmvb200_matrix* sell = nullptr;
-        const bool hybrid = m->lmax > (uint32_t) VEC_MID;
-        const int rc = sell_build(m, 0, hybrid ? (uint32_t) VEC_MID : 0xffffffffu, &sell);
-        g_quiet = 0;
-        if (!rc) {
-            float ms_min = 1e30f;
-            if (sell->slots <= m->NZ + m->NZ / 4) {
-                cudaEvent_t s0, s1;
-                CU_TRY(cudaEventCreate(&s0));
-                CU_TRY(cudaEventCreate(&s1));
-                launch_sell(sell, d_x, d_y, st);
-                for (int rep = 0; rep < 2; ++rep) {
-                    CU_TRY(cudaEventRecord(s0, st));
+    // SELL-32-sigma copy (a thread walks its whole row, coalesced, no shuffles)
+    if (big && (!force || atoi(force) == CAND_SELL)) {
+        ScopedChild sell;
+        if (!build_child(m, CAND_SELL, false, &sell.m)) {
+            const bool hybrid = m->lmax > (uint32_t) VEC_MID;
+            float ms = 1e30f;
+            if (time_best_of_2([&] {
                     if (hybrid) tail_fork(m, d_x, d_y, st);
-                    launch_sell(sell, d_x, d_y, st);
+                    launch_sell(sell.m, d_x, d_y, st);
                     if (hybrid) tail_join(m, st);
-                    CU_TRY(cudaEventRecord(s1, st));
-                    CU_TRY(cudaEventSynchronize(s1));
-                    float ms = 0;
-                    CU_TRY(cudaEventElapsedTime(&ms, s0, s1));
-                    ms_min = std::min(ms_min, ms);
-                }
-                cudaEventDestroy(s0);
-                cudaEventDestroy(s1);
-                m->tuned_ms[CAND_SELL] = ms_min;
-            }
-            if (ms_min < 0.95f * best_ms || (force && ms_min < 1e30f)) {
+                }, st, &ms)) return 1;
+            m->tuned_ms[CAND_SELL] = ms;
+            if (ms < 0.95f * best_ms || force) {
                 if (m->xw_child) spmvb200_free(m->xw_child);
-                m->xw_child = sell;
-                best_ms = ms_min;
+                m->xw_child = sell.release();
+                best_ms = ms;
                 best = CAND_SELL;
-            } else {
-                spmvb200_free(sell);
             }
         }
-        g_err[0] = 0;
     }
     m->tuned = best;
     if (getenv("SPMVB200_VERBOSE")) {
@@ -332,30 +406,9 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
     return 0;
 }
 
-// ---- SPMVB200_CSR_ROWS, the kind that must reproduce sgemvSerial bit for bit: the stream kernel, or -- timed at first use, for
+// ---- SPMVB200_CSR_ROWS, the kind that must reproduce sgemvSerial bit for bit: the stream kernel, or -- picked at first use, for
 // matrices of at least 2^20 non-zeros -- an x-window copy (column-sorted rows only) or a SELL copy (no row longer than VEC_MID);
 // all three add a row's products left to right with separate mul / add roundings.
-template <typename F>
-static int time_best_of_2(F&& run, cudaStream_t st, float* ms_out) {
-    cudaEvent_t e0, e1;
-    CU_TRY(cudaEventCreate(&e0));
-    CU_TRY(cudaEventCreate(&e1));
-    run();
-    float best = 1e30f;
-    for (int rep = 0; rep < 2; ++rep) {
-        CU_TRY(cudaEventRecord(e0, st));
-        run();
-        CU_TRY(cudaEventRecord(e1, st));
-        CU_TRY(cudaEventSynchronize(e1));
-        float ms = 0;
-        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
-        best = std::min(best, ms);
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    *ms_out = best;
-    return 0;
-}
 static void launch_exact_sell(spmvb200_matrix* m, const spmvb200_matrix* sell, const double* x, double* y, cudaStream_t st) {
     const bool hybrid = m->lmax > (uint32_t) VEC_MID;  // rows the capped SELL copy left out (it does not write their y)
     if (hybrid) tail_fork(m, x, y, st, true);
@@ -363,34 +416,45 @@ static void launch_exact_sell(spmvb200_matrix* m, const spmvb200_matrix* sell, c
     if (hybrid) tail_join(m, st);
 }
 static int tune_exact(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
+    const bool big = m->NZ >= (1u << 20) && !getenv("SPMVB200_EXACT_ONLY_STREAM");  // developer knob
+    m->tuned_x_ms[0] = m->tuned_x_ms[1] = m->tuned_x_ms[2] = -1.f;
+    if (tune_mode() == 1) {
+        spmvb200_matrix* ch = nullptr;
+        if (big && !build_child(m, CAND_XWIN, true, &ch)) {
+            ch->xw_mode = xwin_mode_rule(ch);
+            m->x_child = ch;
+            m->tuned_x = CAND_XWIN;
+        } else if (big && !build_child(m, CAND_SELL, true, &ch)) {
+            m->x_child = ch;
+            m->tuned_x = CAND_SELL;
+        } else {
+            m->tuned_x = 0;
+        }
+        return 0;
+    }
     float best_ms = 0;
     if (time_best_of_2([&] { launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles); }, st, &best_ms)) return 1;
     int best = 0;
     m->tuned_x_ms[0] = best_ms;
-    m->tuned_x_ms[1] = m->tuned_x_ms[2] = -1.f;
-    const char* only = getenv("SPMVB200_EXACT_ONLY_STREAM");  // developer knob
-    if (!only && m->NZ >= (1u << 20)) {
-        g_quiet = 1;
-        spmvb200_matrix* xw = nullptr;
-        if (!xwin_build(m, 0, 0, 15.0, &xw)) {
+    if (big) {
+        ScopedChild xw;
+        if (!build_child(m, CAND_XWIN, true, &xw.m)) {
             float ms = 1e30f;
-            if (xw->xw_sorted && !tune_xwin(xw, d_x, d_y, st, &ms)) m->tuned_x_ms[1] = ms;
-            if (ms < 0.95f * best_ms) { best_ms = ms; best = CAND_XWIN; m->x_child = xw; } else spmvb200_free(xw);
+            if (!tune_xwin(xw.m, d_x, d_y, st, &ms)) m->tuned_x_ms[1] = ms;
+            if (ms < 0.95f * best_ms) { best_ms = ms; best = CAND_XWIN; m->x_child = xw.release(); }
         }
         // rows longer than VEC_MID are left out of the SELL copy: a warp each adds them in the serial order next to it (exact hybrid);
-        // rows longer than a tile are split into segments as in the stream kernel (deterministic, within tolerance)
-        spmvb200_matrix* sell = nullptr;
-        if (!getenv("SPMVB200_NO_SELL") && !sell_build(m, 0, m->lmax <= (uint32_t) VEC_MID ? 0xffffffffu : (uint32_t) VEC_MID, &sell)) {
+        // rows longer than a tile are walked by one CTA with the running sum carried through (csr_longrow_exact_kernel)
+        ScopedChild sell;
+        if (!build_child(m, CAND_SELL, true, &sell.m)) {
             float ms = 1e30f;
-            if (sell->slots <= m->NZ + m->NZ / 4 && !time_best_of_2([&] { launch_exact_sell(m, sell, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
+            if (!time_best_of_2([&] { launch_exact_sell(m, sell.m, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
             const char* f = getenv("SPMVB200_FORCE_EXACT");  // developer knob (tests): 13 = keep the SELL copy whatever the timing says
             if (ms < 0.95f * best_ms || (f && atoi(f) == CAND_SELL && ms < 1e30f)) {
                 if (m->x_child) spmvb200_free(m->x_child);
-                best_ms = ms; best = CAND_SELL; m->x_child = sell;
-            } else spmvb200_free(sell);
+                best_ms = ms; best = CAND_SELL; m->x_child = sell.release();
+            }
         }
-        g_quiet = 0;
-        g_err[0] = 0;
     }
     m->tuned_x = best;
     if (getenv("SPMVB200_VERBOSE"))
@@ -402,28 +466,52 @@ static int tune_exact(spmvb200_matrix* m, const double* d_x, double* d_y, cudaSt
 // ---- SPMVB200_ELL_ROWS on a padded matrix: the column-major kernel exits early per WARP (a warp runs to the longest of its rows), so one
 // long row among 64 short ones keeps the warp's slot busy for K dependent round trips.  When the ELL rectangle is at least 1.25 x the
 // non-zeros, a SELL-32-sigma copy (rows sorted by length inside windows: warps see equal lengths) is built from the ELL arrays on the
-// device and timed against the column-major kernel at first use; it is kept only if it wins by 5 %.  Both add a row's products left
-// to right with separate mul / add roundings: bit-identical results either way.  tuned_x: 0 = column-major ELL, CAND_SELL = the copy.
+// device and timed against the column-major kernel at first use; it is kept only if it wins by 5 % (deterministic mode: always kept --
+// it won every padded case of the cfg5 sweep).  Both add a row's products left to right with separate mul / add roundings:
+// bit-identical results either way.  tuned_x: 0 = column-major ELL, CAND_SELL = the copy.
 static int tune_ell(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
     m->tuned_x = 0;
     if (getenv("SPMVB200_NO_SELL") || getenv("SPMVB200_ELL_NO_SELL") || getenv("SPMVB200_ELL_NO_EARLY_EXIT") || m->NZ < (1u << 20) || !m->rl) return 0;
     if ((double) m->K * (double) m->M < 1.25 * (double) m->NZ) return 0;
-    float ell_ms = 0;
+    m->tuned_x_ms[0] = m->tuned_x_ms[1] = m->tuned_x_ms[2] = -1.f;
+    ScopedChild sell;
+    const int quiet0 = g_quiet;
+    g_quiet = 1;
+    const int rc = sell_build(m, 0, 0xffffffffu, &sell.m);
+    g_quiet = quiet0;
+    g_err[0] = 0;
+    if (rc) return 0;
+    if (tune_mode() == 1) {
+        m->tuned_x = CAND_SELL;
+        m->x_child = sell.release();
+        return 0;
+    }
+    float ell_ms = 0, ms = 1e30f;
     if (time_best_of_2([&] { launch_ell_colmajor(m, d_x, d_y, st, 0, m->M); }, st, &ell_ms)) return 1;
     m->tuned_x_ms[0] = ell_ms;
-    m->tuned_x_ms[1] = m->tuned_x_ms[2] = -1.f;
-    g_quiet = 1;
-    spmvb200_matrix* sell = nullptr;
-    if (!sell_build(m, 0, 0xffffffffu, &sell)) {
-        float ms = 1e30f;
-        if (!time_best_of_2([&] { launch_sell(sell, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
-        if (ms < 0.95f * ell_ms) { m->tuned_x = CAND_SELL; m->x_child = sell; } else spmvb200_free(sell);
-    }
-    g_quiet = 0;
-    g_err[0] = 0;
+    if (!time_best_of_2([&] { launch_sell(sell.m, d_x, d_y, st); }, st, &ms)) m->tuned_x_ms[2] = ms;
+    if (ms < 0.95f * ell_ms) { m->tuned_x = CAND_SELL; m->x_child = sell.release(); }
     if (getenv("SPMVB200_VERBOSE"))
         fprintf(stderr, "spmv_b200: ELL tuning M=%llu K=%llu NZ=%llu -> ell=%.3fms sell=%.3fms, picked %s\n", (unsigned long long) m->M,
                 (unsigned long long) m->K, (unsigned long long) m->NZ, m->tuned_x_ms[0], m->tuned_x_ms[2], m->tuned_x ? "sell" : "ell");
+    return 0;
+}
+
+static int tune_warp(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
+    // first use: the sub-warp width guessed from the mean row length against its two neighbours (the x gather pattern
+    // decides, not the mean: 27-point stencil, mean 26.6 -> guess 16 lanes, 0.203 ms; 4 lanes: 0.141 ms)
+    m->vec_tuned = 1;
+    if (tune_mode() == 1 || getenv("SPMVB200_VEC_LANES") || m->NZ < (1u << 18)) return 0;
+    int best = m->vec_lanes;
+    float best_ms = 1e30f;
+    const int guess = m->vec_lanes;
+    for (int lanes = 2; lanes <= 32; lanes *= 2) {
+        if (lanes > 4 * guess || 4 * lanes < guess) continue;
+        float ms = 0;
+        if (time_best_of_2([&] { launch_csr_vector(m, lanes, d_x, d_y, st, 0, m->M); }, st, &ms)) return 1;
+        if (ms < best_ms) { best_ms = ms; best = lanes; }
+    }
+    m->vec_lanes = best;
     return 0;
 }
 
@@ -436,48 +524,67 @@ static void launch_ell_rowmajor(const spmvb200_matrix* m, const double* x, doubl
     ++g_launches;
 }
 
-static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, cudaStream_t st) {
-    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
-    if (m->M == 0) return 0;
+// does (handle, kind) still have its first-use pick ahead of it?
+static bool needs_tuning(const spmvb200_matrix* m, int kind) {
     switch (kind) {
         case SPMVB200_CSR_ROWS:
-            if (m->tuned_x < 0 && tune_exact(m, d_x, d_y, st)) return 1;
-            if (m->tuned_x == CAND_XWIN) { if (launch_xwin(m->x_child, d_x, d_y, st)) return 1; }
-            else if (m->tuned_x == CAND_SELL) launch_exact_sell(m, m->x_child, d_x, d_y, st);
+        case SPMVB200_ELL_ROWS: return m->tuned_x < 0;
+        case SPMVB200_CSR_ADAPTIVE: return m->tuned < 0;
+        case SPMVB200_CSR_ROWS_WARP: return !m->vec_tuned && m->format == SPMVB200_FMT_CSR;
+        case SPMVB200_XWIN_ROWS: return m->xw_mode < 0;
+        default: return false;
+    }
+}
+// Picking allocates, synchronises and (timed mode) reads events: none of that is legal on a capturing stream.
+static bool stream_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) {  // e.g. the legacy stream while another stream captures in global mode
+        cudaGetLastError();
+        return true;
+    }
+    return cs != cudaStreamCaptureStatusNone;
+}
+
+static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, cudaStream_t st, LaunchCtx* lc = nullptr) {
+    if (!spmvb200_kind_supported(m, kind)) return fail("kind %d (%s) cannot run on format %d", kind, spmvb200_kind_name(kind), m->format);
+    if (m->M == 0) return 0;
+    // A handle whose pick is still ahead of it, launched into a stream capture: run the kind's plain kernel (no allocation, no
+    // synchronisation, the handle stays untuned) -- call spmvb200_tune before capturing to get the tuned kernel into the graph.
+    const bool plain = needs_tuning(m, kind) && stream_capturing(st);
+    switch (kind) {
+        case SPMVB200_CSR_ROWS:
+            if (!plain && m->tuned_x < 0 && tune_exact(m, d_x, d_y, st)) return 1;
+            if (!plain && m->tuned_x == CAND_XWIN) { if (launch_xwin(m->x_child, d_x, d_y, st, lc)) return 1; }
+            else if (!plain && m->tuned_x == CAND_SELL) launch_exact_sell(m, m->x_child, d_x, d_y, st);
             else launch_csr_stream<false, 0>(m, d_x, d_y, st, 0, m->ntiles);
             break;
         case SPMVB200_CSR_ADAPTIVE:
-            if (m->tuned < 0 && tune_adaptive(m, d_x, d_y, st)) return 1;
-            launch_candidate(m, m->tuned, d_x, d_y, st);
+            if (!plain && m->tuned < 0 && tune_adaptive(m, d_x, d_y, st)) return 1;
+            if (plain) launch_csr_vector(m, m->vec_lanes, d_x, d_y, st, 0, m->M);
+            else launch_candidate(m, m->tuned, d_x, d_y, st, lc);
             break;
         case SPMVB200_CSR_ROWS_WARP:
-            if (!m->vec_tuned && m->format == SPMVB200_FMT_CSR) {
-                // first use: the sub-warp width guessed from the mean row length against its two neighbours (the x gather pattern
-                // decides, not the mean: 27-point stencil, mean 26.6 -> guess 16 lanes, 0.203 ms; 4 lanes: 0.141 ms)
-                m->vec_tuned = 1;
-                if (!getenv("SPMVB200_VEC_LANES") && m->NZ >= (1u << 18)) {
-                    int best = m->vec_lanes;
-                    float best_ms = 1e30f;
-                    for (int lanes = 2; lanes <= 32; lanes *= 2) {
-                        if (lanes > 4 * m->vec_lanes || 4 * lanes < m->vec_lanes) continue;
-                        float ms = 0;
-                        if (time_best_of_2([&] { launch_csr_vector(m, lanes, d_x, d_y, st, 0, m->M); }, st, &ms)) return 1;
-                        if (ms < best_ms) { best_ms = ms; best = lanes; }
-                    }
-                    m->vec_lanes = best;
-                }
-            }
+            if (!plain && !m->vec_tuned && m->format == SPMVB200_FMT_CSR && tune_warp(m, d_x, d_y, st)) return 1;
             launch_csr_vector(m, m->vec_lanes, d_x, d_y, st, 0, m->M);
             break;
         case SPMVB200_ELL_ROWS:
-            if (m->tuned_x < 0 && tune_ell(m, d_x, d_y, st)) return 1;
-            if (m->tuned_x == CAND_SELL) launch_sell(m->x_child, d_x, d_y, st);
-            else launch_ell_colmajor(m, d_x, d_y, st, 0, m->M);
+            if (!plain && m->tuned_x < 0 && tune_ell(m, d_x, d_y, st)) return 1;
+            if (!plain && m->tuned_x == CAND_SELL) launch_sell(m->x_child, d_x, d_y, st);
+            else launch_ell_colmajor(m, d_x, d_y, st, 0, m->M, lc);
             break;
-        case SPMVB200_SELL_ROWS: launch_sell(m, d_x, d_y, st); break;
+        case SPMVB200_SELL_ROWS:
+            // skewed matrix: the rows the slices leave out run as a compact CSR handle on the serial-order per-row kernels next to them
+            if (m->tail) tail_fork(m->tail, d_x, m->tail_y, st, true);
+            launch_sell(m, d_x, d_y, st);
+            if (m->tail) {
+                tail_join(m->tail, st);
+                tail_scatter_kernel<<<(unsigned) ((m->tail->M + 255) / 256), 256, 0, st>>>(m->tail_y, m->tail_map, (uint32_t) m->tail->M, d_y);
+                ++g_launches;
+            }
+            break;
         case SPMVB200_XWIN_ROWS:
-            if (m->xw_mode < 0 && tune_xwin(m, d_x, d_y, st, nullptr)) return 1;
-            if (launch_xwin(m, d_x, d_y, st)) return 1;
+            if (!plain && m->xw_mode < 0 && tune_xwin(m, d_x, d_y, st, nullptr)) return 1;
+            if (launch_xwin(m, d_x, d_y, st, lc)) return 1;
             break;
         case SPMVB200_ELL_ROWS_NT:
             switch (m->vec_lanes) {

@@ -7,10 +7,10 @@ extern "C" int spmvb200_spmv_device_push(spmvb200_matrix* m, int kind, const dou
     if (push->n < 0 || push->n > 8) return fail("spmv_device_push: %d destinations (at most 8)", push->n);
     if (prefer_smem_once()) return 1;
     // first use of a self-tuning kind: tune without deliveries (the tuning run launches every candidate)
-    if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || ((kind == SPMVB200_CSR_ROWS || kind == SPMVB200_ELL_ROWS) && m->tuned_x < 0) ||
-        (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned))
+    if (needs_tuning(m, kind) && !stream_capturing((cudaStream_t) stream))
         if (launch(m, kind, d_x, d_y, (cudaStream_t) stream)) return 1;
-    PushArgs a = {};
+    LaunchCtx lc;
+    PushArgs& a = lc.push;
     a.n = push->n;
     for (int i = 0; i < push->n; ++i) {
         if (!push->dst[i] || push->hi[i] > 0xffffffffull || push->lo[i] > push->hi[i]) return fail("spmv_device_push: bad destination %d", i);
@@ -20,11 +20,8 @@ extern "C" int spmvb200_spmv_device_push(spmvb200_matrix* m, int kind, const dou
     }
     if (push->row_offset + m->M > 0xffffffffull) return fail("spmv_device_push: row offset too large");
     a.row_offset = (uint32_t) push->row_offset;
-    g_push = a;
-    g_push_fused = false;
-    const int rc = launch(m, kind, d_x, d_y, (cudaStream_t) stream);
-    const bool fused = g_push_fused;
-    g_push = PushArgs{};
+    const int rc = launch(m, kind, d_x, d_y, (cudaStream_t) stream, &lc);
+    const bool fused = lc.fused;
     if (rc) return 1;
     if (!fused && a.n && m->M) {  // kernels without the fused epilogue: one more pass over y
         push_rows_kernel<<<592, 256, 0, (cudaStream_t) stream>>>(d_y, (uint32_t) m->M, a);
@@ -118,21 +115,20 @@ extern "C" int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a
     cudaGraphExec_t exec = nullptr;
     do {
         // self-tuning kinds tune here (cannot happen inside a capture); d_b is scratch at this point
-        if ((kind == SPMVB200_CSR_ADAPTIVE && m->tuned < 0) || (kind == SPMVB200_XWIN_ROWS && m->xw_mode < 0) || ((kind == SPMVB200_CSR_ROWS || kind == SPMVB200_ELL_ROWS) && m->tuned_x < 0) ||
-            (kind == SPMVB200_CSR_ROWS_WARP && !m->vec_tuned))
+        if (needs_tuning(m, kind))
             if ((rc = launch(m, kind, d_a, d_b, st))) break;
         const int pairs = iters / 2;
         unsigned long long per_replay = 0;
         if (use_graph && pairs > 0) {
-            const unsigned long long l0 = g_launches;
+            const unsigned long long l0 = g_launches.load();
             if ((rc = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess)) break;
             int r1 = launch(m, kind, d_a, d_b, st);
             int r2 = r1 ? 1 : launch(m, kind, d_b, d_a, st);
             cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (r1 || r2 || ce != cudaSuccess) { rc = 1; if (ce != cudaSuccess) fail("iterate_device: capture failed: %s", cudaGetErrorString(ce)); break; }
             if ((rc = cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess)) break;
-            per_replay = g_launches - l0;  // kernels inside the graph: counted per replay below
-            g_launches = l0;
+            per_replay = g_launches.load() - l0;  // kernels inside the graph: counted per replay below
+            g_launches -= per_replay;
         }
         if ((rc = cudaEventRecord(m->ev0, st) != cudaSuccess)) break;
         for (int i = 0; i < pairs && !rc; ++i) {

@@ -464,14 +464,23 @@ __global__ void push_rows_kernel(const double* __restrict__ y, uint32_t M, const
 struct BarrierArgs {
     uint32_t* flags[8];
 };
+// A peer that never arrives (crashed process, a rank that skipped the call) must not hang the GPU: after 60 s the kernel traps and the
+// stream reports a launch failure instead.
 __global__ void peer_barrier_kernel(const BarrierArgs b, int n, int rank, uint32_t epoch) {
     const int p = threadIdx.x;
     if (p >= n) return;
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(b.flags[p] + rank), "r"(epoch) : "memory");
     uint32_t seen;
+    uint64_t t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    uint32_t spins = 0;
     do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(b.flags[rank] + p) : "memory");
+        if ((++spins & 0xfffu) == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 60000000000ull) __trap();
+        }
     } while ((int32_t) (seen - epoch) < 0);
 }
 // range of (col - row) over the valid slots of a column-major ELL, then the 16-bit offsets themselves

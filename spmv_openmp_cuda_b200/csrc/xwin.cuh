@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(32 * NW, 1)
 xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb_tile0, const uint32_t* __restrict__ tile_win,
             const uint32_t* __restrict__ grp_off, const uint16_t* __restrict__ cp, const uint16_t* __restrict__ col,
             const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y, uint32_t M, uint32_t N, uint32_t W,
-            uint32_t nbuf, int x_aligned, const PushArgs push) {
+            uint32_t nbuf, int x_aligned, uint32_t rb_first, const PushArgs push) {
     constexpr uint32_t R = 32u * NW * ACC, G = NW * ACC;
     extern __shared__ __align__(128) unsigned char xw_smem[];
     double* xs = reinterpret_cast<double*>(xw_smem);                              // nbuf windows of W (+2) doubles
@@ -147,8 +147,8 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
     uint32_t* done = reinterpret_cast<uint32_t*>(full + XW_MAX_NBUF);             // [nbuf] warps that have left the slot (monotonic)
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t rb = cta_rb ? __ldg(cta_rb + blockIdx.x) : blockIdx.x;  // no split table: one row block per CTA
-    const uint32_t rb1 = cta_rb ? __ldg(cta_rb + blockIdx.x + 1) : blockIdx.x + 1;
+    uint32_t rb = cta_rb ? __ldg(cta_rb + blockIdx.x) : rb_first + blockIdx.x;  // no split table: one row block per CTA
+    const uint32_t rb1 = cta_rb ? __ldg(cta_rb + blockIdx.x + 1) : rb + 1;
     if (rb >= rb1) return;
     const uint32_t T0 = __ldg(rb_tile0 + rb), T1 = __ldg(rb_tile0 + rb1);  // this CTA's tiles
     if (threadIdx.x == 0) {

@@ -263,3 +263,99 @@ class RowBlockIterate:
             self.dist.barrier(group=self.group)
             for v in self.bufs + [self.flags]:
                 v.free()
+
+
+class RowBlockShard:
+    """This rank's share of a row-block partitioned square matrix, driven entirely inside the C library (spmvb200_shard_*,
+    include/spmv_b200.h): `dmat` holds rows [splits[rank], splits[rank+1]) with global column ids; x is replicated in `nbuf`
+    library-owned device buffers that the peers map through CUDA IPC.  torch.distributed only carries the one-time rendezvous
+    (the IPC handle blobs); no collective runs in the data path.
+
+      step(src, dst)          x[dst] <- A x[src]: the SpMV kernel stores the rows the peers read into THEIR x[dst], flag barrier
+      spmv_host(x_sl, y_sl)   host x slice up, halo delivered to the peers + barrier, row chunks, y slice down -- one C call
+    """
+
+    def __init__(self, dmat, splits, kind, group=None, nbuf=3, col_range=None):
+        import torch.distributed as dist
+        self.dist, self.group, self.kind, self.dmat = dist, group, kind, dmat
+        on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if on else 0
+        self.world = dist.get_world_size(group) if on else 1
+        self.splits = [int(v) for v in splits]
+        assert len(self.splits) == self.world + 1
+        self.r0, self.r1, self.N, self.nbuf = self.splits[self.rank], self.splits[self.rank + 1], dmat.N, nbuf
+        lib, C = engine.lib(), engine.C
+        sp_arr = (C.c_uint64 * (self.world + 1))(*self.splits)
+        cr = None if col_range is None else (C.c_uint64 * 2)(int(col_range[0]), int(col_range[1]))
+        h = C.c_void_p()
+        err = None
+        try:
+            engine.check(lib.spmvb200_shard_create(dmat.handle, kind, self.rank, self.world, sp_arr, nbuf, cr, C.byref(h)), "shard_create")
+            self._h = h.value
+            nb = lib.spmvb200_shard_blob_bytes(self._h)
+            blob = (C.c_ubyte * nb)()
+            engine.check(lib.spmvb200_shard_export(self._h, blob), "shard_export")
+            mine = bytes(blob)
+        except engine.SpmvB200Error as e:  # keep going: every rank must reach the agreement below
+            err, mine, self._h = e, b"", None
+        if self.world > 1:
+            allb = [None] * self.world
+            dist.all_gather_object(allb, mine, group=group)
+            if err is None and all(len(b) == len(mine) for b in allb):
+                try:
+                    joined = b"".join(allb)
+                    engine.check(lib.spmvb200_shard_connect(self._h, (C.c_ubyte * len(joined)).from_buffer_copy(joined)), "shard_connect")
+                except engine.SpmvB200Error as e:
+                    err = e
+            elif err is None:
+                err = engine.SpmvB200Error("another rank could not create its shard")
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None, group=group)
+            if not all(oks):
+                self.close(collective=False)
+                raise engine.SpmvB200Error("shard set-up failed on rank(s) %s: %s" % ([i for i, o in enumerate(oks) if not o], err))
+        elif err is not None:
+            raise err
+
+    def x_ptr(self, buf):
+        return engine.lib().spmvb200_shard_x(self._h, buf)
+
+    def set_x(self, buf, x_host):
+        """replicated x: every rank uploads the whole vector into buffer `buf`"""
+        x_host = np.ascontiguousarray(x_host, dtype=np.float64)
+        assert len(x_host) == self.N
+        engine.check(engine.lib().spmvb200_h2d(self.x_ptr(buf), engine.ptr(x_host), self.N * 8), "h2d")
+
+    @property
+    def halo_rows(self):
+        n = engine.C.c_uint64()
+        engine.check(engine.lib().spmvb200_shard_halo_rows(self._h, engine.C.byref(n)), "shard_halo_rows")
+        return n.value
+
+    def step(self, src, dst, stream=None):
+        engine.check(engine.lib().spmvb200_shard_step(self._h, src, dst, stream), "shard_step")
+
+    def spmv_host(self, x_slice, y_slice):
+        ms = engine.C.c_float(0)
+        engine.check(engine.lib().spmvb200_shard_spmv_host(self._h, engine.ptr(x_slice), engine.ptr(y_slice), engine.C.byref(ms)), "shard_spmv_host")
+        return ms.value
+
+    def rows_of(self, buf, a=None, b=None):
+        """global rows [a, b) (default: my slice) of x[buf] as a host array"""
+        a = self.r0 if a is None else a
+        b = self.r1 if b is None else b
+        out = np.empty(b - a, dtype=np.float64)
+        engine.check(engine.lib().spmvb200_sync(), "sync")
+        if b > a:
+            engine.check(engine.lib().spmvb200_d2h(engine.ptr(out), self.x_ptr(buf) + a * 8, out.nbytes), "d2h")
+        return out
+
+    def close(self, collective=True):
+        if getattr(self, "_h", None):
+            engine.check(engine.lib().spmvb200_sync(), "sync")
+            if collective and self.world > 1:
+                self.dist.barrier(group=self.group)  # nobody unmaps while a peer may still store into its buffers
+            h, self._h = self._h, None
+            engine.lib().spmvb200_shard_free(h)
+            if collective and self.world > 1:
+                self.dist.barrier(group=self.group)

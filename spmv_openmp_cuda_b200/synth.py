@@ -108,6 +108,8 @@ def csr_to_ell_host(mat):
     src/lib/parser.c:245-252).  numpy only -- a data-format helper for tests, not a compute path."""
     rl = np.diff(mat.IRP).astype(np.int64)
     K = int(rl.max()) if mat.M else 0
+    if mat.M and int(rl.min()) == K:  # every row full (cfg4: 32 per row): the row-major ELL arrays ARE the CSR arrays
+        return Spmat.ell(mat.M, mat.N, K, mat.JA, mat.AS, RL=rl.astype(np.uint64), NZ=mat.NZ)
     ja = np.zeros(mat.M * K, dtype=np.uint64)
     as_ = np.zeros(mat.M * K, dtype=np.float64)
     if mat.NZ:

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import spmv_openmp_cuda_b200 as sp  # noqa: E402
 from spmv_openmp_cuda_b200 import synth  # noqa: E402
-from spmv_openmp_cuda_b200.distributed import RowBlockIterate, row_partition_uniform  # noqa: E402
+from spmv_openmp_cuda_b200.distributed import RowBlockIterate, RowBlockShard, row_partition_uniform  # noqa: E402
 
 
 def main():
@@ -67,6 +67,44 @@ def main():
                           getattr(it, "need", None) if mat.M < 10 ** 6 else "", "OK" if flag.item() else "FAILED"), flush=True)
                 ok = ok and bool(flag.item())
                 it.close()
+
+    # ---- the same through the C-level shard (spmvb200_shard_*): device iterates and the one-call host step, every rank's slice
+    for name, spec_or_mat in (("banded", synth.banded(70000 * world, 32, 5000)), ("rmat", None)):
+        mat = synth.host_csr(spec_or_mat) if spec_or_mat is not None else synth.rmat_host_csr(14, 16)
+        splits = row_partition_uniform(mat.M, world)
+        r0, r1 = splits[rank], splits[rank + 1]
+        x0 = synth.host_vector(mat.N) * 1e4
+        ref1 = oracle.sgemv_serial(mat.IRP, mat.JA, mat.AS, x0)
+        ref3 = ref1
+        for _ in range(2):
+            ref3 = oracle.sgemv_serial(mat.IRP, mat.JA, mat.AS, ref3)
+        exact = mat.MAX_ROW_NZ <= 2048
+        for kind_name in ("csr_rows", "xwin", "ell", "adaptive"):
+            d_csr = sp.spMatCpyCSR(mat, r0, r1)
+            if kind_name in ("xwin", "ell") and mat.MAX_ROW_NZ > 255:
+                continue
+            dm, kind = {"csr_rows": (d_csr, sp.CSR_ROWS), "adaptive": (d_csr, sp.CSR_ADAPTIVE)}.get(kind_name) or \
+                ((d_csr.to_xwin(512, 1024), sp.XWIN_ROWS) if kind_name == "xwin" else (d_csr.to_ell(sp.FMT_ELL_COLMAJOR), sp.ELL_ROWS))
+            sh = RowBlockShard(dm, splits, kind, nbuf=3, col_range=d_csr.col_range if d_csr.NZ else (1, 0))
+            sh.set_x(0, x0)
+            sh.step(0, 1, stream)
+            sh.step(1, 2, stream)
+            sh.step(2, 1, stream)
+            torch.cuda.synchronize()
+            mine = sh.rows_of(1)
+            tol = 1e-9 * np.max(np.abs(ref3))
+            good = bool(np.array_equal(mine, ref3[r0:r1])) if (exact and kind_name != "adaptive") else bool(np.max(np.abs(mine - ref3[r0:r1]), initial=0.0) <= tol)
+            y = np.full(r1 - r0, np.nan)
+            for _ in range(3):
+                sh.spmv_host(x0[r0:r1], y)
+            good_h = bool(np.array_equal(y, ref1[r0:r1])) if (exact and kind_name != "adaptive") else bool(np.max(np.abs(y - ref1[r0:r1]), initial=0.0) <= 1e-9 * np.max(np.abs(ref1)))
+            flag = torch.tensor([1 if (good and good_h) else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print("parity shard %-7s %-8s world=%d halo_rows=%d -> %s" % (name, kind_name, world, sh.halo_rows, "OK" if flag.item() else "FAILED"), flush=True)
+            ok = ok and bool(flag.item())
+            sh.close()
+    sp.capi.lib().spmvb200_host_unregister(None)
 
     if "--parity-only" in sys.argv:
         flag = torch.tensor([1 if ok else 0], device="cuda")
