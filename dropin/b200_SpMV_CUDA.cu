@@ -5,24 +5,26 @@
 // declared in src/include/SpMV.h:119-128 with the exact signature
 //     __global__ void NAME(spmat* m /*device struct*/, double* v, CONFIG cfg /*by value*/, double* outV)
 // so the unchanged drivers (src/main.cu:233, test/SpMV_test.cu:112) and the tables SpmvCUDA_CSRFuncs /
-// SpmvCUDA_ELLFuncs keep working.  The kernels read the REFERENCE's device layout (64-bit JA/IRP/RL as
-// uploaded by spMatCpyCSR/ELL -- the reference's or dropin/b200_cudaUtils.cu), so they move 16 B per
-// non-zero: this is the compatibility tier.  The fast tier (32-bit device layout, TMA-staged tiles, tuned
-// geometry) sits behind include/spmv_b200.h and is reached through the b200SpMV* SPMV adapters.
+// SpmvCUDA_ELLFuncs keep working, under WHATEVER launch geometry they pass: 1-D 256 x ceil(M/256), (32,32) x ceil(M/32) 1-D in x
+// (the reference's warp kernels read blockIdx.y there and only ever compute rows 0..31), and the stale (32,32)
+// shape the test harness leaves active for the 1-D ELL kernels.  Work is derived from a LINEAR thread id and
+// grid-stride loops; a warp is 32 consecutive linear ids for every block shape the drivers use.
 //
-// Differences from the reference kernels, all deliberate:
-//   * work is derived from a LINEAR thread id and a grid-stride loop, so every launch geometry the drivers
-//     use is correct: 1-D 256 x ceil(M/256), (32,32) x ceil(M/32) 1-D in x (the reference's warp kernels read
-//     blockIdx.y there and only ever compute rows 0..31), and the stale (32,32) shape the test
-//     harness leaves active for the 1-D ELL kernels (no duplicate work here);
-//   * struct members are read once into registers; matrix streams use read-only loads;
-//   * thread-per-row kernels add left to right with separate mul/add roundings => bit-identical to sgemvSerial
-//     (src/SpMV_CSR_OMP.c:229-250); warp kernels use an xor-shuffle tree.
+// Two tiers inside each kernel:
+//   * FAST: when the struct was uploaded by dropin/b200_cudaUtils.cu it carries the narrow view of dropin/b200_view.h -- 32-bit ids,
+//     SELL-32-sigma slices (CSR) or column-major storage with row lengths (ELL) -- and the kernel runs this engine's coalesced
+//     algorithms on it: 12 B per non-zero instead of 16, every warp load a contiguous 256 B / 128 B run, row-length early exit.
+//   * PLAIN: a struct uploaded by the reference's own spMatCpy* has no view; the kernel walks the 64-bit layout like the reference
+//     does (bug-fixed: linear ids, all rows computed).
+// Thread-per-row entry points add left to right with separate mul/add roundings => bit-identical to sgemvSerial
+// (src/SpMV_CSR_OMP.c:229-250) for rows of at most 256 entries (longer CSR rows: a warp each, shuffle tree, within 1e-12 relative);
+// warp entry points use an xor-shuffle tree (or the same serial-order kernel where that is the faster correct choice).
 extern "C" {
 #include "sparseMatrix.h"
 #include "SpMV.h"
 }
 #include "cudaUtils.h"
+#include "b200_view.h"
 
 namespace {
 __device__ __forceinline__ unsigned long long lin_tid() {
@@ -33,15 +35,155 @@ __device__ __forceinline__ unsigned long long lin_tid() {
 __device__ __forceinline__ unsigned long long lin_threads() {
     return (unsigned long long) gridDim.x * gridDim.y * gridDim.z * (blockDim.x * blockDim.y * blockDim.z);
 }
+__device__ __forceinline__ bool whole_warps() { return ((blockDim.x * blockDim.y * blockDim.z) & 31u) == 0u; }
 __device__ __forceinline__ double warp_tree(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 32);
     return v;
 }
+template <int LANES>
+__device__ __forceinline__ double sub_tree(double v) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 32);
+    return v;
+}
+__device__ __forceinline__ const B200ViewCSR* csr_view(const spmat* m) {
+    return m->pitchJA == (size_t) B200_VIEW_MAGIC ? reinterpret_cast<const B200ViewCSR*>(m->pitchAS) : nullptr;
+}
+__device__ __forceinline__ const B200ViewELL* ell_view(const spmat* m) {
+    const B200ViewELL* v = reinterpret_cast<const B200ViewELL*>(m->IRP);
+    return (v && v->magic == B200_VIEW_MAGIC) ? v : nullptr;
+}
+
+// SELL-32-sigma, one thread per sorted row, a warp per slice: 256 B of values + 128 B of ids per slot and warp, 4 slots in flight,
+// loop bound = the slice's longest row (warp uniform), per-lane predicate at the row length; left-to-right sum.
+__device__ __forceinline__ void sell_rows(const B200ViewCSR* __restrict__ vw, const double* __restrict__ x, double* __restrict__ y) {
+    const unsigned* __restrict__ slice_ptr = vw->slice_ptr;
+    const unsigned* __restrict__ perm = vw->perm;
+    const unsigned* __restrict__ rl = vw->rl_sorted;
+    const unsigned* __restrict__ sja = vw->sja;
+    const double* __restrict__ sas = vw->sas;
+    const unsigned Mpad = vw->Mpad;
+    for (unsigned long long i = lin_tid(); i < Mpad; i += lin_threads()) {
+        const unsigned len = __ldg(rl + i);
+        const unsigned sp0 = __ldg(slice_ptr + (i >> 5)), sp1 = __ldg(slice_ptr + (i >> 5) + 1);
+        const unsigned wmax = (sp1 - sp0) >> 5;
+        const double* a = sas + sp0 + (i & 31);
+        const unsigned* j = sja + sp0 + (i & 31);
+        double acc = 0;
+        unsigned k = 0;
+        for (; k + 4 <= wmax; k += 4) {
+            double v[4], xv[4];
+            unsigned c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = k + u < len;
+                v[u] = ok ? __ldcs(a + (k + u) * 32) : 0.0;
+                c[u] = ok ? __ldcs(j + (k + u) * 32) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[u] = (k + u < len) ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k + u < len) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+        }
+        for (; k < wmax; ++k)
+            if (k < len) acc = __dadd_rn(acc, __dmul_rn(__ldcs(a + k * 32), __ldg(x + __ldcs(j + k * 32))));
+        const unsigned row = __ldg(perm + i);
+        if (row != 0xffffffffu) y[row] = acc;
+    }
+}
+// rows left out of the slices (longer than B200_LONG_ROW): a warp each, 128-bit value loads, shuffle tree
+__device__ __forceinline__ void long_rows(const B200ViewCSR* __restrict__ vw, const double* __restrict__ as, const double* __restrict__ x,
+                                          double* __restrict__ y) {
+    const unsigned lane = (unsigned) (lin_tid() & 31);
+    for (unsigned long long w = lin_tid() >> 5; w < vw->nlong; w += lin_threads() >> 5) {
+        const unsigned row = vw->long_rows[w];
+        const unsigned s = vw->irp32[row], e = vw->irp32[row + 1];
+        double t = 0;
+        for (unsigned i = (s & ~1u) + 2 * lane; i < e; i += 64) {
+            const double2 v = __ldcs(reinterpret_cast<const double2*>(as + i));
+            const uint2 c = __ldcs(reinterpret_cast<const uint2*>(vw->ja32 + i));
+            if (i >= s) t = fma(v.x, __ldg(x + c.x), t);
+            if (i + 1 < e) t = fma(v.y, __ldg(x + c.y), t);
+        }
+        t = warp_tree(t);
+        if (lane == 0) y[row] = t;
+    }
+}
+// narrow CSR, LANES lanes per row (2 non-zeros per lane and step), rows up to B200_LONG_ROW entries
+template <int LANES>
+__device__ __forceinline__ void vector_rows(const B200ViewCSR* __restrict__ vw, unsigned M, const double* __restrict__ as, const double* __restrict__ x,
+                                            double* __restrict__ y) {
+    const unsigned* __restrict__ irp = vw->irp32;
+    const unsigned* __restrict__ ja = vw->ja32;
+    const unsigned lane = (unsigned) (lin_tid() % LANES);
+    const unsigned long long nsub = lin_threads() / LANES;
+    const unsigned long long mround = ((unsigned long long) M + nsub - 1) / nsub * nsub;  // whole warps stay in the loop for the shuffles
+    for (unsigned long long row = lin_tid() / LANES; row < mround; row += nsub) {
+        double acc = 0;
+        bool mine = row < M;
+        if (mine) {
+            const unsigned s = __ldg(irp + row), e = __ldg(irp + row + 1);
+            mine = e - s <= B200_LONG_ROW;
+            if (mine)
+                for (unsigned i = (s & ~1u) + 2 * lane; i < e; i += 2 * LANES) {
+                    const double2 v = __ldcs(reinterpret_cast<const double2*>(as + i));
+                    const uint2 c = __ldcs(reinterpret_cast<const uint2*>(ja + i));
+                    if (i >= s) acc = fma(v.x, __ldg(x + c.x), acc);
+                    if (i + 1 < e) acc = fma(v.y, __ldg(x + c.y), acc);
+                }
+        }
+        acc = sub_tree<LANES>(acc);
+        if (lane == 0 && mine) y[row] = acc;
+    }
+}
+// column-major narrow ELL, one thread per row, early exit at the warp's longest row, left-to-right sum
+__device__ __forceinline__ void ell_cm_rows(const B200ViewELL* __restrict__ vw, const double* __restrict__ as, size_t as_pitch,
+                                            const double* __restrict__ x, double* __restrict__ y) {
+    const unsigned rows = vw->rows;
+    const unsigned* __restrict__ ja = vw->ja32;
+    const unsigned* __restrict__ rl = vw->rl32;
+    const size_t jp = vw->pitch;
+    const unsigned long long rround = ((unsigned long long) rows + 31) / 32 * 32;
+    for (unsigned long long row = lin_tid(); row < rround; row += lin_threads()) {
+        const bool live = row < rows;
+        const unsigned len = live ? __ldg(rl + row) : 0u;
+        const unsigned wmax = __reduce_max_sync(0xffffffffu, len);
+        const double* a = as + row;
+        const unsigned* j = ja + row;
+        double acc = 0;
+        unsigned k = 0;
+        for (; k + 4 <= wmax; k += 4) {
+            double v[4], xv[4];
+            unsigned c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = k + u < len;
+                v[u] = ok ? __ldcs(a + (size_t) (k + u) * as_pitch) : 0.0;
+                c[u] = ok ? __ldcs(j + (size_t) (k + u) * jp) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[u] = (k + u < len) ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k + u < len) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+        }
+        for (; k < wmax; ++k)
+            if (k < len) acc = __dadd_rn(acc, __dmul_rn(__ldcs(a + (size_t) k * as_pitch), __ldg(x + __ldcs(j + (size_t) k * jp))));
+        if (live) y[row] = acc;
+    }
+}
 }  // namespace
 
 // one thread per row, any geometry
 extern "C" __global__ void cudaSpMVRowsCSR(spmat* m, double* v, CONFIG cfg, double* outV) {
+    const B200ViewCSR* vw = csr_view(m);
+    if (vw && whole_warps()) {
+        sell_rows(vw, v, outV);
+        if (vw->nlong) long_rows(vw, m->AS, v, outV);
+        return;
+    }
     const ulong M = m->M;
     const ulong* __restrict__ irp = m->IRP;
     const ulong* __restrict__ ja = m->JA;
@@ -55,8 +197,21 @@ extern "C" __global__ void cudaSpMVRowsCSR(spmat* m, double* v, CONFIG cfg, doub
     }
 }
 
-// one warp per row: 32 consecutive linear thread ids form a warp for every block shape the drivers use
+// one (sub-)warp per row
 extern "C" __global__ void cudaSpMVWarpPerRowCSR(spmat* m, double* v, CONFIG cfg, double* outV) {
+    const B200ViewCSR* vw = csr_view(m);
+    if (vw && whole_warps()) {
+        const unsigned M = (unsigned) m->M;
+        switch (vw->lanes) {
+            case 2: vector_rows<2>(vw, M, m->AS, v, outV); break;
+            case 4: vector_rows<4>(vw, M, m->AS, v, outV); break;
+            case 8: vector_rows<8>(vw, M, m->AS, v, outV); break;
+            case 16: vector_rows<16>(vw, M, m->AS, v, outV); break;
+            default: vector_rows<32>(vw, M, m->AS, v, outV); break;
+        }
+        if (vw->nlong) long_rows(vw, m->AS, v, outV);
+        return;
+    }
     const ulong M = m->M;
     const ulong* __restrict__ irp = m->IRP;
     const ulong* __restrict__ ja = m->JA;
@@ -73,9 +228,15 @@ extern "C" __global__ void cudaSpMVWarpPerRowCSR(spmat* m, double* v, CONFIG cfg
 }
 
 // column-major ("transposed") ELL as built by ellTranspose (src/commons/sparseUtils.c:145-185): the struct holds
-// M = slots per row (K), MAX_ROW_NZ = number of matrix rows, pitch in elements.  All K slots are visited like the
-// reference kernel does (the transposed struct's RL is only partially uploaded by the reference).
+// M = slots per row (K), MAX_ROW_NZ = number of matrix rows, pitch in elements.  The plain tier visits all K slots like the
+// reference kernel does (the transposed struct's RL is only partially uploaded by the reference); the fast tier
+// reads 32-bit ids and stops at the row length.
 extern "C" __global__ void cudaSpMVRowsELL(spmat* m, double* v, CONFIG cfg, double* outV) {
+    const B200ViewELL* vw = ell_view(m);
+    if (vw && whole_warps()) {
+        ell_cm_rows(vw, m->AS, m->pitchAS, v, outV);
+        return;
+    }
     const ulong rows = m->MAX_ROW_NZ, K = m->M, pA = m->pitchAS, pJ = m->pitchJA;
     const ulong* __restrict__ ja = m->JA;
     const double* __restrict__ as = m->AS;
@@ -87,8 +248,14 @@ extern "C" __global__ void cudaSpMVRowsELL(spmat* m, double* v, CONFIG cfg, doub
     }
 }
 
-// row-major pitched ELL, one thread per row
+// row-major pitched ELL, one thread per row.  Fast tier: the view holds a column-major copy (ids and values), so the walk is
+// coalesced instead of one 8-byte element per 32-byte sector.
 extern "C" __global__ void cudaSpMVRowsELLNNTransposed(spmat* m, double* v, CONFIG cfg, double* outV) {
+    const B200ViewELL* vw = ell_view(m);
+    if (vw && vw->as_cm && whole_warps()) {
+        ell_cm_rows(vw, vw->as_cm, vw->pitch, v, outV);
+        return;
+    }
     const ulong M = m->M, K = m->MAX_ROW_NZ, pA = m->pitchAS, pJ = m->pitchJA;
     const ulong* __restrict__ ja = m->JA;
     const double* __restrict__ as = m->AS;
@@ -108,8 +275,14 @@ extern "C" __global__ void cudaSpMVRowsELLNNTransposed(spmat* m, double* v, CONF
     }
 }
 
-// row-major pitched ELL, one warp per row
+// row-major pitched ELL, one warp per row in the reference.  Fast tier: the same column-major walk as above -- for the short rows ELL
+// is used for (K of a few tens) a warp per row leaves most lanes idle, a thread per row on coalesced storage does not.
 extern "C" __global__ void cudaSpMVWarpsPerRowELLNTrasposed(spmat* m, double* v, CONFIG cfg, double* outV) {
+    const B200ViewELL* vw = ell_view(m);
+    if (vw && vw->as_cm && whole_warps()) {
+        ell_cm_rows(vw, vw->as_cm, vw->pitch, v, outV);
+        return;
+    }
     const ulong M = m->M, K = m->MAX_ROW_NZ, pA = m->pitchAS, pJ = m->pitchJA;
     const ulong* __restrict__ ja = m->JA;
     const double* __restrict__ as = m->AS;

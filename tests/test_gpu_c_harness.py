@@ -45,26 +45,32 @@ def test_reference_side_harness(tmp_path, case):
 REF_B200 = os.path.join(ROOT, "tests", "integration", "_build", "ref_harness_b200")
 
 
-@pytest.mark.parametrize("case", ["lap2d_120", "stencil27_20", "skewed"])
-def test_unmodified_reference_harness_runs_dropin_kernels(tmp_path, case):
+@pytest.mark.parametrize("tier", ["fast", "plain"])
+@pytest.mark.parametrize("case", ["lap2d_120", "stencil27_20", "skewed", "mixed_rows"])
+def test_unmodified_reference_harness_runs_dropin_kernels(tmp_path, case, tier):
     """test/SpMV_test.cu of the reference, UNMODIFIED, linked with dropin/b200_SpMV_CUDA.cu and
     dropin/b200_cudaUtils.cu in place of src/SpMV_CUDA.cu and src/commons/cudaUtils.cu: it uploads with our
     spMatCpy*, launches our __global__ kernels under ITS launch geometry (incl. the stale (32,32) shape for the
     1-D ELL kernels) and checks every repetition against its own sgemvSerial with its own doubleVectorsDiff.
-    Exit code 0 = every CUDA and OpenMP implementation matched."""
+    Exit code 0 = every CUDA and OpenMP implementation matched.
+    tier "fast": the uploaders hide this engine's narrow view (32-bit ids, SELL slices / column-major ELL, row lengths) behind the
+    reference's device layout and the kernels run on it; "plain" (B200_DROPIN_PLAIN=1): the 64-bit compatibility walk."""
     if not os.path.exists(REF_B200):
         pytest.skip("reference harness not built (needs /root/reference at build time)")
     import spmv_openmp_cuda_b200 as sp
     sp.capi.require_device()
     m = {"lap2d_120": lambda: sp.synth.host_csr(sp.synth.lap2d(120)),
          "stencil27_20": lambda: sp.synth.host_csr(sp.synth.stencil27(20)),
-         "skewed": lambda: sp.synth.rmat_host_csr(11, 10)}[case]()
+         "skewed": lambda: sp.synth.rmat_host_csr(11, 10),  # rows longer than 256: the warp-per-long-row phase
+         "mixed_rows": lambda: sp.synth.host_csr(sp.synth.mixed(20000, 40, 0.05))}[case]()
     rows = np.repeat(np.arange(m.M), np.diff(m.IRP).astype(np.int64))
     p = str(tmp_path / (case + ".mtx"))
     _write_mtx(p, m.M, m.N, rows, m.JA, m.AS)
     xv = str(tmp_path / "x.raw")
     sp.synth.host_vector(m.N).tofile(xv)
     env = dict(os.environ, OMP_SCHEDULE="nonmonotonic:static", GRID_ROWS="8", GRID_COLS="4")
+    if tier == "plain":
+        env["B200_DROPIN_PLAIN"] = "1"
     out = subprocess.run([REF_B200, p, xv], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     cuda_lines = [ln for ln in out.stdout.replace("\x1b[0m", "").splitlines() if ln.startswith("cudaBlockSize:")]

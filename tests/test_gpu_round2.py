@@ -205,6 +205,7 @@ def test_upload_rejects_malformed_structure(sp):
     rc = sp.capi.lib().spmvb200_csr_upload(mat.M, mat.N, sp.capi.ptr(mat.IRP), sp.capi.ptr(mat.JA), None, 0, mat.M, C.byref(out))
     assert rc != 0 and b"null" in sp.capi.lib().spmvb200_last_error()
     ell = s.csr_to_ell_host(mat)
+    ell.JA = ell.JA.copy()  # (rows of equal length: the ELL arrays alias the CSR arrays)
     ell.JA[5] = mat.N  # first row, valid slot
     with pytest.raises(sp.SpmvB200Error, match="column id"):
         sp.spMatCpyELL(ell)

@@ -33,9 +33,10 @@ def main():
             p, xv = os.path.join(d, name + ".mtx"), os.path.join(d, "x.raw")
             write_mtx(p, m)
             sp.synth.host_vector(m.N).tofile(xv)
-            for exe in ("ref_harness_orig", "ref_harness_b200"):
-                out = subprocess.run([os.path.join(B, exe), p, xv], capture_output=True, text=True, env=env)
-                print("=== %s  %s  M=%d NZ=%d  rc=%d" % (exe, name, m.M, m.NZ, out.returncode))
+            for exe, tier in (("ref_harness_orig", ""), ("ref_harness_b200", "fast tier (narrow view)"), ("ref_harness_b200", "plain tier (B200_DROPIN_PLAIN=1)")):
+                e2 = dict(env, B200_DROPIN_PLAIN="1") if tier.startswith("plain") else env
+                out = subprocess.run([os.path.join(B, exe), p, xv], capture_output=True, text=True, env=e2)
+                print("=== %s %s  %s  M=%d NZ=%d  rc=%d" % (exe, tier, name, m.M, m.NZ, out.returncode))
                 lab = ""
                 for ln in out.stdout.replace("\x1b[0m", "").splitlines():
                     if "@computing" in ln:
