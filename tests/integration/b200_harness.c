@@ -24,6 +24,7 @@
 #include "SpMV.h"
 #include "parser.h"
 #include "utils.h"
+#include "ompGetICV.h"
 #include "spmv_b200.h" /* after the reference headers: defines the b200SpMV* adapters for THIS spmat layout */
 
 #ifndef AVG_TIMES_ITERATION
@@ -65,9 +66,11 @@ int main(int argc, char** argv) {
     if (!x || !y || !oracle_y) return EXIT_FAILURE;
     spmvb200_synth_vector_host(0x5EED0077ull, 0, csr->N, 3e-5, x); /* finite, seeded; |x| < MAXRND (config.h:115) */
     sgemvSerial(csr, x, &Conf, oracle_y);
+    /* the three header lines scripts/parseLog.py splits a matrix group into (test/SpMV_test.cu:255-257, src/commons/ompGetICV.c:43) */
     printf("#%s\n", argv[1]);
     printf("SpMV_OMP_test.c\tAVG_TIMES_ITERATION:%d\tsparse matrix: %lux%lu-%luNNZ-%ld=MAX_ROW_NZ\n", AVG_TIMES_ITERATION, csr->M,
            csr->N, csr->NZ, (long) ell->MAX_ROW_NZ);
+    ompGetRuntimeSchedule(NULL);
 
     static const SPMV_INTERF csr_funcs[] = {&b200SpMVRowsCSR, &b200SpMVWarpPerRowCSR, &b200SpMVAdaptiveCSR, &b200SpMVRowsSELL};
     static const char* csr_names[] = {"B200 CSR 0 (b200SpMVRowsCSR)", "B200 CSR 1 (b200SpMVWarpPerRowCSR)", "B200 CSR 2 (b200SpMVAdaptiveCSR)",

@@ -31,7 +31,7 @@ def test_header_symbols_all_exported(sp):
 
 def test_version_and_kind_names(sp):
     L = sp.capi.lib()
-    assert L.spmvb200_version() == 100
+    assert L.spmvb200_version() == 200
     names = [L.spmvb200_kind_name(k).decode() for k in range(6)]
     assert names[0] == "CUDA_CSR_ROWS" and names[1] == "CUDA_CSR_ROWS_WARP" and names[2] == "CUDA_ELL_ROWS"
     assert names[4] == "CUDA_ELL_ROWS_WARP_NN_TRANSPOSED"  # src/include/SpMV.h:41
@@ -159,3 +159,90 @@ def test_bench_reference_arm_contract_line():
     if not torch.cuda.is_available():
         ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600)
         assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)
+
+
+# ---------------------------------------------------------------------------------------- round 2: comparators, CLI
+def test_strict_comparator_in_the_c_abi_matches_the_oracle(oracle_mod):
+    """spmvb200_compare_strict_csr / _compare_abs (host arrays, no GPU needed) against the oracle's comparators: same verdicts on
+    exact, slightly perturbed, badly perturbed and NaN outputs."""
+    import ctypes as C
+
+    from spmv_openmp_cuda_b200 import capi, synth
+    lib = capi.lib()
+    mat = synth.host_csr(synth.mixed(3000, 24, 0.2))
+    x = synth.host_vector(mat.N)
+    y_ref = oracle_mod.sgemv_serial(mat.IRP, mat.JA, mat.AS, x)
+    cases = {"exact": y_ref.copy(), "ulp": y_ref * (1 + 2e-16), "off": y_ref.copy(), "nan": y_ref.copy(), "inf": y_ref.copy()}
+    cases["off"][17] += 1e-9
+    cases["nan"][5] = np.nan
+    cases["inf"][9] = np.inf
+    for name, y in cases.items():
+        bad, worst = C.c_uint64(99), C.c_double(-1)
+        rc = lib.spmvb200_compare_strict_csr(mat.M, capi.ptr(mat.IRP), capi.ptr(mat.JA), capi.ptr(mat.AS), capi.ptr(x), capi.ptr(y_ref), capi.ptr(y), 1e-12,
+                                             C.byref(bad), C.byref(worst))
+        assert rc == 0
+        want_bad, want_worst = oracle_mod.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=1e-12)
+        assert (bad.value > 0) == (want_bad > 0) == (name in ("off", "nan", "inf")), (name, bad.value, want_bad)
+        failed, dmax = C.c_int(-1), C.c_double(-1)
+        assert lib.spmvb200_compare_abs(mat.M, capi.ptr(y_ref), capi.ptr(y), 7e-4, C.byref(failed), C.byref(dmax)) == 0
+        assert failed.value == (1 if name in ("nan", "inf") else 0), name  # 1e-9 passes the reference's absolute 7e-4; NaN must not
+    # an all-zero row with a zero output is fine, with a non-zero output it is not
+    irp = np.array([0, 0, 1], dtype=np.uint64)
+    ja, as_, xx = np.array([0], dtype=np.uint64), np.array([2.0]), np.array([3.0])
+    for y, want in ((np.array([0.0, 6.0]), 0), (np.array([1e-30, 6.0]), 1)):
+        bad = C.c_uint64(99)
+        assert lib.spmvb200_compare_strict_csr(2, capi.ptr(irp), capi.ptr(ja), capi.ptr(as_), capi.ptr(xx), capi.ptr(np.array([0.0, 6.0])), capi.ptr(y), 1e-12,
+                                               C.byref(bad), None) == 0
+        assert bad.value == want
+
+
+def _write_mtx(path, m):
+    rows = np.repeat(np.arange(m.M), np.diff(m.IRP).astype(np.int64))
+    with open(path, "w") as f:
+        f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (m.M, m.N, m.NZ))
+        for r, c, v in zip(rows, m.JA, m.AS):
+            f.write("%d %d %.17g\n" % (r + 1, c + 1, v))
+
+
+def test_cli_driver_modes_on_cpu(tmp_path):
+    """tests/integration/b200_main: the reference's command line (src/main.cu:69-139).  Without a GPU the OMP modes run (they are
+    the unmodified reference functions), the B200 modes fail LOUDLY (no CPU fallback), an unknown mode prints the usage."""
+    import subprocess
+
+    from spmv_openmp_cuda_b200 import synth
+    exe = os.path.join(ROOT, "tests", "integration", "_build", "b200_main")
+    if not os.path.exists(exe):
+        pytest.skip("b200_main not built (needs /root/reference at build time)")
+    p = str(tmp_path / "m.mtx")
+    _write_mtx(p, synth.host_csr(synth.lap2d(40)))
+    env = dict(os.environ, OMP_SCHEDULE="nonmonotonic:static", CUDA_VISIBLE_DEVICES="")
+    for mode in ("CSR_ROWS", "CSR_ROWS_GROUPS", "ELL_ROWS_GROUPS"):
+        out = subprocess.run([exe, p, "RNDVECT", mode, "--check"], capture_output=True, text=True, env=env, timeout=120)
+        assert out.returncode == 0, out.stderr[-500:]
+        assert "cmode:" in out.stdout and "elapsedInternal" in out.stdout and "doubleVectorsDiff ok" in out.stdout
+    for mode in ("B200_CSR_ROWS", "CUDA_CSR_ROWS_WARP", "B200_ELL_ROWS"):
+        out = subprocess.run([exe, p, "RNDVECT", mode], capture_output=True, text=True, env=env, timeout=120)
+        assert out.returncode != 0 and "no CUDA device" in out.stderr, (mode, out.stderr[-500:])
+    out = subprocess.run([exe, p, "RNDVECT", "NOT_A_MODE"], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode != 0 and "INVALID COMPUTE_MODE" in out.stderr and "B200_CSR_ADAPTIVE" in out.stderr
+
+
+def test_reference_log_parser_reads_the_harness_log():
+    """scripts/parseLog.py of the reference, UNMODIFIED, run on a log the C harness (tests/integration/b200_harness) wrote on the
+    B200 box (committed fixture): it must yield one CSV row per B200 implementation with the matrix sizes and times filled in."""
+    import subprocess
+    import sys
+    parser = "/root/reference/scripts/parseLog.py"
+    log = os.path.join(ROOT, "tests", "golden", "b200_harness_lap2d_150.log")
+    if not os.path.exists(parser) or not os.path.exists(log):
+        pytest.skip("needs the reference tree and the committed harness log")
+    out = subprocess.run([sys.executable, parser, log], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr[-1000:]
+    rows = [ln for ln in out.stdout.splitlines() if "B200" in ln]
+    assert len(rows) == 7, out.stdout
+    hdr = out.stdout.splitlines()[0].split(",")
+    for ln in rows:
+        f = [v.strip() for v in ln.split(",")]
+        rec = dict(zip(hdr, f))
+        assert rec["matRows"] == "22500" and rec["matCols"] == "22500" and int(rec["NNZ"]) == 5 * 150 * 150 - 4 * 150
+        assert float(rec["timeAvg"]) > 0 and rec["sampleSize"] == "5"

@@ -75,3 +75,38 @@ def test_unmodified_reference_harness_runs_dropin_kernels(tmp_path, case, tier):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     cuda_lines = [ln for ln in out.stdout.replace("\x1b[0m", "").splitlines() if ln.startswith("cudaBlockSize:")]
     assert len(cuda_lines) == 5, out.stdout[-2000:]  # 2 CSR + 3 ELL kernels (src/include/SpMV.h:130-140)
+
+
+CLI = os.path.join(ROOT, "tests", "integration", "_build", "b200_main")
+
+
+@pytest.mark.parametrize("case", ["lap2d_100", "skewed"])
+def test_cli_driver_b200_modes(tmp_path, case):
+    """tests/integration/b200_main -- the reference's command line (src/main.cu:69-139) with the engine behind it: every B200 mode
+    and the reference's own CUDA_* mode strings, each checked (--check) against the reference's sgemvSerial with the strict
+    comparator of the C ABI and with doubleVectorsDiff; the final stdout line keeps the reference's format (src/main.cu:268-269)."""
+    if not os.path.exists(CLI):
+        pytest.skip("b200_main not built (needs /root/reference at build time)")
+    import spmv_openmp_cuda_b200 as sp
+    sp.capi.require_device()
+    m = sp.synth.host_csr(sp.synth.lap2d(100)) if case == "lap2d_100" else sp.synth.rmat_host_csr(11, 10)
+    rows = np.repeat(np.arange(m.M), np.diff(m.IRP).astype(np.int64))
+    p = str(tmp_path / (case + ".mtx"))
+    _write_mtx(p, m.M, m.N, rows, m.JA, m.AS)
+    env = dict(os.environ, OMP_SCHEDULE="nonmonotonic:static")
+    modes = ["B200_CSR_ROWS", "B200_CSR_ROWS_WARP", "B200_CSR_ADAPTIVE", "B200_CSR_SELL", "B200_ELL_ROWS", "B200_ELL_ROWS_NN_TRANSPOSED",
+             "B200_ELL_ROWS_WARP_NN_TRANSPOSED", "CUDA_CSR_ROWS", "CUDA_CSR_ROWS_WARP", "CUDA_ELL_ROWS", "CUDA_ELL_ROWS_WARP_NN_TRANSPOSED"]
+    if m.MAX_ROW_NZ <= 255:
+        modes.append("B200_CSR_XWINDOW")
+    seen = {}
+    for mode in modes:
+        out = subprocess.run([CLI, p, "RNDVECT", mode, "--check"], capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0, (mode, out.stdout[-800:], out.stderr[-800:])
+        last = [ln for ln in out.stdout.splitlines() if ln.startswith("cmode:")]
+        assert len(last) == 1 and "elapsedInternal" in last[0], out.stdout[-500:]
+        assert "strict rows failing 0" in out.stdout and "doubleVectorsDiff ok" in out.stdout, out.stdout[-500:]
+        seen[mode] = int(last[0].split()[0].split(":")[1])
+        assert float(last[0].split("elapsedInternal")[1]) > 0  # the kernel's CUDA-event time reached ElapsedInternal
+    # prefix matching: the longer names are not swallowed by their prefixes, and CUDA_* map onto the same kinds
+    assert seen["B200_CSR_ROWS"] != seen["B200_CSR_ROWS_WARP"] and seen["CUDA_CSR_ROWS"] == seen["B200_CSR_ROWS"]
+    assert seen["CUDA_ELL_ROWS_WARP_NN_TRANSPOSED"] == seen["B200_ELL_ROWS_WARP_NN_TRANSPOSED"] != seen["B200_ELL_ROWS"]
