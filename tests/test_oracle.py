@@ -4,11 +4,12 @@
      the reference itself on fresh seeded inputs.
 CPU only."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden
+from conftest import ROOT, golden_names, load_golden
 
 NAMES = golden_names()
 
@@ -149,3 +150,51 @@ def test_live_reference_matches_oracle(oracle_mod, seed, M, N, mean_len):
     assert oracle_mod.ref().doubleVectorsDiff(y_ref, y2, M, C.byref(dm)) != 0
     assert oracle_mod.double_vectors_diff(y_ref, y2)[0] is True
     assert abs(dm.value - oracle_mod.double_vectors_diff(y_ref, y2)[1]) == 0.0
+
+
+def test_cblas_cross_check_of_the_oracle(oracle_mod):
+    """The reference pins sgemvSerial with a dense cblas_dgemv on small cases (test/SpMV_CBLAS.c:32-57, test/SpMV_test.cu:221-236).
+    Same check here, with the reference's own prebuilt reference-BLAS archives (oracle/_ref/cblas_check, built by
+    `make -C oracle cblas`): the restatement, the live reference and CBLAS agree on every golden fixture and on seeded random
+    matrices -- to 1e-13 relative to the row's magnitude (dgemv accumulates in another order)."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "cblas_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/cblas_check not built (needs the reference's CBLAS archives)")
+
+    def dgemv(dense, x):
+        M, N = dense.shape
+        blob = np.array([M, N], dtype=np.uint64).tobytes() + np.ascontiguousarray(dense).tobytes() + np.ascontiguousarray(x).tobytes()
+        out = subprocess.run([exe], input=blob, capture_output=True, timeout=60)
+        assert out.returncode == 0, out.stderr[-300:]
+        return np.frombuffer(out.stdout, dtype=np.float64)
+
+    cases = []
+    for name in golden_names():
+        g = load_golden(name)
+        cases.append((name, int(g["M"]), int(g["N"]), g["irp"], g["ja"], g["as_"], g["x"]))
+    rng = np.random.default_rng(5)
+    for k in range(3):
+        M, N = int(rng.integers(20, 90)), int(rng.integers(20, 90))
+        lens = rng.integers(0, min(N, 12), M)
+        irp = np.zeros(M + 1, dtype=np.uint64)
+        irp[1:] = np.cumsum(lens)
+        ja = np.concatenate([np.sort(rng.choice(N, int(n), replace=False)) for n in lens] + [np.zeros(0, int)]).astype(np.uint64)
+        cases.append(("rand%d" % k, M, N, irp, ja, rng.uniform(-1, 1, int(irp[-1])), rng.uniform(-1, 1, N)))
+    for name, M, N, irp, ja, as_, x in cases:
+        if M * N > 4_000_000:
+            continue
+        dense = np.zeros((M, N))
+        absd = np.zeros((M, N))
+        rows = np.repeat(np.arange(M), np.diff(irp).astype(np.int64))
+        np.add.at(dense, (rows, ja.astype(np.int64)), as_)  # duplicates (if any) accumulate, as CSRToDense would overwrite: fixtures have none
+        np.add.at(absd, (rows, ja.astype(np.int64)), np.abs(as_))
+        y_blas = dgemv(dense, x)
+        y_or = oracle_mod.sgemv_serial(irp, ja, as_, x)
+        scale = absd @ np.abs(x) + 1e-300
+        assert np.all(np.abs(y_blas - y_or) <= 1e-13 * scale), name
+        if oracle_mod.ref_available():
+            rm = oracle_mod.ref_spmat(M, N, int(irp[-1]), ja, as_, irp=irp, rl=np.diff(irp).astype(np.uint64))
+            y_ref = oracle_mod.ref_call("sgemvSerial", rm, x, oracle_mod.ref_config(), M)
+            np.testing.assert_array_equal(y_ref, y_or)
+            assert np.all(np.abs(y_blas - y_ref) <= 1e-13 * scale), name
