@@ -122,15 +122,99 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
 // x gather: read-only path, normal L1/L2 allocation (we WANT x to stay cached)
 __device__ __forceinline__ double ld_x(const double* x, uint32_t c) { return __ldg(x + c); }
 
+// L1 policy pair for gather-bound kernels on matrices with HOT columns (power-law graphs: the 7 296 hottest 32-byte sectors of x --
+// what a 228 KB L1 holds -- serve 46 % of R-MAT's gathers): the matrix stream must not allocate in L1 at all, x lines are kept.
+// POL = 0: the default pair above (ld.global.cs / ld.global.nc).  POL = 1: L1::no_allocate for the stream, L1::evict_last for x.
+template <int POL>
+__device__ __forceinline__ double ld_mat(const double* p) {
+    if (POL == 0) return __ldcs(p);
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+template <int POL>
+__device__ __forceinline__ uint32_t ld_mat(const uint32_t* p) {
+    if (POL == 0) return __ldcs(p);
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+template <int POL>
+__device__ __forceinline__ double2 ld_mat(const double2* p) {
+    if (POL == 0) return __ldcs(p);
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+template <int POL>
+__device__ __forceinline__ uint2 ld_mat(const uint2* p) {
+    if (POL == 0) return __ldcs(p);
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+template <int POL>
+__device__ __forceinline__ double ld_xp(const double* x, uint32_t c) {
+    if (POL == 0) return __ldg(x + c);
+    double v;
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(x + c));
+    return v;
+}
+
 // Fused output delivery (multi-GPU x <- y iterations): besides y[row], the kernel that computes a row stores it to every
 // destination that wants global row (row + row_offset) -- peer-mapped vectors of the other GPUs of the box, written over
 // NVLink as posted stores while the SpMV is still running (the all-gather is the kernel's epilogue, not a collective after it).
+// Fused NEIGHBOUR SYNCHRONISATION of the iterated step (spmvb200_shard_step): instead of a barrier kernel across all GPUs after every
+// SpMV, the SpMV kernel itself (1) waits, before its first access, until each of its nsync neighbours -- the ranks it delivers rows to
+// or receives rows from -- has finished the PREVIOUS step (my_flags[peer] >= wait_epoch: their deliveries into my x have landed, and they
+// no longer read the buffer this step overwrites), and (2) lets its last CTA to finish publish sig_epoch into every neighbour's flag
+// array (system-scope release after all CTAs' peer stores).  One launch per step, and a rank only ever waits for the ranks it actually
+// exchanges rows with, so timing jitter does not add up across the whole box the way it does under a global barrier.
 struct PushArgs {
     int n;
     double* dst[8];
     uint32_t lo[8], hi[8];
     uint32_t row_offset;
+    int nsync;               // 0: no fused synchronisation
+    uint32_t* my_flags;      // my flag array: cell p is written by rank p
+    uint32_t* peer_cell[8];  // cell [my rank] of neighbour i's flag array (peer-mapped)
+    uint8_t peer_rank[8];
+    uint32_t wait_epoch, sig_epoch;
+    uint32_t* ticket;        // device counter: CTAs of this launch that have finished (reset by the last one)
 };
+__device__ __forceinline__ void push_sync_wait(const PushArgs& p) {
+    if (p.nsync == 0) return;  // kernel-uniform
+    if (threadIdx.x == 0) {
+        uint64_t t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int i = 0; i < p.nsync; ++i) {
+            uint32_t seen, spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.my_flags + p.peer_rank[i]) : "memory");
+                if ((++spins & 0xfffu) == 0) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 60000000000ull) __trap();  // a neighbour that never arrives must not hang the GPU
+                }
+            } while ((int32_t) (seen - p.wait_epoch) < 0);
+        }
+    }
+    __syncthreads();
+}
+// every thread of every CTA of the launch must call it, after its last store
+__device__ __forceinline__ void push_sync_signal(const PushArgs& p) {
+    if (p.nsync == 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const uint32_t done = atomicAdd(p.ticket, 1u);
+        if (done == gridDim.x * gridDim.y * gridDim.z - 1u) {
+            *p.ticket = 0u;
+            __threadfence_system();
+            for (int i = 0; i < p.nsync; ++i)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_cell[i]), "r"(p.sig_epoch) : "memory");
+        }
+    }
+}
 __device__ __forceinline__ void push_out(const PushArgs& p, uint32_t row, double v) {
     const uint32_t g = row + p.row_offset;
 #pragma unroll

@@ -70,6 +70,7 @@ struct spmvb200_matrix {
     uint32_t nmid = 0;
     uint32_t* seg_tiles = nullptr;  // indices of the segment tiles (rows longer than one tile)
     uint32_t ntiles = 0, nlong = 0, nseg = 0;
+    int l1pol = 0;  // L1 policy of the gather-bound kernels on this handle (common.cuh ld_mat / ld_xp)
     int vec_lanes = 32;
     int vec_tuned = 0;  // CSR: the sub-warp width of SPMVB200_CSR_ROWS_WARP has been timed on this matrix (first use)
     // SPMVB200_CSR_ADAPTIVE: candidate chosen by the first-use tuning run (-1 = not tuned yet)

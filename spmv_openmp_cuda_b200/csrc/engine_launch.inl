@@ -9,6 +9,12 @@ struct LaunchCtx {
     PushArgs push = {};
     bool fused = false;
 };
+// L1 policy of the gather-bound kernels (common.cuh ld_mat / ld_xp): 0 default loads, 1 stream = L1::no_allocate + x = L1::evict_last.
+// Per handle (m->l1pol, picked at first use on skewed matrices); SPMVB200_L1_POLICY forces it process-wide (developer knob).
+static int l1pol_of(const spmvb200_matrix* m) {
+    static const int env = getenv("SPMVB200_L1_POLICY") ? atoi(getenv("SPMVB200_L1_POLICY")) : -1;
+    return env >= 0 ? env : m->l1pol;
+}
 static const PushArgs NO_PUSH = {};
 static inline const PushArgs& push_of(const LaunchCtx* lc) { return lc ? lc->push : NO_PUSH; }
 
@@ -69,11 +75,13 @@ static void tail_fork(spmvb200_matrix* m, const double* x, double* y, cudaStream
             csr_midrow_exact_kernel<256><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y);
             ++g_launches;
         } else if (warp_mid) {
-            csr_midrow_warp_kernel<256><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y, 0u, (uint32_t) MIDW_MAX);
+            if (l1pol_of(m)) csr_midrow_warp_kernel<256, 1><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y, 0u, (uint32_t) MIDW_MAX);
+            else csr_midrow_warp_kernel<256, 0><<<(m->nmid + 7) / 8, 256, 0, s>>>(m->mid_rows, m->nmid, m->irp, m->ja, m->as, x, y, 0u, (uint32_t) MIDW_MAX);
             ++g_launches;
         }
         if (!exact && (!warp_mid || m->lmax > (uint32_t) MIDW_MAX)) {
-            csr_midrow_kernel<128><<<m->nmid, 128, 0, s>>>(m->mid_rows, m->irp, m->ja, m->as, x, y, lo);
+            if (l1pol_of(m)) csr_midrow_kernel<128, 1><<<m->nmid, 128, 0, s>>>(m->mid_rows, m->irp, m->ja, m->as, x, y, lo);
+            else csr_midrow_kernel<128, 0><<<m->nmid, 128, 0, s>>>(m->mid_rows, m->irp, m->ja, m->as, x, y, lo);
             ++g_launches;
         }
         if (fork) cudaEventRecord(m->e_tail[0], s);
@@ -81,7 +89,8 @@ static void tail_fork(spmvb200_matrix* m, const double* x, double* y, cudaStream
     if (m->nseg) {
         cudaStream_t s = fork ? m->s_tail[1] : st;
         if (fork) cudaStreamWaitEvent(s, m->e_fork, 0);
-        csr_longrow_kernel<128><<<m->nseg, 128, 0, s>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+        if (l1pol_of(m)) csr_longrow_kernel<128, 1><<<m->nseg, 128, 0, s>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
+        else csr_longrow_kernel<128, 0><<<m->nseg, 128, 0, s>>>(m->seg_tiles, m->desc, m->longrec, m->ja, m->as, x, y, m->partial, m->ticket);
         if (fork) cudaEventRecord(m->e_tail[1], s);
         ++g_launches;
     }
@@ -99,8 +108,9 @@ static void launch_csr_vector_t(spmvb200_matrix* m, const double* x, double* y, 
     const uint64_t threads = (r1 - r0) * LANES;
     if (!threads) return;
     // whole-matrix launches leave rows longer than VEC_MID to the per-row CTAs below; row-chunk launches keep them
-    csr_vector_kernel<LANES, BLOCK><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(
-        m->irp, m->ja, m->as, x, y, (uint32_t) r0, (uint32_t) r1, (uint32_t) ((r0 == 0 && r1 == m->M) ? VEC_MID : STREAM_TILE));
+    const uint32_t maxlen = (uint32_t) ((r0 == 0 && r1 == m->M) ? VEC_MID : STREAM_TILE);
+    if (l1pol_of(m)) csr_vector_kernel<LANES, BLOCK, 1><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->irp, m->ja, m->as, x, y, (uint32_t) r0, (uint32_t) r1, maxlen);
+    else csr_vector_kernel<LANES, BLOCK, 0><<<(unsigned) ((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->irp, m->ja, m->as, x, y, (uint32_t) r0, (uint32_t) r1, maxlen);
     ++g_launches;
 }
 // vector kernel for rows up to one tile + the long-row kernel for the rest (same stream, back to back)
@@ -156,11 +166,14 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
     static const int pair_env = getenv("SPMVB200_ELL_PAIR") ? atoi(getenv("SPMVB200_ELL_PAIR")) : 3;  // developer knob: 0 = one row per thread
     if (m->ja16 && !no_exit && pair_env && (r0 % 2) == 0) {
         const unsigned g2 = (unsigned) (((r1 - r0 + 1) / 2 + BLOCK - 1) / BLOCK);
-#define ELLP(U) ell_colmajor_pair_kernel<U, BLOCK><<<g2, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, m->ja16_base, x, y, g_push)
+#define ELLP(U, S) ell_colmajor_pair_kernel<U, BLOCK, S><<<g2, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, m->ja16_base, x, y, g_push)
+        // speculative first batch (fetched before the row lengths arrive) when the rectangle is nearly full: see the kernel
+        static const bool no_spec = getenv("SPMVB200_ELL_NO_SPEC") != nullptr;  // developer knob
+        const bool spec = !no_spec && m->K >= (uint64_t) pair_env && (double) m->K * (double) m->M <= 1.15 * (double) m->NZ;
         switch (pair_env) {
-            case 2: ELLP(2); break;
-            case 3: ELLP(3); break;
-            default: ELLP(4); break;
+            case 2: if (spec) ELLP(2, true); else ELLP(2, false); break;
+            case 3: if (spec) ELLP(3, true); else ELLP(3, false); break;
+            default: if (spec) ELLP(4, true); else ELLP(4, false); break;
         }
 #undef ELLP
     } else if (m->ja16 && !no_exit) {
@@ -264,7 +277,8 @@ static int tune_xwin(spmvb200_matrix* m, const double* x, double* y, cudaStream_
 // SELL-32-sigma, thread per row.  A stand-alone SELL handle built from a CSR parent (spmvb200_sell_from_csr) leaves rows longer than
 // VEC_MID out of the slices and keeps the parent's arrays for them: those rows run on the per-row kernels next to the slices.
 static void launch_sell(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
-    sell_kernel<4, 256><<<(unsigned) ((m->Mpad + 255) / 256), 256, 0, st>>>(m->irp, m->perm, m->rl, m->as, m->ja, (uint32_t) m->Mpad, x, y);
+    if (l1pol_of(m)) sell_kernel<4, 256, 1><<<(unsigned) ((m->Mpad + 255) / 256), 256, 0, st>>>(m->irp, m->perm, m->rl, m->as, m->ja, (uint32_t) m->Mpad, x, y);
+    else sell_kernel<4, 256, 0><<<(unsigned) ((m->Mpad + 255) / 256), 256, 0, st>>>(m->irp, m->perm, m->rl, m->as, m->ja, (uint32_t) m->Mpad, x, y);
     ++g_launches;
 }
 

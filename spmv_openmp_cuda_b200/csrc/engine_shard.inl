@@ -30,6 +30,9 @@ struct spmvb200_shard {
     std::vector<std::pair<uint64_t, uint64_t>> halo;  // merged need ranges (global rows), uploaded first by the host path
     bool halo_first = false;
     uint32_t epoch = 0;
+    uint32_t* ticket = nullptr;  // finished-CTA counter of the fused neighbour synchronisation
+    int nsync = 0;               // neighbours: ranks I deliver rows to or receive rows from
+    int sync_rank[8] = {};
     double* d_y = nullptr;
     bool connected = false;
     int host_cur = 0;
@@ -50,6 +53,7 @@ extern "C" int spmvb200_shard_free(spmvb200_shard* s) {
     }
     for (int b = 0; b < 4; ++b) cudaFree(s->x[b]);
     cudaFree(s->flags);
+    cudaFree(s->ticket);
     cudaFree(s->d_y);
     if (s->e_halo) cudaEventDestroy(s->e_halo);
     delete s;
@@ -86,6 +90,8 @@ extern "C" int spmvb200_shard_create(spmvb200_matrix* m, int kind, int rank, int
         if (rc) break;
         if ((rc = cudaMalloc(&s->flags, 64) != cudaSuccess)) break;
         if ((rc = cudaMemset(s->flags, 0, 64) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&s->ticket, 64) != cudaSuccess)) break;
+        if ((rc = cudaMemset(s->ticket, 0, 64) != cudaSuccess)) break;
         if ((rc = cudaMalloc(&s->d_y, std::max<uint64_t>(m->M, 2) * 8) != cudaSuccess)) break;
         if ((rc = cudaEventCreateWithFlags(&s->e_halo, cudaEventDisableTiming) != cudaSuccess)) break;
         if (col_range) {
@@ -131,6 +137,7 @@ extern "C" int spmvb200_shard_connect(spmvb200_shard* s, const unsigned char* bl
     if (!s || !blobs) return fail("shard_connect: null argument");
     const size_t bb = spmvb200_shard_blob_bytes(s);
     s->npeer = 0;
+    s->nsync = 0;
     s->halo.clear();
     for (int p = 0; p < s->world; ++p) {
         const unsigned char* b = blobs + (size_t) p * bb;
@@ -147,6 +154,10 @@ extern "C" int spmvb200_shard_connect(spmvb200_shard* s, const unsigned char* bl
                 if (i < s->nbuf) s->peer_x[p][i] = (double*) ptr; else s->peer_flags[p] = (uint32_t*) ptr;
             }
         }
+        // neighbour = a rank that reads rows of mine, or whose rows I read (my columns reach into its slice)
+        const bool p_reads_me = lo <= hi && std::max(s->r0, lo) < std::min(s->r1, hi + 1);
+        const bool i_read_p = s->col_lo <= s->col_hi && std::max(s->splits[p], s->col_lo) < std::min(s->splits[p + 1], s->col_hi + 1);
+        if (p_reads_me || i_read_p) s->sync_rank[s->nsync++] = p;
         // rows of mine that rank p reads as columns of x: [r0, r1) intersected with its referenced column range
         if (lo > hi) continue;
         const uint64_t a = std::max(s->r0, lo), e = std::min(s->r1, hi + 1);
@@ -201,14 +212,52 @@ static void shard_push_args(const spmvb200_shard* s, int buf, spmvb200_push* p) 
     p->row_offset = s->r0;
 }
 
-// x[dst][r0..r1) = A_local * x[src]; the rows the peers read are stored into THEIR x[dst] as well; barrier.  Asynchronous on `stream`.
+// x[dst][r0..r1) = A_local * x[src]; the rows the peers read are stored into THEIR x[dst] as well.  Asynchronous on `stream`.
+// Kernels with a delivery epilogue (x-window, column-major ELL) also carry the step's synchronisation: they wait for their neighbours'
+// previous step before the first access and their last CTA publishes this step's completion (PushArgs, common.cuh) -- one launch per
+// step.  Other kinds deliver with one pass over y and pass a flag barrier across all GPUs.  Epochs advance identically on every rank.
 extern "C" int spmvb200_shard_step(spmvb200_shard* s, int src, int dst, void* stream) {
     if (!s || !s->connected) return fail("shard_step: shard not connected");
     if (src < 0 || src >= s->nbuf || dst < 0 || dst >= s->nbuf || src == dst) return fail("shard_step: bad buffers %d -> %d", src, dst);
-    spmvb200_push push;
-    shard_push_args(s, dst, &push);
-    if (spmvb200_spmv_device_push(s->m, s->kind, s->x[src], s->x[dst] + s->r0, &push, stream)) return 1;
-    return shard_barrier(s, (cudaStream_t) stream);
+    spmvb200_matrix* m = s->m;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (prefer_smem_once()) return 1;
+    if (needs_tuning(m, s->kind) && !stream_capturing(st))  // first use: pick without deliveries
+        if (launch(m, s->kind, s->x[src], s->x[dst] + s->r0, st)) return 1;
+    static const bool no_fused_sync = getenv("SPMVB200_SHARD_BARRIER") != nullptr;  // developer knob: always the separate barrier kernel
+    LaunchCtx lc;
+    PushArgs& a = lc.push;
+    a.n = s->npeer;
+    for (int i = 0; i < s->npeer; ++i) {
+        a.dst[i] = s->peer_x[s->peer_id[i]][dst];
+        a.lo[i] = (uint32_t) s->need_lo[i];
+        a.hi[i] = (uint32_t) s->need_hi[i];
+    }
+    a.row_offset = (uint32_t) s->r0;
+    if (s->world > 1 && s->nsync && !no_fused_sync) {
+        a.nsync = s->nsync;
+        a.my_flags = s->flags;
+        for (int i = 0; i < s->nsync; ++i) {
+            a.peer_rank[i] = (uint8_t) s->sync_rank[i];
+            a.peer_cell[i] = s->peer_flags[s->sync_rank[i]] + s->rank;
+        }
+        a.wait_epoch = s->epoch;      // neighbours have finished the previous exchange step
+        a.sig_epoch = s->epoch + 1;   // ... and this is what my completion looks like to them
+        a.ticket = s->ticket;
+    }
+    if (launch(m, s->kind, s->x[src], s->x[dst] + s->r0, st, &lc)) return 1;
+    if (lc.fused && a.nsync) {
+        ++s->epoch;  // the kernel carried the synchronisation
+        return 0;
+    }
+    if (!lc.fused && a.n && m->M) {  // kinds without the delivery epilogue: one more pass over y
+        PushArgs plain = a;
+        plain.nsync = 0;
+        push_rows_kernel<<<592, 256, 0, st>>>(s->x[dst] + s->r0, (uint32_t) m->M, plain);
+        ++g_launches;
+        CU_TRY(cudaPeekAtLastError());
+    }
+    return shard_barrier(s, st);
 }
 
 // Host-buffer step: x_slice = this rank's rows [r0, r1) of x (host), y_slice = the same rows of y = A x (host).  Returns when y_slice is

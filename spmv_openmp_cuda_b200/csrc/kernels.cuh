@@ -249,7 +249,7 @@ csr_stream_kernel(const TileDesc* __restrict__ desc, const LongRec* __restrict__
 // Replaces cudaSpMVWarpPerRowCSR (src/SpMV_CUDA.cu:52-73) and fixes its blockIdx.y defect
 // (SURVEY.md §2.3-1): the row comes from a linear thread id.
 // ---------------------------------------------------------------------------------------------
-template <int LANES, int BLOCK>
+template <int LANES, int BLOCK, int POL = 0>
 __global__ void __launch_bounds__(BLOCK)
 csr_vector_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as,
                   const double* __restrict__ x, double* __restrict__ y, uint32_t row_begin, uint32_t M, uint32_t max_len) {
@@ -262,10 +262,10 @@ csr_vector_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__
         mine = e - s <= max_len;  // longer rows belong to csr_longrow_kernel (same launch sequence)
         if (mine)
             for (uint32_t i = (s & ~1u) + 2 * lane; i < e; i += 2 * LANES) {
-                const double2 v = ld_stream(reinterpret_cast<const double2*>(as + i));
-                const uint2 c = ld_stream(reinterpret_cast<const uint2*>(ja + i));
-                if (i >= s) acc = fma(v.x, ld_x(x, c.x), acc);
-                if (i + 1 < e) acc = fma(v.y, ld_x(x, c.y), acc);
+                const double2 v = ld_mat<POL>(reinterpret_cast<const double2*>(as + i));
+                const uint2 c = ld_mat<POL>(reinterpret_cast<const uint2*>(ja + i));
+                if (i >= s) acc = fma(v.x, ld_xp<POL>(x, c.x), acc);
+                if (i + 1 < e) acc = fma(v.y, ld_xp<POL>(x, c.y), acc);
             }
     }
     acc = subwarp_sum<LANES>(acc);
@@ -305,7 +305,7 @@ csr_vector_span_kernel(const uint32_t* __restrict__ span_b, const uint32_t* __re
 
 // Rows longer than one tile, for the vector kernel: one CTA per <= TILE-non-zero segment (the plan's
 // segment tiles), direct coalesced loads, block sum, ordered combine by the last segment to finish.
-template <int BLOCK>
+template <int BLOCK, int POL = 0>
 __global__ void __launch_bounds__(BLOCK)
 csr_longrow_kernel(const uint32_t* __restrict__ seg_tiles, const TileDesc* __restrict__ desc, const LongRec* __restrict__ longrec,
                    const uint32_t* __restrict__ ja, const double* __restrict__ as, const double* __restrict__ x,
@@ -314,7 +314,7 @@ csr_longrow_kernel(const uint32_t* __restrict__ seg_tiles, const TileDesc* __res
     const uint32_t tid = threadIdx.x, b = seg_tiles[blockIdx.x];
     const uint32_t n0 = desc[b].nnz0, n1 = desc[b + 1].nnz0, rec_id = desc[b].aux;
     double t = 0;
-    for (uint32_t j = n0 + tid; j < n1; j += BLOCK) t = fma(ld_stream(as + j), ld_x(x, ld_stream(ja + j)), t);
+    for (uint32_t j = n0 + tid; j < n1; j += BLOCK) t = fma(ld_mat<POL>(as + j), ld_xp<POL>(x, ld_mat<POL>(ja + j)), t);
     t = subwarp_sum<32>(t);
     if ((tid & 31) == 0) s_red[tid >> 5] = t;
     __syncthreads();
@@ -353,6 +353,7 @@ ell_colmajor_kernel(const double* __restrict__ as, const void* __restrict__ ja_a
                     uint64_t pitch, uint32_t row_begin, uint32_t M, uint32_t K, int32_t base, const double* __restrict__ x, double* __restrict__ y,
                     const PushArgs push) {
     using idx_t = typename std::conditional<IDX16, uint16_t, uint32_t>::type;
+    push_sync_wait(push);
     const uint32_t row = row_begin + blockIdx.x * BLOCK + threadIdx.x;  // rows [row_begin, M)
     const bool live = row < M;
     const uint32_t len = live ? (rl ? __ldg(rl + row) : K) : 0u;
@@ -389,14 +390,21 @@ ell_colmajor_kernel(const double* __restrict__ as, const void* __restrict__ ja_a
         y[row] = acc;
         if (push.n) push_out(push, row, acc);
     }
+    push_sync_signal(push);
 }
 // Two adjacent rows per thread (IDX16 only): slot k of rows 2t, 2t+1 is one 16-byte value load and one 4-byte id load, so a thread
 // has twice the bytes in flight per load instruction -- the 16-bit kernel is bound by bytes in flight (94 % occupancy, 82 KB per SM
 // outstanding at most), not by anything else.  Same left-to-right sums, same early exit (per warp: the longest of its 64 rows).
-template <int UNROLL, int BLOCK>
+// SPEC: the first UNROLL slots are fetched BEFORE the row lengths have arrived (every row of the rectangle has them in memory:
+// padding is AS = 0, id = 0), so the length vector, the first values and the first ids travel together -- one dependent DRAM round
+// trip less per thread, which is what an isolated launch of a small matrix is made of (cfg1: 84 MB, ~13 us of streaming under
+// ~8 us of launch + latency chain).  The x gathers stay predicated on the length (a padding id is not a valid column).  The host
+// asks for it only when the rectangle is nearly full (K*M <= 1.15 NZ) and K >= UNROLL.
+template <int UNROLL, int BLOCK, bool SPEC = false>
 __global__ void __launch_bounds__(BLOCK)
 ell_colmajor_pair_kernel(const double* __restrict__ as, const uint16_t* __restrict__ ja16, const uint32_t* __restrict__ rl, uint64_t pitch,
                          uint32_t row_begin, uint32_t M, int32_t base, const double* __restrict__ x, double* __restrict__ y, const PushArgs push) {
+    push_sync_wait(push);
     const uint32_t row = row_begin + 2u * (blockIdx.x * BLOCK + threadIdx.x);  // row_begin even, pitch a multiple of 64
     const bool live0 = row < M, live1 = row + 1 < M;
     uint32_t len0 = 0, len1 = 0;
@@ -407,14 +415,35 @@ ell_colmajor_pair_kernel(const double* __restrict__ as, const uint16_t* __restri
     } else if (live0) {
         len0 = __ldg(rl + row);
     }
-    const uint32_t lmax = max(len0, len1);
-    const uint32_t wmax = __reduce_max_sync(0xffffffffu, lmax);
     const double2* a = reinterpret_cast<const double2*>(as + row);
     const uint32_t* j = reinterpret_cast<const uint32_t*>(ja16 + row);
     const uint64_t p2 = pitch >> 1;
     const uint32_t cb0 = (uint32_t) ((int32_t) row + base), cb1 = cb0 + 1u;
     double acc0 = 0, acc1 = 0;
     uint32_t k = 0;
+    if (SPEC) {
+        double2 v[UNROLL];
+        uint32_t c[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {  // issued ahead of the first use of len0 / len1: no dependence on the length loads
+            v[u] = live0 ? ld_stream(a + (uint64_t) u * p2) : make_double2(0.0, 0.0);
+            c[u] = live0 ? ld_stream(j + (uint64_t) u * p2) : 0u;
+        }
+        double x0[UNROLL], x1[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            x0[u] = ((uint32_t) u < len0) ? ld_x(x, (c[u] & 0xffffu) + cb0) : 0.0;
+            x1[u] = ((uint32_t) u < len1) ? ld_x(x, (c[u] >> 16) + cb1) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if ((uint32_t) u < len0) acc0 = __dadd_rn(acc0, __dmul_rn(v[u].x, x0[u]));
+            if ((uint32_t) u < len1) acc1 = __dadd_rn(acc1, __dmul_rn(v[u].y, x1[u]));
+        }
+        k = UNROLL;
+    }
+    const uint32_t lmax = max(len0, len1);
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, lmax);
     for (; k + UNROLL <= wmax; k += UNROLL) {
         double2 v[UNROLL];
         uint32_t c[UNROLL];
@@ -453,6 +482,7 @@ ell_colmajor_pair_kernel(const double* __restrict__ as, const uint16_t* __restri
         y[row + 1] = acc1;
         if (push.n) push_out(push, row + 1, acc1);
     }
+    push_sync_signal(push);
 }
 // kinds whose kernels have no fused delivery: copy the finished y to the destinations that want it
 __global__ void push_rows_kernel(const double* __restrict__ y, uint32_t M, const PushArgs push) {
@@ -521,7 +551,7 @@ __global__ void ell_make_idx16_kernel(const uint32_t* __restrict__ ja, const uin
 // bound = the slice length (warp uniform), per-lane predicate at the row length.  Left-to-right sum with separate
 // mul/add => bit-identical to sgemvSerial.  y is written through the permutation (scatter inside one window).
 // ---------------------------------------------------------------------------------------------
-template <int UNROLL, int BLOCK>
+template <int UNROLL, int BLOCK, int POL = 0>
 __global__ void __launch_bounds__(BLOCK)
 sell_kernel(const uint32_t* __restrict__ slice_ptr, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ rl_sorted,
             const double* __restrict__ as, const uint32_t* __restrict__ ja, uint32_t Mpad, const double* __restrict__ x,
@@ -541,18 +571,18 @@ sell_kernel(const uint32_t* __restrict__ slice_ptr, const uint32_t* __restrict__
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const bool ok = k + u < len;
-            v[u] = ok ? ld_stream(a + (k + u) * 32) : 0.0;
-            c[u] = ok ? ld_stream(j + (k + u) * 32) : 0u;
+            v[u] = ok ? ld_mat<POL>(a + (k + u) * 32) : 0.0;
+            c[u] = ok ? ld_mat<POL>(j + (k + u) * 32) : 0u;
         }
         double xv[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) xv[u] = (k + u < len) ? ld_x(x, c[u]) : 0.0;
+        for (int u = 0; u < UNROLL; ++u) xv[u] = (k + u < len) ? ld_xp<POL>(x, c[u]) : 0.0;
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
             if (k + u < len) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
     }
     for (; k < wmax; ++k)
-        if (k < len) acc = __dadd_rn(acc, __dmul_rn(ld_stream(a + k * 32), ld_x(x, ld_stream(j + k * 32))));
+        if (k < len) acc = __dadd_rn(acc, __dmul_rn(ld_mat<POL>(a + k * 32), ld_xp<POL>(x, ld_mat<POL>(j + k * 32))));
     const uint32_t row = __ldg(perm + i);
     if (row != 0xffffffffu) y[row] = acc;
 }
@@ -733,7 +763,7 @@ __global__ void csr_to_ell_kernel(const uint32_t* __restrict__ irp, const uint32
 
 // Rows of medium length (VEC_MID < len <= TILE) for the vector kernels: one CTA per listed row, so that a sub-warp
 // of the vector kernel never iterates over more than VEC_MID non-zeros while its neighbours idle.
-template <int BLOCK>
+template <int BLOCK, int POL = 0>
 __global__ void __launch_bounds__(BLOCK)
 csr_midrow_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja,
                   const double* __restrict__ as, const double* __restrict__ x, double* __restrict__ y, uint32_t len_lo) {
@@ -743,10 +773,10 @@ csr_midrow_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict_
     if (e - s <= len_lo) return;  // block-uniform: the warp-per-row kernel owns this row
     double t = 0;
     for (uint32_t i = (s & ~1u) + 2 * tid; i < e; i += 2 * BLOCK) {
-        const double2 v = ld_stream(reinterpret_cast<const double2*>(as + i));
-        const uint2 c = ld_stream(reinterpret_cast<const uint2*>(ja + i));
-        if (i >= s) t = fma(v.x, ld_x(x, c.x), t);
-        if (i + 1 < e) t = fma(v.y, ld_x(x, c.y), t);
+        const double2 v = ld_mat<POL>(reinterpret_cast<const double2*>(as + i));
+        const uint2 c = ld_mat<POL>(reinterpret_cast<const uint2*>(ja + i));
+        if (i >= s) t = fma(v.x, ld_xp<POL>(x, c.x), t);
+        if (i + 1 < e) t = fma(v.y, ld_xp<POL>(x, c.y), t);
     }
     t = subwarp_sum<32>(t);
     if ((tid & 31) == 0) s_red[tid >> 5] = t;
@@ -763,7 +793,7 @@ csr_midrow_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict_
 // CTA spends its time in the block reduction; a warp keeps 64 rows in flight per SM instead of 16.  Rows above MIDW_MAX stay with
 // the CTA-per-row kernel.
 constexpr int MIDW_MAX = 1024;  // measured on R-MAT: 1024 + CTA-per-row above it beats a warp for every medium row (290 vs 308 us)
-template <int BLOCK>
+template <int BLOCK, int POL = 0>
 __global__ void __launch_bounds__(BLOCK)
 csr_midrow_warp_kernel(const uint32_t* __restrict__ rows, uint32_t nrows, const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja,
                        const double* __restrict__ as, const double* __restrict__ x, double* __restrict__ y, uint32_t len_lo, uint32_t len_hi) {
@@ -774,10 +804,10 @@ csr_midrow_warp_kernel(const uint32_t* __restrict__ rows, uint32_t nrows, const 
     if (e - s <= len_lo || e - s > len_hi) return;  // the other medium-row kernel owns this row
     double t = 0;
     for (uint32_t i = (s & ~1u) + 2 * lane; i < e; i += 64) {
-        const double2 v = ld_stream(reinterpret_cast<const double2*>(as + i));
-        const uint2 c = ld_stream(reinterpret_cast<const uint2*>(ja + i));
-        if (i >= s) t = fma(v.x, ld_x(x, c.x), t);
-        if (i + 1 < e) t = fma(v.y, ld_x(x, c.y), t);
+        const double2 v = ld_mat<POL>(reinterpret_cast<const double2*>(as + i));
+        const uint2 c = ld_mat<POL>(reinterpret_cast<const uint2*>(ja + i));
+        if (i >= s) t = fma(v.x, ld_xp<POL>(x, c.x), t);
+        if (i + 1 < e) t = fma(v.y, ld_xp<POL>(x, c.y), t);
     }
     t = subwarp_sum<32>(t);
     if (lane == 0) y[row] = t;

@@ -149,7 +149,11 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rb = cta_rb ? __ldg(cta_rb + blockIdx.x) : rb_first + blockIdx.x;  // no split table: one row block per CTA
     const uint32_t rb1 = cta_rb ? __ldg(cta_rb + blockIdx.x + 1) : rb + 1;
-    if (rb >= rb1) return;
+    if (rb >= rb1) {  // (CTA-uniform) nothing to do, but the launch's finished-CTA count includes this CTA
+        push_sync_signal(push);
+        return;
+    }
+    push_sync_wait(push);
     const uint32_t T0 = __ldg(rb_tile0 + rb), T1 = __ldg(rb_tile0 + rb1);  // this CTA's tiles
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < nbuf; ++s) {
@@ -261,6 +265,7 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
             if (++rb < rb1) t_end = __ldg(rb_tile0 + rb + 1);
         }
     }
+    push_sync_signal(push);
 }
 
 // row blocks per persistent CTA, balanced by non-zeros: CTA i starts at the first row block whose first entry index
