@@ -165,11 +165,15 @@ __device__ __forceinline__ double ld_xp(const double* x, uint32_t c) {
 // destination that wants global row (row + row_offset) -- peer-mapped vectors of the other GPUs of the box, written over
 // NVLink as posted stores while the SpMV is still running (the all-gather is the kernel's epilogue, not a collective after it).
 // Fused NEIGHBOUR SYNCHRONISATION of the iterated step (spmvb200_shard_step): instead of a barrier kernel across all GPUs after every
-// SpMV, the SpMV kernel itself (1) waits, before its first access, until each of its nsync neighbours -- the ranks it delivers rows to
-// or receives rows from -- has finished the PREVIOUS step (my_flags[peer] >= wait_epoch: their deliveries into my x have landed, and they
-// no longer read the buffer this step overwrites), and (2) lets its last CTA to finish publish sig_epoch into every neighbour's flag
-// array (system-scope release after all CTAs' peer stores).  One launch per step, and a rank only ever waits for the ranks it actually
-// exchanges rows with, so timing jitter does not add up across the whole box the way it does under a global barrier.
+// SpMV, the SpMV kernel itself synchronises -- and only its BOUNDARY CTAs take part: the CTAs whose rows are delivered to a peer or
+// whose x windows reach outside the columns this rank owns (for a banded matrix: the row blocks within the band width of the slab's
+// two edges; every other CTA touches nothing a peer writes or reads and starts / ends as usual).  A boundary CTA
+//   (1) waits, before its first access, until each of the nsync neighbours has finished the PREVIOUS step (my_flags[peer] >=
+//       wait_epoch: their deliveries into my x have landed, and they no longer read the buffer this step's deliveries overwrite);
+//   (2) counts itself out after its last store (system-scope fence, then a ticket); the last of the nboundary boundary CTAs publishes
+//       sig_epoch into every neighbour's flag array.
+// One launch per step, no spinning or fencing in the other CTAs (a first version in which EVERY CTA polled and fenced cost +20 % at
+// 2 GPUs: 8192 one-per-SM CTAs x ~3 us of serial latency each), and a rank only ever waits for the ranks it exchanges rows with.
 struct PushArgs {
     int n;
     double* dst[8];
@@ -180,46 +184,48 @@ struct PushArgs {
     uint32_t* peer_cell[8];  // cell [my rank] of neighbour i's flag array (peer-mapped)
     uint8_t peer_rank[8];
     uint32_t wait_epoch, sig_epoch;
-    uint32_t* ticket;        // device counter: CTAs of this launch that have finished (reset by the last one)
+    uint32_t* ticket;        // device counter: boundary CTAs of this launch that have finished (reset by the last one)
+    uint32_t nboundary;      // boundary CTAs of this launch (counted once per handle and launch shape)
+    uint32_t own_lo, own_hi; // columns of x this rank owns: [own_lo, own_hi)
 };
-__device__ __forceinline__ void push_sync_wait(const PushArgs& p) {
-    if (p.nsync == 0) return;  // kernel-uniform
-    if (threadIdx.x == 0) {
-        uint64_t t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (int i = 0; i < p.nsync; ++i) {
-            uint32_t seen, spins = 0;
-            do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.my_flags + p.peer_rank[i]) : "memory");
-                if ((++spins & 0xfffu) == 0) {
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    if (t1 - t0 > 60000000000ull) __trap();  // a neighbour that never arrives must not hang the GPU
-                }
-            } while ((int32_t) (seen - p.wait_epoch) < 0);
-        }
-    }
-    __syncthreads();
-}
-// every thread of every CTA of the launch must call it, after its last store
-__device__ __forceinline__ void push_sync_signal(const PushArgs& p) {
-    if (p.nsync == 0) return;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const uint32_t done = atomicAdd(p.ticket, 1u);
-        if (done == gridDim.x * gridDim.y * gridDim.z - 1u) {
-            *p.ticket = 0u;
-            __threadfence_system();
-            for (int i = 0; i < p.nsync; ++i)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_cell[i]), "r"(p.sig_epoch) : "memory");
-        }
-    }
-}
 __device__ __forceinline__ void push_out(const PushArgs& p, uint32_t row, double v) {
     const uint32_t g = row + p.row_offset;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
         if (i < p.n && g >= p.lo[i] && g < p.hi[i]) p.dst[i][g] = v;
+}
+__device__ __forceinline__ bool push_rows_wanted(const PushArgs& p, uint32_t row_lo, uint32_t row_hi) {  // local rows [row_lo, row_hi)
+    const uint32_t a = row_lo + p.row_offset, b = row_hi + p.row_offset;
+    bool hit = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hit |= (i < p.n && a < p.hi[i] && b > p.lo[i]);
+    return hit;
+}
+// one thread of a boundary CTA, before the CTA's first access to x or to a peer
+__device__ __forceinline__ void push_sync_wait(const PushArgs& p) {
+    uint64_t t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int i = 0; i < p.nsync; ++i) {
+        uint32_t seen, spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.my_flags + p.peer_rank[i]) : "memory");
+            if ((++spins & 0xfffu) == 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) __trap();  // a neighbour that never arrives must not hang the GPU
+            }
+        } while ((int32_t) (seen - p.wait_epoch) < 0);
+    }
+}
+// one thread of a boundary CTA, after every thread of the CTA has made its last store (CTA-wide barrier before the call)
+__device__ __forceinline__ void push_sync_signal(const PushArgs& p) {
+    __threadfence_system();
+    const uint32_t done = atomicAdd(p.ticket, 1u);
+    if (done == p.nboundary - 1u) {
+        *p.ticket = 0u;
+        __threadfence_system();
+        for (int i = 0; i < p.nsync; ++i)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_cell[i]), "r"(p.sig_epoch) : "memory");
+    }
 }
 
 template <int LANES>

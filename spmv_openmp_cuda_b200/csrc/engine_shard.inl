@@ -33,6 +33,8 @@ struct spmvb200_shard {
     uint32_t* ticket = nullptr;  // finished-CTA counter of the fused neighbour synchronisation
     int nsync = 0;               // neighbours: ranks I deliver rows to or receive rows from
     int sync_rank[8] = {};
+    int nb_mode = -2;            // x-window launch shape the boundary CTAs were counted for (-2: not counted yet)
+    uint32_t nboundary = 0;
     double* d_y = nullptr;
     bool connected = false;
     int host_cur = 0;
@@ -234,16 +236,36 @@ extern "C" int spmvb200_shard_step(spmvb200_shard* s, int src, int dst, void* st
         a.hi[i] = (uint32_t) s->need_hi[i];
     }
     a.row_offset = (uint32_t) s->r0;
-    if (s->world > 1 && s->nsync && !no_fused_sync) {
+    // the x-window kernel can carry the step's synchronisation in its boundary CTAs
+    const spmvb200_matrix* xw = xwin_of(m, s->kind);
+    if (xw && s->world > 1 && s->nsync && !no_fused_sync && !stream_capturing(st)) {
         a.nsync = s->nsync;
         a.my_flags = s->flags;
         for (int i = 0; i < s->nsync; ++i) {
             a.peer_rank[i] = (uint8_t) s->sync_rank[i];
             a.peer_cell[i] = s->peer_flags[s->sync_rank[i]] + s->rank;
         }
+        a.ticket = s->ticket;
+        a.own_lo = (uint32_t) s->r0;
+        a.own_hi = (uint32_t) s->r1;
+        const int mode = xw->xw_mode == 1 ? 1 : 0;
+        if (s->nb_mode != mode) {  // count the boundary CTAs of this launch shape once
+            uint32_t* d_cnt = nullptr;
+            CU_TRY(cudaMalloc(&d_cnt, 4));
+            CU_TRY(cudaMemsetAsync(d_cnt, 0, 4, st));
+            const uint32_t ncta = mode ? xw->xw_ncta : xw->xw_nrb;
+            xw_count_boundary_kernel<<<(ncta + 255) / 256, 256, 0, st>>>(mode ? xw->xw_cta_rb : nullptr, xw->xw_rb_tile0, xw->xw_tile_win, ncta, xw->xw_R, xw->xw_W,
+                                                                        (uint32_t) xw->M, (uint32_t) xw->N, a, d_cnt);
+            cudaError_t e = cudaMemcpyAsync(&s->nboundary, d_cnt, 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            cudaFree(d_cnt);
+            if (e != cudaSuccess) return fail("shard_step: boundary count: %s", cudaGetErrorString(e));
+            s->nb_mode = mode;
+        }
+        a.nboundary = s->nboundary;
         a.wait_epoch = s->epoch;      // neighbours have finished the previous exchange step
         a.sig_epoch = s->epoch + 1;   // ... and this is what my completion looks like to them
-        a.ticket = s->ticket;
+        if (a.nboundary == 0) a.nsync = 0;  // cannot happen with neighbours, but never launch a kernel nobody would signal from
     }
     if (launch(m, s->kind, s->x[src], s->x[dst] + s->r0, st, &lc)) return 1;
     if (lc.fused && a.nsync) {

@@ -353,7 +353,6 @@ ell_colmajor_kernel(const double* __restrict__ as, const void* __restrict__ ja_a
                     uint64_t pitch, uint32_t row_begin, uint32_t M, uint32_t K, int32_t base, const double* __restrict__ x, double* __restrict__ y,
                     const PushArgs push) {
     using idx_t = typename std::conditional<IDX16, uint16_t, uint32_t>::type;
-    push_sync_wait(push);
     const uint32_t row = row_begin + blockIdx.x * BLOCK + threadIdx.x;  // rows [row_begin, M)
     const bool live = row < M;
     const uint32_t len = live ? (rl ? __ldg(rl + row) : K) : 0u;
@@ -390,7 +389,6 @@ ell_colmajor_kernel(const double* __restrict__ as, const void* __restrict__ ja_a
         y[row] = acc;
         if (push.n) push_out(push, row, acc);
     }
-    push_sync_signal(push);
 }
 // Two adjacent rows per thread (IDX16 only): slot k of rows 2t, 2t+1 is one 16-byte value load and one 4-byte id load, so a thread
 // has twice the bytes in flight per load instruction -- the 16-bit kernel is bound by bytes in flight (94 % occupancy, 82 KB per SM
@@ -404,7 +402,6 @@ template <int UNROLL, int BLOCK, bool SPEC = false>
 __global__ void __launch_bounds__(BLOCK)
 ell_colmajor_pair_kernel(const double* __restrict__ as, const uint16_t* __restrict__ ja16, const uint32_t* __restrict__ rl, uint64_t pitch,
                          uint32_t row_begin, uint32_t M, int32_t base, const double* __restrict__ x, double* __restrict__ y, const PushArgs push) {
-    push_sync_wait(push);
     const uint32_t row = row_begin + 2u * (blockIdx.x * BLOCK + threadIdx.x);  // row_begin even, pitch a multiple of 64
     const bool live0 = row < M, live1 = row + 1 < M;
     uint32_t len0 = 0, len1 = 0;
@@ -482,7 +479,6 @@ ell_colmajor_pair_kernel(const double* __restrict__ as, const uint16_t* __restri
         y[row + 1] = acc1;
         if (push.n) push_out(push, row + 1, acc1);
     }
-    push_sync_signal(push);
 }
 // kinds whose kernels have no fused delivery: copy the finished y to the destinations that want it
 __global__ void push_rows_kernel(const double* __restrict__ y, uint32_t M, const PushArgs push) {
@@ -494,7 +490,7 @@ __global__ void push_rows_kernel(const double* __restrict__ y, uint32_t M, const
 struct BarrierArgs {
     uint32_t* flags[8];
 };
-// A peer that never arrives (crashed process, a rank that skipped the call) must not hang the GPU: after 60 s the kernel traps and the
+// A peer that never arrives (crashed process, a rank that skipped the call) must not hang the GPU: after 20 s the kernel traps and the
 // stream reports a launch failure instead.
 __global__ void peer_barrier_kernel(const BarrierArgs b, int n, int rank, uint32_t epoch) {
     const int p = threadIdx.x;
@@ -509,7 +505,7 @@ __global__ void peer_barrier_kernel(const BarrierArgs b, int n, int rank, uint32
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(b.flags[rank] + p) : "memory");
         if ((++spins & 0xfffu) == 0) {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 60000000000ull) __trap();
+            if (t1 - t0 > 20000000000ull) __trap();
         }
     } while ((int32_t) (seen - epoch) < 0);
 }

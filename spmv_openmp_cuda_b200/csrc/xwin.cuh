@@ -123,6 +123,21 @@ __device__ __forceinline__ void xw_batch(double (&acc)[ACC], const double* (&pv)
         for (int a = 0; a < ACC; ++a) xw_slot_fma(acc[a], v[u][a], cc[u][a], xw);
 }
 
+// Does the CTA that owns row blocks [rb, rb1) take part in the fused neighbour synchronisation?  Yes if some of its rows are
+// delivered to a peer, or if one of its x windows reaches outside the columns this rank owns (windows are ascending per row block).
+__device__ __forceinline__ bool xw_cta_is_boundary(const PushArgs& push, uint32_t rb, uint32_t rb1, const uint32_t* __restrict__ rb_tile0,
+                                                   const uint32_t* __restrict__ tile_win, uint32_t R, uint32_t W, uint32_t M, uint32_t N) {
+    const uint64_t row_hi = min((uint64_t) rb1 * R, (uint64_t) M);
+    if (push_rows_wanted(push, rb * R, (uint32_t) row_hi)) return true;
+    for (uint32_t b = rb; b < rb1; ++b) {
+        const uint32_t t0 = __ldg(rb_tile0 + b), t1 = __ldg(rb_tile0 + b + 1);
+        if (t1 <= t0) continue;
+        const uint64_t cmin = (uint64_t) __ldg(tile_win + t0) * W, cmax = min(((uint64_t) __ldg(tile_win + t1 - 1) + 1) * W, (uint64_t) N);
+        if (cmin < push.own_lo || cmax > push.own_hi) return true;
+    }
+    return false;
+}
+
 // No producer warp and no CTA-wide barrier in the loop: every warp counts itself out of a ring slot (shared-memory
 // atomic, acq_rel); the LAST warp to leave slot s refills it with the window of tile t + nbuf.
 // Latency: the matrix stream lands in registers (shared memory belongs to the x windows).  A warp issues the loads of
@@ -149,13 +164,17 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rb = cta_rb ? __ldg(cta_rb + blockIdx.x) : rb_first + blockIdx.x;  // no split table: one row block per CTA
     const uint32_t rb1 = cta_rb ? __ldg(cta_rb + blockIdx.x + 1) : rb + 1;
-    if (rb >= rb1) {  // (CTA-uniform) nothing to do, but the launch's finished-CTA count includes this CTA
-        push_sync_signal(push);
-        return;
-    }
-    push_sync_wait(push);
+    if (rb >= rb1) return;
     const uint32_t T0 = __ldg(rb_tile0 + rb), T1 = __ldg(rb_tile0 + rb1);  // this CTA's tiles
+    __shared__ uint32_t s_boundary;
     if (threadIdx.x == 0) {
+        // fused neighbour synchronisation (common.cuh): only CTAs that deliver rows or read columns owned by a peer take part
+        bool boundary = false;
+        if (push.nsync) {
+            boundary = xw_cta_is_boundary(push, rb, rb1, rb_tile0, tile_win, R, W, M, N);
+            if (boundary) push_sync_wait(push);
+        }
+        s_boundary = boundary;
         for (uint32_t s = 0; s < nbuf; ++s) {
             mbar_init(full + s, 1);
             done[s] = 0;
@@ -265,7 +284,19 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
             if (++rb < rb1) t_end = __ldg(rb_tile0 + rb + 1);
         }
     }
-    push_sync_signal(push);
+    if (push.nsync && s_boundary) {  // CTA-uniform
+        __syncthreads();
+        if (threadIdx.x == 0) push_sync_signal(push);
+    }
+}
+
+// how many CTAs of a launch (same grid shape as xwin_kernel) are boundary CTAs: counted once per handle, mode and partition
+__global__ void xw_count_boundary_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb_tile0, const uint32_t* __restrict__ tile_win,
+                                         uint32_t ncta, uint32_t R, uint32_t W, uint32_t M, uint32_t N, const PushArgs push, uint32_t* __restrict__ count) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncta) return;
+    const uint32_t rb = cta_rb ? cta_rb[c] : c, rb1 = cta_rb ? cta_rb[c + 1] : c + 1;
+    if (rb < rb1 && xw_cta_is_boundary(push, rb, rb1, rb_tile0, tile_win, R, W, M, N)) atomicAdd(count, 1u);
 }
 
 // row blocks per persistent CTA, balanced by non-zeros: CTA i starts at the first row block whose first entry index

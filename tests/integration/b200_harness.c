@@ -51,7 +51,7 @@ static int run_impl(const char* label, SPMV_INTERF f, spmat* mat, double* x, dou
     }
     statsAvgVar(wall, AVG_TIMES_ITERATION, s_wall);
     statsAvgVar(internal, AVG_TIMES_ITERATION, s_int);
-    printf("@computing SpMV   with func: %s\n", label);
+    printf("@computing SpMV   with func: %s at:%p\n", label, (void*) f); /* "func:<id> at:<ptr>": scripts/parseLog.py:102 */
     printf("threadNum: %d\tompGridSize: %ux%u\ttimeAvg:%le timeVar:%le\ttimeInternalAvg:%le timeInternalVar:%le \n",
            omp_get_max_threads(), Conf.gridRows, Conf.gridCols, s_wall[0], s_wall[1], s_int[0], s_int[1]);
     return EXIT_SUCCESS;

@@ -245,4 +245,4 @@ def test_reference_log_parser_reads_the_harness_log():
         f = [v.strip() for v in ln.split(",")]
         rec = dict(zip(hdr, f))
         assert rec["matRows"] == "22500" and rec["matCols"] == "22500" and int(rec["NNZ"]) == 5 * 150 * 150 - 4 * 150
-        assert float(rec["timeAvg"]) > 0 and rec["sampleSize"] == "5"
+        assert float(rec["timeAvg"]) > 0 and rec["sampleSize"] in ("5", "25")  # AVG_TIMES_ITERATION of the harness build
