@@ -172,8 +172,10 @@ __device__ __forceinline__ double ld_xp(const double* x, uint32_t c) {
 //       wait_epoch: their deliveries into my x have landed, and they no longer read the buffer this step's deliveries overwrite);
 //   (2) counts itself out after its last store (system-scope fence, then a ticket); the last of the nboundary boundary CTAs publishes
 //       sig_epoch into every neighbour's flag array.
-// One launch per step, no spinning or fencing in the other CTAs (a first version in which EVERY CTA polled and fenced cost +20 % at
-// 2 GPUs: 8192 one-per-SM CTAs x ~3 us of serial latency each), and a rank only ever waits for the ranks it exchanges rows with.
+// One launch per step, no spinning or fencing in the other CTAs, and a rank only ever waits for the ranks it exchanges rows with.
+// Measured at 2 GPUs on cfg4 (1.21 ms kernel): EVERY CTA polling and fencing +20 % (8192 one-per-SM CTAs x ~3 us of serial latency);
+// boundary CTAs only, but each CTA working out whether it is one from the tile lists, +3.8 % (two more dependent loads at every CTA
+// start); a precomputed per-CTA flag: see DESIGN.md; the separate barrier kernel: +2.3 %.
 struct PushArgs {
     int n;
     double* dst[8];
@@ -186,6 +188,7 @@ struct PushArgs {
     uint32_t wait_epoch, sig_epoch;
     uint32_t* ticket;        // device counter: boundary CTAs of this launch that have finished (reset by the last one)
     uint32_t nboundary;      // boundary CTAs of this launch (counted once per handle and launch shape)
+    const uint8_t* cta_boundary;  // [grid] 1 = boundary CTA (precomputed: the kernel must not pay dependent loads to find out)
     uint32_t own_lo, own_hi; // columns of x this rank owns: [own_lo, own_hi)
 };
 __device__ __forceinline__ void push_out(const PushArgs& p, uint32_t row, double v) {

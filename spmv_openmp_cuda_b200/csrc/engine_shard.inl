@@ -35,6 +35,7 @@ struct spmvb200_shard {
     int sync_rank[8] = {};
     int nb_mode = -2;            // x-window launch shape the boundary CTAs were counted for (-2: not counted yet)
     uint32_t nboundary = 0;
+    uint8_t* cta_boundary = nullptr;  // [grid of that launch shape] 1 = boundary CTA
     double* d_y = nullptr;
     bool connected = false;
     int host_cur = 0;
@@ -56,6 +57,7 @@ extern "C" int spmvb200_shard_free(spmvb200_shard* s) {
     for (int b = 0; b < 4; ++b) cudaFree(s->x[b]);
     cudaFree(s->flags);
     cudaFree(s->ticket);
+    cudaFree(s->cta_boundary);
     cudaFree(s->d_y);
     if (s->e_halo) cudaEventDestroy(s->e_halo);
     delete s;
@@ -254,8 +256,11 @@ extern "C" int spmvb200_shard_step(spmvb200_shard* s, int src, int dst, void* st
             CU_TRY(cudaMalloc(&d_cnt, 4));
             CU_TRY(cudaMemsetAsync(d_cnt, 0, 4, st));
             const uint32_t ncta = mode ? xw->xw_ncta : xw->xw_nrb;
+            cudaFree(s->cta_boundary);
+            s->cta_boundary = nullptr;
+            CU_TRY(cudaMalloc(&s->cta_boundary, std::max<uint32_t>(ncta, 1)));
             xw_count_boundary_kernel<<<(ncta + 255) / 256, 256, 0, st>>>(mode ? xw->xw_cta_rb : nullptr, xw->xw_rb_tile0, xw->xw_tile_win, ncta, xw->xw_R, xw->xw_W,
-                                                                        (uint32_t) xw->M, (uint32_t) xw->N, a, d_cnt);
+                                                                        (uint32_t) xw->M, (uint32_t) xw->N, a, d_cnt, s->cta_boundary);
             cudaError_t e = cudaMemcpyAsync(&s->nboundary, d_cnt, 4, cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
             cudaFree(d_cnt);
@@ -263,6 +268,7 @@ extern "C" int spmvb200_shard_step(spmvb200_shard* s, int src, int dst, void* st
             s->nb_mode = mode;
         }
         a.nboundary = s->nboundary;
+        a.cta_boundary = s->cta_boundary;
         a.wait_epoch = s->epoch;      // neighbours have finished the previous exchange step
         a.sig_epoch = s->epoch + 1;   // ... and this is what my completion looks like to them
         if (a.nboundary == 0) a.nsync = 0;  // cannot happen with neighbours, but never launch a kernel nobody would signal from

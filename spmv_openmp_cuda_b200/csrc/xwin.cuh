@@ -169,11 +169,8 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
     __shared__ uint32_t s_boundary;
     if (threadIdx.x == 0) {
         // fused neighbour synchronisation (common.cuh): only CTAs that deliver rows or read columns owned by a peer take part
-        bool boundary = false;
-        if (push.nsync) {
-            boundary = xw_cta_is_boundary(push, rb, rb1, rb_tile0, tile_win, R, W, M, N);
-            if (boundary) push_sync_wait(push);
-        }
+        const bool boundary = push.nsync && push.cta_boundary[blockIdx.x];
+        if (boundary) push_sync_wait(push);
         s_boundary = boundary;
         for (uint32_t s = 0; s < nbuf; ++s) {
             mbar_init(full + s, 1);
@@ -292,11 +289,14 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
 
 // how many CTAs of a launch (same grid shape as xwin_kernel) are boundary CTAs: counted once per handle, mode and partition
 __global__ void xw_count_boundary_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb_tile0, const uint32_t* __restrict__ tile_win,
-                                         uint32_t ncta, uint32_t R, uint32_t W, uint32_t M, uint32_t N, const PushArgs push, uint32_t* __restrict__ count) {
+                                         uint32_t ncta, uint32_t R, uint32_t W, uint32_t M, uint32_t N, const PushArgs push, uint32_t* __restrict__ count,
+                                         uint8_t* __restrict__ cta_flag) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncta) return;
     const uint32_t rb = cta_rb ? cta_rb[c] : c, rb1 = cta_rb ? cta_rb[c + 1] : c + 1;
-    if (rb < rb1 && xw_cta_is_boundary(push, rb, rb1, rb_tile0, tile_win, R, W, M, N)) atomicAdd(count, 1u);
+    const bool b = rb < rb1 && xw_cta_is_boundary(push, rb, rb1, rb_tile0, tile_win, R, W, M, N);
+    cta_flag[c] = b ? 1 : 0;
+    if (b) atomicAdd(count, 1u);
 }
 
 // row blocks per persistent CTA, balanced by non-zeros: CTA i starts at the first row block whose first entry index
