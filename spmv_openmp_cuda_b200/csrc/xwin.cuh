@@ -166,8 +166,11 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
     const uint32_t rb1 = cta_rb ? __ldg(cta_rb + blockIdx.x + 1) : rb + 1;
     if (rb >= rb1) return;
     const uint32_t T0 = __ldg(rb_tile0 + rb), T1 = __ldg(rb_tile0 + rb1);  // this CTA's tiles
-    __shared__ uint32_t s_boundary;
+    __shared__ uint32_t s_boundary, s_delivers;
     if (threadIdx.x == 0) {
+        // does any row of this CTA go to a peer?  Decided once per CTA (two compares per destination, no loads): the per-row range
+        // tests of push_out in the epilogue of EVERY row were what the fused delivery cost (+2-3 % at 2 GPUs), not the stores
+        s_delivers = push.n && push_rows_wanted(push, rb * R, (uint32_t) min((uint64_t) rb1 * R, (uint64_t) M));
         // fused neighbour synchronisation (common.cuh): only CTAs that deliver rows or read columns owned by a peer take part
         const bool boundary = push.nsync && push.cta_boundary[blockIdx.x];
         if (boundary) push_sync_wait(push);
@@ -181,6 +184,7 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
         mbar_fence_init();
     }
     __syncthreads();
+    const bool delivers = s_delivers != 0;
     const uint64_t pol = policy_evict_last();
     if (warp == 0)
         for (uint32_t i = 0; i < nbuf && T0 + i < T1; ++i)
@@ -208,7 +212,7 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
             const uint32_t row = rb * R + a * NW * 32u + myrow;
             if (row < M) {
                 y[row] = 0.0;
-                if (push.n) push_out(push, row, 0.0);
+                if (delivers) push_out(push, row, 0.0);
             }
         }
         if (++rb < rb1) t_end = __ldg(rb_tile0 + rb + 1);
@@ -274,7 +278,7 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
                 const uint32_t row = rb * R + a * NW * 32u + myrow;
                 if (row < M) {
                     y[row] = acc[a];
-                    if (push.n) push_out(push, row, acc[a]);
+                    if (delivers) push_out(push, row, acc[a]);
                 }
                 acc[a] = 0.0;
             }
