@@ -420,19 +420,27 @@ def main():
         capi.check(lib.spmvb200_spmv_device(dm.handle, kind, X0, shard.x_ptr(2), stream), "spmv_device")
 
     def timed(fn, steps, warm):
+        """W untimed warm-up steps, barrier + synchronize, then EXACTLY `steps` steps between two CUDA events on the launch stream,
+        barrier + synchronize again; max over ranks.  Nothing but event records sits between the barrier and the first timed step
+        (the NVML sampler thread and the events exist before it), and the ranks' STREAMS are aligned by one flag barrier across
+        the GPUs right before the first event: with a step that exchanges data every step, host-side skew between the ranks'
+        start would otherwise be paid by the early ranks as waiting inside their timed region (measured at 8 GPUs, 20 steps of
+        0.32 ms: +50 % from NVML initialisation alone sitting after the barrier)."""
+        sampler = ClockSampler(local_rank).start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(warm):
             fn()
         sync_all()
         l0 = lib.spmvb200_launch_count()
-        sampler = ClockSampler(local_rank).start()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            shard.barrier(stream)
         ev0.record()
         for _ in range(steps):
             fn()
         ev1.record()
         sync_all()
         clocks = sampler.stop()
-        return allmax(ev0.elapsed_time(ev1)) / steps, int(lib.spmvb200_launch_count() - l0), clocks
+        return allmax(ev0.elapsed_time(ev1)) / steps, int(lib.spmvb200_launch_count() - l0) - (1 if world > 1 else 0), clocks
 
     ms_step, launches, clocks = timed(step, args.steps, args.warmup)
     ms_kernel = ms_step

@@ -217,6 +217,7 @@ int spmvb200_shard_connect(spmvb200_shard* s, const unsigned char* blobs);
 double* spmvb200_shard_x(spmvb200_shard* s, int buf);
 int spmvb200_shard_halo_rows(const spmvb200_shard* s, uint64_t* rows); /* rows of mine delivered to peers per step (sum over peers) */
 int spmvb200_shard_step(spmvb200_shard* s, int src, int dst, void* stream);
+int spmvb200_shard_barrier(spmvb200_shard* s, void* stream); /* the flag barrier across the GPUs on its own; every rank calls it */
 int spmvb200_shard_spmv_host(spmvb200_shard* s, const double* x_slice, double* y_slice, float* kernel_ms);
 int spmvb200_shard_free(spmvb200_shard* s);
 

@@ -66,6 +66,7 @@ _SIGS = {
     "spmvb200_shard_x": (_vp, [_vp, C.c_int]),
     "spmvb200_shard_halo_rows": (C.c_int, [_vp, C.POINTER(_u64)]),
     "spmvb200_shard_step": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "spmvb200_shard_barrier": (C.c_int, [_vp, _vp]),
     "spmvb200_shard_spmv_host": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_float)]),
     "spmvb200_shard_free": (C.c_int, [_vp]),
     "spmvb200_host_unregister": (C.c_int, [_vp]),

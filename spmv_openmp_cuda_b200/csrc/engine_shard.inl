@@ -205,6 +205,12 @@ static int shard_barrier(spmvb200_shard* s, cudaStream_t st) {
     CU_TRY(cudaPeekAtLastError());
     return 0;
 }
+// The cross-GPU flag barrier on its own (asynchronous on `stream`): every rank's earlier work on its stream, including stores to
+// peer memory, is visible to the others' later work.  Every rank must make the call.
+extern "C" int spmvb200_shard_barrier(spmvb200_shard* s, void* stream) {
+    if (!s || !s->connected) return fail("shard_barrier: shard not connected");
+    return shard_barrier(s, (cudaStream_t) stream);
+}
 static void shard_push_args(const spmvb200_shard* s, int buf, spmvb200_push* p) {
     memset(p, 0, sizeof(*p));
     p->n = s->npeer;

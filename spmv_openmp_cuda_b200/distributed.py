@@ -335,6 +335,10 @@ class RowBlockShard:
     def step(self, src, dst, stream=None):
         engine.check(engine.lib().spmvb200_shard_step(self._h, src, dst, stream), "shard_step")
 
+    def barrier(self, stream=None):
+        """the cross-GPU flag barrier on its own, asynchronous on `stream` (every rank calls it)"""
+        engine.check(engine.lib().spmvb200_shard_barrier(self._h, stream), "shard_barrier")
+
     def spmv_host(self, x_slice, y_slice):
         ms = engine.C.c_float(0)
         engine.check(engine.lib().spmvb200_shard_spmv_host(self._h, engine.ptr(x_slice), engine.ptr(y_slice), engine.C.byref(ms)), "shard_spmv_host")
