@@ -26,6 +26,13 @@ extern "C" {
 #include "cudaUtils.h"
 #include "b200_view.h"
 
+// Register budget: the drivers launch blocks of 256 and of 32 x 32 = 1024 threads.  B200_MIN_BLOCKS = 2 (two 1024-thread blocks per SM:
+// 32 registers per thread, full occupancy) or 1 (64 registers); measured on B200 in profiles/r02*_dropin_bench.log.
+#ifndef B200_MIN_BLOCKS
+#define B200_MIN_BLOCKS 1
+#endif
+#define B200_BOUNDS __launch_bounds__(1024, B200_MIN_BLOCKS)
+
 namespace {
 __device__ __forceinline__ unsigned long long lin_tid() {
     const unsigned long long blk = blockIdx.x + (unsigned long long) gridDim.x * (blockIdx.y + (unsigned long long) gridDim.y * blockIdx.z);
@@ -64,7 +71,9 @@ __device__ __forceinline__ void sell_rows(const B200ViewCSR* __restrict__ vw, co
     const unsigned* __restrict__ sja = vw->sja;
     const double* __restrict__ sas = vw->sas;
     const unsigned Mpad = vw->Mpad;
-    for (unsigned long long i = lin_tid(); i < Mpad; i += lin_threads()) {
+    const unsigned stride = (unsigned) min(lin_threads(), 0x80000000ull);  // 32-bit index arithmetic (Mpad < 2^31): registers matter here
+    if (lin_tid() >= Mpad) return;
+    for (unsigned i = (unsigned) lin_tid(); i < Mpad; i += stride) {
         const unsigned len = __ldg(rl + i);
         const unsigned sp0 = __ldg(slice_ptr + (i >> 5)), sp1 = __ldg(slice_ptr + (i >> 5) + 1);
         const unsigned wmax = (sp1 - sp0) >> 5;
@@ -117,10 +126,13 @@ __device__ __forceinline__ void vector_rows(const B200ViewCSR* __restrict__ vw, 
                                             double* __restrict__ y) {
     const unsigned* __restrict__ irp = vw->irp32;
     const unsigned* __restrict__ ja = vw->ja32;
-    const unsigned lane = (unsigned) (lin_tid() % LANES);
-    const unsigned long long nsub = lin_threads() / LANES;
-    const unsigned long long mround = ((unsigned long long) M + nsub - 1) / nsub * nsub;  // whole warps stay in the loop for the shuffles
-    for (unsigned long long row = lin_tid() / LANES; row < mround; row += nsub) {
+    constexpr unsigned RPW = 32 / LANES;  // rows per warp
+    const unsigned lane = (unsigned) (lin_tid() % LANES), sub = (unsigned) ((lin_tid() & 31) / LANES);
+    const unsigned long long nwarps = lin_threads() >> 5;
+    // warp-uniform loop bound: a warp whose rows all lie beyond the matrix leaves at once (the (32,32) x ceil(M/32) geometry launches
+    // one WARP per row, 32 / LANES times more sub-warps than rows)
+    for (unsigned long long row0 = (lin_tid() >> 5) * RPW; row0 < M; row0 += nwarps * RPW) {
+        const unsigned long long row = row0 + sub;
         double acc = 0;
         bool mine = row < M;
         if (mine) {
@@ -177,7 +189,7 @@ __device__ __forceinline__ void ell_cm_rows(const B200ViewELL* __restrict__ vw, 
 }  // namespace
 
 // one thread per row, any geometry
-extern "C" __global__ void cudaSpMVRowsCSR(spmat* m, double* v, CONFIG cfg, double* outV) {
+extern "C" __global__ void B200_BOUNDS cudaSpMVRowsCSR(spmat* m, double* v, CONFIG cfg, double* outV) {
     const B200ViewCSR* vw = csr_view(m);
     if (vw && whole_warps()) {
         sell_rows(vw, v, outV);
@@ -198,7 +210,7 @@ extern "C" __global__ void cudaSpMVRowsCSR(spmat* m, double* v, CONFIG cfg, doub
 }
 
 // one (sub-)warp per row
-extern "C" __global__ void cudaSpMVWarpPerRowCSR(spmat* m, double* v, CONFIG cfg, double* outV) {
+extern "C" __global__ void B200_BOUNDS cudaSpMVWarpPerRowCSR(spmat* m, double* v, CONFIG cfg, double* outV) {
     const B200ViewCSR* vw = csr_view(m);
     if (vw && whole_warps()) {
         const unsigned M = (unsigned) m->M;
@@ -231,7 +243,7 @@ extern "C" __global__ void cudaSpMVWarpPerRowCSR(spmat* m, double* v, CONFIG cfg
 // M = slots per row (K), MAX_ROW_NZ = number of matrix rows, pitch in elements.  The plain tier visits all K slots like the
 // reference kernel does (the transposed struct's RL is only partially uploaded by the reference); the fast tier
 // reads 32-bit ids and stops at the row length.
-extern "C" __global__ void cudaSpMVRowsELL(spmat* m, double* v, CONFIG cfg, double* outV) {
+extern "C" __global__ void B200_BOUNDS cudaSpMVRowsELL(spmat* m, double* v, CONFIG cfg, double* outV) {
     const B200ViewELL* vw = ell_view(m);
     if (vw && whole_warps()) {
         ell_cm_rows(vw, m->AS, m->pitchAS, v, outV);
@@ -250,7 +262,7 @@ extern "C" __global__ void cudaSpMVRowsELL(spmat* m, double* v, CONFIG cfg, doub
 
 // row-major pitched ELL, one thread per row.  Fast tier: the view holds a column-major copy (ids and values), so the walk is
 // coalesced instead of one 8-byte element per 32-byte sector.
-extern "C" __global__ void cudaSpMVRowsELLNNTransposed(spmat* m, double* v, CONFIG cfg, double* outV) {
+extern "C" __global__ void B200_BOUNDS cudaSpMVRowsELLNNTransposed(spmat* m, double* v, CONFIG cfg, double* outV) {
     const B200ViewELL* vw = ell_view(m);
     if (vw && vw->as_cm && whole_warps()) {
         ell_cm_rows(vw, vw->as_cm, vw->pitch, v, outV);
@@ -277,7 +289,7 @@ extern "C" __global__ void cudaSpMVRowsELLNNTransposed(spmat* m, double* v, CONF
 
 // row-major pitched ELL, one warp per row in the reference.  Fast tier: the same column-major walk as above -- for the short rows ELL
 // is used for (K of a few tens) a warp per row leaves most lanes idle, a thread per row on coalesced storage does not.
-extern "C" __global__ void cudaSpMVWarpsPerRowELLNTrasposed(spmat* m, double* v, CONFIG cfg, double* outV) {
+extern "C" __global__ void B200_BOUNDS cudaSpMVWarpsPerRowELLNTrasposed(spmat* m, double* v, CONFIG cfg, double* outV) {
     const B200ViewELL* vw = ell_view(m);
     if (vw && vw->as_cm && whole_warps()) {
         ell_cm_rows(vw, vw->as_cm, vw->pitch, v, outV);
