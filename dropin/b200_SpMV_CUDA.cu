@@ -27,9 +27,11 @@ extern "C" {
 #include "b200_view.h"
 
 // Register budget: the drivers launch blocks of 256 and of 32 x 32 = 1024 threads.  B200_MIN_BLOCKS = 2 (two 1024-thread blocks per SM:
-// 32 registers per thread, full occupancy) or 1 (64 registers); measured on B200 in profiles/r02*_dropin_bench.log.
+// 32 registers per thread, full occupancy; a few spills outside the hot loops) or 1 (64 registers, no spills).  These kernels live on
+// loads in flight, so occupancy wins -- measured on B200 (profiles/r02d_dropin_regs.log): 27-point 128^3, CSR 0 129 vs 162 us, ELL 0 113 vs
+// 161 us; 5-point 1024^2, CSR 0 26.9 vs 32.9 us.
 #ifndef B200_MIN_BLOCKS
-#define B200_MIN_BLOCKS 1
+#define B200_MIN_BLOCKS 2
 #endif
 #define B200_BOUNDS __launch_bounds__(1024, B200_MIN_BLOCKS)
 
