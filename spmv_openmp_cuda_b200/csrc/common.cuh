@@ -189,6 +189,11 @@ struct PushArgs {
     uint32_t* ticket;        // device counter: boundary CTAs of this launch that have finished (reset by the last one)
     uint32_t nboundary;      // boundary CTAs of this launch (counted once per handle and launch shape)
     const uint8_t* cta_boundary;  // [grid] 1 = boundary CTA (precomputed: the kernel must not pay dependent loads to find out)
+    uint32_t rb_rot;         // one-CTA-per-row-block launches: CTA b takes row block (b + rb_rot) mod grid, so that the boundary row
+                             // blocks at the LOW end of the slab are scheduled last, like those at the high end -- every signal is
+                             // then sent at the end of a kernel and first needed at the end of the next one: a whole kernel of slack
+                             // between neighbours instead of none (the low-end CTAs would otherwise start first and stall on a
+                             // neighbour that is a few microseconds behind)
     uint32_t own_lo, own_hi; // columns of x this rank owns: [own_lo, own_hi)
 };
 __device__ __forceinline__ void push_out(const PushArgs& p, uint32_t row, double v) {

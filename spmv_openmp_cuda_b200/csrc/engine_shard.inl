@@ -36,6 +36,7 @@ struct spmvb200_shard {
     int nb_mode = -2;            // x-window launch shape the boundary CTAs were counted for (-2: not counted yet)
     uint32_t nboundary = 0;
     uint8_t* cta_boundary = nullptr;  // [grid of that launch shape] 1 = boundary CTA
+    uint32_t rb_rot = 0;              // rotation of the row-block order (PushArgs::rb_rot)
     double* d_y = nullptr;
     bool connected = false;
     int host_cur = 0;
@@ -260,21 +261,39 @@ extern "C" int spmvb200_shard_step(spmvb200_shard* s, int src, int dst, void* st
         if (s->nb_mode != mode) {  // count the boundary CTAs of this launch shape once
             uint32_t* d_cnt = nullptr;
             CU_TRY(cudaMalloc(&d_cnt, 4));
-            CU_TRY(cudaMemsetAsync(d_cnt, 0, 4, st));
             const uint32_t ncta = mode ? xw->xw_ncta : xw->xw_nrb;
             cudaFree(s->cta_boundary);
             s->cta_boundary = nullptr;
             CU_TRY(cudaMalloc(&s->cta_boundary, std::max<uint32_t>(ncta, 1)));
-            xw_count_boundary_kernel<<<(ncta + 255) / 256, 256, 0, st>>>(mode ? xw->xw_cta_rb : nullptr, xw->xw_rb_tile0, xw->xw_tile_win, ncta, xw->xw_R, xw->xw_W,
-                                                                        (uint32_t) xw->M, (uint32_t) xw->N, a, d_cnt, s->cta_boundary);
-            cudaError_t e = cudaMemcpyAsync(&s->nboundary, d_cnt, 4, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            static const bool no_rot = getenv("SPMVB200_SHARD_NO_ROTATION") != nullptr;  // developer knob
+            s->rb_rot = 0;
+            cudaError_t e = cudaSuccess;
+            for (int pass = 0; pass < 2 && e == cudaSuccess; ++pass) {
+                // pass 0: flags in natural order -> how many boundary CTAs lead the grid; pass 1 (if any do): flags for the rotated order
+                a.rb_rot = s->rb_rot;
+                CU_TRY(cudaMemsetAsync(d_cnt, 0, 4, st));
+                xw_count_boundary_kernel<<<(ncta + 255) / 256, 256, 0, st>>>(mode ? xw->xw_cta_rb : nullptr, xw->xw_rb_tile0, xw->xw_tile_win, ncta, xw->xw_R, xw->xw_W,
+                                                                            (uint32_t) xw->M, (uint32_t) xw->N, a, d_cnt, s->cta_boundary);
+                e = cudaMemcpyAsync(&s->nboundary, d_cnt, 4, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (pass == 0 && e == cudaSuccess && mode == 0 && !no_rot && s->nboundary && s->nboundary < ncta) {
+                    std::vector<uint8_t> h(ncta);
+                    e = cudaMemcpy(h.data(), s->cta_boundary, ncta, cudaMemcpyDeviceToHost);
+                    uint32_t lead = 0;
+                    while (lead < ncta && h[lead]) ++lead;
+                    if (lead == 0 || lead == ncta) break;
+                    s->rb_rot = lead;
+                } else {
+                    break;
+                }
+            }
             cudaFree(d_cnt);
             if (e != cudaSuccess) return fail("shard_step: boundary count: %s", cudaGetErrorString(e));
             s->nb_mode = mode;
         }
         a.nboundary = s->nboundary;
         a.cta_boundary = s->cta_boundary;
+        a.rb_rot = s->rb_rot;
         a.wait_epoch = s->epoch;      // neighbours have finished the previous exchange step
         a.sig_epoch = s->epoch + 1;   // ... and this is what my completion looks like to them
         if (a.nboundary == 0) a.nsync = 0;  // cannot happen with neighbours, but never launch a kernel nobody would signal from

@@ -162,7 +162,8 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
     uint32_t* done = reinterpret_cast<uint32_t*>(full + XW_MAX_NBUF);             // [nbuf] warps that have left the slot (monotonic)
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t rb = cta_rb ? __ldg(cta_rb + blockIdx.x) : rb_first + blockIdx.x;  // no split table: one row block per CTA
+    // no split table: one row block per CTA (rotated under the fused neighbour synchronisation, see PushArgs::rb_rot)
+    uint32_t rb = cta_rb ? __ldg(cta_rb + blockIdx.x) : rb_first + (push.rb_rot ? (blockIdx.x + push.rb_rot) % gridDim.x : blockIdx.x);
     const uint32_t rb1 = cta_rb ? __ldg(cta_rb + blockIdx.x + 1) : rb + 1;
     if (rb >= rb1) return;
     const uint32_t T0 = __ldg(rb_tile0 + rb), T1 = __ldg(rb_tile0 + rb1);  // this CTA's tiles
@@ -297,7 +298,7 @@ __global__ void xw_count_boundary_kernel(const uint32_t* __restrict__ cta_rb, co
                                          uint8_t* __restrict__ cta_flag) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncta) return;
-    const uint32_t rb = cta_rb ? cta_rb[c] : c, rb1 = cta_rb ? cta_rb[c + 1] : c + 1;
+    const uint32_t rb = cta_rb ? cta_rb[c] : (push.rb_rot ? (c + push.rb_rot) % ncta : c), rb1 = cta_rb ? cta_rb[c + 1] : rb + 1;
     const bool b = rb < rb1 && xw_cta_is_boundary(push, rb, rb1, rb_tile0, tile_win, R, W, M, N);
     cta_flag[c] = b ? 1 : 0;
     if (b) atomicAdd(count, 1u);
