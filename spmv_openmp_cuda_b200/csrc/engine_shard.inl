@@ -235,7 +235,11 @@ extern "C" int spmvb200_shard_step(spmvb200_shard* s, int src, int dst, void* st
     if (prefer_smem_once()) return 1;
     if (needs_tuning(m, s->kind) && !stream_capturing(st))  // first use: pick without deliveries
         if (launch(m, s->kind, s->x[src], s->x[dst] + s->r0, st)) return 1;
-    static const bool no_fused_sync = getenv("SPMVB200_SHARD_BARRIER") != nullptr;  // developer knob: always the separate barrier kernel
+    // Synchronisation of the step: by default a one-block flag-barrier kernel after the SpMV.  SPMVB200_SHARD_FUSED_SYNC=1 moves it into
+    // the boundary CTAs of the x-window kernel instead (PushArgs, common.cuh).  Both were measured on cfg4: 2 GPUs
+    // 1.227 ms (barrier kernel) vs 1.234-1.239 ms (fused) on a 1.215 ms kernel; 8 GPUs 0.3321 vs 0.3329 ms on 0.320 ms -- no gain from
+    // the fused form, so the simpler one is the default.
+    static const bool no_fused_sync = getenv("SPMVB200_SHARD_FUSED_SYNC") == nullptr || getenv("SPMVB200_SHARD_BARRIER") != nullptr;
     LaunchCtx lc;
     PushArgs& a = lc.push;
     a.n = s->npeer;

@@ -9,8 +9,8 @@ if [ "$N" = "2" ]; then
 fi
 BENCH_VERBOSE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 20 --warmup 5 > $O/r02_bench_n$N.json 2> $O/r02_bench_n$N.err
 tail -c 400 $O/r02_bench_n$N.err
-# A/B: the separate barrier kernel instead of the synchronisation fused into the SpMV kernel
-SPMVB200_SHARD_BARRIER=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus $N --steps 20 --warmup 5 --e2e-steps 5 --e2e-blocks 1 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('barrier-kernel variant: value %.1f  %.4f ms (kernel only %.4f)' % (d['value'], d['ms_per_step'], d['kernel_only']['ms_per_step']))" | tee $O/r02_bench_n${N}_barrier_variant.log
+# A/B: the synchronisation fused into the boundary CTAs of the SpMV kernel instead of the separate barrier kernel
+SPMVB200_SHARD_FUSED_SYNC=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus $N --steps 20 --warmup 5 --e2e-steps 5 --e2e-blocks 1 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('fused-sync variant: value %.1f  %.4f ms (kernel only %.4f)' % (d['value'], d['ms_per_step'], d['kernel_only']['ms_per_step']))" | tee $O/r02_bench_n${N}_fused_sync_variant.log
 python - <<PY
 import json
 d = json.load(open("$O/r02_bench_n$N.json"))

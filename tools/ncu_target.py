@@ -27,6 +27,8 @@ def main():
         d = synth.device_csr(synth.stencil27(128))
     elif cfg == "cfg3":
         d = synth.rmat_device_csr(int(sys.argv[3]) if len(sys.argv) > 3 else 22, 16)
+    elif cfg == "cfg4s":  # one GPU's slice of cfg4 in an 8-GPU run: rows [0, 2^22) of the 2^25-row matrix
+        d = synth.device_csr(synth.banded(1 << 25, 32, 1 << 15), 0, 1 << 22)
     elif cfg == "cfg4":
         d = synth.device_csr(synth.banded(1 << 25, 32, int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 15))
     else:
