@@ -285,7 +285,9 @@ def _launch(kind, m, v, cfg, outV, stream=None):
 
 
 def cudaSpMVRowsCSR(m, v, cfg, outV, stream=None):
-    """src/SpMV_CUDA.cu:33-49 -> TMA-staged CSR stream kernel, bit-identical to sgemvSerial."""
+    """src/SpMV_CUDA.cu:33-49 -> TMA-staged CSR stream kernel / x-window or SELL copy (picked at first use), bit-identical to
+    sgemvSerial for every row of at most 2048 non-zeros; a longer row is split into 2048-entry segments combined in segment order
+    (deterministic, within 1e-12 * sum|a_ij x_j| of the serial sum, not the same bits)."""
     return _launch(CSR_ROWS, m, v, cfg, outV, stream)
 
 
@@ -305,7 +307,8 @@ def cudaSpMVRowsELL(m, v, cfg, outV, stream=None):
 
 
 def cudaSpMVRowsSELL(m, v, cfg, outV, stream=None):
-    """new mode: sliced ELL (SELL-32-sigma), thread per row, bit-identical to sgemvSerial."""
+    """new mode: sliced ELL (SELL-32-sigma), thread per row, bit-identical to sgemvSerial for rows of at most 2048 non-zeros (rows
+    longer than 256 run on the serial-order per-row kernels next to the slices; beyond 2048 they are split into segments)."""
     return _launch(SELL_ROWS, m, v, cfg, outV, stream)
 
 
@@ -403,3 +406,48 @@ SpmvB200ELLFuncs = [b200SpMVRowsELL, b200SpMVRowsELLNNTransposed, b200SpMVWarpsP
 
 def cache_drop(mat=None):
     check(lib().spmvb200_cache_drop(None if mat is None else id(mat)), "cache_drop")
+
+
+# ---------------------------------------------------------------------------------------- first-use picks, comparators
+def tune(kind, m, v, outV, stream=None):
+    """Make the first-use pick of a self-tuning kind now (blocking; outV is scratch).  Afterwards launches of that kind are pure
+    asynchronous launches and can be captured into a CUDA graph with the tuned kernel inside (spmvb200_tune)."""
+    check(lib().spmvb200_tune(m.handle, kind, ptr(v), ptr(outV), stream), "tune")
+    return EXIT_SUCCESS
+
+
+def set_tuning_mode(deterministic):
+    """False (default): candidates are timed, the fastest wins (may differ from run to run).  True: the pick is a pure function of
+    the matrix structure -- tolerance kinds then return the same bits in every process.  Process-wide."""
+    check(lib().spmvb200_set_tuning_mode(1 if deterministic else 0), "set_tuning_mode")
+
+
+def tuning_get(m):
+    """the handle's picks as 8 integers (install them in another handle of the same matrix with tuning_set)"""
+    p = (C.c_int32 * 8)()
+    check(lib().spmvb200_tuning_get(m.handle, p), "tuning_get")
+    return list(p)
+
+
+def tuning_set(m, picks):
+    p = (C.c_int32 * 8)(*[int(v) for v in picks])
+    check(lib().spmvb200_tuning_set(m.handle, p), "tuning_set")
+
+
+def compare_strict_csr(mat, x, y_ref, y, tau=1e-12):
+    """|y_i - yref_i| <= tau * sum_j |a_ij x_j| for every row, NaN / Inf fails.  Returns (rows failing, worst ratio).
+    Host arrays in, host loop inside the library: a comparator, not a compute path."""
+    bad, worst = C.c_uint64(0), C.c_double(0)
+    check(lib().spmvb200_compare_strict_csr(mat.M, ptr(mat.IRP), ptr(mat.JA), ptr(mat.AS), ptr(np.ascontiguousarray(x, dtype=np.float64)),
+                                            ptr(np.ascontiguousarray(y_ref, dtype=np.float64)), ptr(np.ascontiguousarray(y, dtype=np.float64)),
+                                            tau, C.byref(bad), C.byref(worst)), "compare_strict_csr")
+    return bad.value, worst.value
+
+
+def compare_abs(a, b, threshold=7e-4):
+    """doubleVectorsDiff semantics (src/commons/utils.c:362-393; threshold DOUBLE_DIFF_THREASH = 7e-4), but NaN fails.
+    Returns (failed, max |a-b|)."""
+    a, b = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64)
+    failed, dmax = C.c_int(0), C.c_double(0)
+    check(lib().spmvb200_compare_abs(len(a), ptr(a), ptr(b), threshold, C.byref(failed), C.byref(dmax)), "compare_abs")
+    return bool(failed.value), dmax.value
