@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "plan.cuh"
 #include "xwin.cuh"
+#include "hotx.cuh"
 
 namespace spmvb200 {
 thread_local char g_err[512] = "";
@@ -54,6 +55,14 @@ static void free_arrays(spmvb200_matrix* m) {
         spmvb200_free(m->tail);
         m->tail = nullptr;
     }
+    if (m->hot_sell) {
+        spmvb200_free(m->hot_sell);
+        m->hot_sell = nullptr;
+    }
+    cudaFree(m->hot_cols);
+    cudaFree(m->ja_hot);
+    m->hot_cols = nullptr;
+    m->ja_hot = nullptr;
     cudaFree(m->tail_map);
     cudaFree(m->tail_y);
     if (m->own) {
@@ -270,7 +279,10 @@ extern "C" int spmvb200_tuning_set(spmvb200_matrix* m, const int32_t t[8]) {
         if (t[0] >= N_CAND) return fail("tuning_set: adaptive candidate %d out of range", t[0]);
         if (m->xw_child) { spmvb200_free(m->xw_child); m->xw_child = nullptr; }
         m->tuned = -1;
-        if (t[0] == CAND_XWIN || t[0] == CAND_SELL) {
+        hotx_drop(m);
+        if (t[0] == CAND_HOTX) {
+            if (hotx_build_quiet(m)) return fail("tuning_set: the matrix does not fit the hot-x hybrid");
+        } else if (t[0] == CAND_XWIN || t[0] == CAND_SELL) {
             if (build_child(m, t[0], false, &m->xw_child)) return fail("tuning_set: the matrix does not fit the %s copy", CAND_NAME[t[0]]);
             if (t[0] == CAND_XWIN) m->xw_child->xw_mode = t[3] >= 0 ? (t[3] ? 1 : 0) : xwin_mode_rule(m->xw_child);
         }

@@ -54,6 +54,13 @@ struct spmvb200_matrix {
     uint16_t* xw_cnt = nullptr;       // [ntiles*R] entries of a row inside a tile | its place in the group's sorted order << 8
     uint16_t* xw_col = nullptr;       // [NZ+PAD] window-local column ids
     int own = 1;
+    // hot-x hybrid (hotx.cuh; adaptive kind on matrices with power-law column popularity): the H hottest columns, the CSR column ids
+    // remapped (hot column -> its rank < H, cold column c -> c + H) and a SELL copy of the short rows built from the remapped ids
+    uint32_t* hot_cols = nullptr;
+    uint32_t hot_H = 0;
+    uint32_t* ja_hot = nullptr;
+    spmvb200_matrix* hot_sell = nullptr;
+    float hot_cover = 0.f;  // fraction of the non-zeros whose column is hot
     // stand-alone SELL handle of a skewed matrix: rows longer than VEC_MID live in `tail` (a compact CSR handle of just those rows,
     // run by the per-row / per-segment kernels next to the slices); tail_map[i] = original row of tail row i, tail_y = its scratch output
     spmvb200_matrix* tail = nullptr;

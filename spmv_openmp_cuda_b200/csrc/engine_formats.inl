@@ -582,6 +582,82 @@ static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, 
 }
 
 
+// ------------------------------------------------------------------------------------------------- hot-x hybrid (hotx.cuh)
+// Column histogram -> H hottest columns -> remapped ids -> SELL copy of the short rows.  Fails (quietly, under g_quiet) when the hot
+// columns cover less than min_cover of the non-zeros: uniform column distributions gain nothing from the cache.
+static int hotx_build(spmvb200_matrix* m, uint32_t H, double min_cover) {
+    if (m->format != SPMVB200_FMT_CSR) return fail("hotx: source is not a CSR handle");
+    if (m->hot_sell) return 0;
+    if (m->N < 4ull * H || m->NZ < (1u << 20) || m->N + H > 0xffffffffull) return fail("hotx: matrix too small (or too wide) for a hot-column cache");
+    const uint32_t N = (uint32_t) m->N;
+    uint32_t *cnt = nullptr, *cnt_s = nullptr, *cols = nullptr, *cols_s = nullptr, *remap = nullptr;
+    void* tmp = nullptr;
+    int rc = 0;
+    do {
+        if ((rc = cudaMalloc(&cnt, (size_t) N * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&cnt_s, (size_t) N * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&cols, (size_t) N * 4) != cudaSuccess)) break;
+        if ((rc = cudaMalloc(&cols_s, (size_t) N * 4) != cudaSuccess)) break;
+        cudaMemset(cnt, 0, (size_t) N * 4);
+        hotx_hist_kernel<<<1184, 256>>>(m->ja, m->NZ, cnt);
+        hotx_iota_kernel<<<(N + 255) / 256, 256>>>(cols, N);
+        size_t b1 = 0;
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, b1, cnt, cnt_s, cols, cols_s, (int) N);
+        if ((rc = cudaMalloc(&tmp, b1 + 16) != cudaSuccess)) break;
+        if ((rc = cub::DeviceRadixSort::SortPairsDescending(tmp, b1, cnt, cnt_s, cols, cols_s, (int) N) != cudaSuccess)) break;
+        std::vector<uint32_t> h(H);
+        if ((rc = cudaMemcpy(h.data(), cnt_s, (size_t) H * 4, cudaMemcpyDeviceToHost) != cudaSuccess)) break;
+        uint64_t covered = 0;
+        for (uint32_t i = 0; i < H; ++i) covered += h[i];
+        m->hot_cover = (float) ((double) covered / (double) std::max<uint64_t>(m->NZ, 1));
+        if ((double) m->hot_cover < min_cover) { rc = fail("hotx: the %u hottest columns cover only %.1f %% of the non-zeros", H, 100.0 * m->hot_cover); break; }
+        if ((rc = cudaMalloc(&m->hot_cols, (size_t) H * 4) != cudaSuccess)) break;
+        if ((rc = cudaMemcpy(m->hot_cols, cols_s, (size_t) H * 4, cudaMemcpyDeviceToDevice) != cudaSuccess)) break;
+        remap = cnt;  // the histogram is not needed any more
+        hotx_remap_init_kernel<<<(N + 255) / 256, 256>>>(remap, N, H);
+        hotx_remap_hot_kernel<<<(H + 255) / 256, 256>>>(remap, m->hot_cols, H);
+        if ((rc = cudaMalloc(&m->ja_hot, (m->NZ + PAD) * 4) != cudaSuccess)) break;
+        cudaMemset(m->ja_hot + m->NZ, 0, PAD * 4);
+        hotx_apply_kernel<<<1184, 256>>>(m->ja, remap, m->NZ, m->ja_hot);
+        if ((rc = cudaDeviceSynchronize() != cudaSuccess)) break;
+        // SELL copy of the rows of at most VEC_MID entries, from the remapped ids (a shallow view of the parent with ja swapped)
+        spmvb200_matrix view;
+        view.format = SPMVB200_FMT_CSR;
+        view.M = m->M;
+        view.N = m->N;
+        view.NZ = m->NZ;
+        view.irp = m->irp;
+        view.ja = m->ja_hot;
+        view.as = m->as;
+        if ((rc = sell_build(&view, 0, m->lmax <= (uint32_t) VEC_MID ? 0xffffffffu : (uint32_t) VEC_MID, &m->hot_sell))) break;
+        m->hot_H = H;
+    } while (0);
+    cudaFree(cnt);
+    cudaFree(cnt_s);
+    cudaFree(cols);
+    cudaFree(cols_s);
+    cudaFree(tmp);
+    if (rc) {
+        if (!g_err[0] || cudaPeekAtLastError() != cudaSuccess) fail("hotx: %s", cudaGetErrorString(cudaGetLastError()));
+        if (m->hot_sell) { spmvb200_free(m->hot_sell); m->hot_sell = nullptr; }
+        cudaFree(m->hot_cols);
+        cudaFree(m->ja_hot);
+        m->hot_cols = nullptr;
+        m->ja_hot = nullptr;
+        m->hot_H = 0;
+        return 1;
+    }
+    return 0;
+}
+static void hotx_drop(spmvb200_matrix* m) {
+    if (m->hot_sell) { spmvb200_free(m->hot_sell); m->hot_sell = nullptr; }
+    cudaFree(m->hot_cols);
+    cudaFree(m->ja_hot);
+    m->hot_cols = nullptr;
+    m->ja_hot = nullptr;
+    m->hot_H = 0;
+}
+
 // ------------------------------------------------------------------------------------------------- x-window CSR
 // (xwin.cuh) built on the device from a CSR handle: mark (row block, window) pairs -> scan -> tile list ->
 // per-row counts -> scan -> jagged slot-major fill.

@@ -283,14 +283,52 @@ static void launch_sell(const spmvb200_matrix* m, const double* x, double* y, cu
 }
 
 // ---- SPMVB200_CSR_ADAPTIVE: candidates; the fastest on this matrix is picked at first use
-static const int N_CAND = 14;
+static const int N_CAND = 15;
+static const int CAND_HOTX = 14;  // hot-x hybrid (hotx.cuh): power-law column popularity, one persistent kernel with the hot x in shared memory
 static const int CAND_XWIN = 12;  // x-window copy (built during tuning when the tile census says it can pay off)
 static const int CAND_SELL = 13;  // SELL-32-sigma copy (matrices without long rows: thread per row, coalesced, no shuffles)
 static const char* CAND_NAME[N_CAND] = {"stream/8cta", "stream/bigL1", "vector/2", "vector/4", "vector/8", "vector/16", "vector/32",
-                                        "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32", "xwindow", "sell"};
+                                        "vspan/2", "vspan/4", "vspan/8", "vspan/16", "vspan/32", "xwindow", "sell", "hotx"};
 static int cand_lanes(int c) { return c < 2 ? 0 : 2 << ((c - 2) % 5); }
 static int cand_of_lanes(int lanes) { int c = 2; while (c < 6 && cand_lanes(c) < lanes) ++c; return c; }
+static int launch_hotx(spmvb200_matrix* m, const double* x, double* y, cudaStream_t st) {
+    const spmvb200_matrix* sl = m->hot_sell;
+    HotxArgs a = {};
+    a.slice_ptr = sl->irp;
+    a.perm = sl->perm;
+    a.rl = sl->rl;
+    a.sas = sl->as;
+    a.sja = sl->ja;
+    a.nslices = (uint32_t) (sl->Mpad / 32);
+    a.irp = m->irp;
+    a.ja = m->ja_hot;
+    a.as = m->as;
+    a.mid_rows = m->mid_rows;
+    a.nmid = m->nmid;
+    a.seg_tiles = m->seg_tiles;
+    a.nseg = m->nseg;
+    a.desc = m->desc;
+    a.longrec = m->longrec;
+    a.partial = m->partial;
+    a.ticket = m->ticket;
+    a.hot_cols = m->hot_cols;
+    a.H = m->hot_H;
+    const size_t smem = (size_t) m->hot_H * 8;
+    static size_t configured[64] = {0};
+    static int sms[64] = {0};
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if (smem > configured[dev & 63]) {
+        CU_TRY(cudaFuncSetAttribute(hotx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured[dev & 63] = smem;
+    }
+    if (!sms[dev & 63]) CU_TRY(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    hotx_kernel<<<sms[dev & 63], HOTX_BLOCK, smem, st>>>(a, x, y);
+    ++g_launches;
+    return 0;
+}
 static void launch_candidate(spmvb200_matrix* m, int c, const double* x, double* y, cudaStream_t st, LaunchCtx* lc = nullptr) {
+    if (c == CAND_HOTX) { launch_hotx(m, x, y, st); return; }
     if (c == 0) launch_csr_stream<true, 0>(m, x, y, st, 0, m->ntiles);
     else if (c == 1) launch_csr_stream<true, 1>(m, x, y, st, 0, m->ntiles);
     else if (c < 7) launch_csr_vector(m, cand_lanes(c), x, y, st, 0, m->M);
@@ -348,6 +386,14 @@ static int time_best_of_2(F&& run, cudaStream_t st, float* ms_out) {
     return 0;
 }
 
+static int hotx_build_quiet(spmvb200_matrix* m) {
+    const int quiet0 = g_quiet;
+    g_quiet = 1;
+    const int rc = hotx_build(m, 16384, 0.25);
+    g_quiet = quiet0;
+    g_err[0] = 0;
+    return rc;
+}
 static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
     for (int c = 0; c < N_CAND; ++c) m->tuned_ms[c] = -1.f;
     const bool big = m->NZ >= (1u << 20);  // a second copy of the matrix (10.x B per non-zero) only when the matrix is big enough to matter
@@ -359,6 +405,8 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
             ch->xw_mode = xwin_mode_rule(ch);
             m->xw_child = ch;
             m->tuned = CAND_XWIN;
+        } else if (big && !getenv("SPMVB200_NO_HOTX") && !hotx_build_quiet(m)) {
+            m->tuned = CAND_HOTX;
         } else if (big && !build_child(m, CAND_SELL, false, &ch)) {
             m->xw_child = ch;
             m->tuned = CAND_SELL;
@@ -408,6 +456,26 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
                 m->xw_child = sell.release();
                 best_ms = ms;
                 best = CAND_SELL;
+            }
+        }
+    }
+    // hot-x hybrid: only where the column popularity is skewed enough for a 128 KB cache of x to matter
+    if (big && !getenv("SPMVB200_NO_HOTX") && (!force || atoi(force) == CAND_HOTX)) {
+        const int quiet0 = g_quiet;
+        g_quiet = 1;
+        const int rc = hotx_build(m, 16384, 0.25);
+        g_quiet = quiet0;
+        g_err[0] = 0;
+        if (!rc) {
+            float ms = 1e30f;
+            if (time_best_of_2([&] { launch_hotx(m, d_x, d_y, st); }, st, &ms)) return 1;
+            m->tuned_ms[CAND_HOTX] = ms;
+            if (ms < 0.95f * best_ms || force) {
+                if (m->xw_child) { spmvb200_free(m->xw_child); m->xw_child = nullptr; }
+                best_ms = ms;
+                best = CAND_HOTX;
+            } else {
+                hotx_drop(m);
             }
         }
     }

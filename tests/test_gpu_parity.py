@@ -289,6 +289,39 @@ def test_adaptive_sell_hybrid_on_skewed_rows(sp, orc, monkeypatch):
     assert dm.adaptive_choice == "sell"
 
 
+def test_adaptive_hotx_hybrid_on_power_law_columns(sp, orc, monkeypatch):
+    """Forced hot-x candidate (csrc/hotx.cuh) on an R-MAT matrix: ONE persistent kernel, the 16 384 hottest x entries in shared memory, column
+    ids remapped; rows up to 256 entries from a SELL copy in the serial order (bit-identical), longer rows and the segments of rows longer
+    than a tile by a warp each.  Repeated launches (ticket counters reset), the iterated path and the host path included."""
+    monkeypatch.setenv("SPMVB200_FORCE_CAND", "14")
+    mat = sp.synth.rmat_host_csr(17, 16)
+    assert mat.MAX_ROW_NZ > 2048 and mat.NZ >= 1 << 20 and mat.N >= 4 * 16384
+    x = sp.synth.host_vector(mat.N)
+    y_ref = _oracle_y(orc, mat, x)
+    dm, dx, dy = sp.spMatCpyCSR(mat), sp.DeviceVector.from_host(x), sp.DeviceVector(mat.M)
+    short = np.diff(mat.IRP) <= 256
+    for _ in range(3):
+        dy.fill_bytes(0xFF)
+        sp.cudaSpMVAdaptiveCSR(dm, dx, sp.Config(), dy)
+        y = dy.to_host()
+        assert orc.strict_diff_csr(mat.IRP, mat.JA, mat.AS, x, y_ref, y, tau=TAU)[0] == 0
+        np.testing.assert_array_equal(y[short], y_ref[short])
+    assert dm.adaptive_choice == "hotx"
+    yh = np.full(mat.M, np.nan)
+    sp.spmv_host(sp.CSR_ADAPTIVE, dm, x, yh)
+    np.testing.assert_array_equal(yh, y)
+    # the other kinds of the same handle are untouched by the remapped copy
+    dy.fill_bytes(0xFF)
+    sp.cudaSpMVRowsCSR(dm, dx, sp.Config(), dy)
+    np.testing.assert_array_equal(dy.to_host()[np.diff(mat.IRP) <= STREAM_TILE], y_ref[np.diff(mat.IRP) <= STREAM_TILE])
+    # a matrix with uniform columns does not qualify (the cache would cover < 25 % of the gathers): the pick falls back
+    uni = sp.synth.host_csr(sp.synth.mixed(400000, 32, 0.1))
+    du, dxu, dyu = sp.spMatCpyCSR(uni), sp.DeviceVector.from_host(sp.synth.host_vector(uni.N)), sp.DeviceVector(uni.M)
+    monkeypatch.delenv("SPMVB200_FORCE_CAND")
+    sp.cudaSpMVAdaptiveCSR(du, dxu, sp.Config(), dyu)
+    assert du.adaptive_choice != "hotx"
+
+
 def test_ell_rows_picks_sell_copy_on_padded_matrix(sp, orc, monkeypatch):
     """ELL_ROWS on mixed short/long rows (ELL rectangle >= 1.25 x nnz, >= 2^20 nnz): the handle times the column-major kernel against a
     SELL copy built from the ELL arrays; whichever runs, y is bit-identical to sgemvSerial.  With the knob set the copy is never built."""
