@@ -61,8 +61,10 @@ static void free_arrays(spmvb200_matrix* m) {
     }
     cudaFree(m->hot_cols);
     cudaFree(m->ja_hot);
+    cudaFree(m->hot_slice_order);
     m->hot_cols = nullptr;
     m->ja_hot = nullptr;
+    m->hot_slice_order = nullptr;
     cudaFree(m->tail_map);
     cudaFree(m->tail_y);
     if (m->own) {

@@ -61,6 +61,8 @@ struct spmvb200_matrix {
     uint32_t* ja_hot = nullptr;
     spmvb200_matrix* hot_sell = nullptr;
     float hot_cover = 0.f;  // fraction of the non-zeros whose column is hot
+    uint32_t* hot_slice_order = nullptr;  // slices of hot_sell by decreasing length
+    int hot_shape = 0;                    // 0: 1024 threads x 1 CTA per SM, 1: 512 threads x 3 CTAs per SM (first-use timing)
     // stand-alone SELL handle of a skewed matrix: rows longer than VEC_MID live in `tail` (a compact CSR handle of just those rows,
     // run by the per-row / per-segment kernels next to the slices); tail_map[i] = original row of tail row i, tail_y = its scratch output
     spmvb200_matrix* tail = nullptr;

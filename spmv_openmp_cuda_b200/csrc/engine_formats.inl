@@ -585,9 +585,11 @@ static int sell_build(const spmvb200_matrix* csr, uint32_t sigma, uint32_t cap, 
 // ------------------------------------------------------------------------------------------------- hot-x hybrid (hotx.cuh)
 // Column histogram -> H hottest columns -> remapped ids -> SELL copy of the short rows.  Fails (quietly, under g_quiet) when the hot
 // columns cover less than min_cover of the non-zeros: uniform column distributions gain nothing from the cache.
+static void hotx_drop(spmvb200_matrix* m);
 static int hotx_build(spmvb200_matrix* m, uint32_t H, double min_cover) {
     if (m->format != SPMVB200_FMT_CSR) return fail("hotx: source is not a CSR handle");
-    if (m->hot_sell) return 0;
+    if (m->hot_sell && m->hot_H == H) return 0;
+    if (m->hot_sell) hotx_drop(m);
     if (m->N < 4ull * H || m->NZ < (1u << 20) || m->N + H > 0xffffffffull) return fail("hotx: matrix too small (or too wide) for a hot-column cache");
     const uint32_t N = (uint32_t) m->N;
     uint32_t *cnt = nullptr, *cnt_s = nullptr, *cols = nullptr, *cols_s = nullptr, *remap = nullptr;
@@ -630,6 +632,25 @@ static int hotx_build(spmvb200_matrix* m, uint32_t H, double min_cover) {
         view.ja = m->ja_hot;
         view.as = m->as;
         if ((rc = sell_build(&view, 0, m->lmax <= (uint32_t) VEC_MID ? 0xffffffffu : (uint32_t) VEC_MID, &m->hot_sell))) break;
+        {   // slices by decreasing length
+            const uint32_t nsl = (uint32_t) (m->hot_sell->Mpad / 32);
+            uint32_t *k0 = nullptr, *k1 = nullptr, *v0 = nullptr;
+            void* t2 = nullptr;
+            size_t b2 = 0;
+            if ((rc = cudaMalloc(&k0, (size_t) nsl * 4) != cudaSuccess)) break;
+            if (!rc) rc = cudaMalloc(&k1, (size_t) nsl * 4) != cudaSuccess;
+            if (!rc) rc = cudaMalloc(&v0, (size_t) nsl * 4) != cudaSuccess;
+            if (!rc) rc = cudaMalloc(&m->hot_slice_order, (size_t) nsl * 4) != cudaSuccess;
+            if (!rc) {
+                hotx_slice_keys_kernel<<<(nsl + 255) / 256, 256>>>(m->hot_sell->irp, nsl, k0, v0);
+                cub::DeviceRadixSort::SortPairs(nullptr, b2, k0, k1, v0, m->hot_slice_order, (int) nsl);
+                rc = cudaMalloc(&t2, b2 + 16) != cudaSuccess;
+                if (!rc) rc = cub::DeviceRadixSort::SortPairs(t2, b2, k0, k1, v0, m->hot_slice_order, (int) nsl) != cudaSuccess;
+                if (!rc) rc = cudaDeviceSynchronize() != cudaSuccess;
+            }
+            cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(t2);
+            if (rc) break;
+        }
         m->hot_H = H;
     } while (0);
     cudaFree(cnt);
@@ -642,8 +663,10 @@ static int hotx_build(spmvb200_matrix* m, uint32_t H, double min_cover) {
         if (m->hot_sell) { spmvb200_free(m->hot_sell); m->hot_sell = nullptr; }
         cudaFree(m->hot_cols);
         cudaFree(m->ja_hot);
+        cudaFree(m->hot_slice_order);
         m->hot_cols = nullptr;
         m->ja_hot = nullptr;
+        m->hot_slice_order = nullptr;
         m->hot_H = 0;
         return 1;
     }
@@ -653,8 +676,10 @@ static void hotx_drop(spmvb200_matrix* m) {
     if (m->hot_sell) { spmvb200_free(m->hot_sell); m->hot_sell = nullptr; }
     cudaFree(m->hot_cols);
     cudaFree(m->ja_hot);
+    cudaFree(m->hot_slice_order);
     m->hot_cols = nullptr;
     m->ja_hot = nullptr;
+    m->hot_slice_order = nullptr;
     m->hot_H = 0;
 }
 

@@ -312,18 +312,26 @@ static int launch_hotx(spmvb200_matrix* m, const double* x, double* y, cudaStrea
     a.partial = m->partial;
     a.ticket = m->ticket;
     a.hot_cols = m->hot_cols;
-    a.H = m->hot_H;
-    const size_t smem = (size_t) m->hot_H * 8;
-    static size_t configured[64] = {0};
+    a.slice_order = m->hot_slice_order;
     static int sms[64] = {0};
+    static bool configured[64] = {false};
     int dev = 0;
     CU_TRY(cudaGetDevice(&dev));
-    if (smem > configured[dev & 63]) {
-        CU_TRY(cudaFuncSetAttribute(hotx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        configured[dev & 63] = smem;
+    if (!configured[dev & 63]) {
+        CU_TRY(cudaFuncSetAttribute(hotx_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        CU_TRY(cudaFuncSetAttribute(hotx_kernel<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        CU_TRY(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+        configured[dev & 63] = true;
     }
-    if (!sms[dev & 63]) CU_TRY(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
-    hotx_kernel<<<sms[dev & 63], HOTX_BLOCK, smem, st>>>(a, x, y);
+    // the hot columns are stored by decreasing popularity: a smaller cache is a prefix of a bigger one, ids >= H_used but < hot_H
+    // ... are NOT cold ids, so the kernel is always given the H the ids were remapped with and a shape whose cache holds it
+    if (m->hot_shape == 1 && m->hot_H <= 8192) {
+        a.H = m->hot_H;
+        hotx_kernel<512, 3><<<3 * sms[dev & 63], 512, (size_t) a.H * 8, st>>>(a, x, y);
+    } else {
+        a.H = m->hot_H;
+        hotx_kernel<1024, 1><<<sms[dev & 63], 1024, (size_t) a.H * 8, st>>>(a, x, y);
+    }
     ++g_launches;
     return 0;
 }
@@ -386,12 +394,15 @@ static int time_best_of_2(F&& run, cudaStream_t st, float* ms_out) {
     return 0;
 }
 
-static int hotx_build_quiet(spmvb200_matrix* m) {
+// shape 0: 16384 hot columns, 1024 threads x 1 CTA per SM; shape 1: 8192 hot columns, 512 threads x 3 CTAs per SM
+static int hotx_build_quiet(spmvb200_matrix* m, int shape = -1) {
+    if (shape < 0) shape = getenv("SPMVB200_HOTX_SHAPE") ? atoi(getenv("SPMVB200_HOTX_SHAPE")) : 1;  // developer knob; default: the measured winner
     const int quiet0 = g_quiet;
     g_quiet = 1;
-    const int rc = hotx_build(m, 16384, 0.25);
+    const int rc = hotx_build(m, shape == 1 ? 8192 : 16384, 0.25);
     g_quiet = quiet0;
     g_err[0] = 0;
+    if (!rc) m->hot_shape = shape == 1 ? 1 : 0;
     return rc;
 }
 static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cudaStream_t st) {
@@ -459,23 +470,25 @@ static int tune_adaptive(spmvb200_matrix* m, const double* d_x, double* d_y, cud
             }
         }
     }
-    // hot-x hybrid: only where the column popularity is skewed enough for a 128 KB cache of x to matter
+    // hot-x hybrid: only where the column popularity is skewed enough for a 64-128 KB cache of x to matter; both launch shapes are timed
     if (big && !getenv("SPMVB200_NO_HOTX") && (!force || atoi(force) == CAND_HOTX)) {
-        const int quiet0 = g_quiet;
-        g_quiet = 1;
-        const int rc = hotx_build(m, 16384, 0.25);
-        g_quiet = quiet0;
-        g_err[0] = 0;
-        if (!rc) {
-            float ms = 1e30f;
-            if (time_best_of_2([&] { launch_hotx(m, d_x, d_y, st); }, st, &ms)) return 1;
+        float shape_ms[2] = {1e30f, 1e30f};
+        const char* only = getenv("SPMVB200_HOTX_SHAPE");
+        for (int shape = 0; shape < 2; ++shape) {
+            if (only && atoi(only) != shape) continue;
+            if (hotx_build_quiet(m, shape)) break;  // not skewed enough: neither shape qualifies
+            if (time_best_of_2([&] { launch_hotx(m, d_x, d_y, st); }, st, &shape_ms[shape])) return 1;
+            hotx_drop(m);
+        }
+        const int shape = shape_ms[1] < shape_ms[0] ? 1 : 0;
+        const float ms = shape_ms[shape];
+        if (ms < 1e30f) {
             m->tuned_ms[CAND_HOTX] = ms;
-            if (ms < 0.95f * best_ms || force) {
+            if (getenv("SPMVB200_VERBOSE")) fprintf(stderr, "spmv_b200: hot-x shapes: 16384 x 1 CTA %.3f ms, 8192 x 3 CTAs %.3f ms\n", shape_ms[0], shape_ms[1]);
+            if ((ms < 0.95f * best_ms || force) && !hotx_build_quiet(m, shape)) {
                 if (m->xw_child) { spmvb200_free(m->xw_child); m->xw_child = nullptr; }
                 best_ms = ms;
                 best = CAND_HOTX;
-            } else {
-                hotx_drop(m);
             }
         }
     }

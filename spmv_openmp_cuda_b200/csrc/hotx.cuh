@@ -21,7 +21,8 @@
 
 namespace spmvb200 {
 
-constexpr int HOTX_BLOCK = 1024;  // threads per CTA (one CTA per SM: the hot cache takes most of the shared memory)
+// launch shapes: <threads per CTA, CTAs per SM>; the hot cache is H * 8 bytes of shared memory per CTA (H = 16384 with one CTA per SM,
+// 8192 with three): more resident warps hide more gather latency, a bigger cache removes more gathers -- picked by timing
 
 __global__ void hotx_hist_kernel(const uint32_t* __restrict__ ja, uint64_t nz, uint32_t* __restrict__ cnt) {
     const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
@@ -43,6 +44,15 @@ __global__ void hotx_remap_hot_kernel(uint32_t* __restrict__ remap, const uint32
 __global__ void hotx_apply_kernel(const uint32_t* __restrict__ ja, const uint32_t* __restrict__ remap, uint64_t nz, uint32_t* __restrict__ out) {
     const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; j < nz; j += stride) out[j] = remap[ja[j]];
+}
+
+// sort keys for the slice order: 2^32-1 - slots of the slice (ascending sort = decreasing length)
+__global__ void hotx_slice_keys_kernel(const uint32_t* __restrict__ slice_ptr, uint32_t nsl, uint32_t* __restrict__ keys, uint32_t* __restrict__ ids) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nsl) {
+        keys[i] = 0xffffffffu - (slice_ptr[i + 1] - slice_ptr[i]);
+        ids[i] = i;
+    }
 }
 
 // x value of remapped column id c: shared memory for the hot ones, L2 gather for the rest (both predicated: no branch)
@@ -76,9 +86,11 @@ struct HotxArgs {
     // hot cache
     const uint32_t* hot_cols;
     uint32_t H;
+    const uint32_t* slice_order;  // slices by decreasing length: the heavy ones first, so that the kernel's tail is made of tiny slices
 };
 
-__global__ void __launch_bounds__(HOTX_BLOCK, 1)
+template <int HOTX_BLOCK, int MINB>
+__global__ void __launch_bounds__(HOTX_BLOCK, MINB)
 hotx_kernel(const HotxArgs a, const double* __restrict__ x, double* __restrict__ y) {
     extern __shared__ __align__(16) double hx_s[];  // [H] hot x values
     const uint32_t H = a.H;
@@ -138,7 +150,8 @@ hotx_kernel(const HotxArgs a, const double* __restrict__ x, double* __restrict__
         }
     }
     // (b) SELL slices, a lane per row, 4 slots in flight, left-to-right sums
-    for (uint32_t sl = gw; sl < a.nslices; sl += nw) {
+    for (uint32_t so = gw; so < a.nslices; so += nw) {
+        const uint32_t sl = __ldg(a.slice_order + so);
         const uint32_t i = sl * 32 + lane;
         const uint32_t len = __ldg(a.rl + i);
         const uint32_t sp0 = __ldg(a.slice_ptr + sl), sp1 = __ldg(a.slice_ptr + sl + 1);
