@@ -173,6 +173,8 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
         switch (pair_env) {
             case 2: if (spec) ELLP(2, true); else ELLP(2, false); break;
             case 3: if (spec) ELLP(3, true); else ELLP(3, false); break;
+            case 5: if (spec) ELLP(5, true); else ELLP(5, false); break;
+            case 6: if (spec) ELLP(6, true); else ELLP(6, false); break;
             default: if (spec) ELLP(4, true); else ELLP(4, false); break;
         }
 #undef ELLP
