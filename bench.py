@@ -263,6 +263,50 @@ def side_line(name, steps, peak):
     return out
 
 
+class NcclFallbackShard:
+    """Same interface as distributed.RowBlockShard for boxes where the GPUs cannot map each other's memory (CUDA IPC / peer access
+    refused): the exchange is an NCCL all-gather of the y slices into the next x after the SpMV instead of peer stores from its
+    epilogue.  Slower (the whole block travels, as a collective after the kernel) but the same arithmetic; the JSON line says which
+    exchange ran."""
+
+    def __init__(self, dm, splits, kind, torch, dist, lib, capi, why):
+        self.dm, self.kind, self.torch, self.dist, self.lib, self.capi, self.why = dm, kind, torch, dist, lib, capi, why
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.r0, self.r1 = splits[self.rank], splits[self.rank + 1]
+        assert len({b - a for a, b in zip(splits[:-1], splits[1:])}) == 1, "the all-gather fallback needs equal slices"
+        self.x = [torch.zeros(dm.N, dtype=torch.float64, device="cuda") for _ in range(3)]
+        self.y = torch.zeros(dm.M, dtype=torch.float64, device="cuda")
+        self.halo_rows = (self.world - 1) * dm.M
+        self._one = torch.zeros(1, device="cuda")
+
+    def x_ptr(self, buf):
+        return self.x[buf].data_ptr()
+
+    def step(self, src, dst, stream=None):
+        self.capi.check(self.lib.spmvb200_spmv_device(self.dm.handle, self.kind, self.x[src].data_ptr(), self.y.data_ptr(), stream), "spmv_device")
+        self.dist.all_gather_into_tensor(self.x[dst], self.y)
+
+    def barrier(self, stream=None):
+        self.dist.all_reduce(self._one)
+
+    def rows_of(self, buf, a, b):
+        return self.x[buf][a:b].cpu().numpy()
+
+    def spmv_host(self, x_slice, y_slice):
+        torch = self.torch
+        xs = x_slice if torch.is_tensor(x_slice) else torch.from_numpy(x_slice)
+        ys = y_slice if torch.is_tensor(y_slice) else torch.from_numpy(y_slice)
+        self.x[1][self.r0:self.r1].copy_(xs, non_blocking=True)
+        self.dist.all_gather_into_tensor(self.x[2], self.x[1][self.r0:self.r1])
+        self.capi.check(self.lib.spmvb200_spmv_device(self.dm.handle, self.kind, self.x[2].data_ptr(), self.y.data_ptr(),
+                                                      torch.cuda.current_stream().cuda_stream), "spmv_device")
+        ys.copy_(self.y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def close(self):
+        pass
+
+
 def link_ceiling(nbytes_up, nbytes_down, world, dist, torch, reps=10):
     """Bare duplex copy of this rank's per-step host<->device bytes (pinned, two streams, nothing else): the floor any host-buffer
     step has on this box.  All ranks copy at once (they share the host's memory / PCIe root); max over ranks."""
@@ -392,12 +436,23 @@ def main():
     rowmeta = 4 * rows_total if fmt == "ell" else 4 * (rows_total + 1)
     bytes_local = (12 * nnz_total + rowmeta + 8 * Ncols + 8 * rows_total) // nr
 
-    shard = RowBlockShard(dm, splits, kind, nbuf=3, col_range=col_range)
     stream = torch.cuda.current_stream().cuda_stream
     if world > 1:  # a stream of our own: the legacy default stream synchronises implicitly with every other blocking stream
         own = torch.cuda.Stream()
         torch.cuda.set_stream(own)
         stream = own.cuda_stream
+    exchange = "peer stores from the SpMV epilogue (CUDA IPC) + flag barrier" if world > 1 else "none (one GPU)"
+    try:
+        if os.environ.get("BENCH_FORCE_NCCL_EXCHANGE") and world > 1:
+            raise sp.SpmvB200Error("forced by BENCH_FORCE_NCCL_EXCHANGE")
+        shard = RowBlockShard(dm, splits, kind, nbuf=3, col_range=col_range)
+    except sp.SpmvB200Error as e:  # every rank raises together (RowBlockShard agrees on the outcome before returning)
+        if world == 1:
+            raise
+        shard = NcclFallbackShard(dm, splits, kind, torch, dist, lib, capi, repr(e))
+        exchange = "NCCL all-gather of the y slices after the SpMV (peer mapping unavailable: %s)" % repr(e)[:200]
+        if rank == 0:
+            sys.stderr.write("bench.py: %s\n" % exchange)
     X0 = shard.x_ptr(0)
     synth.device_vector_fill(X0, Ncols)  # replicated x0: every rank generates the whole vector (pure function of the index)
     capi.check(lib.spmvb200_tune(dm.handle, kind, X0, shard.x_ptr(1), stream), "tune")  # first-use pick, outside every timed region
@@ -533,6 +588,7 @@ def main():
                 "x <- A x on one GPU (ping-pong vectors; source reset to x0 every %d steps)" % RESET_EVERY,
         "kernel_only": {"ms_per_step": ms_kernel, "value": 2.0 * nnz_total / (ms_kernel * 1e-3) / 1e9, "unit": UNIT,
                         "exchange_overhead_frac": ms_step / ms_kernel - 1.0},
+        "exchange": exchange,
         "nvlink_bytes_per_step": int(allsum(torch, dist, world, shard.halo_rows * 8)),
         "hbm_gbs": achieved * nr, "clocks": clocks,
         "e2e": {"value": 2.0 * nnz_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,

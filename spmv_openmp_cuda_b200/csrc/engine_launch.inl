@@ -163,7 +163,11 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
     const unsigned grid = (unsigned) ((r1 - r0 + BLOCK - 1) / BLOCK);
 #define ELL16(U) ell_colmajor_kernel<U, BLOCK, true><<<grid, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, (uint32_t) m->K, m->ja16_base, x, y, g_push)
     // 16-bit ids: two rows per thread, 3 slots in flight (measured on cfg2: 96.9 us; one row per thread 103.0; pair x2 100.7, pair x4 107.1)
-    static const int pair_env = getenv("SPMVB200_ELL_PAIR") ? atoi(getenv("SPMVB200_ELL_PAIR")) : 3;  // developer knob: 0 = one row per thread
+    // Short rows (K <= 6: 5-point / 7-point stencils) take ALL their slots in one batch -- one DRAM round trip per thread instead of two is
+    // what an isolated launch of a small matrix is made of: cfg1 (K = 5, L2 flushed) 20.6 -> 18.5 us, 0.62 -> 0.69 of the roofline
+    // (profiles/r02g_cfg1_ell_variants.log).
+    static const int pair_knob = getenv("SPMVB200_ELL_PAIR") ? atoi(getenv("SPMVB200_ELL_PAIR")) : -1;  // developer knob: 0 = one row per thread
+    const int pair_env = pair_knob >= 0 ? pair_knob : (m->K >= 2 && m->K <= 6 ? (int) m->K : 3);
     if (m->ja16 && !no_exit && pair_env && (r0 % 2) == 0) {
         const unsigned g2 = (unsigned) (((r1 - r0 + 1) / 2 + BLOCK - 1) / BLOCK);
 #define ELLP(U, S) ell_colmajor_pair_kernel<U, BLOCK, S><<<g2, BLOCK, 0, st>>>(m->as, m->ja16, m->rl, m->pitch, (uint32_t) r0, (uint32_t) r1, m->ja16_base, x, y, g_push)
