@@ -236,7 +236,8 @@ extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x,
     for (int k = 0; k < p->nch; ++k) {
         CU_TRY(cudaStreamWaitEvent(p->s_comp, p->x_ready[k], 0));
         CU_TRY(cudaEventRecord(p->k_start[k], p->s_comp));
-        launch_chunk(m, p, k, m->d_x, y_map ? y_map : m->d_y);
+        static const bool no_kernel = getenv("SPMVB200_PIPE_NO_KERNEL") != nullptr;  // developer knob: copies only (timeline experiments)
+        if (!no_kernel) launch_chunk(m, p, k, m->d_x, y_map ? y_map : m->d_y);
         CU_TRY(cudaEventRecord(p->k_end[k], p->s_comp));
         const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
         if (r1 > r0 && !y_map) {
