@@ -540,7 +540,7 @@ def main():
     def e2e_step_of(xbuf, ybuf):
         if world == 1:
             return lambda: capi.check(lib.spmvb200_spmv_host(dm.handle, kind, capi.ptr(xbuf), capi.ptr(ybuf), None), "spmv_host")
-        return lambda: shard.spmv_host(xbuf, ybuf)
+        return lambda: shard.spmv_host(xbuf, ybuf, timed=False) if hasattr(shard, "_h") else shard.spmv_host(xbuf, ybuf)
 
     def e2e_timed(fn, blocks_n):
         sync_all()

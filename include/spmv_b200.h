@@ -231,7 +231,9 @@ int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a, double* d
  *   int f(spmat* mat, double* x, CONFIG* cfg, double* y)        src/include/SpMV.h:63-64
  * x (N doubles) is copied to the device, the kernel runs, y (rows doubles) is copied back; the call
  * returns after y is complete.  *kernel_ms (may be NULL) receives the CUDA-event time of the kernel
- * alone -- the value a driver stores in ElapsedInternal (src/include/config.h:112). */
+ * alone -- the value a driver stores in ElapsedInternal (src/include/config.h:112).  Long vectors run as a pipeline
+ * of row chunks (x pieces up, kernel chunks, y chunks down); asking for kernel_ms puts time-stamped events between the chunks,
+ * which costs ~10 % of the call on 268 MB vectors (tools/pipe_lab.cu): pass NULL when the kernel time is not needed. */
 int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms);
 /* Pageable x / y (what the reference driver passes: malloc, src/main.cu:155,181) are page-locked in place with cudaHostRegister the
  * second time the same address and size come back, and stay so until this call (p == NULL: all) or spmvb200_cache_drop(NULL).

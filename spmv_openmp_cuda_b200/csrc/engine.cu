@@ -36,9 +36,12 @@ static void destroy_pipe(HostPipe* p) {
     for (auto e : p->x_ready) cudaEventDestroy(e);
     for (auto e : p->k_start) cudaEventDestroy(e);
     for (auto e : p->k_end) cudaEventDestroy(e);
+    for (auto e : p->k_done) cudaEventDestroy(e);
     if (p->s_up) cudaStreamDestroy(p->s_up);
     if (p->s_comp) cudaStreamDestroy(p->s_comp);
     if (p->s_down) cudaStreamDestroy(p->s_down);
+    if (p->s_up2) cudaStreamDestroy(p->s_up2);
+    if (p->s_down2) cudaStreamDestroy(p->s_down2);
     delete p;
 }
 

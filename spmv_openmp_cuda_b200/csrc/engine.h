@@ -16,7 +16,9 @@ struct HostPipe {
     std::vector<uint32_t> tile_b;  // nch+1 tile bounds (CSR stream kernel)
     std::vector<uint64_t> x_b;     // nch+1 bounds of the x pieces: chunk k reads only x[0, x_b[k+1])
     cudaStream_t s_up = nullptr, s_comp = nullptr, s_down = nullptr;
-    std::vector<cudaEvent_t> x_ready, k_start, k_end;
+    cudaStream_t s_up2 = nullptr, s_down2 = nullptr;  // optional second copy stream per direction (SPMVB200_HOST_COPY_STREAMS=2)
+    std::vector<cudaEvent_t> x_ready, k_start, k_end;  // k_start / k_end carry time stamps: recorded only when the caller asks for kernel_ms
+    std::vector<cudaEvent_t> k_done;                   // chunk finished, no time stamp (tools/pipe_lab.cu: 32 timing events cost 0.65 ms per call)
 };
 constexpr uint64_t PAD = 16;  // readable slack after ja/as (vector loads and 16-byte aligned TMA tiles overrun)
 }  // namespace spmvb200

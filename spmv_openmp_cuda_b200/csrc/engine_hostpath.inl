@@ -42,6 +42,33 @@ static int host_chunks_wanted(const spmvb200_matrix* m) {
     if (const char* e = getenv("SPMVB200_HOST_CHUNKS")) nch = std::max(1, atoi(e));  // developer knob
     return nch;
 }
+// Cumulative chunk bounds as fractions of the rows.  Short vectors: equal chunks.  Long vectors (>= 64 MB): a RAMP -- the first
+// chunks double in size (1, 2, 4, 8 parts), the middle is made of equal large chunks, the last ones halve again -- so that the serial
+// head of the pipeline (first x piece up + first kernel chunk, nothing coming down yet) and its serial tail (last kernel chunk + last
+// y chunk down, nothing going up any more) are a sixteenth of what equal chunks make them, while the bulk moves in few large copies
+// (every copy costs ~20 us of link idle time: tools/duplex_probe.py, 64 equal chunks 6.46 ms against 5.36 ms for one).
+// SPMVB200_HOST_SCHED=uniform|ramp overrides (developer knob).
+static std::vector<double> host_chunk_fractions(const spmvb200_matrix* m, int& nch) {
+    const char* e = getenv("SPMVB200_HOST_SCHED");
+    const uint64_t bytes = std::max(m->M, m->N) * 8;
+    const bool ramp = e ? !strcmp(e, "ramp") : bytes >= (64ull << 20);
+    std::vector<double> w;
+    if (ramp && nch >= 10) {
+        const int mid = nch - 8;  // 4 doubling chunks at either end
+        for (int k = 0; k < 4; ++k) w.push_back((double) (1 << k));
+        for (int k = 0; k < mid; ++k) w.push_back(16.0);
+        for (int k = 3; k >= 0; --k) w.push_back((double) (1 << k));
+    } else {
+        w.assign(nch, 1.0);
+    }
+    nch = (int) w.size();
+    double tot = 0;
+    for (double v : w) tot += v;
+    std::vector<double> cum(nch + 1, 0.0);
+    for (int k = 0; k < nch; ++k) cum[k + 1] = cum[k] + w[k] / tot;
+    cum[nch] = 1.0;
+    return cum;
+}
 static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
     destroy_pipe(m->pipe);  // rebuilt only when another kind is used through the host path
     m->pipe = nullptr;
@@ -56,6 +83,7 @@ static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
     const spmvb200_matrix* xw = cand == 200 ? xwin_of(m, kind) : nullptr;
     if (stream) nch = (int) std::max<uint32_t>(1, std::min<uint32_t>(nch, m->ntiles));
     if (xw) nch = (int) std::max<uint32_t>(1, std::min<uint32_t>(nch, xw->xw_nrb));
+    const std::vector<double> cum = host_chunk_fractions(m, nch);
     p->nch = nch;
     p->row_b.assign(nch + 1, m->M);
     p->tile_b.assign(nch + 1, m->ntiles);
@@ -63,7 +91,7 @@ static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
     p->tile_b[0] = 0;
     for (int k = 1; k < nch; ++k) {
         if (stream) {
-            uint32_t t = (uint32_t) ((uint64_t) m->ntiles * k / nch);
+            uint32_t t = (uint32_t) ((double) m->ntiles * cum[k]);
             // never cut inside the segment run of a long row: its y entry is written by whichever segment finishes last
             while (t < m->ntiles && t > 0 && (m->h_tile_row0[t] & SEG_FLAG) && (m->h_tile_row0[t - 1] & SEG_FLAG) &&
                    (m->h_tile_row0[t] == m->h_tile_row0[t - 1]))
@@ -72,9 +100,9 @@ static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
             p->tile_b[k] = t;
             p->row_b[k] = m->h_tile_row0[t] & ~SEG_FLAG;
         } else if (xw) {
-            p->row_b[k] = std::min<uint64_t>(m->M, ((uint64_t) xw->xw_nrb * k / nch) * xw->xw_R);  // whole row blocks
+            p->row_b[k] = std::max<uint64_t>(p->row_b[k - 1], std::min<uint64_t>(m->M, (uint64_t) ((double) xw->xw_nrb * cum[k]) * xw->xw_R));  // whole row blocks
         } else {
-            p->row_b[k] = std::max<uint64_t>(p->row_b[k - 1], (m->M * k / nch) & ~255ull);
+            p->row_b[k] = std::max<uint64_t>(p->row_b[k - 1], (uint64_t) ((double) m->M * cum[k]) & ~255ull);
         }
     }
     // x pieces: piece k ends right after the largest column id row chunks 0..k read, so that chunk k can start
@@ -125,12 +153,19 @@ static int build_pipe(spmvb200_matrix* m, int kind, int cand) {
     CU_TRY(cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking));
+    if (const char* e = getenv("SPMVB200_HOST_COPY_STREAMS"))  // developer knob: copies of one direction alternate between two streams
+        if (atoi(e) >= 2) {
+            CU_TRY(cudaStreamCreateWithFlags(&p->s_up2, cudaStreamNonBlocking));
+            CU_TRY(cudaStreamCreateWithFlags(&p->s_down2, cudaStreamNonBlocking));
+        }
     p->x_ready.resize(nch);
     p->k_start.resize(nch);
     p->k_end.resize(nch);
+    p->k_done.resize(nch);
     for (auto& ev : p->x_ready) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : p->k_start) CU_TRY(cudaEventCreate(&ev));
     for (auto& ev : p->k_end) CU_TRY(cudaEventCreate(&ev));
+    for (auto& ev : p->k_done) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     return 0;
 }
 
@@ -221,6 +256,7 @@ extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x,
     HostPipe* p = m->pipe;
     double* const y_map = mapped_alias(y, true, false);
     const bool dbg = getenv("SPMVB200_PIPE_DEBUG") != nullptr;
+    const bool timed = kernel_ms != nullptr || dbg;  // time-stamped events between the chunks slow the pipeline down by ~10 %: only on request
     std::vector<cudaEvent_t> dbg_up, dbg_down;
     cudaEvent_t dbg0 = nullptr;
     if (dbg) {
@@ -229,27 +265,34 @@ extern "C" int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x,
     }
     for (int j = 0; j < p->nch; ++j) {
         const uint64_t o = p->x_b[j], n = p->x_b[j + 1] - o;
-        if (n) CU_TRY(cudaMemcpyAsync(m->d_x + o, x + o, n * 8, cudaMemcpyHostToDevice, p->s_up));
-        CU_TRY(cudaEventRecord(p->x_ready[j], p->s_up));
-        if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, p->s_up); dbg_up.push_back(e); }
+        cudaStream_t su = (p->s_up2 && (j & 1)) ? p->s_up2 : p->s_up;
+        if (n) CU_TRY(cudaMemcpyAsync(m->d_x + o, x + o, n * 8, cudaMemcpyHostToDevice, su));
+        CU_TRY(cudaEventRecord(p->x_ready[j], su));
+        if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, su); dbg_up.push_back(e); }
     }
     for (int k = 0; k < p->nch; ++k) {
         CU_TRY(cudaStreamWaitEvent(p->s_comp, p->x_ready[k], 0));
-        CU_TRY(cudaEventRecord(p->k_start[k], p->s_comp));
+        if (timed) CU_TRY(cudaEventRecord(p->k_start[k], p->s_comp));
         static const bool no_kernel = getenv("SPMVB200_PIPE_NO_KERNEL") != nullptr;  // developer knob: copies only (timeline experiments)
         if (!no_kernel) launch_chunk(m, p, k, m->d_x, y_map ? y_map : m->d_y);
-        CU_TRY(cudaEventRecord(p->k_end[k], p->s_comp));
+        cudaEvent_t const kdone = timed ? p->k_end[k] : p->k_done[k];
+        CU_TRY(cudaEventRecord(kdone, p->s_comp));
         const uint64_t r0 = p->row_b[k], r1 = p->row_b[k + 1];
         if (r1 > r0 && !y_map) {
-            CU_TRY(cudaStreamWaitEvent(p->s_down, p->k_end[k], 0));
-            CU_TRY(cudaMemcpyAsync(y + r0, m->d_y + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, p->s_down));
-            if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, p->s_down); dbg_down.push_back(e); }
+            cudaStream_t sd = (p->s_down2 && (k & 1)) ? p->s_down2 : p->s_down;
+            CU_TRY(cudaStreamWaitEvent(sd, kdone, 0));
+            CU_TRY(cudaMemcpyAsync(y + r0, m->d_y + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, sd));
+            if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sd); dbg_down.push_back(e); }
         }
     }
     CU_TRY(cudaPeekAtLastError());
     CU_TRY(cudaStreamSynchronize(p->s_comp));
     CU_TRY(cudaStreamSynchronize(p->s_down));
     CU_TRY(cudaStreamSynchronize(p->s_up));
+    if (p->s_up2) {
+        CU_TRY(cudaStreamSynchronize(p->s_down2));
+        CU_TRY(cudaStreamSynchronize(p->s_up2));
+    }
     if (dbg) {
         float ms;
         fprintf(stderr, "pipe: x piece bounds=");

@@ -378,13 +378,14 @@ extern "C" int spmvb200_shard_spmv_host(spmvb200_shard* s, const double* x_slice
     // 3. row chunks as their pieces land; y chunks go down while later chunks compute
     for (int k = 0; k < p->nch; ++k) {
         CU_TRY(cudaStreamWaitEvent(p->s_comp, p->x_ready[k], 0));
-        CU_TRY(cudaEventRecord(p->k_start[k], p->s_comp));
+        if (kernel_ms) CU_TRY(cudaEventRecord(p->k_start[k], p->s_comp));  // time stamps only on request (they slow the pipeline down)
         if (p->nch <= 1 && cand < 0) { if (launch(m, kind, xd, s->d_y, p->s_comp)) return 1; }
         else launch_chunk(m, p, k, xd, s->d_y);
-        CU_TRY(cudaEventRecord(p->k_end[k], p->s_comp));
+        cudaEvent_t const kdone = kernel_ms ? p->k_end[k] : p->k_done[k];
+        CU_TRY(cudaEventRecord(kdone, p->s_comp));
         const uint64_t a = p->row_b[k], e = p->row_b[k + 1];
         if (e > a) {
-            CU_TRY(cudaStreamWaitEvent(p->s_down, p->k_end[k], 0));
+            CU_TRY(cudaStreamWaitEvent(p->s_down, kdone, 0));
             CU_TRY(cudaMemcpyAsync(y_slice + a, s->d_y + a, (e - a) * 8, cudaMemcpyDeviceToHost, p->s_down));
         }
     }
