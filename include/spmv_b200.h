@@ -235,9 +235,19 @@ int spmvb200_iterate_device(spmvb200_matrix* m, int kind, double* d_a, double* d
  * of row chunks (x pieces up, kernel chunks, y chunks down); asking for kernel_ms puts time-stamped events between the chunks,
  * which costs ~10 % of the call on 268 MB vectors (tools/pipe_lab.cu): pass NULL when the kernel time is not needed. */
 int spmvb200_spmv_host(spmvb200_matrix* m, int kind, const double* x, double* y, float* kernel_ms);
-/* Pageable x / y (what the reference driver passes: malloc, src/main.cu:155,181) are page-locked in place with cudaHostRegister the
- * second time the same address and size come back, and stay so until this call (p == NULL: all) or spmvb200_cache_drop(NULL).
- * Call it before free()ing such a buffer.  SPMVB200_NO_HOST_REGISTER=1 disables the registration altogether. */
+/* Pageable x / y (what the reference driver passes: malloc, src/main.cu:155,181) move at about half the page-locked rate and cannot
+ * overlap with the kernel.  spmvb200_host_register page-locks a caller buffer IN PLACE (cudaHostRegister; no-op for memory that is
+ * page-locked already) until spmvb200_host_unregister(p) (p == NULL: all; also done by spmvb200_cache_drop(NULL)) -- the one call a
+ * driver adds next to its malloc, and the other before its free().  A buffer freed while registered leaves a stale registration
+ * behind (later CUDA calls on a re-used address fail with "invalid argument"), which is why the library does not register
+ * buffers on its own unless SPMVB200_HOST_REGISTER=auto is set (then: the second time the same address and size come back). */
+int spmvb200_host_register(const void* p, size_t bytes);
+/* Page-locked vectors allocated by the library (cudaHostAlloc) -- the other one-line change: malloc -> spmvb200_host_alloc, free ->
+ * spmvb200_host_free.  Fastest kind of host buffer: in-place registration of malloc'ed memory keeps its 4 KB pages, which cost ~18 % of
+ * the duplex copy rate on the B200 box (tools/hostmem_lab.cu).  NULL on failure (spmvb200_last_error). */
+void* spmvb200_host_alloc(size_t bytes);
+int spmvb200_host_free(void* p);
+int spmvb200_host_registered(const void* p); /* 1 if this library holds a registration of p */
 int spmvb200_host_unregister(const void* p);
 
 /* Repeat the kernel `reps` times on device-resident vectors and return per-repetition CUDA-event

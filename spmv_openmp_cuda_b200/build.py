@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libspmv_b200.so")
 SOURCES = ["engine.cu", "synth.cu"]
-DEPS = SOURCES + ["engine_formats.inl", "engine_launch.inl", "engine_multigpu.inl", "engine_hostpath.inl",
+DEPS = SOURCES + ["engine_formats.inl", "engine_launch.inl", "engine_multigpu.inl", "engine_hostpath.inl", "engine_shard.inl", "hotx.cuh",
                   "kernels.cuh", "plan.cuh", "xwin.cuh", "common.cuh", "engine.h", os.path.join("..", "..", "include", "spmv_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp,-O2", "--shared", "-lgomp"]

@@ -70,6 +70,10 @@ _SIGS = {
     "spmvb200_shard_spmv_host": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_float)]),
     "spmvb200_shard_free": (C.c_int, [_vp]),
     "spmvb200_host_unregister": (C.c_int, [_vp]),
+    "spmvb200_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "spmvb200_host_registered": (C.c_int, [_vp]),
+    "spmvb200_host_alloc": (_vp, [C.c_size_t]),
+    "spmvb200_host_free": (C.c_int, [_vp]),
     "spmvb200_compare_strict_csr": (C.c_int, [_u64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.POINTER(_u64), C.POINTER(C.c_double)]),
     "spmvb200_compare_abs": (C.c_int, [_u64, _vp, _vp, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "spmvb200_ipc_export": (C.c_int, [_vp, _vp]),

@@ -187,9 +187,13 @@ static double* mapped_alias(double* y, bool chunked, bool xwin_launch) {
 
 // ---- pageable caller buffers --------------------------------------------------------------------
 // The reference driver hands malloc'ed x and y (src/main.cu:155,181): pageable memory goes through the driver's staging copies at
-// roughly half the pinned rate and cannot overlap with anything.  A buffer that comes back a SECOND time with the same address and
-// size (the harness reuses its vectors for every repetition) is page-locked in place with cudaHostRegister and stays so until
-// spmvb200_host_unregister (or spmvb200_cache_drop(NULL)); at most 16 buffers are tracked.  SPMVB200_NO_HOST_REGISTER switches it off.
+// roughly half the pinned rate and cannot overlap with anything.  spmvb200_host_register(p, bytes) page-locks such a buffer IN PLACE
+// (cudaHostRegister) until spmvb200_host_unregister(p) -- the one call a driver adds next to its malloc.  It is explicit on purpose:
+// a buffer that is free()d while still registered leaves a stale registration behind, and the next allocation that lands on the same
+// address makes unrelated CUDA calls fail with "invalid argument" (seen in this repo's own tests with numpy buffers), so the library
+// never registers memory whose lifetime it does not know -- unless SPMVB200_HOST_REGISTER=auto asks for it: then a buffer that comes
+// back a SECOND time with the same address and size is registered (a harness that reuses its vectors for every repetition and calls
+// spmvb200_host_unregister(NULL) / spmvb200_cache_drop(NULL) before freeing them).  At most 16 buffers are tracked.
 namespace {
 struct HostReg {
     size_t bytes = 0;
@@ -199,9 +203,42 @@ struct HostReg {
 std::map<const void*, HostReg> g_hostreg;
 std::mutex g_hostreg_mu;
 }  // namespace
+// Page-locked host vectors from the library (cudaHostAlloc): what a driver swaps its malloc / free of x and y for.  Measured on the B200
+// box with 268 MB vectors (tools/hostmem_lab.cu): duplex copy 5.36 ms, against 6.35 ms for malloc'ed memory page-locked in place (4 KB
+// pages; with transparent huge pages behind the buffer the in-place registration reaches 5.37 ms too) and 37 ms for pageable memory.
+extern "C" void* spmvb200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, std::max<size_t>(bytes, 8), cudaHostAllocDefault) != cudaSuccess) {
+        fail("host_alloc: cudaHostAlloc(%zu) -> %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" int spmvb200_host_free(void* p) {
+    if (p) CU_TRY(cudaFreeHost(p));
+    return 0;
+}
+extern "C" int spmvb200_host_register(const void* p, size_t bytes) {
+    if (!p || !bytes) return fail("host_register: null buffer");
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return fail("host_register: cannot query the pointer"); }
+    if (a.type != cudaMemoryTypeUnregistered) return 0;  // already page-locked (cudaHostAlloc / registered by the caller)
+    std::lock_guard<std::mutex> lk(g_hostreg_mu);
+    if (g_hostreg.size() >= 16 && !g_hostreg.count(p)) return fail("host_register: 16 buffers are registered already");
+    cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail("host_register: cudaHostRegister -> %s", cudaGetErrorString(e));
+    }
+    HostReg& r = g_hostreg[p];
+    r.bytes = bytes;
+    r.seen = 2;
+    r.registered = true;
+    return 0;
+}
 static void host_buffer_seen(const void* p, size_t bytes) {
-    static const bool off = getenv("SPMVB200_NO_HOST_REGISTER") != nullptr;
-    if (off || bytes < (1u << 20)) return;
+    static const bool automatic = getenv("SPMVB200_HOST_REGISTER") && !strcmp(getenv("SPMVB200_HOST_REGISTER"), "auto");
+    if (!automatic || bytes < (1u << 20)) return;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return; }
     if (a.type != cudaMemoryTypeUnregistered) return;  // already page-locked (or not host memory at all)
@@ -212,6 +249,11 @@ static void host_buffer_seen(const void* p, size_t bytes) {
     if (r.seen < 0 || ++r.seen < 2) return;
     if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) r.registered = true;
     else { cudaGetLastError(); r.seen = -1; }  // e.g. read-only mapping: stay on the pageable path for this buffer
+}
+extern "C" int spmvb200_host_registered(const void* p) {
+    std::lock_guard<std::mutex> lk(g_hostreg_mu);
+    auto it = g_hostreg.find(p);
+    return it != g_hostreg.end() && it->second.registered ? 1 : 0;
 }
 extern "C" int spmvb200_host_unregister(const void* p) {
     std::lock_guard<std::mutex> lk(g_hostreg_mu);

@@ -111,6 +111,10 @@ int main(int argc, char** argv) {
     }
     if (!(outV = malloc(mat->M * sizeof(*outV)))) { ERRPRINT("outV malloc errd\n"); goto _free; }
     memset(outV, 0xFF, mat->M * sizeof(*outV));
+    if (cmode >= _B200_CSR_ROWS) { /* page-lock the caller's vectors in place (optional) -- released at _free before free() */
+        spmvb200_host_register(vector, vectSize * sizeof(*vector));
+        spmvb200_host_register(outV, mat->M * sizeof(*outV));
+    }
     double start = omp_get_wtime();
     if ((out = func(mat, vector, &Conf, outV))) { ERRPRINT("compute function selected failed...\n"); goto _free; }
     double elapsed = omp_get_wtime() - start;
@@ -134,7 +138,7 @@ int main(int argc, char** argv) {
         out = (bad || failed || ref_failed) ? EXIT_FAILURE : EXIT_SUCCESS;
     }
 _free:
-    spmvb200_cache_drop(NULL);
+    spmvb200_cache_drop(NULL); /* also releases the page-lock registrations */
     if (csr && csr != mat) freeSpmat(csr);
     if (mat) freeSpmat(mat);
     free(vector);

@@ -53,10 +53,17 @@ def test_shard_single_rank_step_and_host(sp, orc, kind_name):
         want = _y(orc, mat, want)
     np.testing.assert_array_equal(sh.rows_of(1), want)
     y_ref = _y(orc, mat, x0)
-    for rep in range(3):  # pageable buffers: plain copies on the first call, page-locked in place from the second on
-        y = np.full(mat.M, np.nan)
+    y = np.full(mat.M, np.nan)
+    for rep in range(3):  # pageable buffers: plain copies first, then page-locked in place by the explicit call
+        y.fill(np.nan)
+        if rep == 1:
+            assert sp.capi.lib().spmvb200_host_register(sp.capi.ptr(x0), x0.nbytes) == 0
+            assert sp.capi.lib().spmvb200_host_register(sp.capi.ptr(y), y.nbytes) == 0
         assert sh.spmv_host(x0, y) > 0
         np.testing.assert_array_equal(y, y_ref)
+    y.fill(np.nan)
+    assert sh.spmv_host(x0, y, timed=False) is None  # no time-stamped events between the chunks
+    np.testing.assert_array_equal(y, y_ref)
     sh.close()
     assert sp.capi.lib().spmvb200_host_unregister(None) == 0
 
@@ -262,9 +269,65 @@ def test_host_path_xwindow_runs_in_row_block_chunks(sp, orc, pinned, monkeypatch
     for chunks in ("1", "3", "7"):
         monkeypatch.setenv("SPMVB200_HOST_CHUNKS", chunks)
         for dm, kind in ((d_xw, sp.XWIN_ROWS), (d_csr, sp.CSR_ROWS)):
-            for rep in range(3):
-                y = buf(mat.M)
+            y = buf(mat.M)
+            for rep in range(4):
                 y.fill(np.nan)
-                assert sp.spmv_host(kind, dm, xb, y) > 0
+                if rep == 1 and not pinned:  # pageable -> page-locked in place (explicit: the library never guesses a buffer's lifetime)
+                    assert sp.capi.lib().spmvb200_host_register(sp.capi.ptr(xb), xb.nbytes) == 0
+                    assert sp.capi.lib().spmvb200_host_register(sp.capi.ptr(y), y.nbytes) == 0
+                if rep == 3:
+                    assert sp.spmv_host(kind, dm, xb, y, timed=False) is None
+                else:
+                    assert sp.spmv_host(kind, dm, xb, y) > 0
                 np.testing.assert_array_equal(y, y_ref, err_msg="%s chunks=%s rep=%d" % (kind, chunks, rep))
+            assert sp.capi.lib().spmvb200_host_unregister(sp.capi.ptr(y)) == 0  # before y is freed
     assert sp.capi.lib().spmvb200_host_unregister(None) == 0
+
+
+def test_host_register_auto_policy_is_opt_in(sp):
+    """Without SPMVB200_HOST_REGISTER=auto the library leaves caller buffers alone: a pageable buffer stays pageable however often
+    it comes back (a buffer freed while registered would poison its address range for every later CUDA call)."""
+    s = sp.synth
+    mat = s.host_csr(s.banded(300_000, 8, 500))
+    dm = sp.spMatCpyCSR(mat)
+    x, y = s.host_vector(mat.N), np.empty(mat.M)
+    L = sp.capi.lib()
+    for _ in range(3):
+        sp.spmv_host(sp.CSR_ROWS, dm, x, y)
+    assert L.spmvb200_host_registered(sp.capi.ptr(x)) == 0 and L.spmvb200_host_registered(sp.capi.ptr(y)) == 0
+    assert L.spmvb200_host_register(sp.capi.ptr(x), x.nbytes) == 0
+    assert L.spmvb200_host_register(sp.capi.ptr(x), x.nbytes) == 0  # idempotent
+    assert L.spmvb200_host_registered(sp.capi.ptr(x)) == 1
+    sp.spmv_host(sp.CSR_ROWS, dm, x, y)
+    assert L.spmvb200_host_unregister(sp.capi.ptr(x)) == 0
+    assert L.spmvb200_host_registered(sp.capi.ptr(x)) == 0
+    assert sp.capi.lib().spmvb200_host_unregister(sp.capi.ptr(x)) == 0  # unknown pointer: no-op
+
+
+# ---------------------------------------------------------------------------------------------- x-window launch shapes
+@pytest.mark.parametrize("R,W,w", [(512, 1024, 3000), (1024, 2048, 9000), (512, 256, 300)])
+def test_xwin_launch_shapes_agree_bit_for_bit(sp, orc, R, W, w):
+    """One CTA per row block (0) and persistent CTAs over contiguous row blocks (1: window ring and prefetch carried across row
+    blocks) return the oracle's bits; so do the row-block chunks of the host path and the delivery epilogue of the shard step."""
+    s = sp.synth
+    mat = s.host_csr(s.banded(400_003, 32, w))  # > 148 row blocks for every R here, last row block ragged
+    x = s.host_vector(mat.N) * 1e3
+    y_ref = _y(orc, mat, x)
+    d_csr = sp.spMatCpyCSR(mat)
+    dxw = d_csr.to_xwin(R, W)
+    dx, dy = sp.DeviceVector.from_host(x), sp.DeviceVector(mat.M)
+    for shape in (0, 1):
+        sp.tuning_set(dxw, [-1, -1, 0, shape, -1, 0, 0, 0])
+        assert sp.tuning_get(dxw)[3] == shape
+        dy.fill_bytes(0xFF)
+        sp.cudaSpMVRowsXWIN(dxw, dx, sp.Config(), dy)
+        np.testing.assert_array_equal(dy.to_host(), y_ref)
+        yh = np.full(mat.M, np.nan)
+        sp.spmv_host(sp.XWIN_ROWS, dxw, x, yh, timed=False)
+        np.testing.assert_array_equal(yh, y_ref)
+        from spmv_openmp_cuda_b200.distributed import RowBlockShard
+        sh = RowBlockShard(dxw, [0, mat.M], sp.XWIN_ROWS, nbuf=2, col_range=d_csr.col_range)
+        sh.set_x(0, x)
+        sh.step(0, 1)
+        np.testing.assert_array_equal(sh.rows_of(1), y_ref)
+        sh.close()
