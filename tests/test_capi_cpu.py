@@ -58,6 +58,13 @@ def test_no_cpu_fallback(sp):
         sp.b200SpMVRowsCSR(mat, g["x"], sp.Config(), np.zeros(mat.M))
     with pytest.raises(sp.SpmvB200Error):
         sp.synth.device_csr(sp.synth.lap2d(8))
+    # host-buffer helpers: no device, no page-locking -- loud failure, nothing registered
+    L = sp.capi.lib()
+    buf = np.zeros(1 << 18)
+    assert L.spmvb200_host_alloc(1 << 20) is None and L.spmvb200_last_error()
+    assert L.spmvb200_host_register(sp.capi.ptr(buf), buf.nbytes) != 0
+    assert L.spmvb200_host_registered(sp.capi.ptr(buf)) == 0
+    assert L.spmvb200_host_unregister(None) == 0 and L.spmvb200_host_free(None) == 0
 
 
 def test_product_never_imports_oracle():
