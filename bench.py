@@ -17,9 +17,12 @@ A "step" is one SpMV (y = A*x, fp64) over the workload.
            separates iterations -- the exchange is INSIDE the timed region (at N=1 there is nobody to deliver to).  CUDA events on
            the launch stream, barrier + synchronize on both sides, max over ranks.  `kernel_only` = the same kernel without the
            exchange.
-`e2e`    : the same metric through the host-buffer entry point with caller-allocated (malloc / numpy, i.e. pageable) buffers, as
-           the reference's driver passes them (src/main.cu:155,181): N=1 spmvb200_spmv_host, N>1 spmvb200_shard_spmv_host (every
-           rank: its x slice up over its own PCIe link, halo rows to the peers, kernel chunks, its y slice down).
+`e2e`    : the same metric through the host-buffer entry point, every step moving x up and y down: N=1 spmvb200_spmv_host, N>1
+           spmvb200_shard_spmv_host (every rank: its x slice up over its own PCIe link, halo rows to the peers, kernel chunks, its y
+           slice down).  Headline: page-locked vectors from spmvb200_host_alloc (the contract's "pinned host memory").  Beside it:
+           `registered` = caller-allocated malloc / numpy vectors as the reference's driver has them (src/main.cu:155,181),
+           page-locked in place by one spmvb200_host_register call each, `unregistered` = the same vectors left pageable, and the
+           bare duplex-copy ceiling of the box for both kinds of page-locked memory.
 --impl reference times the reference's own OpenMP CPU implementation (oracle/_ref, compiled from the unmodified sources; the
 oracle port if that is absent) on the host cores over the FULL matrix of the same workload, rank 0 only.
 """
