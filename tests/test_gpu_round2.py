@@ -287,6 +287,9 @@ def test_host_path_xwindow_runs_in_row_block_chunks(sp, orc, pinned, monkeypatch
 def test_host_register_auto_policy_is_opt_in(sp):
     """Without SPMVB200_HOST_REGISTER=auto the library leaves caller buffers alone: a pageable buffer stays pageable however often
     it comes back (a buffer freed while registered would poison its address range for every later CUDA call)."""
+    import os
+    if os.environ.get("SPMVB200_HOST_REGISTER") == "auto":
+        pytest.skip("this process opted in to the automatic policy")
     s = sp.synth
     mat = s.host_csr(s.banded(300_000, 8, 500))
     dm = sp.spMatCpyCSR(mat)
