@@ -799,7 +799,9 @@ static int xwin_build(const spmvb200_matrix* csr, uint32_t rows_per_block, uint3
         uint32_t nbuf = (uint32_t) std::min<uint64_t>(XW_MAX_NBUF, (232448 - 256) / (((uint64_t) W + 2) * 8));
         if (const char* e = getenv("SPMVB200_XW_NBUF")) nbuf = std::min<uint32_t>(nbuf, (uint32_t) std::max(1, atoi(e)));
         if (nbuf < 2) { rc = fail("xwin_from_csr: window of %u columns leaves no room for double buffering", W); break; }
-        m->xw_nbuf = std::min<uint32_t>(nbuf, 4);
+        uint32_t nbuf_cap = 4;
+        if (const char* e = getenv("SPMVB200_XW_NBUF_CAP")) nbuf_cap = (uint32_t) std::min(std::max(atoi(e), 2), (int) XW_MAX_NBUF);  // developer knob
+        m->xw_nbuf = std::min<uint32_t>(nbuf, nbuf_cap);
         m->xw_nw = R >= 1024 ? 32 : 16;
         if (const char* e = getenv("SPMVB200_XW_NW")) m->xw_nw = (uint32_t) atoi(e);
         if ((m->xw_nw != 16 && m->xw_nw != 32) || R / (32 * m->xw_nw) < 1 || R / (32 * m->xw_nw) > (m->xw_nw == 32 ? 4u : 8u)) { rc = fail("xwin_from_csr: no kernel for R=%u with %u warps", R, m->xw_nw); break; }

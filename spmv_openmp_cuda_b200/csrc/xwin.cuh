@@ -239,6 +239,10 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
                 off_nx[a] = __ldg(grp_off + (size_t) (t + 1) * G + a * NW + warp);
             }
         }
+        // the window id the LAST warp to leave this tile will refill the slot with: fetched by every warp now, so that the refill is one
+        // TMA issue away when the slot frees up instead of a dependent load + a TMA issue (the ring's turn-around time bounds the tile rate
+        // when a row block has more tiles than the ring has slots)
+        const uint32_t win_nx = (t + nbuf < T1) ? __ldg(tile_win + t + nbuf) : 0u;
         kmax = __reduce_max_sync(0xffffffffu, kmax);
         const uint32_t xw = smem_u32(xs + (size_t) s * WS);
         if (kmax == 0) mbar_wait(full + s, ph);  // nothing of this warp's rows here: still keep step with the ring
@@ -271,7 +275,7 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last && t + nbuf < T1)
-            xw_load_window(x, __ldg(tile_win + t + nbuf), W, N, xs + (size_t) s * WS, full + s, x_aligned, lane, pol);
+            xw_load_window(x, win_nx, W, N, xs + (size_t) s * WS, full + s, x_aligned, lane, pol);
         if (++s == nbuf) { s = 0; ph ^= 1u; }
         while (t + 1 == t_end && rb < rb1) {  // row block finished (and any tile-less row blocks after it)
 #pragma unroll
