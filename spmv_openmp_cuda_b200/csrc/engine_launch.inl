@@ -736,7 +736,16 @@ static int launch(spmvb200_matrix* m, int kind, const double* d_x, double* d_y, 
                 default: launch_ell_rowmajor<32>(m, d_x, d_y, st); break;
             }
             break;
-        case SPMVB200_ELL_ROWS_WARP_NT: launch_ell_rowmajor<32>(m, d_x, d_y, st); break;
+        case SPMVB200_ELL_ROWS_WARP_NT: {  // warp per row, four rows of a warp in flight
+            static const bool plain_warp = getenv("SPMVB200_ELL_WARP_PLAIN") != nullptr;  // developer knob: one row per warp at a time
+            if (plain_warp) { launch_ell_rowmajor<32>(m, d_x, d_y, st); break; }
+            constexpr int BLOCK = 256, ROWS = 4;
+            const uint64_t warps = (m->M + ROWS - 1) / ROWS;
+            ell_rowmajor_warp_kernel<ROWS, BLOCK><<<(unsigned) ((warps * 32 + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(m->as, m->ja, m->rl, m->pitch, (uint32_t) m->M,
+                                                                                                               (uint32_t) m->K, d_x, d_y);
+            ++g_launches;
+            break;
+        }
     }
     CU_TRY(cudaPeekAtLastError());
     return 0;

@@ -659,6 +659,61 @@ ell_rowmajor_kernel(const double* __restrict__ as, const uint32_t* __restrict__ 
     if (lane == 0 && row < M) y[row] = acc;
 }
 
+// Warp per row with ROWS rows of a warp in flight at once (cudaSpMVWarpsPerRowELLNTrasposed, src/SpMV_CUDA.cu:116-135): a whole warp on a
+// 27-entry row has 14 working lanes and one dependent chain load -> gather -> 5 shuffle steps per row; with one row per warp at a time that
+// chain is exposed 2 M times (0.32 of the roofline on cfg2).  Here a warp owns ROWS consecutive rows: their loads are issued together, their
+// gathers together, and the ROWS shuffle trees run interleaved.  Short rows (K <= 64): one double2 / uint2 per lane covers the row.
+template <int ROWS, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+ell_rowmajor_warp_kernel(const double* __restrict__ as, const uint32_t* __restrict__ ja, const uint32_t* __restrict__ rl, uint64_t pitch,
+                         uint32_t M, uint32_t K, const double* __restrict__ x, double* __restrict__ y) {
+    const uint32_t warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t row0 = warp * ROWS;
+    if (row0 >= M) return;
+    double2 v[ROWS];
+    uint2 c[ROWS];
+    uint32_t len[ROWS];
+    double acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const uint32_t row = min(row0 + r, M - 1);  // a clamped duplicate row is computed and not stored
+        len[r] = rl ? __ldg(rl + row) : K;
+        acc[r] = 0.0;
+    }
+    for (uint32_t k = 2 * lane; k < K; k += 64) {  // one pass for K <= 64
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const uint64_t base = (uint64_t) min(row0 + r, M - 1) * pitch;
+            v[r] = make_double2(0.0, 0.0);
+            c[r] = make_uint2(0u, 0u);
+            if (k < len[r]) {
+                v[r] = ld_stream(reinterpret_cast<const double2*>(as + base + k));
+                c[r] = ld_stream(reinterpret_cast<const uint2*>(ja + base + k));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            if (k < len[r]) acc[r] = fma(v[r].x, ld_x(x, c[r].x), acc[r]);
+            if (k + 1 < len[r]) acc[r] = fma(v[r].y, ld_x(x, c[r].y), acc[r]);
+        }
+    }
+    // Four sums over 32 lanes with 6 exchanged doubles instead of 4 x 5 (the plain trees made the kernel shuffle-bound: 10 SHFL per row):
+    // at distance 16 the lower half-warp keeps rows 0, 1 and takes the upper half's partials of them (and vice versa for rows 2, 3); at
+    // distance 8 each quarter keeps one row; distances 4, 2, 1 finish it.  Row 2 * (lane >> 4) + ((lane >> 3) & 1) ends up in every lane of
+    // its octet.
+    static_assert(ROWS == 4, "the exchange below is written for four rows per warp");
+    const bool up16 = lane & 16, up8 = lane & 8;
+    double k0 = up16 ? acc[2] : acc[0], k1 = up16 ? acc[3] : acc[1];
+    k0 += __shfl_xor_sync(0xffffffffu, up16 ? acc[0] : acc[2], 16, 32);
+    k1 += __shfl_xor_sync(0xffffffffu, up16 ? acc[1] : acc[3], 16, 32);
+    double k = up8 ? k1 : k0;
+    k += __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8, 32);
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off, 32);
+    const uint32_t r = 2 * (lane >> 4) + ((lane >> 3) & 1);
+    if ((lane & 7) == 0 && row0 + r < M) y[row0 + r] = k;
+}
+
 // ---------------------------------------------------------------------------------------------
 // upload-side helpers (run once per matrix, not on the hot path)
 // ---------------------------------------------------------------------------------------------
