@@ -123,6 +123,47 @@ __device__ __forceinline__ void xw_batch(double (&acc)[ACC], const double* (&pv)
         for (int a = 0; a < ACC; ++a) xw_slot_fma(acc[a], v[u][a], cc[u][a], xw);
 }
 
+// The same slot load through ONE 32-bit entry index per group instead of two 64-bit pointers: six registers less per lane for two
+// more address instructions per slot -- ALU instructions are not what this kernel pays for (profiles/r02x_*), registers are: the lean
+// form uses them for a deeper batch.
+__device__ __forceinline__ void xw_slot_load_e(double& v, uint32_t& cc, uint32_t& e, const double* val, const uint16_t* col, uint32_t c,
+                                               uint32_t k, uint32_t W) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        ".reg .b32 m;\n"
+        ".reg .b64 a;\n"
+        "setp.gt.u32 q, %5, %6;\n"
+        "vote.sync.ballot.b32 m, q, 0xffffffff;\n"
+        "popc.b32 m, m;\n"
+        "mov.f64 %0, 0d0000000000000000;\n"
+        "mov.b32 %1, %7;\n"
+        "mad.wide.u32 a, %2, 8, %3;\n"
+        "@q ld.global.cs.f64 %0, [a];\n"
+        "mad.wide.u32 a, %2, 2, %4;\n"
+        "@q ld.global.cs.u16 %1, [a];\n"
+        "add.u32 %2, %2, m;\n"
+        "}\n"
+        : "=d"(v), "=r"(cc), "+r"(e)
+        : "l"(val), "l"(col), "r"(c), "r"(k), "r"(W)
+        : "memory");
+}
+template <int ACC, int U>
+__device__ __forceinline__ void xw_batch_e(double (&acc)[ACC], uint32_t (&e)[ACC], const double* __restrict__ val, const uint16_t* __restrict__ col,
+                                           const uint32_t (&c)[ACC], uint32_t k0, uint32_t W, uint32_t xw, uint64_t* bar, uint32_t ph) {
+    double v[U][ACC];
+    uint32_t cc[U][ACC];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int a = 0; a < ACC; ++a) xw_slot_load_e(v[u][a], cc[u][a], e[a], val, col, c[a], k0 + u, W);
+    if (k0 == 0) mbar_wait(bar, ph);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int a = 0; a < ACC; ++a) xw_slot_fma(acc[a], v[u][a], cc[u][a], xw);
+}
+
 // Does the CTA that owns row blocks [rb, rb1) take part in the fused neighbour synchronisation?  Yes if some of its rows are
 // delivered to a peer, or if one of its x windows reaches outside the columns this rank owns (windows are ascending per row block).
 __device__ __forceinline__ bool xw_cta_is_boundary(const PushArgs& push, uint32_t rb, uint32_t rb1, const uint32_t* __restrict__ rb_tile0,
@@ -148,7 +189,9 @@ __device__ __forceinline__ bool xw_cta_is_boundary(const PushArgs& push, uint32_
 // CTA i owns the contiguous row blocks [cta_rb[i], cta_rb[i+1]) and runs their tiles as ONE sequence: tile ids are
 // global and consecutive across row blocks, so the window ring and the metadata prefetch keep going at a row-block
 // boundary; only the sums are written out and reset there.  One row block per CTA is the plain launch.
-template <int NW, int ACC, int UMAX>
+// LEAN: one row block per CTA only (the plain launch), without the persistent form's bookkeeping (row-block range, end-of-row-block test per
+// tile) and with one 32-bit entry index per group instead of two 64-bit pointers: -3 % on cfg4 (profiles/r02ae_*).
+template <int NW, int ACC, int UMAX, bool LEAN = false>
 __global__ void __launch_bounds__(32 * NW, 1)
 xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb_tile0, const uint32_t* __restrict__ tile_win,
             const uint32_t* __restrict__ grp_off, const uint16_t* __restrict__ cp, const uint16_t* __restrict__ col,
@@ -163,8 +206,8 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // no split table: one row block per CTA (rotated under the fused neighbour synchronisation, see PushArgs::rb_rot)
-    uint32_t rb = cta_rb ? __ldg(cta_rb + blockIdx.x) : rb_first + (push.rb_rot ? (blockIdx.x + push.rb_rot) % gridDim.x : blockIdx.x);
-    const uint32_t rb1 = cta_rb ? __ldg(cta_rb + blockIdx.x + 1) : rb + 1;
+    uint32_t rb = (!LEAN && cta_rb) ? __ldg(cta_rb + blockIdx.x) : rb_first + (push.rb_rot ? (blockIdx.x + push.rb_rot) % gridDim.x : blockIdx.x);
+    const uint32_t rb1 = (!LEAN && cta_rb) ? __ldg(cta_rb + blockIdx.x + 1) : rb + 1;
     if (rb >= rb1) return;
     const uint32_t T0 = __ldg(rb_tile0 + rb), T1 = __ldg(rb_tile0 + rb1);  // this CTA's tiles
     __shared__ uint32_t s_boundary, s_delivers;
@@ -205,7 +248,7 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
             off_nx[a] = __ldg(grp_off + (size_t) T0 * G + a * NW + warp);
         }
     }
-    uint32_t t_end = __ldg(rb_tile0 + rb + 1);
+    uint32_t t_end = LEAN ? T1 : __ldg(rb_tile0 + rb + 1);
     // row blocks without tiles at the start of the range
     while (t_end == T0 && rb < rb1) {
 #pragma unroll
@@ -221,15 +264,18 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
     uint32_t s = 0, ph = 0;
 #pragma unroll 1
     for (uint32_t t = T0; t < T1; ++t) {
-        uint32_t c[ACC], kmax = 0;
+        uint32_t c[ACC], e[ACC], kmax = 0;
         const double* pv[ACC];
         const uint16_t* pc[ACC];
 #pragma unroll
         for (int a = 0; a < ACC; ++a) {
             c[a] = cp_nx[a] & 0xffu;                               // entries of my row in this tile
             const uint32_t first = off_nx[a] + (cp_nx[a] >> 8);    // group base + my place in the sorted order
-            pv[a] = val + first;
-            pc[a] = col + first;
+            e[a] = first;
+            if constexpr (!LEAN) {
+                pv[a] = val + first;
+                pc[a] = col + first;
+            }
             kmax = max(kmax, c[a]);
         }
         if (t + 1 < T1) {  // next tile's metadata (possibly the next row block's): in flight while this tile is processed
@@ -247,6 +293,27 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
         const uint32_t xw = smem_u32(xs + (size_t) s * WS);
         if (kmax == 0) mbar_wait(full + s, ph);  // nothing of this warp's rows here: still keep step with the ring
         uint32_t k0 = 0;
+        if constexpr (LEAN) {
+#pragma unroll 1
+        while (k0 < kmax) {
+            const uint32_t rem = kmax - k0;
+            if (rem >= (uint32_t) UMAX) {
+                xw_batch_e<ACC, UMAX>(acc, e, val, col, c, k0, W, xw, full + s, ph);
+                k0 += UMAX;
+            } else {
+                switch (rem) {  // exact tail (or whole short tile) in one batch
+                    case 1: xw_batch_e<ACC, 1>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 2: xw_batch_e<ACC, (UMAX > 2 ? 2 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 3: xw_batch_e<ACC, (UMAX > 3 ? 3 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 4: xw_batch_e<ACC, (UMAX > 4 ? 4 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 5: xw_batch_e<ACC, (UMAX > 5 ? 5 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 6: xw_batch_e<ACC, (UMAX > 6 ? 6 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    default: xw_batch_e<ACC, (UMAX > 7 ? 7 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                }
+                k0 = kmax;
+            }
+        }
+        } else {
 #pragma unroll 1
         while (k0 < kmax) {
             const uint32_t rem = kmax - k0;
@@ -266,6 +333,7 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
                 k0 = kmax;
             }
         }
+        }
         __syncwarp();
         uint32_t last = 0;
         if (lane == 0) {
@@ -277,7 +345,7 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
         if (last && t + nbuf < T1)
             xw_load_window(x, win_nx, W, N, xs + (size_t) s * WS, full + s, x_aligned, lane, pol);
         if (++s == nbuf) { s = 0; ph ^= 1u; }
-        while (t + 1 == t_end && rb < rb1) {  // row block finished (and any tile-less row blocks after it)
+        while (!LEAN && t + 1 == t_end && rb < rb1) {  // row block finished (and any tile-less row blocks after it)
 #pragma unroll
             for (int a = 0; a < ACC; ++a) {
                 const uint32_t row = rb * R + a * NW * 32u + myrow;
@@ -288,6 +356,19 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
                 acc[a] = 0.0;
             }
             if (++rb < rb1) t_end = __ldg(rb_tile0 + rb + 1);
+        }
+    }
+    if constexpr (LEAN) {
+        if (T1 > T0) {  // one row block per CTA: its sums leave here
+            const bool dl = s_delivers != 0;
+#pragma unroll
+            for (int a = 0; a < ACC; ++a) {
+                const uint32_t row = rb * R + a * NW * 32u + myrow;
+                if (row < M) {
+                    y[row] = acc[a];
+                    if (dl) push_out(push, row, acc[a]);
+                }
+            }
         }
     }
     if (push.nsync && s_boundary) {  // CTA-uniform
