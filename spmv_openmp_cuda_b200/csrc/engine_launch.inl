@@ -203,14 +203,14 @@ static void launch_ell_colmajor(const spmvb200_matrix* m, const double* x, doubl
 
 
 // ---- x-window CSR: one CTA per row block, NW warps, ring of x windows in shared memory
-template <int NW, int ACC, int UMAX, bool LEAN = false>
+template <int NW, int ACC, int UMAX>
 static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, LaunchCtx* lc, uint32_t rb0, uint32_t rb1) {
     const size_t smem = (size_t) m->xw_nbuf * (m->xw_W + 2) * 8 + XW_MAX_NBUF * 12;
     static size_t configured[64] = {0};  // per device: function attributes belong to the device's context
     int dev = 0;
     CU_TRY(cudaGetDevice(&dev));
     if (smem > configured[dev & 63]) {
-        CU_TRY(cudaFuncSetAttribute(xwin_kernel<NW, ACC, UMAX, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CU_TRY(cudaFuncSetAttribute(xwin_kernel<NW, ACC, UMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         configured[dev & 63] = smem;
     }
     // a row-block sub-range (chunked host path) always runs one CTA per row block
@@ -218,7 +218,7 @@ static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, c
     const bool persist = m->xw_mode == 1 && whole;
     if (rb1 > m->xw_nrb) rb1 = m->xw_nrb;
     if (rb1 <= rb0) return 0;
-    xwin_kernel<NW, ACC, UMAX, LEAN><<<persist ? m->xw_ncta : rb1 - rb0, 32 * NW, smem, st>>>(persist ? m->xw_cta_rb : nullptr, m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
+    xwin_kernel<NW, ACC, UMAX><<<persist ? m->xw_ncta : rb1 - rb0, 32 * NW, smem, st>>>(persist ? m->xw_cta_rb : nullptr, m->xw_rb_tile0, m->xw_tile_win, m->xw_grp_off, m->xw_cnt, m->xw_col, m->as, x, y,
                                                                  (uint32_t) m->M, (uint32_t) m->N, m->xw_W, m->xw_nbuf, ((uintptr_t) x & 15) == 0, rb0, push_of(lc));
     if (lc) lc->fused = true;
     ++g_launches;
@@ -228,12 +228,6 @@ static int launch_xwin_t(const spmvb200_matrix* m, const double* x, double* y, c
 static int launch_xwin(const spmvb200_matrix* m, const double* x, double* y, cudaStream_t st, LaunchCtx* lc = nullptr, uint32_t rb0 = 0, uint32_t rb1 = 0xffffffffu) {
     const uint32_t acc = m->xw_R / (32 * m->xw_nw);
     static const int u_env = getenv("SPMVB200_XW_U") ? atoi(getenv("SPMVB200_XW_U")) : 0;  // developer knob
-    // one CTA per row block at the default shape (32 warps x 2 groups): the lean form of the kernel (knob: 0 = the general form, 6 = a batch of 6)
-    static const int lean_env = getenv("SPMVB200_XW_LEAN") ? atoi(getenv("SPMVB200_XW_LEAN")) : 5;
-    if (lean_env && m->xw_nw == 32 && acc == 2 && !u_env && !(m->xw_mode == 1 && rb0 == 0 && rb1 >= m->xw_nrb)) {
-        if (lean_env == 6) return launch_xwin_t<32, 2, 6, true>(m, x, y, st, lc, rb0, rb1);
-        return launch_xwin_t<32, 2, 5, true>(m, x, y, st, lc, rb0, rb1);
-    }
 #define XW_CASE(NW, ACC, UDEF, UALT, UALT2)                                                  \
     if (m->xw_nw == NW && acc == ACC) {                                                      \
         if (u_env == UALT) return launch_xwin_t<NW, ACC, UALT>(m, x, y, st, lc, rb0, rb1);   \

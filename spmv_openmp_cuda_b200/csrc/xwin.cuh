@@ -13,8 +13,8 @@
 // SORTED: slot k holds the k-th non-zero (in this window) of every row that has one, rows ordered by decreasing count,
 // with no padding at all.  A row's place p in that order is stored with its count (one u16 per row and tile), so the
 // rows active in slot k are exactly the places [0, n_k) and lane l finds its entry at  (group base + S_k) + p_l  with
-// S_k = n_0 + ... + n_{k-1} warp-uniform: per slot the kernel spends ONE ballot + popc and advances two per-lane
-// pointers -- no per-slot rank, no 64-bit address rebuild (the SpMV is instruction-issue bound long before it is HBM
+// S_k = n_0 + ... + n_{k-1} warp-uniform: per slot the kernel spends ONE ballot + popc and advances one per-lane
+// entry index -- no per-slot rank (the SpMV is instruction-issue bound long before it is HBM
 // bound if every non-zero costs a rank computation: measured 1.9 warp instructions per non-zero, 58 % issue
 // utilisation at 0.6 of the roofline for the unsorted layout).  The warp's loads stay contiguous (<= 256 B of values,
 // <= 64 B of 16-bit window-local column ids); lanes keep their own rows (sums stay in registers across tiles).
@@ -41,28 +41,32 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 
 constexpr int XW_MAX_NBUF = 8;
 
-// One slot of one 32-row group, load half.  Lanes with cnt > k fetch their entry through their own pointers, which
-// then advance by the slot's population n_k = popc(ballot(cnt > k)).  Inactive lanes keep v = 0 and cc = W (the index
-// of a zero kept behind every x window), so the consume half needs no predicate.  PTX so that a batch of these is
-// emitted back to back ahead of the first use (asm volatile keeps program order).
-__device__ __forceinline__ void xw_slot_load(double& v, uint32_t& cc, const double*& pv, const uint16_t*& pc, uint32_t c, uint32_t k,
-                                             uint32_t W) {
+// One slot of one 32-row group, load half.  Lanes with cnt > k fetch their entry, entry index e (ONE 32-bit index per group serves the
+// value and the id array: two address instructions per slot more than two running 64-bit pointers, six registers per lane less -- this
+// kernel does not pay for ALU instructions, it pays for registers: -3 % on cfg4, profiles/r02ae_*, r02ag_*), which then advances by the
+// slot's population n_k = popc(ballot(cnt > k)).  Inactive lanes keep v = 0 and cc = W (the index of a zero kept behind every x window),
+// so the consume half needs no predicate.  PTX so that a batch of these is emitted back to back ahead of the first use (asm volatile
+// keeps program order).
+__device__ __forceinline__ void xw_slot_load(double& v, uint32_t& cc, uint32_t& e, const double* val, const uint16_t* col, uint32_t c,
+                                             uint32_t k, uint32_t W) {
     asm volatile(
         "{\n"
         ".reg .pred q;\n"
         ".reg .b32 m;\n"
-        "setp.gt.u32 q, %4, %5;\n"
+        ".reg .b64 a;\n"
+        "setp.gt.u32 q, %5, %6;\n"
         "vote.sync.ballot.b32 m, q, 0xffffffff;\n"
         "popc.b32 m, m;\n"
         "mov.f64 %0, 0d0000000000000000;\n"
-        "mov.b32 %1, %6;\n"
-        "@q ld.global.cs.f64 %0, [%2];\n"
-        "@q ld.global.cs.u16 %1, [%3];\n"
-        "mad.wide.u32 %2, m, 8, %2;\n"
-        "mad.wide.u32 %3, m, 2, %3;\n"
+        "mov.b32 %1, %7;\n"
+        "mad.wide.u32 a, %2, 8, %3;\n"
+        "@q ld.global.cs.f64 %0, [a];\n"
+        "mad.wide.u32 a, %2, 2, %4;\n"
+        "@q ld.global.cs.u16 %1, [a];\n"
+        "add.u32 %2, %2, m;\n"
         "}\n"
-        : "=d"(v), "=r"(cc), "+l"(pv), "+l"(pc)
-        : "r"(c), "r"(k), "r"(W)
+        : "=d"(v), "=r"(cc), "+r"(e)
+        : "l"(val), "l"(col), "r"(c), "r"(k), "r"(W)
         : "memory");
 }
 // consume half: acc += v * xw[cc] with separate mul / add roundings (the order and rounding of sgemvSerial,
@@ -108,55 +112,14 @@ __device__ __forceinline__ void xw_load_window(const double* __restrict__ x, uin
 // The first batch of a tile waits for the tile's x window only AFTER its loads are out: window and matrix latencies
 // overlap.
 template <int ACC, int U>
-__device__ __forceinline__ void xw_batch(double (&acc)[ACC], const double* (&pv)[ACC], const uint16_t* (&pc)[ACC], const uint32_t (&c)[ACC],
-                                         uint32_t k0, uint32_t W, uint32_t xw, uint64_t* bar, uint32_t ph) {
+__device__ __forceinline__ void xw_batch(double (&acc)[ACC], uint32_t (&e)[ACC], const double* __restrict__ val, const uint16_t* __restrict__ col,
+                                         const uint32_t (&c)[ACC], uint32_t k0, uint32_t W, uint32_t xw, uint64_t* bar, uint32_t ph) {
     double v[U][ACC];
     uint32_t cc[U][ACC];
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int a = 0; a < ACC; ++a) xw_slot_load(v[u][a], cc[u][a], pv[a], pc[a], c[a], k0 + u, W);
-    if (k0 == 0) mbar_wait(bar, ph);
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int a = 0; a < ACC; ++a) xw_slot_fma(acc[a], v[u][a], cc[u][a], xw);
-}
-
-// The same slot load through ONE 32-bit entry index per group instead of two 64-bit pointers: six registers less per lane for two
-// more address instructions per slot -- ALU instructions are not what this kernel pays for (profiles/r02x_*), registers are: the lean
-// form uses them for a deeper batch.
-__device__ __forceinline__ void xw_slot_load_e(double& v, uint32_t& cc, uint32_t& e, const double* val, const uint16_t* col, uint32_t c,
-                                               uint32_t k, uint32_t W) {
-    asm volatile(
-        "{\n"
-        ".reg .pred q;\n"
-        ".reg .b32 m;\n"
-        ".reg .b64 a;\n"
-        "setp.gt.u32 q, %5, %6;\n"
-        "vote.sync.ballot.b32 m, q, 0xffffffff;\n"
-        "popc.b32 m, m;\n"
-        "mov.f64 %0, 0d0000000000000000;\n"
-        "mov.b32 %1, %7;\n"
-        "mad.wide.u32 a, %2, 8, %3;\n"
-        "@q ld.global.cs.f64 %0, [a];\n"
-        "mad.wide.u32 a, %2, 2, %4;\n"
-        "@q ld.global.cs.u16 %1, [a];\n"
-        "add.u32 %2, %2, m;\n"
-        "}\n"
-        : "=d"(v), "=r"(cc), "+r"(e)
-        : "l"(val), "l"(col), "r"(c), "r"(k), "r"(W)
-        : "memory");
-}
-template <int ACC, int U>
-__device__ __forceinline__ void xw_batch_e(double (&acc)[ACC], uint32_t (&e)[ACC], const double* __restrict__ val, const uint16_t* __restrict__ col,
-                                           const uint32_t (&c)[ACC], uint32_t k0, uint32_t W, uint32_t xw, uint64_t* bar, uint32_t ph) {
-    double v[U][ACC];
-    uint32_t cc[U][ACC];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int a = 0; a < ACC; ++a) xw_slot_load_e(v[u][a], cc[u][a], e[a], val, col, c[a], k0 + u, W);
+        for (int a = 0; a < ACC; ++a) xw_slot_load(v[u][a], cc[u][a], e[a], val, col, c[a], k0 + u, W);
     if (k0 == 0) mbar_wait(bar, ph);
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -189,9 +152,7 @@ __device__ __forceinline__ bool xw_cta_is_boundary(const PushArgs& push, uint32_
 // CTA i owns the contiguous row blocks [cta_rb[i], cta_rb[i+1]) and runs their tiles as ONE sequence: tile ids are
 // global and consecutive across row blocks, so the window ring and the metadata prefetch keep going at a row-block
 // boundary; only the sums are written out and reset there.  One row block per CTA is the plain launch.
-// LEAN: one row block per CTA only (the plain launch), without the persistent form's bookkeeping (row-block range, end-of-row-block test per
-// tile) and with one 32-bit entry index per group instead of two 64-bit pointers: -3 % on cfg4 (profiles/r02ae_*).
-template <int NW, int ACC, int UMAX, bool LEAN = false>
+template <int NW, int ACC, int UMAX>
 __global__ void __launch_bounds__(32 * NW, 1)
 xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb_tile0, const uint32_t* __restrict__ tile_win,
             const uint32_t* __restrict__ grp_off, const uint16_t* __restrict__ cp, const uint16_t* __restrict__ col,
@@ -206,8 +167,8 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // no split table: one row block per CTA (rotated under the fused neighbour synchronisation, see PushArgs::rb_rot)
-    uint32_t rb = (!LEAN && cta_rb) ? __ldg(cta_rb + blockIdx.x) : rb_first + (push.rb_rot ? (blockIdx.x + push.rb_rot) % gridDim.x : blockIdx.x);
-    const uint32_t rb1 = (!LEAN && cta_rb) ? __ldg(cta_rb + blockIdx.x + 1) : rb + 1;
+    uint32_t rb = cta_rb ? __ldg(cta_rb + blockIdx.x) : rb_first + (push.rb_rot ? (blockIdx.x + push.rb_rot) % gridDim.x : blockIdx.x);
+    const uint32_t rb1 = cta_rb ? __ldg(cta_rb + blockIdx.x + 1) : rb + 1;
     if (rb >= rb1) return;
     const uint32_t T0 = __ldg(rb_tile0 + rb), T1 = __ldg(rb_tile0 + rb1);  // this CTA's tiles
     __shared__ uint32_t s_boundary, s_delivers;
@@ -248,7 +209,7 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
             off_nx[a] = __ldg(grp_off + (size_t) T0 * G + a * NW + warp);
         }
     }
-    uint32_t t_end = LEAN ? T1 : __ldg(rb_tile0 + rb + 1);
+    uint32_t t_end = __ldg(rb_tile0 + rb + 1);
     // row blocks without tiles at the start of the range
     while (t_end == T0 && rb < rb1) {
 #pragma unroll
@@ -265,17 +226,10 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
 #pragma unroll 1
     for (uint32_t t = T0; t < T1; ++t) {
         uint32_t c[ACC], e[ACC], kmax = 0;
-        const double* pv[ACC];
-        const uint16_t* pc[ACC];
 #pragma unroll
         for (int a = 0; a < ACC; ++a) {
-            c[a] = cp_nx[a] & 0xffu;                               // entries of my row in this tile
-            const uint32_t first = off_nx[a] + (cp_nx[a] >> 8);    // group base + my place in the sorted order
-            e[a] = first;
-            if constexpr (!LEAN) {
-                pv[a] = val + first;
-                pc[a] = col + first;
-            }
+            c[a] = cp_nx[a] & 0xffu;                 // entries of my row in this tile
+            e[a] = off_nx[a] + (cp_nx[a] >> 8);      // my first entry: group base + my place in the sorted order
             kmax = max(kmax, c[a]);
         }
         if (t + 1 < T1) {  // next tile's metadata (possibly the next row block's): in flight while this tile is processed
@@ -293,46 +247,24 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
         const uint32_t xw = smem_u32(xs + (size_t) s * WS);
         if (kmax == 0) mbar_wait(full + s, ph);  // nothing of this warp's rows here: still keep step with the ring
         uint32_t k0 = 0;
-        if constexpr (LEAN) {
 #pragma unroll 1
         while (k0 < kmax) {
             const uint32_t rem = kmax - k0;
             if (rem >= (uint32_t) UMAX) {
-                xw_batch_e<ACC, UMAX>(acc, e, val, col, c, k0, W, xw, full + s, ph);
+                xw_batch<ACC, UMAX>(acc, e, val, col, c, k0, W, xw, full + s, ph);
                 k0 += UMAX;
             } else {
                 switch (rem) {  // exact tail (or whole short tile) in one batch
-                    case 1: xw_batch_e<ACC, 1>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
-                    case 2: xw_batch_e<ACC, (UMAX > 2 ? 2 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
-                    case 3: xw_batch_e<ACC, (UMAX > 3 ? 3 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
-                    case 4: xw_batch_e<ACC, (UMAX > 4 ? 4 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
-                    case 5: xw_batch_e<ACC, (UMAX > 5 ? 5 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
-                    case 6: xw_batch_e<ACC, (UMAX > 6 ? 6 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
-                    default: xw_batch_e<ACC, (UMAX > 7 ? 7 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 1: xw_batch<ACC, 1>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 2: xw_batch<ACC, (UMAX > 2 ? 2 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 3: xw_batch<ACC, (UMAX > 3 ? 3 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 4: xw_batch<ACC, (UMAX > 4 ? 4 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 5: xw_batch<ACC, (UMAX > 5 ? 5 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    case 6: xw_batch<ACC, (UMAX > 6 ? 6 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
+                    default: xw_batch<ACC, (UMAX > 7 ? 7 : 1)>(acc, e, val, col, c, k0, W, xw, full + s, ph); break;
                 }
                 k0 = kmax;
             }
-        }
-        } else {
-#pragma unroll 1
-        while (k0 < kmax) {
-            const uint32_t rem = kmax - k0;
-            if (rem >= (uint32_t) UMAX) {
-                xw_batch<ACC, UMAX>(acc, pv, pc, c, k0, W, xw, full + s, ph);
-                k0 += UMAX;
-            } else {
-                switch (rem) {  // exact tail (or whole short tile) in one batch
-                    case 1: xw_batch<ACC, 1>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
-                    case 2: xw_batch<ACC, (UMAX > 2 ? 2 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
-                    case 3: xw_batch<ACC, (UMAX > 3 ? 3 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
-                    case 4: xw_batch<ACC, (UMAX > 4 ? 4 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
-                    case 5: xw_batch<ACC, (UMAX > 5 ? 5 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
-                    case 6: xw_batch<ACC, (UMAX > 6 ? 6 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
-                    default: xw_batch<ACC, (UMAX > 7 ? 7 : 1)>(acc, pv, pc, c, k0, W, xw, full + s, ph); break;
-                }
-                k0 = kmax;
-            }
-        }
         }
         __syncwarp();
         uint32_t last = 0;
@@ -345,7 +277,7 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
         if (last && t + nbuf < T1)
             xw_load_window(x, win_nx, W, N, xs + (size_t) s * WS, full + s, x_aligned, lane, pol);
         if (++s == nbuf) { s = 0; ph ^= 1u; }
-        while (!LEAN && t + 1 == t_end && rb < rb1) {  // row block finished (and any tile-less row blocks after it)
+        while (t + 1 == t_end && rb < rb1) {  // row block finished (and any tile-less row blocks after it)
 #pragma unroll
             for (int a = 0; a < ACC; ++a) {
                 const uint32_t row = rb * R + a * NW * 32u + myrow;
@@ -356,19 +288,6 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
                 acc[a] = 0.0;
             }
             if (++rb < rb1) t_end = __ldg(rb_tile0 + rb + 1);
-        }
-    }
-    if constexpr (LEAN) {
-        if (T1 > T0) {  // one row block per CTA: its sums leave here
-            const bool dl = s_delivers != 0;
-#pragma unroll
-            for (int a = 0; a < ACC; ++a) {
-                const uint32_t row = rb * R + a * NW * 32u + myrow;
-                if (row < M) {
-                    y[row] = acc[a];
-                    if (dl) push_out(push, row, acc[a]);
-                }
-            }
         }
     }
     if (push.nsync && s_boundary) {  // CTA-uniform
