@@ -752,11 +752,15 @@ static int xwin_build(const spmvb200_matrix* csr, uint32_t rows_per_block, uint3
         if ((rc = cudaMalloc(&m->xw_cnt, std::max<size_t>(1, (size_t) ntiles * R) * 2) != cudaSuccess)) break;
         if ((rc = cudaMalloc(&grp_cnt, (ngroups + 1) * 4) != cudaSuccess)) break;
         if ((rc = cudaMalloc(&m->xw_grp_off, (ngroups + 1) * 4) != cudaSuccess)) break;
+        // warps per CTA: fixed before the counts are stored, the layout of the per-row words follows the kernel shape (xw_cp_index)
+        m->xw_nw = R >= 1024 ? 32 : 16;
+        if (const char* e = getenv("SPMVB200_XW_NW")) m->xw_nw = (uint32_t) atoi(e);
+        if ((m->xw_nw != 16 && m->xw_nw != 32) || R / (32 * m->xw_nw) < 1 || R / (32 * m->xw_nw) > (m->xw_nw == 32 ? 4u : 8u)) { rc = fail("xwin_from_csr: no kernel for R=%u with %u warps", R, m->xw_nw); break; }
         const unsigned cblocks = (unsigned) (((ngroups + 1) * 32 + 255) / 256);
         if (m->xw_sorted)
-            xw_count_kernel<true><<<cblocks, 256>>>(csr->irp, csr->ja, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, grp_cnt, d_flags + 1);
+            xw_count_kernel<true><<<cblocks, 256>>>(csr->irp, csr->ja, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, grp_cnt, d_flags + 1, m->xw_nw);
         else
-            xw_count_kernel<false><<<cblocks, 256>>>(csr->irp, csr->ja, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, grp_cnt, d_flags + 1);
+            xw_count_kernel<false><<<cblocks, 256>>>(csr->irp, csr->ja, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, grp_cnt, d_flags + 1, m->xw_nw);
         size_t b2 = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, b2, grp_cnt, m->xw_grp_off, (int) (ngroups + 1));
         if (b2 > b1) {
@@ -777,9 +781,9 @@ static int xwin_build(const spmvb200_matrix* csr, uint32_t rows_per_block, uint3
         if (ngroups) {
             const unsigned fblocks = (unsigned) ((ngroups * 32 + 255) / 256);
             if (m->xw_sorted)
-                xw_fill_kernel<true><<<fblocks, 256>>>(csr->irp, csr->ja, csr->as, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, m->xw_grp_off, m->xw_col, m->as);
+                xw_fill_kernel<true><<<fblocks, 256>>>(csr->irp, csr->ja, csr->as, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, m->xw_grp_off, m->xw_col, m->as, m->xw_nw);
             else
-                xw_fill_kernel<false><<<fblocks, 256>>>(csr->irp, csr->ja, csr->as, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, m->xw_grp_off, m->xw_col, m->as);
+                xw_fill_kernel<false><<<fblocks, 256>>>(csr->irp, csr->ja, csr->as, M, R, W, m->xw_tile_win, tile_rb, ngroups, m->xw_cnt, m->xw_grp_off, m->xw_col, m->as, m->xw_nw);
         }
         {   // persistent CTAs: one per SM (or per row block if there are fewer), contiguous row blocks balanced by non-zeros
             int dev = 0, sms = 148;
@@ -802,9 +806,6 @@ static int xwin_build(const spmvb200_matrix* csr, uint32_t rows_per_block, uint3
         uint32_t nbuf_cap = 4;
         if (const char* e = getenv("SPMVB200_XW_NBUF_CAP")) nbuf_cap = (uint32_t) std::min(std::max(atoi(e), 2), (int) XW_MAX_NBUF);  // developer knob
         m->xw_nbuf = std::min<uint32_t>(nbuf, nbuf_cap);
-        m->xw_nw = R >= 1024 ? 32 : 16;
-        if (const char* e = getenv("SPMVB200_XW_NW")) m->xw_nw = (uint32_t) atoi(e);
-        if ((m->xw_nw != 16 && m->xw_nw != 32) || R / (32 * m->xw_nw) < 1 || R / (32 * m->xw_nw) > (m->xw_nw == 32 ? 4u : 8u)) { rc = fail("xwin_from_csr: no kernel for R=%u with %u warps", R, m->xw_nw); break; }
     } while (0);
     cudaFree(bitmap);
     cudaFree(pc);

@@ -41,6 +41,14 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 
 constexpr int XW_MAX_NBUF = 8;
 
+// Where the (count | place << 8) word of row (group g, lane) of tile t lives.  A warp owns the groups a * nw + warp (a < R / (32 nw)): the
+// words of one lane are stored next to each other, so that the kernel fetches them with ONE load per lane and tile (two u16 = one u32
+// for the default shape).
+__host__ __device__ __forceinline__ size_t xw_cp_index(uint32_t t, uint32_t g, uint32_t lane, uint32_t R, uint32_t nw) {
+    const uint32_t acc = R / (32u * nw), a = g / nw, warp = g % nw;
+    return (size_t) t * R + (size_t) (warp * 32u + lane) * acc + a;
+}
+
 // One slot of one 32-row group, load half.  Lanes with cnt > k fetch their entry, entry index e (ONE 32-bit index per group serves the
 // value and the id array: two address instructions per slot more than two running 64-bit pointers, six registers per lane less -- this
 // kernel does not pay for ALU instructions, it pays for registers: -3 % on cfg4, profiles/r02ae_*, r02ag_*), which then advances by the
@@ -127,6 +135,36 @@ __device__ __forceinline__ void xw_batch(double (&acc)[ACC], uint32_t (&e)[ACC],
         for (int a = 0; a < ACC; ++a) xw_slot_fma(acc[a], v[u][a], cc[u][a], xw);
 }
 
+// the ACC 16-bit (count | place << 8) words of one lane, fetched with one load
+template <int ACC> struct XwCp;
+template <> struct XwCp<1> {
+    uint32_t w;
+    __device__ __forceinline__ void clear() { w = 0; }
+    __device__ __forceinline__ void load(const uint16_t* p) { w = __ldg(p); }
+    __device__ __forceinline__ uint32_t get(int) const { return w; }
+};
+template <> struct XwCp<2> {
+    uint32_t w;
+    __device__ __forceinline__ void clear() { w = 0; }
+    __device__ __forceinline__ void load(const uint16_t* p) { w = __ldg(reinterpret_cast<const uint32_t*>(p)); }
+    __device__ __forceinline__ uint32_t get(int a) const { return a ? w >> 16 : w & 0xffffu; }
+};
+template <> struct XwCp<4> {
+    uint2 w;
+    __device__ __forceinline__ void clear() { w = make_uint2(0u, 0u); }
+    __device__ __forceinline__ void load(const uint16_t* p) { w = __ldg(reinterpret_cast<const uint2*>(p)); }
+    __device__ __forceinline__ uint32_t get(int a) const { const uint32_t v = a < 2 ? w.x : w.y; return (a & 1) ? v >> 16 : v & 0xffffu; }
+};
+template <> struct XwCp<8> {
+    uint4 w;
+    __device__ __forceinline__ void clear() { w = make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ void load(const uint16_t* p) { w = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ uint32_t get(int a) const {
+        const uint32_t v = a < 2 ? w.x : a < 4 ? w.y : a < 6 ? w.z : w.w;
+        return (a & 1) ? v >> 16 : v & 0xffffu;
+    }
+};
+
 // Does the CTA that owns row blocks [rb, rb1) take part in the fused neighbour synchronisation?  Yes if some of its rows are
 // delivered to a peer, or if one of its x windows reaches outside the columns this rank owns (windows are ascending per row block).
 __device__ __forceinline__ bool xw_cta_is_boundary(const PushArgs& push, uint32_t rb, uint32_t rb1, const uint32_t* __restrict__ rb_tile0,
@@ -198,17 +236,16 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
     // warp owns row groups g = a*NW + warp (a < ACC) of every row block, lane = row inside the group
     const uint32_t myrow = warp * 32u + lane;  // + rb*R + a*NW*32
     double acc[ACC];
-    uint32_t cp_nx[ACC], off_nx[ACC];
+    XwCp<ACC> cp_nx;  // my ACC rows' (count | place << 8) words of the next tile: one load (xw_cp_index)
+    uint32_t off_nx[ACC];
+    cp_nx.clear();
 #pragma unroll
     for (int a = 0; a < ACC; ++a) {
         acc[a] = 0.0;
-        cp_nx[a] = 0;
         off_nx[a] = 0;
-        if (T0 < T1) {
-            cp_nx[a] = __ldg(cp + (size_t) T0 * R + a * NW * 32u + myrow);
-            off_nx[a] = __ldg(grp_off + (size_t) T0 * G + a * NW + warp);
-        }
+        if (T0 < T1) off_nx[a] = __ldg(grp_off + (size_t) T0 * G + a * NW + warp);
     }
+    if (T0 < T1) cp_nx.load(cp + (size_t) T0 * R + (size_t) myrow * ACC);
     uint32_t t_end = __ldg(rb_tile0 + rb + 1);
     // row blocks without tiles at the start of the range
     while (t_end == T0 && rb < rb1) {
@@ -228,16 +265,14 @@ xwin_kernel(const uint32_t* __restrict__ cta_rb, const uint32_t* __restrict__ rb
         uint32_t c[ACC], e[ACC], kmax = 0;
 #pragma unroll
         for (int a = 0; a < ACC; ++a) {
-            c[a] = cp_nx[a] & 0xffu;                 // entries of my row in this tile
-            e[a] = off_nx[a] + (cp_nx[a] >> 8);      // my first entry: group base + my place in the sorted order
+            c[a] = cp_nx.get(a) & 0xffu;             // entries of my row in this tile
+            e[a] = off_nx[a] + (cp_nx.get(a) >> 8);  // my first entry: group base + my place in the sorted order
             kmax = max(kmax, c[a]);
         }
         if (t + 1 < T1) {  // next tile's metadata (possibly the next row block's): in flight while this tile is processed
+            cp_nx.load(cp + (size_t) (t + 1) * R + (size_t) myrow * ACC);
 #pragma unroll
-            for (int a = 0; a < ACC; ++a) {
-                cp_nx[a] = __ldg(cp + (size_t) (t + 1) * R + a * NW * 32u + myrow);
-                off_nx[a] = __ldg(grp_off + (size_t) (t + 1) * G + a * NW + warp);
-            }
+            for (int a = 0; a < ACC; ++a) off_nx[a] = __ldg(grp_off + (size_t) (t + 1) * G + a * NW + warp);
         }
         // the window id the LAST warp to leave this tile will refill the slot with: fetched by every warp now, so that the refill is one
         // TMA issue away when the slot frees up instead of a dependent load + a TMA issue (the ring's turn-around time bounds the tile rate
@@ -381,7 +416,7 @@ __device__ __forceinline__ uint32_t xw_lower_bound(const uint32_t* __restrict__ 
 template <bool SORTED>
 __global__ void xw_count_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, uint32_t M, uint32_t R, uint32_t W,
                                 const uint32_t* __restrict__ tile_win, const uint32_t* __restrict__ tile_rb, uint64_t ngroups,
-                                uint16_t* __restrict__ cp, uint32_t* __restrict__ grp_cnt, int* __restrict__ overflow) {
+                                uint16_t* __restrict__ cp, uint32_t* __restrict__ grp_cnt, int* __restrict__ overflow, uint32_t nw) {
     const uint64_t wg = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31, G = R / 32;
     if (wg > ngroups) return;
@@ -405,7 +440,7 @@ __global__ void xw_count_kernel(const uint32_t* __restrict__ irp, const uint32_t
         const uint32_t cj = __shfl_sync(0xffffffffu, c, j);
         place += (cj > c) || (cj == c && j < lane);
     }
-    cp[(size_t) t * R + g * 32 + lane] = (uint16_t) (c | (place << 8));
+    cp[xw_cp_index(t, g, lane, R, nw)] = (uint16_t) (c | (place << 8));
     const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0) grp_cnt[wg] = tot;
 }
@@ -414,14 +449,14 @@ template <bool SORTED>
 __global__ void xw_fill_kernel(const uint32_t* __restrict__ irp, const uint32_t* __restrict__ ja, const double* __restrict__ as, uint32_t M,
                                uint32_t R, uint32_t W, const uint32_t* __restrict__ tile_win, const uint32_t* __restrict__ tile_rb,
                                uint64_t ngroups, const uint16_t* __restrict__ cp, const uint32_t* __restrict__ grp_off,
-                               uint16_t* __restrict__ col, double* __restrict__ val) {
+                               uint16_t* __restrict__ col, double* __restrict__ val, uint32_t nw) {
     const uint64_t wg = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31, G = R / 32;
     if (wg >= ngroups) return;
     const uint32_t t = (uint32_t) (wg / G), g = (uint32_t) (wg % G);
     const uint32_t row = tile_rb[t] * R + g * 32 + lane;
     const uint64_t lo_c = (uint64_t) tile_win[t] * W, hi_c = lo_c + W;
-    const uint32_t cpv = cp[(size_t) t * R + g * 32 + lane], c = cpv & 0xffu, place = cpv >> 8;
+    const uint32_t cpv = cp[xw_cp_index(t, g, lane, R, nw)], c = cpv & 0xffu, place = cpv >> 8;
     uint32_t j = 0, e = 0;
     if (row < M && c) {
         j = irp[row];
